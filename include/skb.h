@@ -1,0 +1,152 @@
+/*
+ * skb.h -- C ABI of the B200-native GP-posterior + acquisition engine ("skb" = scikit-optimize on Blackwell).
+ *
+ * The reference (scikit-optimize 0.9.0) is pure Python and has no FFI layer; its boundary for this path is duck
+ * typing.  Every entry point below therefore names the reference interface it stands in for
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add at those call sites.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes, no torch / C++ types; all matrices row-major (C-contiguous) float64.
+ *   - every function returns SKB_OK (0) or a negative skb_status; skb_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws across the ABI.
+ *   - a skb_state owns device memory on ONE GPU and is not thread-safe; different states are independent.
+ *   - "dev" entry points take DEVICE pointers on the state's GPU and enqueue on `stream` (a cudaStream_t passed
+ *     as void*; NULL = the state's own stream) without synchronising the host.
+ *     "host" entry points take HOST pointers, stage through pinned buffers, and return when results are in place.
+ *   - there is no CPU fallback: without a usable sm_100 device skb_state_create fails with SKB_ERR_NO_DEVICE.
+ */
+#ifndef SKB_H_
+#define SKB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_ABI_VERSION 1
+
+typedef enum {
+    SKB_OK = 0,
+    SKB_ERR_INVALID = -1,       /* bad argument (NULL, negative size, unknown enum) */
+    SKB_ERR_UNSUPPORTED = -2,   /* outside the supported grammar / size limits */
+    SKB_ERR_NO_DEVICE = -3,     /* no CUDA device, or not sm_100 */
+    SKB_ERR_CUDA = -4,          /* a CUDA runtime call failed; see skb_last_error() */
+    SKB_ERR_NOMEM = -5
+} skb_status;
+
+/* Stationary base kernels of the hot path: sklearn RBF.__call__ (sklearn kernels.py:1558-1570) and
+ * Matern.__call__ (:1713-1729) as subclassed by skopt/learning/gaussian_process/kernels.py:68-200. */
+typedef enum {
+    SKB_KERNEL_RBF = 0,
+    SKB_KERNEL_MATERN12 = 1,    /* nu = 0.5 */
+    SKB_KERNEL_MATERN32 = 2,    /* nu = 1.5 */
+    SKB_KERNEL_MATERN52 = 3     /* nu = 2.5 */
+} skb_kernel_kind;
+
+/* Acquisition functions of skopt/acquisition.py: gaussian_ei (:232-321), gaussian_pi (:149-229),
+ * gaussian_lcb (:90-146).  Values follow _gaussian_acquisition (:20-87): -EI, -PI, LCB, all to be MINIMISED. */
+typedef enum { SKB_ACQ_EI = 0, SKB_ACQ_PI = 1, SKB_ACQ_LCB = 2, SKB_NUM_ACQ = 3 } skb_acq_kind;
+
+/* Everything GaussianProcessRegressor.predict reads from a fitted model (skopt gpr.py:315-356), flattened.
+ *   kernel_(x, X_i) = amplitude * base(|| (x - X_i) / length_scale ||) + bias        (White is 0 off-diagonal)
+ *   kernel_.diag(x) = amplitude + bias + white
+ * L_inv is the inverse of the lower Cholesky factor est.L_ (row-major, entries above the diagonal ignored), so
+ * that K_inv_ (gpr.py:223-224) = L_inv^T L_inv and  k^T K_inv_ k = || L_inv k ||^2.  The caller keeps ownership
+ * of all host arrays; they are copied during skb_state_create. */
+typedef struct {
+    int32_t n_train;
+    int32_t n_dims;
+    int32_t kernel;              /* skb_kernel_kind */
+    int32_t reserved;
+    double amplitude;
+    double bias;
+    double white;
+    double y_mean;               /* est.y_train_mean_ */
+    double y_std;                /* est.y_train_std_ */
+    const double* length_scale;  /* [n_dims] */
+    const double* X_train;       /* [n_train * n_dims] == est.X_train_ */
+    const double* alpha;         /* [n_train]          == est.alpha_ */
+    const double* L_inv;         /* [n_train * n_train] lower triangular */
+} skb_state_desc;
+
+/* acq_func_kwargs of _gaussian_acquisition (acquisition.py:32-35) and y_opt = min(yi) (optimizer.py:558). */
+typedef struct {
+    double y_opt;
+    double xi;                   /* default 0.01 */
+    double kappa;                /* default 1.96; ignored when kappa_inf != 0 */
+    int32_t kappa_inf;           /* kappa == "inf": LCB = -std (acquisition.py:138,144) */
+    int32_t acq_mask;            /* bit i set -> evaluate skb_acq_kind i */
+    int32_t top_k;               /* number of (value, index) pairs to return per requested acquisition, >= 0 */
+    int32_t reserved;
+} skb_acq_params;
+
+/* Outputs of one scoring call over m candidates.  Any pointer may be NULL (that output is skipped).
+ *   mean/std      == predict(X, return_std=True)                       (gpr.py:316-343)
+ *   acq[a]        == _gaussian_acquisition(X, est, y_opt, a)           (acquisition.py:20-87)
+ *   topk_val/idx  == values[order[:top_k]], order[:top_k] + index_offset, order = lexsort by (value, index):
+ *                    element 0 is np.argmin (first minimum, optimizer.py:564); the set is argsort[:k] (:570).
+ *                    NaN sorts last; first_nan[a] receives the lowest global index holding NaN or -1. */
+typedef struct {
+    double* mean;                /* [m] */
+    double* std;                 /* [m] */
+    double* acq[SKB_NUM_ACQ];    /* [m] each */
+    double* topk_val[SKB_NUM_ACQ];   /* [top_k] each */
+    int64_t* topk_idx[SKB_NUM_ACQ];  /* [top_k] each */
+    int64_t* first_nan[SKB_NUM_ACQ]; /* [1] each */
+} skb_score_out;
+
+/* Gradient outputs (batched extension of gpr.py:345-362 + acquisition.py:218-227,305-319: the reference
+ * evaluates one point per call; here every row of X gets its own gradient). */
+typedef struct {
+    double* mean;                /* [m] */
+    double* std;                 /* [m] */
+    double* mean_grad;           /* [m * n_dims] */
+    double* std_grad;            /* [m * n_dims] */
+    double* acq[SKB_NUM_ACQ];        /* [m] each */
+    double* acq_grad[SKB_NUM_ACQ];   /* [m * n_dims] each */
+} skb_grad_out;
+
+typedef struct skb_state skb_state;
+
+int skb_abi_version(void);
+const char* skb_last_error(void);
+/* Number of visible CUDA devices whose compute capability is 10.x; <0 on error. */
+int skb_device_count(void);
+
+/* Replaces: the attribute reads est.X_train_/alpha_/K_inv_/kernel_/y_train_mean_/y_train_std_ at gpr.py:315-356. */
+int skb_state_create(const skb_state_desc* desc, int device, skb_state** out);
+void skb_state_destroy(skb_state* st);
+/* cudaStream_t owned by the state (so callers can record events on it). */
+void* skb_state_stream(skb_state* st);
+int skb_state_sync(skb_state* st);
+/* Upper bound (bytes) of scratch memory the scoring calls may allocate; 0 keeps the default (2 GiB). */
+int skb_state_set_scratch_limit(skb_state* st, uint64_t bytes);
+
+/* Replaces: _gaussian_acquisition(X, model, y_opt, acq_func, acq_func_kwargs) for each requested acquisition
+ * (optimizer.py:557-560, acquisition.py:20-87) composed with model.predict(X, return_std=True) (gpr.py:239-343),
+ * plus np.argmin / np.argsort[:k] of the values (optimizer.py:564,570).  X: [m * n_dims] candidates. */
+int skb_score_dev(skb_state* st, const double* X, int64_t m, int64_t index_offset,
+                  const skb_acq_params* params, const skb_score_out* out, void* stream);
+int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offset,
+                   const skb_acq_params* params, const skb_score_out* out);
+
+/* Replaces: model.predict(X) mean-only (optimizer.py:539 gp_hedge gains; gpr.py:315-318). */
+int skb_predict_mean_dev(skb_state* st, const double* X, int64_t m, double* mean, void* stream);
+int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mean);
+
+/* Replaces: gaussian_acquisition_1D(x, model, y_opt, acq_func, acq_func_kwargs) (acquisition.py:7-17) and
+ * predict(x, return_std=True, return_mean_grad=True, return_std_grad=True) (gpr.py:345-362), batched over rows. */
+int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_params* params,
+                       const skb_grad_out* out, void* stream);
+int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq_params* params,
+                        const skb_grad_out* out);
+
+/* Number of kernel launches issued through this library by the calling process so far (bench.py reports it). */
+int64_t skb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKB_H_ */

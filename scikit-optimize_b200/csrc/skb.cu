@@ -1,0 +1,489 @@
+// C-ABI implementation (include/skb.h): device state of a fitted GP, and the scoring entry points that drive
+// K1 (kcross.cuh) -> K2 (trmm.cuh) -> K3 (topk.cuh).  sm_100a only; there is no CPU path in this library.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/skb.h"
+#include "kcross.cuh"
+#include "layout.cuh"
+#include "topk.cuh"
+#include "trmm.cuh"
+
+using namespace skb;
+
+// ------------------------------------------------------------------------------------------------
+// errors, bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? SKB_ERR_NOMEM : SKB_ERR_CUDA, "%s -> %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                               \
+    } while (0)
+
+#define LAUNCHED()                   \
+    do {                             \
+        g_launches.fetch_add(1);     \
+        CU(cudaGetLastError());      \
+    } while (0)
+
+struct skb_state {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    int n = 0, n_pad = 0, d = 0, d_pad = 0, kernel = 0;
+    double amplitude = 0, bias = 0, white = 0, y_mean = 0, y_std = 1;
+    double* d_ls = nullptr;
+    double* d_Xp = nullptr;
+    double* d_alpha_p = nullptr;
+    double* d_Vp = nullptr;
+    // grow-only scratch
+    uint64_t scratch_limit = 2ull << 30;
+    double* d_Kt = nullptr;      size_t kt_tiles = 0;
+    double* d_kdot = nullptr;    size_t kdot_cap = 0;
+    double* d_acq[3] = {nullptr, nullptr, nullptr};  size_t acq_cap = 0;
+    double* d_part_v = nullptr;  int64_t* d_part_i = nullptr;  int64_t* d_part_nan = nullptr;  size_t part_cap = 0;
+    double* d_topk_v = nullptr;  int64_t* d_topk_i = nullptr;  int64_t* d_topk_nan = nullptr;  size_t topk_cap = 0;
+    // host entry points
+    double* d_X = nullptr;       size_t x_cap = 0;
+    double* d_out = nullptr;     size_t out_cap = 0;
+};
+
+namespace {
+constexpr int TOPK_BLOCKS_PER_SM = 2;
+
+template <typename T>
+int grow(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return SKB_OK;
+    if (*ptr) CU(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(ptr), need * sizeof(T)));
+    *cap = need;
+    return SKB_OK;
+}
+
+// ---------------- pack kernels (run once per state) ----------------
+// Xp[(jg*d_pad + k)*4 + r] = X_train[jg*4+r][k] / ls[k]   (sklearn: Y / length_scale, kernels.py:1720), zero padded
+__global__ void pack_xtrain_kernel(const double* __restrict__ X, const double* __restrict__ ls, double* __restrict__ Xp,
+                                   int n, int n_pad, int d, int d_pad) {
+    const int64_t total = (int64_t)n_pad * d_pad;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = e & 3;
+        const int64_t t = e >> 2;
+        const int k = t % d_pad;
+        const int jg = t / d_pad;
+        const int j = jg * 4 + r;
+        Xp[e] = (j < n && k < d) ? X[(int64_t)j * d + k] / ls[k] : 0.0;
+    }
+}
+
+// Vp: for each row block I and stage kb <= (I+1)*BM/BK - 1 one (BM x BK) tile in k4-interleaved layout:
+//   tile[(g*BM + i)*4 + r] = L_inv[I*BM + i][kb*BK + g*4 + r]   (0 above the diagonal and in the padding)
+__global__ void pack_linv_kernel(const double* __restrict__ V, double* __restrict__ Vp, int n, int n_pad) {
+    const int I = blockIdx.y;
+    const int kb = blockIdx.x;
+    if (kb >= (I + 1) * (BM / BK)) return;
+    double* tile = Vp + (size_t)(vp_tiles_before(I) + kb) * (BM * BK);
+    for (int e = threadIdx.x; e < BM * BK; e += blockDim.x) {
+        const int r = e & 3;
+        const int i = (e >> 2) % BM;
+        const int g = (e >> 2) / BM;
+        const int row = I * BM + i, col = kb * BK + g * 4 + r;
+        tile[e] = (row < n && col <= row) ? V[(size_t)row * n + col] : 0.0;
+    }
+}
+
+__global__ void mean_affine_kernel(const double* __restrict__ kdot, double* __restrict__ mean, int64_t m, double y_std,
+                                   double y_mean) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < m) mean[i] = y_std * kdot[i] + y_mean;
+}
+
+int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t s) {
+    const size_t smem = kcross_smem_bytes(p.d_pad);
+    switch (st->kernel) {
+        case SKB_KERNEL_RBF: kcross_mean_kernel<0><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN12: kcross_mean_kernel<1><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN32: kcross_mean_kernel<2><<<tiles, 256, smem, s>>>(p); break;
+        default: kcross_mean_kernel<3><<<tiles, 256, smem, s>>>(p); break;
+    }
+    LAUNCHED();
+    return SKB_OK;
+}
+
+int set_kernel_attributes(skb_state* st) {
+    const int smem1 = (int)kcross_smem_bytes(st->d_pad);
+    CU(cudaFuncSetAttribute(kcross_mean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_mean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_mean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(trmm_sqnorm_acq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
+    return SKB_OK;
+}
+
+int check_params(const skb_acq_params* p) {
+    if (!p) return fail(SKB_ERR_INVALID, "params is NULL");
+    if (p->acq_mask < 0 || p->acq_mask > 7) return fail(SKB_ERR_INVALID, "acq_mask %d out of range", p->acq_mask);
+    if (p->top_k < 0 || p->top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [0, 4096]", p->top_k);
+    return SKB_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int skb_abi_version(void) { return SKB_ABI_VERSION; }
+const char* skb_last_error(void) { return g_err; }
+int64_t skb_launch_count(void) { return g_launches.load(); }
+
+int skb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+void skb_state_destroy(skb_state* st) {
+    if (!st) return;
+    cudaSetDevice(st->device);
+    if (st->stream) cudaStreamSynchronize(st->stream);
+    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
+                    st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
+                    st->d_topk_nan, st->d_X, st->d_out};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    delete st;
+}
+
+int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
+    if (!desc || !out) return fail(SKB_ERR_INVALID, "desc/out is NULL");
+    *out = nullptr;
+    if (desc->n_train <= 0 || desc->n_dims <= 0) return fail(SKB_ERR_INVALID, "n_train and n_dims must be positive");
+    if (!desc->length_scale || !desc->X_train || !desc->alpha || !desc->L_inv)
+        return fail(SKB_ERR_INVALID, "length_scale / X_train / alpha / L_inv must not be NULL");
+    if (desc->kernel < SKB_KERNEL_RBF || desc->kernel > SKB_KERNEL_MATERN52)
+        return fail(SKB_ERR_UNSUPPORTED, "kernel kind %d is outside the hot-path grammar (RBF, Matern 1/2, 3/2, 5/2)",
+                    desc->kernel);
+    if (desc->n_dims > MAX_DIMS) return fail(SKB_ERR_UNSUPPORTED, "n_dims %d > %d", desc->n_dims, MAX_DIMS);
+    for (int k = 0; k < desc->n_dims; ++k)
+        if (!(desc->length_scale[k] > 0.0)) return fail(SKB_ERR_INVALID, "length_scale[%d] must be > 0", k);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKB_ERR_NO_DEVICE, "device %d not in [0, %d)", device, ndev);
+    int major = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) return fail(SKB_ERR_NO_DEVICE, "device %d has compute capability %d.x; sm_100 is required", device, major);
+    CU(cudaSetDevice(device));
+
+    skb_state* st = new (std::nothrow) skb_state();
+    if (!st) return fail(SKB_ERR_NOMEM, "host allocation failed");
+    st->device = device;
+    st->sm_count = sms;
+    st->n = desc->n_train;
+    st->d = desc->n_dims;
+    st->n_pad = round_up(st->n, BM);
+    st->d_pad = round_up(st->d, 4);
+    st->kernel = desc->kernel;
+    st->amplitude = desc->amplitude;
+    st->bias = desc->bias;
+    st->white = desc->white;
+    st->y_mean = desc->y_mean;
+    st->y_std = desc->y_std;
+
+    const size_t n = st->n, d = st->d;
+    const int nI = st->n_pad / BM;
+    const size_t vp_elems = (size_t)vp_tiles_before(nI) * BM * BK;
+    double *dX = nullptr, *dV = nullptr;
+    int rc = SKB_OK;
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&st->d_ls, d * sizeof(double)));
+        CU(cudaMalloc(&st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double)));
+        CU(cudaMalloc(&st->d_alpha_p, (size_t)st->n_pad * sizeof(double)));
+        CU(cudaMalloc(&st->d_Vp, vp_elems * sizeof(double)));
+        CU(cudaMalloc(&dX, n * d * sizeof(double)));
+        CU(cudaMalloc(&dV, n * n * sizeof(double)));
+        CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemcpyAsync(dX, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemcpyAsync(dV, desc->L_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemsetAsync(st->d_alpha_p, 0, (size_t)st->n_pad * sizeof(double), st->stream));
+        CU(cudaMemcpyAsync(st->d_alpha_p, desc->alpha, n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        pack_xtrain_kernel<<<std::min(1024, (st->n_pad * st->d_pad + 255) / 256), 256, 0, st->stream>>>(
+            dX, st->d_ls, st->d_Xp, st->n, st->n_pad, st->d, st->d_pad);
+        LAUNCHED();
+        pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(st->stream));
+        return set_kernel_attributes(st);
+    };
+    rc = body();
+    if (dX) cudaFree(dX);
+    if (dV) cudaFree(dV);
+    if (rc != SKB_OK) {
+        skb_state_destroy(st);
+        return rc;
+    }
+    *out = st;
+    return SKB_OK;
+}
+
+void* skb_state_stream(skb_state* st) { return st ? (void*)st->stream : nullptr; }
+
+int skb_state_sync(skb_state* st) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    CU(cudaSetDevice(st->device));
+    CU(cudaStreamSynchronize(st->stream));
+    return SKB_OK;
+}
+
+int skb_state_set_scratch_limit(skb_state* st, uint64_t bytes) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    st->scratch_limit = bytes ? bytes : (2ull << 30);
+    return SKB_OK;
+}
+
+static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
+                          const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out) {
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    const int64_t tiles = (m + BN - 1) / BN;
+    const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
+    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / tile_bytes));
+    if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;   // whole waves per chunk
+    const int64_t chunk_tiles = std::min(tiles, cap);
+
+    int rc;
+    if (!mean_only) {
+        if ((rc = grow(&st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    }
+    if ((rc = grow(&st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
+
+    const int top_k = (!mean_only && prm) ? prm->top_k : 0;
+    double* acq_ptr[3] = {nullptr, nullptr, nullptr};
+    if (!mean_only) {
+        bool need_internal = false;
+        for (int a = 0; a < 3; ++a) {
+            if (!((prm->acq_mask >> a) & 1)) continue;
+            acq_ptr[a] = out->acq[a];
+            if (!acq_ptr[a] && top_k > 0) need_internal = true;
+        }
+        if (need_internal) {
+            if ((size_t)m > st->acq_cap) {
+                for (int a = 0; a < 3; ++a) {
+                    size_t cap_a = st->acq_cap;
+                    if ((rc = grow(&st->d_acq[a], &cap_a, (size_t)m)) != SKB_OK) return rc;
+                }
+                st->acq_cap = (size_t)m;
+            }
+            for (int a = 0; a < 3; ++a)
+                if (((prm->acq_mask >> a) & 1) && !acq_ptr[a]) acq_ptr[a] = st->d_acq[a];
+        }
+    }
+
+    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles) {
+        const int64_t nt = std::min(chunk_tiles, tiles - t0);
+        const int64_t c0 = t0 * BN;
+        const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
+        KCrossParams kp;
+        kp.X = X + c0 * st->d;
+        kp.ls = st->d_ls;
+        kp.Xp = st->d_Xp;
+        kp.alpha_p = st->d_alpha_p;
+        kp.Kt = mean_only ? nullptr : st->d_Kt;
+        kp.kdot = st->d_kdot;
+        kp.m = mc;
+        kp.n = st->n;
+        kp.n_pad = st->n_pad;
+        kp.d = st->d;
+        kp.d_pad = st->d_pad;
+        kp.amplitude = st->amplitude;
+        kp.bias = st->bias;
+        if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
+        if (mean_only) {
+            // mean = y_std * kdot + y_mean (gpr.py:316-318)
+            mean_affine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(st->d_kdot, mean_only_out + c0, mc, st->y_std, st->y_mean);
+            LAUNCHED();
+            continue;
+        }
+        TrmmParams tp;
+        tp.Vp = st->d_Vp;
+        tp.Kt = st->d_Kt;
+        tp.kdot = st->d_kdot;
+        tp.n_pad = st->n_pad;
+        tp.m = mc;
+        tp.a.prior_var = st->amplitude + st->bias + st->white;
+        tp.a.y_mean = st->y_mean;
+        tp.a.y_std = st->y_std;
+        tp.a.y_opt = prm->y_opt;
+        tp.a.xi = prm->xi;
+        tp.a.kappa = prm->kappa;
+        tp.a.kappa_inf = prm->kappa_inf;
+        tp.a.acq_mask = prm->acq_mask;
+        tp.mean = out->mean ? out->mean + c0 : nullptr;
+        tp.std = out->std ? out->std + c0 : nullptr;
+        for (int a = 0; a < 3; ++a) tp.acq[a] = acq_ptr[a] ? acq_ptr[a] + c0 : nullptr;
+        tp.qout = nullptr;
+        trmm_sqnorm_acq_kernel<<<(unsigned)nt, TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
+        LAUNCHED();
+    }
+
+    if (top_k > 0) {
+        const int nblk = (int)std::min<int64_t>((int64_t)st->sm_count * TOPK_BLOCKS_PER_SM, (m + 1023) / 1024);
+        const int64_t slice = (m + nblk - 1) / nblk;
+        if ((size_t)nblk * top_k > st->part_cap) {
+            size_t c1 = st->part_cap, c2 = st->part_cap, c3 = st->part_cap;
+            if ((rc = grow(&st->d_part_v, &c1, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            if ((rc = grow(&st->d_part_i, &c2, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            if ((rc = grow(&st->d_part_nan, &c3, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            st->part_cap = (size_t)nblk * top_k;
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (!((prm->acq_mask >> a) & 1)) continue;
+            if (!out->topk_val[a] || !out->topk_idx[a])
+                return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+            topk_partial_kernel<<<nblk, TOPK_THREADS, 0, s>>>(acq_ptr[a], m, slice, index_offset, top_k, st->d_part_v,
+                                                              st->d_part_i, st->d_part_nan);
+            LAUNCHED();
+            topk_merge_kernel<<<1, TOPK_THREADS, 0, s>>>(st->d_part_v, st->d_part_i, st->d_part_nan, nblk, top_k,
+                                                         out->topk_val[a], out->topk_idx[a], out->first_nan[a]);
+            LAUNCHED();
+        }
+    }
+    return SKB_OK;
+}
+
+int skb_score_dev(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* params,
+                  const skb_score_out* out, void* stream) {
+    if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    int rc = check_params(params);
+    if (rc != SKB_OK) return rc;
+    return score_dev_impl(st, X, m, index_offset, params, out, stream ? (cudaStream_t)stream : st->stream, false, nullptr);
+}
+
+int skb_predict_mean_dev(skb_state* st, const double* X, int64_t m, double* mean, void* stream) {
+    if (!st || !mean) return fail(SKB_ERR_INVALID, "state/mean is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    return score_dev_impl(st, X, m, 0, nullptr, nullptr, stream ? (cudaStream_t)stream : st->stream, true, mean);
+}
+
+int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* params,
+                   const skb_score_out* out) {
+    if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    int rc = check_params(params);
+    if (rc != SKB_OK) return rc;
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    cudaStream_t s = st->stream;
+    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
+    // device mirror of the requested outputs: [mean][std][acq0][acq1][acq2] (m each, only those requested)
+    int n_vec = (out->mean ? 1 : 0) + (out->std ? 1 : 0);
+    for (int a = 0; a < 3; ++a)
+        if (((params->acq_mask >> a) & 1) && out->acq[a]) ++n_vec;
+    const int k = params->top_k;
+    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)n_vec * m + 1)) != SKB_OK) return rc;
+    if ((size_t)3 * std::max(k, 1) > st->topk_cap) {
+        size_t c1 = st->topk_cap, c2 = st->topk_cap, c3 = st->topk_cap;
+        if ((rc = grow(&st->d_topk_v, &c1, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        if ((rc = grow(&st->d_topk_i, &c2, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        if ((rc = grow(&st->d_topk_nan, &c3, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        st->topk_cap = (size_t)3 * std::max(k, 1);
+    }
+    skb_score_out dout;
+    std::memset(&dout, 0, sizeof(dout));
+    double* cur = st->d_out;
+    if (out->mean) { dout.mean = cur; cur += m; }
+    if (out->std) { dout.std = cur; cur += m; }
+    for (int a = 0; a < 3; ++a) {
+        if (!((params->acq_mask >> a) & 1)) continue;
+        if (out->acq[a]) { dout.acq[a] = cur; cur += m; }
+        if (k > 0) {
+            dout.topk_val[a] = st->d_topk_v + (size_t)a * k;
+            dout.topk_idx[a] = st->d_topk_i + (size_t)a * k;
+            dout.first_nan[a] = st->d_topk_nan + a;
+        }
+    }
+    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr)) != SKB_OK) return rc;
+    if (out->mean) CU(cudaMemcpyAsync(out->mean, dout.mean, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->std) CU(cudaMemcpyAsync(out->std, dout.std, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    for (int a = 0; a < 3; ++a) {
+        if (!((params->acq_mask >> a) & 1)) continue;
+        if (out->acq[a]) CU(cudaMemcpyAsync(out->acq[a], dout.acq[a], m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (k > 0) {
+            if (!out->topk_val[a] || !out->topk_idx[a])
+                return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+            CU(cudaMemcpyAsync(out->topk_val[a], dout.topk_val[a], k * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(out->topk_idx[a], dout.topk_idx[a], k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            if (out->first_nan[a])
+                CU(cudaMemcpyAsync(out->first_nan[a], dout.first_nan[a], sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CU(cudaStreamSynchronize(s));
+    return SKB_OK;
+}
+
+int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mean) {
+    if (!st || !mean) return fail(SKB_ERR_INVALID, "state/mean is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    int rc;
+    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
+    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)m)) != SKB_OK) return rc;
+    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+    if ((rc = score_dev_impl(st, st->d_X, m, 0, nullptr, nullptr, st->stream, true, st->d_out)) != SKB_OK) return rc;
+    CU(cudaMemcpyAsync(mean, st->d_out, m * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+    CU(cudaStreamSynchronize(st->stream));
+    return SKB_OK;
+}
+
+int skb_score_grad_dev(skb_state*, const double*, int64_t, const skb_acq_params*, const skb_grad_out*, void*) {
+    return fail(SKB_ERR_UNSUPPORTED, "gradient path not built yet");
+}
+int skb_score_grad_host(skb_state*, const double*, int64_t, const skb_acq_params*, const skb_grad_out*) {
+    return fail(SKB_ERR_UNSUPPORTED, "gradient path not built yet");
+}
+
+}  // extern "C"

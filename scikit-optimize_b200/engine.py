@@ -1,0 +1,262 @@
+"""Host side of the device boundary: flatten a fitted GP into the POD the C ABI takes, and drive the scoring calls.
+
+Reference interfaces mirrored (paths relative to the reference tree):
+  * attribute reads of GaussianProcessRegressor.predict       skopt/learning/gaussian_process/gpr.py:315-356
+  * kernel algebra of sklearn Sum / Product / Constant / White sklearn kernels.py:871,890,971,990,1278,1315,1418,1438
+  * _gaussian_acquisition + argmin / argsort[:k]               skopt/acquisition.py:20-87, optimizer.py:557-570
+"""
+import ctypes as C
+import math
+import weakref
+
+import numpy as np
+from scipy.linalg import solve_triangular
+
+from . import _lib
+
+ACQ_NAMES = ("EI", "PI", "LCB")
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel tree -> amplitude * base(r) + bias (+ white on the diagonal)
+# ----------------------------------------------------------------------------------------------
+class _Affine:
+    """k(x, y) = a * base(x, y) + c  off the diagonal;  diag(x) = a + c + w."""
+    __slots__ = ("a", "c", "w", "base")
+
+    def __init__(self, a=0.0, c=0.0, w=0.0, base=None):
+        self.a, self.c, self.w, self.base = a, c, w, base
+
+
+def _flatten_kernel(kernel):
+    cls = type(kernel).__name__
+    if cls == "ConstantKernel":
+        return _Affine(c=float(kernel.constant_value))
+    if cls == "WhiteKernel":
+        return _Affine(w=float(kernel.noise_level))
+    if cls == "RBF":
+        return _Affine(a=1.0, base=(_lib.KERNEL_RBF, np.asarray(kernel.length_scale, dtype=np.float64)))
+    if cls == "Matern":
+        kinds = {0.5: _lib.KERNEL_MATERN12, 1.5: _lib.KERNEL_MATERN32, 2.5: _lib.KERNEL_MATERN52}
+        if kernel.nu == math.inf:
+            kind = _lib.KERNEL_RBF          # sklearn kernels.py:1730-1731
+        elif kernel.nu in kinds:
+            kind = kinds[kernel.nu]
+        else:
+            raise NotImplementedError("Matern(nu=%r): only nu in {0.5, 1.5, 2.5, inf} run on the GPU path" % kernel.nu)
+        return _Affine(a=1.0, base=(kind, np.asarray(kernel.length_scale, dtype=np.float64)))
+    if cls in ("Sum", "Product"):
+        l, r = _flatten_kernel(kernel.k1), _flatten_kernel(kernel.k2)
+        if l.base is not None and r.base is not None:
+            raise NotImplementedError("%s of two stationary kernels is outside the GPU hot-path grammar "
+                                      "([Constant *] {RBF|Matern} [+ Constant] [+ White])" % cls)
+        base = l.base if l.base is not None else r.base
+        if cls == "Sum":
+            return _Affine(l.a + r.a, l.c + r.c, l.w + r.w, base)
+        off_l, off_r = l.a + l.c, r.a + r.c                 # value at r = 0 without the white term
+        return _Affine(l.a * r.c + l.c * r.a, l.c * r.c, (off_l + l.w) * (off_r + r.w) - off_l * off_r, base)
+    raise NotImplementedError("kernel %s is outside the GPU hot-path grammar "
+                              "([Constant *] {RBF|Matern} [+ Constant] [+ White])" % cls)
+
+
+class HostState:
+    """Plain arrays describing a fitted GP (the argument of skb_state_create)."""
+
+    def __init__(self, X_train, alpha, L_inv, length_scale, kernel, amplitude, bias, white, y_mean, y_std):
+        self.X_train = np.ascontiguousarray(X_train, dtype=np.float64)
+        self.alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        self.L_inv = np.ascontiguousarray(L_inv, dtype=np.float64)
+        n, d = self.X_train.shape
+        if self.alpha.shape != (n,):
+            raise ValueError("alpha must have shape (n_train,); multi-output targets are not supported on the GPU path")
+        if self.L_inv.shape != (n, n):
+            raise ValueError("L_inv must have shape (n_train, n_train)")
+        self.length_scale = np.ascontiguousarray(np.broadcast_to(np.asarray(length_scale, dtype=np.float64), (d,)))
+        self.kernel = int(kernel)
+        self.amplitude, self.bias, self.white = float(amplitude), float(bias), float(white)
+        self.y_mean, self.y_std = float(y_mean), float(y_std)
+
+    @property
+    def n_train(self):
+        return self.X_train.shape[0]
+
+    @property
+    def n_dims(self):
+        return self.X_train.shape[1]
+
+    @property
+    def prior_var(self):
+        return self.amplitude + self.bias + self.white
+
+
+def host_state_from_estimator(est):
+    """Flatten a fitted skopt-style GaussianProcessRegressor (outputs of gpr.py:166-237)."""
+    if not hasattr(est, "X_train_"):
+        raise ValueError("estimator is not fitted")
+    aff = _flatten_kernel(est.kernel_)
+    d = est.X_train_.shape[1]
+    if aff.base is None:
+        kind, ls, amp = _lib.KERNEL_RBF, np.ones(d), 0.0
+    else:
+        (kind, ls), amp = aff.base, aff.a
+    L_inv = getattr(est, "_L_inv_lower", None)
+    if L_inv is None:
+        L_inv = solve_triangular(est.L_, np.eye(est.L_.shape[0]), lower=True)
+    return HostState(est.X_train_, est.alpha_, L_inv, ls, kind, amp, aff.c, aff.w,
+                     np.ravel(est.y_train_mean_)[0], np.ravel(est.y_train_std_)[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# device state
+# ----------------------------------------------------------------------------------------------
+def _mask(acq_funcs):
+    m = 0
+    for a in acq_funcs:
+        if a not in _lib.ACQ_INDEX:
+            raise ValueError("Acquisition function not implemented.")
+        m |= 1 << _lib.ACQ_INDEX[a]
+    return m
+
+
+def _acq_params(y_opt, xi, kappa, acq_funcs, top_k):
+    p = _lib.AcqParams()
+    p.y_opt = 0.0 if y_opt is None else float(y_opt)
+    p.xi = float(xi)
+    p.kappa_inf = 1 if isinstance(kappa, str) and kappa == "inf" else 0
+    p.kappa = 0.0 if p.kappa_inf else float(kappa)
+    p.acq_mask = _mask(acq_funcs)
+    p.top_k = int(top_k)
+    return p
+
+
+class DeviceState:
+    """A fitted GP resident on one B200 (owner of a skb_state handle)."""
+
+    def __init__(self, host_state, device=0):
+        L = _lib.lib()
+        self.host = host_state
+        self.device = int(device)
+        desc = _lib.StateDesc()
+        desc.n_train, desc.n_dims, desc.kernel = host_state.n_train, host_state.n_dims, host_state.kernel
+        desc.amplitude, desc.bias, desc.white = host_state.amplitude, host_state.bias, host_state.white
+        desc.y_mean, desc.y_std = host_state.y_mean, host_state.y_std
+        desc.length_scale = host_state.length_scale.ctypes.data
+        desc.X_train = host_state.X_train.ctypes.data
+        desc.alpha = host_state.alpha.ctypes.data
+        desc.L_inv = host_state.L_inv.ctypes.data
+        handle = C.c_void_p()
+        _lib.check(L.skb_state_create(C.byref(desc), self.device, C.byref(handle)))
+        self._h = handle
+        self._finalizer = weakref.finalize(self, L.skb_state_destroy, handle)
+
+    @classmethod
+    def from_estimator(cls, est, device=0):
+        return cls(host_state_from_estimator(est), device)
+
+    def close(self):
+        self._finalizer()
+
+    @property
+    def n_dims(self):
+        return self.host.n_dims
+
+    @property
+    def stream(self):
+        return _lib.lib().skb_state_stream(self._h)
+
+    def sync(self):
+        _lib.check(_lib.lib().skb_state_sync(self._h))
+
+    def set_scratch_limit(self, nbytes):
+        _lib.check(_lib.lib().skb_state_set_scratch_limit(self._h, int(nbytes)))
+
+    # ---------------------------------------------------------------- host (NumPy) entry points
+    def _check_X(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X is {}-dimensional, however, it must be 2-dimensional.".format(X.ndim))
+        if X.shape[1] != self.n_dims:
+            raise ValueError("X has %d features, the model was fitted with %d" % (X.shape[1], self.n_dims))
+        return X
+
+    def predict_mean(self, X):
+        X = self._check_X(X)
+        mean = np.empty(X.shape[0])
+        _lib.check(_lib.lib().skb_predict_mean_host(self._h, X.ctypes.data, X.shape[0], mean.ctypes.data))
+        return mean
+
+    def score(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0,
+              want_posterior=True, want_values=True):
+        """One pass over the candidates: posterior, every requested acquisition, and their top-k.
+
+        Returns a dict with 'mean', 'std' (if want_posterior), per acquisition name 'values' (if want_values),
+        'topk_val', 'topk_idx', 'first_nan' (if top_k > 0).
+        """
+        X = self._check_X(X)
+        m = X.shape[0]
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k)
+        out = _lib.ScoreOut()
+        res = {}
+        if want_posterior:
+            res["mean"], res["std"] = np.empty(m), np.empty(m)
+            out.mean, out.std = res["mean"].ctypes.data, res["std"].ctypes.data
+        for name in acq_funcs:
+            a = _lib.ACQ_INDEX[name]
+            r = res.setdefault(name, {})
+            if want_values:
+                r["values"] = np.empty(m)
+                out.acq[a] = r["values"].ctypes.data
+            if top_k > 0:
+                r["topk_val"] = np.full(top_k, np.nan)
+                r["topk_idx"] = np.full(top_k, -1, dtype=np.int64)
+                r["_nan"] = np.full(1, -1, dtype=np.int64)
+                out.topk_val[a] = r["topk_val"].ctypes.data
+                out.topk_idx[a] = r["topk_idx"].ctypes.data
+                out.first_nan[a] = r["_nan"].ctypes.data
+        _lib.check(_lib.lib().skb_score_host(self._h, X.ctypes.data, m, int(index_offset), C.byref(prm), C.byref(out)))
+        for name in acq_funcs:
+            r = res[name]
+            if "_nan" in r:
+                r["first_nan"] = int(r.pop("_nan")[0])
+        return res
+
+    # ---------------------------------------------------------------- device (torch tensor) entry points
+    def score_tensors(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0,
+                      want_posterior=False, want_values=False, stream=None):
+        """Same as score() for a CUDA float64 tensor already resident on this state's GPU.  Asynchronous:
+        work is enqueued on `stream` (a torch.cuda.Stream; default: torch's current stream)."""
+        import torch
+        if not (X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.is_contiguous()):
+            raise ValueError("X must be a contiguous 2-D float64 CUDA tensor")
+        if X.device.index != self.device or X.shape[1] != self.n_dims:
+            raise ValueError("X is on the wrong device or has the wrong number of features")
+        m = X.shape[0]
+        dev = X.device
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k)
+        out = _lib.ScoreOut()
+        res = {}
+        if want_posterior:
+            res["mean"] = torch.empty(m, dtype=torch.float64, device=dev)
+            res["std"] = torch.empty(m, dtype=torch.float64, device=dev)
+            out.mean, out.std = res["mean"].data_ptr(), res["std"].data_ptr()
+        for name in acq_funcs:
+            a = _lib.ACQ_INDEX[name]
+            r = res.setdefault(name, {})
+            if want_values:
+                r["values"] = torch.empty(m, dtype=torch.float64, device=dev)
+                out.acq[a] = r["values"].data_ptr()
+            if top_k > 0:
+                r["topk_val"] = torch.empty(top_k, dtype=torch.float64, device=dev)
+                r["topk_idx"] = torch.empty(top_k, dtype=torch.int64, device=dev)
+                r["first_nan"] = torch.empty(1, dtype=torch.int64, device=dev)
+                out.topk_val[a] = r["topk_val"].data_ptr()
+                out.topk_idx[a] = r["topk_idx"].data_ptr()
+                out.first_nan[a] = r["first_nan"].data_ptr()
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        _lib.check(_lib.lib().skb_score_dev(self._h, X.data_ptr(), m, int(index_offset), C.byref(prm), C.byref(out),
+                                            C.c_void_p(s.cuda_stream)))
+        return res
+
+
+def launch_count():
+    return int(_lib.lib().skb_launch_count())
