@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Headline benchmark: GP-posterior + EI candidate evaluations per second (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2]): synthetic GP, n_train=2048, d=20, Matern-5/2 with fixed
+hyper-parameters, 1,000,000 candidates per GPU, FP64.  A step = one pass of the hot path over the candidate set:
+posterior mean/std, -EI, and the top-k (value, index) pairs; with N GPUs every rank owns its own 1M candidates
+(weak scaling, GP state replicated) and the only collective is the all-gather of the per-rank top-k (NCCL).
+
+  value : evals/s, candidates resident in HBM (device entry point, CUDA-event timed, max over ranks)
+  e2e   : evals/s through the host entry point (pinned host candidates -> H2D -> kernels -> D2H of the top-k)
+  roofline : dominant kernel (K2, DMMA triangular contraction) algorithmic FP64 flops / its CUDA-event time
+  cpu_baseline : the CPU oracle (a port of the reference's NumPy/SciPy path) on a bounded sample, this host
+
+`--impl reference` times the reference algorithm (oracle port, einsum contraction exactly as gpr.py:332) on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN, N_DIMS, M_PER_GPU, TOP_K = 2048, 20, 1_000_000, 16
+FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue peak on this pool's B200 (profiles/r01_fp64_peaks.txt); cuBLAS DGEMM: 35.5
+METRIC = "GP-EI candidate evals/sec at n_train=2048,d=20"
+
+
+def flops_value_path(n, d):
+    """Algorithmic flops per candidate: kernel row + mean dot, whitened solve, epilogue."""
+    return n * (3 * d + 12) + (n * n + 2 * n) + 40
+
+
+def flops_k2(n):
+    return n * n + 2 * n + 40
+
+
+def make_problem(n, d, seed=0):
+    """SURVEY.md 8(d) recipe, built with the product's own estimator class (host-side fit, hyper-parameters fixed)."""
+    from skopt_b200.learning import GaussianProcessRegressor
+    from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
+    rng = np.random.RandomState(seed)
+    X_train = rng.rand(n, d)
+    w = rng.randn(d)
+    y = np.sin(X_train @ w) + 0.1 * rng.randn(n)
+    kernel = ConstantKernel(1.3, "fixed") * Matern(np.full(d, 1.5), "fixed", nu=2.5)
+    gpr = GaussianProcessRegressor(kernel, normalize_y=True, noise=1e-4, optimizer=None).fit(X_train, y)
+    return gpr, float(y.min())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
+    """Oracle (port of the reference's NumPy/SciPy path) timed on this host on `sample_m` candidates."""
+    from oracle import gp_oracle as orc
+    st = orc.make_synthetic_state(n, d, noise=1e-4, seed=seed)
+    Xc = np.random.RandomState(seed + 1).rand(sample_m, d)
+    y_opt = float(st.meta["y"].min())
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        v = orc.gaussian_acquisition(Xc, st, y_opt, "EI", acq_func_kwargs=dict(xi=0.01, kappa=1.96), quad=quad)
+        int(np.argmin(v))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_m / best, best
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference algorithm on the host cores (bounded sample per step)."""
+    if rank != 0:
+        return
+    sample = args.ref_sample
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, sample, quad="einsum", seed=0)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic GP posterior + EI: n_train=2048, d=20, FP64; reference algorithm "
+                               "(NumPy/SciPy: cdist-style distances, Matern-5/2, dgemv mean, einsum('ki,kj,ij->k') "
+                               "variance as skopt gpr.py:332) on a bounded sample of %d candidates per step" % sample,
+                   "n_train": N_TRAIN, "n_dims": N_DIMS, "candidates_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d candidates per step; einsum contraction is single-threaded as in the "
+                                   "reference, BLAS parts may use all %d host threads" % (sample, cores)},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m", type=int, default=M_PER_GPU, help="candidates per GPU per step")
+    ap.add_argument("--ref-sample", type=int, default=256, help="candidates per step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="candidates of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import skopt_b200
+    from skopt_b200 import engine
+    from skopt_b200.distributed import merge_topk_allgather
+    from skopt_b200.learning.gaussian_process import gpr as gpr_mod
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    gpr_mod.set_default_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gpr, y_opt = make_problem(N_TRAIN, N_DIMS)
+    dev = gpr.device_state(local_rank)
+    m = args.m
+    offset = rank * m
+    Xc_host = torch.from_numpy(np.random.RandomState(1000 + rank).rand(m, N_DIMS)).pin_memory()
+    Xc_dev = Xc_host.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        res = dev.score_tensors(Xc_dev, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
+                                index_offset=offset)
+        return merge_topk_allgather(res["EI"]["topk_val"], res["EI"]["topk_idx"], TOP_K) if world > 1 else \
+            (res["EI"]["topk_val"], res["EI"]["topk_idx"])
+
+    def step_host():
+        res = dev.score(Xc_host.numpy(), y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
+                        index_offset=offset, want_posterior=False, want_values=False)
+        if world > 1:
+            v = torch.from_numpy(res["EI"]["topk_val"]).cuda()
+            i = torch.from_numpy(res["EI"]["topk_idx"]).cuda()
+            v, i = merge_topk_allgather(v, i, TOP_K)
+            return v.cpu(), i.cpu()
+        return res["EI"]["topk_val"], res["EI"]["topk_idx"]
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for _ in range(args.warmup):
+        step_dev()
+    dev.set_timing(True)
+    dev.get_timing()
+    barrier()
+    launches0 = engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            best = step_dev()
+        e1.record(stream)
+        barrier()
+    launches = engine.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    timing = dev.get_timing()
+    dev.set_timing(False)
+    argmin_idx = int(best[1][0].item())
+
+    # ---------------------------------------------------------------- end to end through host buffers
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = world * m / (ms_per_step / 1e3)
+    e2e_value = world * m * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        k2_ms, k2_launches = timing["k2"]
+        k1_ms, _ = timing["k1"]
+        cand_per_k2 = m * args.steps / max(k2_launches, 1)
+        k2_avg_ms = k2_ms / max(k2_launches, 1)
+        achieved = flops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "k2_dram_bytes_per_launch.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic GP posterior + EI: n_train=2048, d=20, %d candidates per GPU, FP64 "
+                                   "(BASELINE.json configs[2])" % m,
+                       "n_train": N_TRAIN, "n_dims": N_DIMS, "candidates_per_gpu": m, "top_k": TOP_K,
+                       "kernel": "1.3 * Matern(nu=2.5, length_scale=1.5) + noise 1e-4, normalize_y",
+                       "sharding": "candidates sharded across ranks, GP state replicated, NCCL all-gather of top-k",
+                       "l2_policy": "inputs larger than L2 (candidates %.0f MB + 1 GiB cross-covariance scratch per "
+                                    "chunk vs 126 MB L2)" % (m * N_DIMS * 8 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": m * N_DIMS * 8,
+                    "d2h_bytes_per_step": TOP_K * 16 + 16},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                         "kernel": "trmm_sqnorm_acq_kernel (K2)", "peak_source": "measured FP64 DMMA issue peak on this "
+                         "pool (tools/microbench/fp64_peaks.cu -> profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json has "
+                         "no FP64 entry; cuBLAS DGEMM 8192^3 measured 35.5",
+                         "algorithmic_flops_per_candidate": flops_k2(N_TRAIN), "candidates_per_launch": cand_per_k2,
+                         "avg_launch_ms": k2_avg_ms, "k2_share_of_step": k2_ms / ms_total,
+                         "k1_share_of_step": k1_ms / ms_total,
+                         "whole_path_tflops": flops_value_path(N_TRAIN, N_DIMS) * value / world / 1e12},
+            "argmin_index": argmin_idx,
+        }
+        if not args.no_cpu_baseline:
+            evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, args.cpu_sample, quad="einsum")
+            evals_s_gemm, _ = cpu_baseline(N_TRAIN, N_DIMS, 4 * args.cpu_sample, quad="gemm")
+            line["cpu_baseline"] = {
+                "value": evals_s, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": "%d candidates of the same workload, %.1f s; oracle port with the reference's einsum "
+                          "contraction (single-threaded as in the reference; BLAS parts on all host threads)"
+                          % (args.cpu_sample, dt),
+                "tuned_gemm_variant_evals_s": evals_s_gemm}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,8 @@
  *     last failure on the calling thread.  Nothing throws across the ABI.
  *   - a skb_state owns device memory on ONE GPU and is not thread-safe; different states are independent.
  *   - "dev" entry points take DEVICE pointers on the state's GPU and enqueue on `stream` (a cudaStream_t passed
- *     as void*; NULL = the state's own stream) without synchronising the host.
+ *     as void*; NULL = the CUDA default stream, skb_state_stream(st) = the state's own stream) without
+ *     synchronising the host.  Scratch buffers belong to the state: do not overlap two calls on one state.
  *     "host" entry points take HOST pointers, stage through pinned buffers, and return when results are in place.
  *   - there is no CPU fallback: without a usable sm_100 device skb_state_create fails with SKB_ERR_NO_DEVICE.
  */
@@ -95,6 +96,7 @@ typedef struct {
     double* topk_val[SKB_NUM_ACQ];   /* [top_k] each */
     int64_t* topk_idx[SKB_NUM_ACQ];  /* [top_k] each */
     int64_t* first_nan[SKB_NUM_ACQ]; /* [1] each */
+    int64_t* n_var_clamped;      /* [1] number of candidates whose variance was < 0 and set to 0 (gpr.py:336-340) */
 } skb_score_out;
 
 /* Gradient outputs (batched extension of gpr.py:345-362 + acquisition.py:218-227,305-319: the reference
@@ -142,6 +144,13 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
                        const skb_grad_out* out, void* stream);
 int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq_params* params,
                         const skb_grad_out* out);
+
+/* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
+ * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind
+ * (0 = K1 cross-kernel + mean, 1 = K2 triangular contraction + acquisition, 2 = top-k, 3 = gradient kernels),
+ * counts the spans, and resets the accumulation. */
+int skb_state_set_timing(skb_state* st, int enabled);
+int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
 
 /* Number of kernel launches issued through this library by the calling process so far (bench.py reports it). */
 int64_t skb_launch_count(void);

@@ -31,7 +31,8 @@ class AcqParams(C.Structure):
 
 class ScoreOut(C.Structure):
     _fields_ = [("mean", C.c_void_p), ("std", C.c_void_p), ("acq", C.c_void_p * 3),
-                ("topk_val", C.c_void_p * 3), ("topk_idx", C.c_void_p * 3), ("first_nan", C.c_void_p * 3)]
+                ("topk_val", C.c_void_p * 3), ("topk_idx", C.c_void_p * 3), ("first_nan", C.c_void_p * 3),
+                ("n_var_clamped", C.c_void_p)]
 
 
 class GradOut(C.Structure):
@@ -49,6 +50,8 @@ SYMBOLS = [
     ("skb_state_stream", C.c_void_p, [C.c_void_p]),
     ("skb_state_sync", C.c_int, [C.c_void_p]),
     ("skb_state_set_scratch_limit", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("skb_state_set_timing", C.c_int, [C.c_void_p, C.c_int]),
+    ("skb_state_get_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     ("skb_score_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(AcqParams),
                                 C.POINTER(ScoreOut), C.c_void_p]),
     ("skb_score_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(AcqParams),

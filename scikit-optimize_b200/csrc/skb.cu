@@ -64,9 +64,15 @@ struct skb_state {
     double* d_acq[3] = {nullptr, nullptr, nullptr};  size_t acq_cap = 0;
     double* d_part_v = nullptr;  int64_t* d_part_i = nullptr;  int64_t* d_part_nan = nullptr;  size_t part_cap = 0;
     double* d_topk_v = nullptr;  int64_t* d_topk_i = nullptr;  int64_t* d_topk_nan = nullptr;  size_t topk_cap = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool timing = false;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    size_t spans_used = 0;
     // host entry points
     double* d_X = nullptr;       size_t x_cap = 0;
     double* d_out = nullptr;     size_t out_cap = 0;
+    unsigned long long* d_clamp = nullptr;
 };
 
 namespace {
@@ -118,6 +124,27 @@ __global__ void mean_affine_kernel(const double* __restrict__ kdot, double* __re
                                    double y_mean) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < m) mean[i] = y_std * kdot[i] + y_mean;
+}
+
+// kinds: 0 = K1 cross-kernel+mean, 1 = K2 triangular contraction+acquisition, 2 = top-k, 3 = gradient kernels
+int span_begin(skb_state* st, int kind, cudaStream_t s) {
+    if (!st->timing) return SKB_OK;
+    if (st->spans_used == st->spans.size()) {
+        skb_state::Span sp;
+        sp.kind = kind;
+        CU(cudaEventCreate(&sp.a));
+        CU(cudaEventCreate(&sp.b));
+        st->spans.push_back(sp);
+    }
+    st->spans[st->spans_used].kind = kind;
+    CU(cudaEventRecord(st->spans[st->spans_used].a, s));
+    return SKB_OK;
+}
+int span_end(skb_state* st, cudaStream_t s) {
+    if (!st->timing) return SKB_OK;
+    CU(cudaEventRecord(st->spans[st->spans_used].b, s));
+    st->spans_used++;
+    return SKB_OK;
 }
 
 int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t s) {
@@ -179,9 +206,13 @@ void skb_state_destroy(skb_state* st) {
     if (st->stream) cudaStreamSynchronize(st->stream);
     void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
-                    st->d_topk_nan, st->d_X, st->d_out};
+                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& sp : st->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
     if (st->stream) cudaStreamDestroy(st->stream);
     delete st;
 }
@@ -237,6 +268,7 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         CU(cudaMalloc(&st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double)));
         CU(cudaMalloc(&st->d_alpha_p, (size_t)st->n_pad * sizeof(double)));
         CU(cudaMalloc(&st->d_Vp, vp_elems * sizeof(double)));
+        CU(cudaMalloc(&st->d_clamp, sizeof(unsigned long long)));
         CU(cudaMalloc(&dX, n * d * sizeof(double)));
         CU(cudaMalloc(&dV, n * n * sizeof(double)));
         CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
@@ -278,6 +310,34 @@ int skb_state_set_scratch_limit(skb_state* st, uint64_t bytes) {
     return SKB_OK;
 }
 
+int skb_state_set_timing(skb_state* st, int enabled) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    st->timing = enabled != 0;
+    st->spans_used = 0;
+    return SKB_OK;
+}
+
+int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by_kind, int n_kinds) {
+    if (!st || !ms_by_kind || !launches_by_kind) return fail(SKB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(st->device));
+    for (int k = 0; k < n_kinds; ++k) {
+        ms_by_kind[k] = 0.0;
+        launches_by_kind[k] = 0;
+    }
+    for (size_t i = 0; i < st->spans_used; ++i) {
+        CU(cudaEventSynchronize(st->spans[i].b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, st->spans[i].a, st->spans[i].b));
+        const int k = st->spans[i].kind;
+        if (k >= 0 && k < n_kinds) {
+            ms_by_kind[k] += ms;
+            launches_by_kind[k] += 1;
+        }
+    }
+    st->spans_used = 0;
+    return SKB_OK;
+}
+
 static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
                           const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out) {
     CU(cudaSetDevice(st->device));
@@ -316,6 +376,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         }
     }
 
+    if (!mean_only && out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
     for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles) {
         const int64_t nt = std::min(chunk_tiles, tiles - t0);
         const int64_t c0 = t0 * BN;
@@ -334,7 +395,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         kp.d_pad = st->d_pad;
         kp.amplitude = st->amplitude;
         kp.bias = st->bias;
+        if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
         if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
+        if ((rc = span_end(st, s)) != SKB_OK) return rc;
         if (mean_only) {
             // mean = y_std * kdot + y_mean (gpr.py:316-318)
             mean_affine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(st->d_kdot, mean_only_out + c0, mc, st->y_std, st->y_mean);
@@ -359,8 +422,11 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         tp.std = out->std ? out->std + c0 : nullptr;
         for (int a = 0; a < 3; ++a) tp.acq[a] = acq_ptr[a] ? acq_ptr[a] + c0 : nullptr;
         tp.qout = nullptr;
+        tp.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
+        if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
         trmm_sqnorm_acq_kernel<<<(unsigned)nt, TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
         LAUNCHED();
+        if ((rc = span_end(st, s)) != SKB_OK) return rc;
     }
 
     if (top_k > 0) {
@@ -377,12 +443,14 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             if (!((prm->acq_mask >> a) & 1)) continue;
             if (!out->topk_val[a] || !out->topk_idx[a])
                 return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+            if ((rc = span_begin(st, 2, s)) != SKB_OK) return rc;
             topk_partial_kernel<<<nblk, TOPK_THREADS, 0, s>>>(acq_ptr[a], m, slice, index_offset, top_k, st->d_part_v,
                                                               st->d_part_i, st->d_part_nan);
             LAUNCHED();
             topk_merge_kernel<<<1, TOPK_THREADS, 0, s>>>(st->d_part_v, st->d_part_i, st->d_part_nan, nblk, top_k,
                                                          out->topk_val[a], out->topk_idx[a], out->first_nan[a]);
             LAUNCHED();
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
         }
     }
     return SKB_OK;
@@ -395,14 +463,14 @@ int skb_score_dev(skb_state* st, const double* X, int64_t m, int64_t index_offse
     if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
     int rc = check_params(params);
     if (rc != SKB_OK) return rc;
-    return score_dev_impl(st, X, m, index_offset, params, out, stream ? (cudaStream_t)stream : st->stream, false, nullptr);
+    return score_dev_impl(st, X, m, index_offset, params, out, (cudaStream_t)stream, false, nullptr);
 }
 
 int skb_predict_mean_dev(skb_state* st, const double* X, int64_t m, double* mean, void* stream) {
     if (!st || !mean) return fail(SKB_ERR_INVALID, "state/mean is NULL");
     if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
     if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
-    return score_dev_impl(st, X, m, 0, nullptr, nullptr, stream ? (cudaStream_t)stream : st->stream, true, mean);
+    return score_dev_impl(st, X, m, 0, nullptr, nullptr, (cudaStream_t)stream, true, mean);
 }
 
 int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* params,
@@ -443,8 +511,11 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
             dout.first_nan[a] = st->d_topk_nan + a;
         }
     }
+    if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
     CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, s));
     if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr)) != SKB_OK) return rc;
+    if (out->n_var_clamped)
+        CU(cudaMemcpyAsync(out->n_var_clamped, st->d_clamp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     if (out->mean) CU(cudaMemcpyAsync(out->mean, dout.mean, m * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (out->std) CU(cudaMemcpyAsync(out->std, dout.std, m * sizeof(double), cudaMemcpyDeviceToHost, s));
     for (int a = 0; a < 3; ++a) {

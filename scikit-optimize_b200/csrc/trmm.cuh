@@ -34,6 +34,7 @@ struct TrmmParams {
     double* std;              // [m] or nullptr
     double* acq[3];           // [m] or nullptr
     double* qout;             // [m] or nullptr: raw quadratic form (diagnostics / gradient path)
+    unsigned long long* clamp_count;   // or nullptr: number of negative variances set to zero
 };
 
 constexpr size_t trmm_smem_bytes() {
@@ -60,12 +61,14 @@ __device__ __forceinline__ void acquisition_values(const AcqConsts& a, double mu
     }
 }
 
-__device__ __forceinline__ void posterior_from_q(const AcqConsts& a, double kdot, double q, double& mu, double& sd) {
+__device__ __forceinline__ bool posterior_from_q(const AcqConsts& a, double kdot, double q, double& mu, double& sd) {
     mu = a.y_std * kdot + a.y_mean;               // gpr.py:316-318
     double var = a.prior_var - q;                  // gpr.py:331-332
-    if (var < 0.0) var = 0.0;                      // gpr.py:336-340
+    const bool clamped = var < 0.0;                // gpr.py:336-340
+    if (clamped) var = 0.0;
     var = var * (a.y_std * a.y_std);               // gpr.py:342
     sd = sqrt(var);
+    return clamped;
 }
 
 __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const TrmmParams p) {
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
         if (cand < p.m) {
             const double q = sRed[threadIdx.x] + sRed[BN + threadIdx.x];
             double mu, sd, acq[3];
-            posterior_from_q(p.a, p.kdot[cand], q, mu, sd);
+            if (posterior_from_q(p.a, p.kdot[cand], q, mu, sd) && p.clamp_count) atomicAdd(p.clamp_count, 1ull);
             acquisition_values(p.a, mu, sd, acq);
             if (p.qout) p.qout[cand] = q;
             if (p.mean) p.mean[cand] = mu;

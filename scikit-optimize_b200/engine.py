@@ -170,6 +170,16 @@ class DeviceState:
     def set_scratch_limit(self, nbytes):
         _lib.check(_lib.lib().skb_state_set_scratch_limit(self._h, int(nbytes)))
 
+    def set_timing(self, enabled):
+        _lib.check(_lib.lib().skb_state_set_timing(self._h, 1 if enabled else 0))
+
+    def get_timing(self):
+        """{kind: (milliseconds, spans)} accumulated since the last call; kinds: k1, k2, topk, grad."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().skb_state_get_timing(self._h, ms, cnt, 4))
+        return {name: (ms[i], int(cnt[i])) for i, name in enumerate(("k1", "k2", "topk", "grad"))}
+
     # ---------------------------------------------------------------- host (NumPy) entry points
     def _check_X(self, X):
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -197,6 +207,8 @@ class DeviceState:
         prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k)
         out = _lib.ScoreOut()
         res = {}
+        clamped = np.zeros(1, dtype=np.int64)
+        out.n_var_clamped = clamped.ctypes.data
         if want_posterior:
             res["mean"], res["std"] = np.empty(m), np.empty(m)
             out.mean, out.std = res["mean"].ctypes.data, res["std"].ctypes.data
@@ -218,6 +230,7 @@ class DeviceState:
             r = res[name]
             if "_nan" in r:
                 r["first_nan"] = int(r.pop("_nan")[0])
+        res["clamped"] = int(clamped[0])
         return res
 
     # ---------------------------------------------------------------- device (torch tensor) entry points

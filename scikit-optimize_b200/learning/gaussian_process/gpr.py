@@ -1,0 +1,137 @@
+"""GaussianProcessRegressor whose posterior (mean, std, input gradients) is evaluated on a B200.
+
+Drop-in for skopt.learning.GaussianProcessRegressor (skopt/learning/gaussian_process/gpr.py:39-368): same
+constructor, same fitted attributes (noise_, K_inv_, y_train_mean_, y_train_std_), same predict() signature, return
+shapes and exceptions.  fit() stays on the host (scikit-learn's marginal-likelihood optimisation) and
+produces the state; predict() ships that state to the GPU once and runs the CUDA kernels.  There is no CPU fallback
+for the posterior: without the CUDA library or a B200, predict() on a fitted model raises.
+"""
+import warnings
+
+import numpy as np
+from scipy.linalg import cho_solve, solve_triangular
+from sklearn.gaussian_process import GaussianProcessRegressor as _SkGPR
+from sklearn.utils import check_array
+
+from ... import engine
+from .kernels import RBF, ConstantKernel, Sum, WhiteKernel
+
+_DEFAULT_DEVICE = [0]
+
+
+def set_default_device(index):
+    """CUDA device new models are placed on (one process per GPU: pass LOCAL_RANK)."""
+    _DEFAULT_DEVICE[0] = int(index)
+
+
+def _white_kernel_key(kernel, prefix=""):
+    """get_params() key of the first WhiteKernel that is a direct operand in a tree of Sums (gpr.py:17-36)."""
+    if isinstance(kernel, Sum):
+        for name in ("k1", "k2"):
+            child = getattr(kernel, name)
+            if isinstance(child, WhiteKernel):
+                return prefix + name
+            found = _white_kernel_key(child, prefix + name + "__")
+            if found is not None:
+                return found
+    return None
+
+
+class GaussianProcessRegressor(_SkGPR):
+    def __init__(self, kernel=None, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
+                 normalize_y=False, copy_X_train=True, random_state=None, noise=None):
+        self.noise = noise
+        super().__init__(kernel=kernel, alpha=alpha, optimizer=optimizer, n_restarts_optimizer=n_restarts_optimizer,
+                         normalize_y=normalize_y, copy_X_train=copy_X_train, random_state=random_state)
+
+    # device handles must not be pickled / cloned (checkpoint row)
+    def __getstate__(self):
+        state = super().__getstate__()
+        state = dict(state)
+        state.pop("_skb_device_state", None)
+        return state
+
+    def fit(self, X, y):
+        """gpr.py:166-237: add the noise kernel, fit with scikit-learn, silence the noise for prediction,
+        precompute K_inv_ (here together with the triangular factor the GPU kernels contract with)."""
+        if isinstance(self.noise, str) and self.noise != "gaussian":
+            raise ValueError("expected noise to be 'gaussian', got %s" % self.noise)
+        if self.kernel is None:
+            self.kernel = ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(1.0, length_scale_bounds="fixed")
+        if self.noise == "gaussian":
+            self.kernel = self.kernel + WhiteKernel()
+        elif self.noise:
+            self.kernel = self.kernel + WhiteKernel(noise_level=self.noise, noise_level_bounds="fixed")
+        self.__dict__.pop("_skb_device_state", None)
+        super().fit(X, y)
+
+        self.noise_ = None
+        if self.noise:
+            # K(X*, X*) must not contain the observation noise (GPML eq. 2.24); alpha_ already has it.
+            if isinstance(self.kernel_, WhiteKernel):
+                self.kernel_.set_params(noise_level=0.0)
+            else:
+                key = _white_kernel_key(self.kernel_)
+                if key is not None:
+                    self.noise_ = self.kernel_.get_params()[key].noise_level
+                    self.kernel_.set_params(**{key: WhiteKernel(noise_level=0.0)})
+
+        n = self.L_.shape[0]
+        self._L_inv_lower = solve_triangular(self.L_, np.eye(n), lower=True)
+        self.K_inv_ = self._L_inv_lower.T.dot(self._L_inv_lower)
+        self.y_train_std_ = self._y_train_std
+        self.y_train_mean_ = self._y_train_mean
+        return self
+
+    def device_state(self, device=None):
+        """The fitted state resident on the GPU (created on first use, rebuilt after every fit)."""
+        dev = self.__dict__.get("_skb_device_state")
+        want = _DEFAULT_DEVICE[0] if device is None else int(device)
+        if dev is None or dev.device != want:
+            dev = engine.DeviceState.from_estimator(self, want)
+            self.__dict__["_skb_device_state"] = dev
+        return dev
+
+    def predict(self, X, return_std=False, return_cov=False, return_mean_grad=False, return_std_grad=False):
+        """gpr.py:239-368.  The gradient outputs are also available for more than one row (an extension: the
+        reference raises "Not implemented for n_samples > 1"); for one row the shapes are the reference's."""
+        if return_std and return_cov:
+            raise RuntimeError("Not returning standard deviation of predictions when returning full covariance.")
+        if return_std_grad and not return_std:
+            raise ValueError("Not returning std_gradient without returning the std.")
+        X = check_array(X)
+
+        if not hasattr(self, "X_train_"):       # unfitted: GP prior (gpr.py:303-312), no arithmetic worth a launch
+            if X.shape[0] != 1 and (return_mean_grad or return_std_grad):
+                raise ValueError("Not implemented for n_samples > 1")
+            y_mean = np.zeros(X.shape[0])
+            if return_cov:
+                return y_mean, self.kernel(X)
+            if return_std:
+                return y_mean, np.sqrt(self.kernel.diag(X))
+            return y_mean
+
+        if return_cov:
+            # off the hot path: joint covariance of a handful of points, kept on the host
+            K_trans = self.kernel_(X, self.X_train_)
+            y_mean = self.y_train_std_ * K_trans.dot(self.alpha_) + self.y_train_mean_
+            y_cov = self.kernel_(X) - K_trans.dot(cho_solve((self.L_, True), K_trans.T))
+            return y_mean, y_cov * self.y_train_std_ ** 2
+
+        dev = self.device_state()
+        if return_mean_grad or return_std_grad:
+            g = dev.score_grad(X, acq_funcs=())
+            one = X.shape[0] == 1
+            mean_grad = g["mean_grad"][0] if one else g["mean_grad"]
+            std_grad = g["std_grad"][0] if one else g["std_grad"]
+            if return_std_grad:
+                return g["mean"], g["std"], mean_grad, std_grad
+            if return_std:
+                return g["mean"], g["std"], mean_grad
+            return g["mean"], mean_grad
+        if return_std:
+            res = dev.score(X, acq_funcs=(), want_posterior=True)
+            if np.any(res["clamped"]):
+                warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
+            return res["mean"], res["std"]
+        return dev.predict_mean(X)
