@@ -260,7 +260,7 @@ def main():
         traffic = None
         prof = os.path.join(ROOT, "profiles", "k2_dram_bytes_per_launch.json")
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("dram_bytes_per_candidate", 0.0) * cand_per_k2
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
