@@ -70,6 +70,8 @@ typedef struct {
     const double* X_train;       /* [n_train * n_dims] == est.X_train_ */
     const double* alpha;         /* [n_train]          == est.alpha_ */
     const double* L_inv;         /* [n_train * n_train] lower triangular */
+    const double* K_inv;         /* [n_train * n_train] == est.K_inv_ (symmetric); optional: NULL disables the
+                                    gradient entry points (they contract with K_inv like gpr.py:353-354) */
 } skb_state_desc;
 
 /* acq_func_kwargs of _gaussian_acquisition (acquisition.py:32-35) and y_opt = min(yi) (optimizer.py:558). */

@@ -21,7 +21,7 @@ class StateDesc(C.Structure):
     _fields_ = [("n_train", C.c_int32), ("n_dims", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32),
                 ("amplitude", C.c_double), ("bias", C.c_double), ("white", C.c_double),
                 ("y_mean", C.c_double), ("y_std", C.c_double),
-                ("length_scale", C.c_void_p), ("X_train", C.c_void_p), ("alpha", C.c_void_p), ("L_inv", C.c_void_p)]
+                ("length_scale", C.c_void_p), ("X_train", C.c_void_p), ("alpha", C.c_void_p), ("L_inv", C.c_void_p), ("K_inv", C.c_void_p)]
 
 
 class AcqParams(C.Structure):

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/skb.h"
+#include "grad.cuh"
 #include "kcross.cuh"
 #include "layout.cuh"
 #include "topk.cuh"
@@ -57,10 +58,12 @@ struct skb_state {
     double* d_Xp = nullptr;
     double* d_alpha_p = nullptr;
     double* d_Vp = nullptr;
+    double* d_Ap = nullptr;      // packed dense K_inv (gradient path), nullptr when the caller gave no K_inv
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
     double* d_kdot = nullptr;    size_t kdot_cap = 0;
+    double* d_Wt = nullptr;      size_t wt_cap = 0;
     double* d_acq[3] = {nullptr, nullptr, nullptr};  size_t acq_cap = 0;
     double* d_part_v = nullptr;  int64_t* d_part_i = nullptr;  int64_t* d_part_nan = nullptr;  size_t part_cap = 0;
     double* d_topk_v = nullptr;  int64_t* d_topk_i = nullptr;  int64_t* d_topk_nan = nullptr;  size_t topk_cap = 0;
@@ -120,6 +123,20 @@ __global__ void pack_linv_kernel(const double* __restrict__ V, double* __restric
     }
 }
 
+// Ap: all (BM x BK) tiles of the dense symmetric K_inv, tile (I, kb) at (I * n_pad/BK + kb), same in-tile layout
+__global__ void pack_dense_kernel(const double* __restrict__ K, double* __restrict__ Ap, int n, int n_pad) {
+    const int I = blockIdx.y;
+    const int kb = blockIdx.x;
+    double* tile = Ap + ((size_t)I * (n_pad / BK) + kb) * (BM * BK);
+    for (int e = threadIdx.x; e < BM * BK; e += blockDim.x) {
+        const int r = e & 3;
+        const int i = (e >> 2) % BM;
+        const int g = (e >> 2) / BM;
+        const int row = I * BM + i, col = kb * BK + g * 4 + r;
+        tile[e] = (row < n && col < n) ? K[(size_t)row * n + col] : 0.0;
+    }
+}
+
 __global__ void mean_affine_kernel(const double* __restrict__ kdot, double* __restrict__ mean, int64_t m, double y_std,
                                    double y_mean) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -165,7 +182,13 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(trmm_sqnorm_acq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
+    CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
+    CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
+    const int smem3 = (int)grad_smem_bytes(st->d_pad);
+    CU(cudaFuncSetAttribute(grad_contract_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CU(cudaFuncSetAttribute(grad_contract_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CU(cudaFuncSetAttribute(grad_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CU(cudaFuncSetAttribute(grad_contract_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     return SKB_OK;
 }
 
@@ -204,7 +227,7 @@ void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     if (st->stream) cudaStreamSynchronize(st->stream);
-    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
+    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp};
     for (void* p : ptrs)
@@ -281,6 +304,12 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         LAUNCHED();
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
+        if (desc->K_inv) {
+            CU(cudaMalloc(&st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double)));
+            CU(cudaMemcpyAsync(dV, desc->K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+            pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dV, st->d_Ap, st->n, st->n_pad);
+            LAUNCHED();
+        }
         CU(cudaStreamSynchronize(st->stream));
         return set_kernel_attributes(st);
     };
@@ -424,7 +453,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         tp.qout = nullptr;
         tp.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
         if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
-        trmm_sqnorm_acq_kernel<<<(unsigned)nt, TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
+        tp.Ap = nullptr;
+        tp.Wt = nullptr;
+        trmm_kernel<0><<<(unsigned)nt, TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
         LAUNCHED();
         if ((rc = span_end(st, s)) != SKB_OK) return rc;
     }
@@ -550,11 +581,158 @@ int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mea
     return SKB_OK;
 }
 
-int skb_score_grad_dev(skb_state*, const double*, int64_t, const skb_acq_params*, const skb_grad_out*, void*) {
-    return fail(SKB_ERR_UNSUPPORTED, "gradient path not built yet");
+static int launch_grad(skb_state* st, const GradParams& p, int tiles, cudaStream_t s) {
+    const size_t smem = grad_smem_bytes(p.d_pad);
+    switch (st->kernel) {
+        case SKB_KERNEL_RBF: grad_contract_kernel<0><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN12: grad_contract_kernel<1><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN32: grad_contract_kernel<2><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
+        default: grad_contract_kernel<3><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
+    }
+    LAUNCHED();
+    return SKB_OK;
 }
-int skb_score_grad_host(skb_state*, const double*, int64_t, const skb_acq_params*, const skb_grad_out*) {
-    return fail(SKB_ERR_UNSUPPORTED, "gradient path not built yet");
+
+static int check_grad_args(skb_state* st, const double* X, int64_t m, const skb_acq_params* params, const skb_grad_out* out) {
+    if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    if (!st->d_Ap) return fail(SKB_ERR_UNSUPPORTED, "state was created without K_inv: gradient entry points are unavailable");
+    return check_params(params);
+}
+
+int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_params* prm, const skb_grad_out* out,
+                       void* stream) {
+    int rc = check_grad_args(st, X, m, prm, out);
+    if (rc != SKB_OK) return rc;
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t tiles = (m + BN - 1) / BN;
+    const size_t tile_bytes = 2 * (size_t)st->n_pad * BN * sizeof(double);       // Kt + Wt
+    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / tile_bytes));
+    if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
+    const int64_t chunk_tiles = std::min(tiles, cap);
+    if ((rc = grow(&st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(&st->d_Wt, &st->wt_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(&st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
+    const int nI = st->n_pad / BM;
+
+    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles) {
+        const int64_t nt = std::min(chunk_tiles, tiles - t0);
+        const int64_t c0 = t0 * BN;
+        const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
+        KCrossParams kp;
+        kp.X = X + c0 * st->d;
+        kp.ls = st->d_ls;
+        kp.Xp = st->d_Xp;
+        kp.alpha_p = st->d_alpha_p;
+        kp.Kt = st->d_Kt;
+        kp.kdot = st->d_kdot;
+        kp.m = mc;
+        kp.n = st->n;
+        kp.n_pad = st->n_pad;
+        kp.d = st->d;
+        kp.d_pad = st->d_pad;
+        kp.amplitude = st->amplitude;
+        kp.bias = st->bias;
+        if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
+        if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
+        if ((rc = span_end(st, s)) != SKB_OK) return rc;
+
+        TrmmParams tp;
+        std::memset(&tp, 0, sizeof(tp));
+        tp.Kt = st->d_Kt;
+        tp.n_pad = st->n_pad;
+        tp.m = mc;
+        tp.Ap = st->d_Ap;
+        tp.Wt = st->d_Wt;
+        if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
+        trmm_kernel<1><<<dim3(nI, (unsigned)nt), TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
+        LAUNCHED();
+        if ((rc = span_end(st, s)) != SKB_OK) return rc;
+
+        GradParams gp;
+        std::memset(&gp, 0, sizeof(gp));
+        gp.X = X + c0 * st->d;
+        gp.ls = st->d_ls;
+        gp.Xp = st->d_Xp;
+        gp.alpha_p = st->d_alpha_p;
+        gp.Wt = st->d_Wt;
+        gp.m = mc;
+        gp.n = st->n;
+        gp.n_pad = st->n_pad;
+        gp.d = st->d;
+        gp.d_pad = st->d_pad;
+        gp.amplitude = st->amplitude;
+        gp.bias = st->bias;
+        gp.a.prior_var = st->amplitude + st->bias + st->white;
+        gp.a.y_mean = st->y_mean;
+        gp.a.y_std = st->y_std;
+        gp.a.y_opt = prm->y_opt;
+        gp.a.xi = prm->xi;
+        gp.a.kappa = prm->kappa;
+        gp.a.kappa_inf = prm->kappa_inf;
+        gp.a.acq_mask = prm->acq_mask;
+        gp.mean = out->mean ? out->mean + c0 : nullptr;
+        gp.std = out->std ? out->std + c0 : nullptr;
+        gp.mean_grad = out->mean_grad ? out->mean_grad + c0 * st->d : nullptr;
+        gp.std_grad = out->std_grad ? out->std_grad + c0 * st->d : nullptr;
+        for (int a = 0; a < 3; ++a) {
+            gp.acq[a] = out->acq[a] ? out->acq[a] + c0 : nullptr;
+            gp.acq_grad[a] = out->acq_grad[a] ? out->acq_grad[a] + c0 * st->d : nullptr;
+        }
+        if ((rc = span_begin(st, 3, s)) != SKB_OK) return rc;
+        if ((rc = launch_grad(st, gp, (int)nt, s)) != SKB_OK) return rc;
+        if ((rc = span_end(st, s)) != SKB_OK) return rc;
+    }
+    return SKB_OK;
+}
+
+int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq_params* prm, const skb_grad_out* out) {
+    int rc = check_grad_args(st, X, m, prm, out);
+    if (rc != SKB_OK) return rc;
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    cudaStream_t s = st->stream;
+    const size_t d = st->d;
+    // device mirror: [mean][std][acq x3] (m each) then [mean_grad][std_grad][acq_grad x3] (m*d each)
+    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * d)) != SKB_OK) return rc;
+    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)m * 5 + (size_t)m * d * 5)) != SKB_OK) return rc;
+    skb_grad_out dout;
+    std::memset(&dout, 0, sizeof(dout));
+    double* cur = st->d_out;
+    auto take = [&](bool want, size_t count) -> double* {
+        if (!want) return nullptr;
+        double* r = cur;
+        cur += count;
+        return r;
+    };
+    dout.mean = take(out->mean != nullptr, m);
+    dout.std = take(out->std != nullptr, m);
+    dout.mean_grad = take(out->mean_grad != nullptr, m * d);
+    dout.std_grad = take(out->std_grad != nullptr, m * d);
+    for (int a = 0; a < 3; ++a) {
+        const bool on = (prm->acq_mask >> a) & 1;
+        dout.acq[a] = take(on && out->acq[a], m);
+        dout.acq_grad[a] = take(on && out->acq_grad[a], m * d);
+    }
+    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = skb_score_grad_dev(st, st->d_X, m, prm, &dout, s)) != SKB_OK) return rc;
+    auto back = [&](double* host, const double* dev, size_t count) -> int {
+        if (host && dev) CU(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, s));
+        return SKB_OK;
+    };
+    if ((rc = back(out->mean, dout.mean, m)) != SKB_OK) return rc;
+    if ((rc = back(out->std, dout.std, m)) != SKB_OK) return rc;
+    if ((rc = back(out->mean_grad, dout.mean_grad, m * d)) != SKB_OK) return rc;
+    if ((rc = back(out->std_grad, dout.std_grad, m * d)) != SKB_OK) return rc;
+    for (int a = 0; a < 3; ++a) {
+        if ((rc = back(out->acq[a], dout.acq[a], m)) != SKB_OK) return rc;
+        if ((rc = back(out->acq_grad[a], dout.acq_grad[a], m * d)) != SKB_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(s));
+    return SKB_OK;
 }
 
 }  // extern "C"

@@ -35,6 +35,9 @@ struct TrmmParams {
     double* acq[3];           // [m] or nullptr
     double* qout;             // [m] or nullptr: raw quadratic form (diagnostics / gradient path)
     unsigned long long* clamp_count;   // or nullptr: number of negative variances set to zero
+    // MODE 1 (dense): A = packed K_inv (all tiles), result rows are stored instead of squared
+    const double* Ap;         // packed dense K_inv: tile (I, kb) at (I * n_pad/BK + kb) * BM*BK
+    double* Wt;               // [tiles][n_pad][BN]: W = K_inv . K_trans^T
 };
 
 constexpr size_t trmm_smem_bytes() {
@@ -71,7 +74,10 @@ __device__ __forceinline__ bool posterior_from_q(const AcqConsts& a, double kdot
     return clamped;
 }
 
-__global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const TrmmParams p) {
+// MODE 0: triangular L_inv contraction + square-norm + acquisition epilogue, one CTA per candidate tile (grid.x).
+// MODE 1: dense K_inv contraction, W rows stored for the gradient kernel; one CTA per (row block = grid.x, tile = grid.y).
+template <int MODE>
+__global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_kernel(const TrmmParams p) {
     extern __shared__ __align__(128) unsigned char smem_k2[];
     double* sV = reinterpret_cast<double*>(smem_k2);              // [STAGES][BK/4][BM][4]
     double* sK = sV + TRMM_STAGES * BM * BK;                       // [STAGES][BK/4][BN][4]
@@ -89,16 +95,20 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
     }
     __syncthreads();
 
-    const int nI = p.n_pad / BM;
-    const double* kt_tile = p.Kt + (size_t)blockIdx.x * p.n_pad * BN;
+    const int tile_id = MODE == 0 ? blockIdx.x : blockIdx.y;
+    const int I_begin = MODE == 0 ? 0 : blockIdx.x;
+    const int I_end = MODE == 0 ? p.n_pad / BM : blockIdx.x + 1;
+    const int nkb_dense = p.n_pad / BK;
+    const double* kt_tile = p.Kt + (size_t)tile_id * p.n_pad * BN;
 
     if (warp == 8) {
         // ---------------- producer: one lane streams operand tiles with bulk copies ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int I = 0; I < nI; ++I) {
-                const int nkb = (I + 1) * (BM / BK);
-                const double* vrow = p.Vp + (size_t)vp_tiles_before(I) * (BM * BK);
+            for (int I = I_begin; I < I_end; ++I) {
+                const int nkb = MODE == 0 ? (I + 1) * (BM / BK) : nkb_dense;
+                const double* vrow = MODE == 0 ? p.Vp + (size_t)vp_tiles_before(I) * (BM * BK)
+                                               : p.Ap + (size_t)I * nkb_dense * (BM * BK);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % TRMM_STAGES;
                     const uint32_t ph = (it / TRMM_STAGES) & 1;
@@ -124,8 +134,8 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
     for (int ni = 0; ni < 4; ++ni) qacc[ni][0] = qacc[ni][1] = 0.0;
 
     uint32_t it = 0;
-    for (int I = 0; I < nI; ++I) {
-        const int nkb = (I + 1) * (BM / BK);
+    for (int I = I_begin; I < I_end; ++I) {
+        const int nkb = MODE == 0 ? (I + 1) * (BM / BK) : nkb_dense;
         const int row0 = I * BM + wm * 64;                 // first global row of this warp's accumulator tile
         for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % TRMM_STAGES;
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
             const double* v = sV + s * BM * BK + wm * 64 * 4 + lane;
             const double* k = sK + s * BK * BN + wn * 32 * 4 + lane;
             const int col0 = kb * BK;
-            if (col0 + BK - 1 <= row0) {
+            if (MODE == 1 || col0 + BK - 1 <= row0) {
                 // every (row, col) of this stage is at or below the diagonal
 #pragma unroll
                 for (int g = 0; g < BK / 4; ++g) {
@@ -170,6 +180,16 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
+        if (MODE == 1) {
+            // store this warp's 64 x 32 block of W: lane holds rows (l>>2), column pair 2*(l&3)
+            double* w = p.Wt + ((size_t)tile_id * p.n_pad + row0 + (lane >> 2)) * BN + wn * 32 + 2 * (lane & 3);
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(w + (size_t)mi * 8 * BN + ni * 8) = make_double2(c[mi][ni][0], c[mi][ni][1]);
+            continue;
+        }
         // row block done: fold U^2 into the running column sums and clear the accumulators
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
@@ -180,6 +200,8 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_sqnorm_acq_kernel(const 
                 c[mi][ni][0] = c[mi][ni][1] = 0.0;
             }
     }
+
+    if (MODE == 1) return;
 
     // the 8 lanes that share (lane & 3) hold the 8 row groups of the same columns
 #pragma unroll

@@ -62,10 +62,14 @@ def _flatten_kernel(kernel):
 class HostState:
     """Plain arrays describing a fitted GP (the argument of skb_state_create)."""
 
-    def __init__(self, X_train, alpha, L_inv, length_scale, kernel, amplitude, bias, white, y_mean, y_std):
+    def __init__(self, X_train, alpha, L_inv, length_scale, kernel, amplitude, bias, white, y_mean, y_std,
+                 K_inv=None):
         self.X_train = np.ascontiguousarray(X_train, dtype=np.float64)
         self.alpha = np.ascontiguousarray(alpha, dtype=np.float64)
         self.L_inv = np.ascontiguousarray(L_inv, dtype=np.float64)
+        self.K_inv = None if K_inv is None else np.ascontiguousarray(K_inv, dtype=np.float64)
+        if self.K_inv is not None and self.K_inv.shape != self.L_inv.shape:
+            raise ValueError("K_inv must have shape (n_train, n_train)")
         n, d = self.X_train.shape
         if self.alpha.shape != (n,):
             raise ValueError("alpha must have shape (n_train,); multi-output targets are not supported on the GPU path")
@@ -103,7 +107,7 @@ def host_state_from_estimator(est):
     if L_inv is None:
         L_inv = solve_triangular(est.L_, np.eye(est.L_.shape[0]), lower=True)
     return HostState(est.X_train_, est.alpha_, L_inv, ls, kind, amp, aff.c, aff.w,
-                     np.ravel(est.y_train_mean_)[0], np.ravel(est.y_train_std_)[0])
+                     np.ravel(est.y_train_mean_)[0], np.ravel(est.y_train_std_)[0], K_inv=getattr(est, "K_inv_", None))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -144,6 +148,7 @@ class DeviceState:
         desc.X_train = host_state.X_train.ctypes.data
         desc.alpha = host_state.alpha.ctypes.data
         desc.L_inv = host_state.L_inv.ctypes.data
+        desc.K_inv = host_state.K_inv.ctypes.data if host_state.K_inv is not None else None
         handle = C.c_void_p()
         _lib.check(L.skb_state_create(C.byref(desc), self.device, C.byref(handle)))
         self._h = handle
@@ -231,6 +236,24 @@ class DeviceState:
             if "_nan" in r:
                 r["first_nan"] = int(r.pop("_nan")[0])
         res["clamped"] = int(clamped[0])
+        return res
+
+    def score_grad(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96):
+        """Posterior, acquisition values and their input gradients for every row of X (batched extension of
+        gaussian_acquisition_1D / predict(..., return_mean_grad, return_std_grad); the reference takes one row)."""
+        X = self._check_X(X)
+        m, d = X.shape
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, 0)
+        out = _lib.GradOut()
+        res = {"mean": np.empty(m), "std": np.empty(m), "mean_grad": np.empty((m, d)), "std_grad": np.empty((m, d))}
+        out.mean, out.std = res["mean"].ctypes.data, res["std"].ctypes.data
+        out.mean_grad, out.std_grad = res["mean_grad"].ctypes.data, res["std_grad"].ctypes.data
+        for name in acq_funcs:
+            a = _lib.ACQ_INDEX[name]
+            res[name] = {"values": np.empty(m), "grad": np.empty((m, d))}
+            out.acq[a] = res[name]["values"].ctypes.data
+            out.acq_grad[a] = res[name]["grad"].ctypes.data
+        _lib.check(_lib.lib().skb_score_grad_host(self._h, X.ctypes.data, m, C.byref(prm), C.byref(out)))
         return res
 
     # ---------------------------------------------------------------- device (torch tensor) entry points

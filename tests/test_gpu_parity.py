@@ -24,7 +24,7 @@ def host_state_from_oracle_state(st):
             (orc.KIND_MATERN, 2.5): 3}[(st.kind, st.nu)]
     L_inv = solve_triangular(st.L, np.eye(st.n), lower=True)
     return engine.HostState(st.X_train, st.alpha, L_inv, st.length_scale, kind, st.amplitude, st.bias, st.white,
-                            st.y_mean, st.y_std)
+                            st.y_mean, st.y_std, K_inv=st.K_inv)
 
 
 def _acq_from_posterior(a, mu, sd, y_opt, xi, kappa):
@@ -148,4 +148,104 @@ def test_torch_device_entry_point_matches_host_entry_point():
     res2 = dev.score_tensors(Xt, y_opt=-1.0, acq_funcs=("EI",), top_k=4)
     torch.cuda.synchronize()
     assert np.array_equal(res2["EI"]["topk_idx"].cpu().numpy(), ref["EI"]["topk_idx"])
+    dev.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gradient path
+# ----------------------------------------------------------------------------------------------------------------
+def check_grads(st, g, ref_mu, ref_sd, ref_gm, ref_gs, acq_ref, vtol):
+    """Gate (SURVEY 8d iv): |dg| <= 1e-9 * max|g| per candidate; sigma*grad(sigma) on the variance scale when K is
+    ill-conditioned (same reasoning as tests/test_oracle_golden.py)."""
+    n = ref_mu.shape[0]
+    assert np.max(np.abs(g["mean"][:n] - ref_mu)) <= 1e-9 * max(np.max(np.abs(ref_mu)), st.y_std)
+    var_scale = st.prior_var * st.y_std ** 2
+    assert np.max(np.abs(g["std"][:n] ** 2 - ref_sd ** 2)) <= vtol * var_scale
+    assert np.max(np.abs(g["mean_grad"][:n] - ref_gm)) <= 1e-9 * np.max(np.abs(ref_gm))
+    gv_scale = var_scale / np.min(st.length_scale)
+    assert np.max(np.abs((g["std_grad"][:n] - ref_gs) * ref_sd[:, None])) <= 10 * vtol * gv_scale
+    if vtol <= 1e-9:
+        for i in range(n):
+            rel_var = (ref_sd[i] / st.y_std) ** 2 / st.prior_var
+            tol = (1e-9 + 1e-12 / max(rel_var, 1e-300)) * max(np.max(np.abs(ref_gs[i])), 1e-300)
+            assert np.max(np.abs(g["std_grad"][i] - ref_gs[i])) <= tol, i
+    for a, (v_ref, g_ref, z2) in acq_ref.items():
+        for i in range(n):
+            rel_var = (ref_sd[i] / st.y_std) ** 2 / st.prior_var
+            if rel_var < 1e4 * vtol and vtol > 1e-9:
+                continue
+            ptol = (1e-9 + max(vtol, 1e-12) / max(rel_var, 1e-300)) * (1.0 + z2[i])
+            assert abs(g[a]["values"][i] - v_ref[i]) <= ptol * abs(v_ref[i]) + 1e-300, (a, i)
+            assert np.max(np.abs(g[a]["grad"][i] - g_ref[i])) <= ptol * np.max(np.abs(g_ref[i])) + 1e-300, (a, i)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_gradients(name):
+    rec, meta, est = load(name)
+    _, _, ost = load_state(name)
+    ng = meta["n_grad"]
+    if ng == 0:
+        pytest.skip("the reference itself raises for this kernel's gradient")
+    dev = engine.DeviceState.from_estimator(est)
+    y_opt, xi, kappa = float(rec["y_opt"]), float(rec["xi"]), float(rec["kappa"])
+    g = dev.score_grad(rec["Xc"], y_opt=y_opt, acq_funcs=ACQS, xi=xi, kappa=kappa)      # all rows in one launch
+    z2 = ((y_opt - xi - rec["mean"][:ng]) / np.maximum(rec["std"][:ng], 1e-300)) ** 2
+    acq_ref = {a: (rec["acq_1d_" + a], rec["acq_grad_" + a], z2) for a in ACQS}
+    check_grads(ost, g, rec["mean"][:ng], rec["std"][:ng], rec["mean_grad"], rec["std_grad"], acq_ref, var_tol(ost))
+    # a one-row call returns bit-identical numbers to the same row inside the batch
+    g1 = dev.score_grad(rec["Xc"][3:4], y_opt=y_opt, acq_funcs=ACQS, xi=xi, kappa=kappa)
+    assert np.array_equal(g1["mean_grad"][0], g["mean_grad"][3]) and np.array_equal(g1["std_grad"][0], g["std_grad"][3])
+    assert np.array_equal(g1["EI"]["grad"][0], g["EI"]["grad"][3])
+    dev.close()
+
+
+@pytest.mark.parametrize("n,d,m,kind,nu", [
+    (300, 7, 200, orc.KIND_MATERN, 2.5),
+    (129, 3, 130, orc.KIND_MATERN, 1.5),
+    (200, 50, 100, orc.KIND_MATERN, 2.5),
+    (256, 20, 150, orc.KIND_RBF, np.inf),
+    (90, 4, 64, orc.KIND_MATERN, 0.5),
+])
+def test_synthetic_gradients_vs_oracle_loop(n, d, m, kind, nu):
+    """Batched device gradients against a loop of single-point oracle calls (the reference is 1-point only)."""
+    st = orc.make_synthetic_state(n, d, noise=1e-3, seed=n + d, kind=kind, nu=nu)
+    rng = np.random.RandomState(11)
+    Xc = rng.rand(m, d)
+    if not (kind == orc.KIND_MATERN and nu == 0.5):
+        Xc[3] = st.X_train[0]                 # r = 0 corner (finite gradients, test_kernels.py:87-99)
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    g = dev.score_grad(Xc, y_opt=y_opt, acq_funcs=ACQS)
+    mu, sd, gm, gs = orc.predict_with_grads_batched(st, Xc)
+    acq_ref = {}
+    z2 = ((y_opt - 0.01 - mu) / np.maximum(sd, 1e-300)) ** 2
+    for a in ACQS:
+        vs, grads = np.empty(m), np.empty((m, d))
+        for i in range(m):
+            v, gr = orc.gaussian_acquisition_1D(Xc[i], st, y_opt, a, dict(xi=0.01, kappa=1.96))
+            vs[i], grads[i] = v[0], gr
+        acq_ref[a] = (vs, grads, z2)
+    assert np.all(np.isfinite(g["mean_grad"])) and np.all(np.isfinite(g["std_grad"]))
+    check_grads(st, g, mu, sd, gm, gs, acq_ref, var_tol(st))
+    dev.close()
+
+
+def test_gradient_matches_finite_differences():
+    """The reference's own style of check (test_gpr.py:65-98, test_acquisition.py:98-132): analytic vs numeric."""
+    st = orc.make_synthetic_state(60, 3, noise=1e-2, seed=21)
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    x = np.array([[0.31, 0.62, 0.47]])
+    g = dev.score_grad(x, y_opt=-0.5, acq_funcs=ACQS)
+    eps = 1e-6
+    Xp = np.repeat(x, 6, axis=0)
+    for k in range(3):
+        Xp[2 * k, k] += eps
+        Xp[2 * k + 1, k] -= eps
+    f = dev.score(Xp, y_opt=-0.5, acq_funcs=ACQS)
+    for k in range(3):
+        assert abs((f["mean"][2 * k] - f["mean"][2 * k + 1]) / (2 * eps) - g["mean_grad"][0, k]) < 1e-5
+        assert abs((f["std"][2 * k] - f["std"][2 * k + 1]) / (2 * eps) - g["std_grad"][0, k]) < 1e-5
+        for a in ACQS:
+            fd = (f[a]["values"][2 * k] - f[a]["values"][2 * k + 1]) / (2 * eps)
+            assert abs(fd - g[a]["grad"][0, k]) < 1e-5, (a, k)
     dev.close()
