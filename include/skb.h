@@ -147,6 +147,13 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
 int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq_params* params,
                         const skb_grad_out* out);
 
+/* Replaces: the arithmetic of gaussian_ei / gaussian_pi / gaussian_lcb (acquisition.py:129-146, 211-229, 295-321)
+ * for a posterior produced by ANY regressor (the duck-typed `model.predict(X, return_std=True[, grads])` boundary).
+ * Host pointers; mu_grad / std_grad ([m * n_dims]) may be NULL (then acq_grad is not written). */
+int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const double* mu, const double* std,
+                                const double* mu_grad, const double* std_grad, const skb_acq_params* params,
+                                double* const acq[3], double* const acq_grad[3]);
+
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind
  * (0 = K1 cross-kernel + mean, 1 = K2 triangular contraction + acquisition, 2 = top-k, 3 = gradient kernels),

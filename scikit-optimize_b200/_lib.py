@@ -61,6 +61,8 @@ SYMBOLS = [
     ("skb_score_grad_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AcqParams), C.POINTER(GradOut),
                                      C.c_void_p]),
     ("skb_score_grad_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AcqParams), C.POINTER(GradOut)]),
+    ("skb_acq_from_posterior_host", C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.POINTER(AcqParams), C.c_void_p * 3, C.c_void_p * 3]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

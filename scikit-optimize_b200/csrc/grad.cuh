@@ -235,4 +235,57 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_contract_kernel(const GradP
     }
 }
 
+// Stateless acquisition epilogue for posteriors that were produced elsewhere (any regressor with predict(return_std),
+// the duck-typed boundary of acquisition.py:134-143,198-202,280-285): values and, when gradients of mu / std are
+// given, the chain rule of acquisition.py:218-227, 305-319.  One thread per row.
+struct AcqOnlyParams {
+    const double* mu;
+    const double* sd;
+    const double* mu_grad;    // [m][d] or nullptr
+    const double* sd_grad;    // [m][d] or nullptr
+    int64_t m;
+    int d;
+    AcqConsts a;
+    double* acq[3];
+    double* acq_grad[3];
+};
+
+__global__ void acq_from_posterior_kernel(const AcqOnlyParams p) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const AcqConsts& A = p.a;
+    const double mu = p.mu[i], sd = p.sd[i];
+    double acq[3];
+    acquisition_values(A, mu, sd, acq);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (((A.acq_mask >> a) & 1) && p.acq[a]) p.acq[a][i] = acq[a];
+    if (!p.mu_grad || !p.sd_grad) return;
+    const bool mask = sd > 0.0;
+    double improve = 0.0, cdf = 0.0, pdf = 0.0;
+    if (mask && (A.acq_mask & 3)) {
+        improve = A.y_opt - A.xi - mu;
+        const double z = improve / sd;
+        cdf = normcdf(z);
+        pdf = exp(-(z * z) / 2.0) * 0.3989422804014327;
+    }
+    for (int k = 0; k < p.d; ++k) {
+        const int64_t o = i * p.d + k;
+        const double gmu = p.mu_grad[o], gsd = p.sd_grad[o];
+        if ((A.acq_mask & 4) && p.acq_grad[2]) p.acq_grad[2][o] = A.kappa_inf ? -gsd : gmu - A.kappa * gsd;
+        if (A.acq_mask & 3) {
+            double g_ei = 0.0, g_pi = 0.0;
+            if (mask) {
+                const double improve_grad = (-gmu * sd - gsd * improve) / (sd * sd);
+                const double cdf_grad = improve_grad * pdf;
+                g_pi = cdf_grad;
+                const double pdf_grad = -improve * cdf_grad;
+                g_ei = (-gmu * cdf - pdf_grad) + (gsd * pdf + pdf_grad);
+            }
+            if ((A.acq_mask & 1) && p.acq_grad[0]) p.acq_grad[0][o] = -g_ei;
+            if ((A.acq_mask & 2) && p.acq_grad[1]) p.acq_grad[1][o] = -g_pi;
+        }
+    }
+}
+
 }  // namespace skb

@@ -735,4 +735,60 @@ int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq
     return SKB_OK;
 }
 
+int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const double* mu, const double* sd,
+                                const double* mu_grad, const double* sd_grad, const skb_acq_params* prm,
+                                double* const acq[3], double* const acq_grad[3]) {
+    if (m < 0 || n_dims < 0) return fail(SKB_ERR_INVALID, "negative size");
+    if (m > 0 && (!mu || !sd)) return fail(SKB_ERR_INVALID, "mu/std is NULL");
+    int rc = check_params(prm);
+    if (rc != SKB_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKB_ERR_NO_DEVICE, "device %d not in [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    if (m == 0) return SKB_OK;
+    const bool grads = mu_grad && sd_grad;
+    const size_t md = (size_t)m * (size_t)n_dims;
+    const size_t total = 2 * (size_t)m + (grads ? 2 * md : 0) + 3 * (size_t)m + (grads ? 3 * md : 0);
+    double* buf = nullptr;
+    CU(cudaMalloc(&buf, total * sizeof(double)));
+    auto body = [&]() -> int {
+        AcqOnlyParams p;
+        std::memset(&p, 0, sizeof(p));
+        double* cur = buf;
+        double* d_mu = cur; cur += m;
+        double* d_sd = cur; cur += m;
+        double *d_gm = nullptr, *d_gs = nullptr;
+        if (grads) { d_gm = cur; cur += md; d_gs = cur; cur += md; }
+        CU(cudaMemcpy(d_mu, mu, m * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_sd, sd, m * sizeof(double), cudaMemcpyHostToDevice));
+        if (grads) {
+            CU(cudaMemcpy(d_gm, mu_grad, md * sizeof(double), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d_gs, sd_grad, md * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        p.mu = d_mu; p.sd = d_sd; p.mu_grad = d_gm; p.sd_grad = d_gs;
+        p.m = m; p.d = n_dims;
+        p.a.y_opt = prm->y_opt; p.a.xi = prm->xi; p.a.kappa = prm->kappa;
+        p.a.kappa_inf = prm->kappa_inf; p.a.acq_mask = prm->acq_mask;
+        for (int a = 0; a < 3; ++a) {
+            if (!((prm->acq_mask >> a) & 1)) continue;
+            if (acq && acq[a]) { p.acq[a] = cur; cur += m; }
+            if (grads && acq_grad && acq_grad[a]) { p.acq_grad[a] = cur; cur += md; }
+        }
+        acq_from_posterior_kernel<<<(unsigned)((m + 255) / 256), 256>>>(p);
+        LAUNCHED();
+        for (int a = 0; a < 3; ++a) {
+            if (p.acq[a]) CU(cudaMemcpy(acq[a], p.acq[a], m * sizeof(double), cudaMemcpyDeviceToHost));
+            if (p.acq_grad[a]) CU(cudaMemcpy(acq_grad[a], p.acq_grad[a], md * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        return SKB_OK;
+    };
+    rc = body();
+    cudaFree(buf);
+    return rc;
+}
+
 }  // extern "C"

@@ -1,0 +1,3 @@
+from .base import base_minimize  # noqa: F401
+from .gp import gp_minimize  # noqa: F401
+from .optimizer import Optimizer  # noqa: F401

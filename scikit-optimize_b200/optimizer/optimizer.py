@@ -1,0 +1,294 @@
+"""Ask/tell engine whose candidate-scoring block runs on the GPU.
+
+Mirror of skopt/optimizer/optimizer.py: Optimizer.__init__ :163-305, copy :307-333, ask :335-421, _ask :423-453,
+tell :455-493, _tell :495-615, run :642-651, update_next :653-661, get_result :663-676.  Everything that is not
+arithmetic on the candidate set (state, validation, RNG draw order, constant-liar loop, hedge bookkeeping) follows
+the reference so that trajectories stay comparable; the scoring block (:550-608) is replaced:
+
+  reference                                                    here
+  ---------                                                    ----
+  X = space.transform(space.rvs(n_points, rng))  (lists)       space.rvs_transformed: same bits, vectorised
+  for acq in cand_acq_funcs_:  (posterior recomputed 3x)       ONE fused pass: posterior + EI + LCB + PI + top-k
+      values = _gaussian_acquisition(X, est, ...)
+      argmin / argsort[:n_restarts]                            device top-k by (value, index)
+      n_restarts x fmin_l_bfgs_b(gaussian_acquisition_1D)      lock-step batched restarts, one launch per L-BFGS step
+  gains_ -= est.predict(next_xs_)                              device mean-only predict
+"""
+import sys
+import warnings
+from math import log
+from numbers import Number
+
+import numpy as np
+from sklearn.base import clone, is_regressor
+from sklearn.utils import check_random_state
+
+from ..learning import GaussianProcessRegressor
+from ..space import Categorical, Space
+from ..utils import (check_x_in_space, cook_estimator, create_result, has_gradients, is_2Dlistlike, is_listlike,
+                     normalize_dimensions)
+from .lbfgs import minimize_batch
+
+_INT32_MAX = np.iinfo(np.int32).max
+
+
+class Optimizer(object):
+    def __init__(self, dimensions, base_estimator="gp", n_random_starts=None, n_initial_points=10,
+                 initial_point_generator="random", n_jobs=1, acq_func="gp_hedge", acq_optimizer="auto",
+                 random_state=None, model_queue_size=None, acq_func_kwargs=None, acq_optimizer_kwargs=None):
+        args = locals().copy()
+        del args["self"]
+        self.specs = {"args": args, "function": "Optimizer"}
+        self.rng = check_random_state(random_state)
+
+        self.acq_func = acq_func
+        self.acq_func_kwargs = acq_func_kwargs
+        allowed = ["gp_hedge", "EI", "LCB", "PI", "EIps", "PIps"]
+        if self.acq_func not in allowed:
+            raise ValueError("expected acq_func to be in %s, got %s" % (",".join(allowed), self.acq_func))
+        if "ps" in self.acq_func:
+            raise NotImplementedError("per-second acquisitions (EIps / PIps) need a second surrogate for the "
+                                      "evaluation time; they are not on the GPU path yet")
+        if self.acq_func == "gp_hedge":
+            self.cand_acq_funcs_ = ["EI", "LCB", "PI"]
+            self.gains_ = np.zeros(3)
+        else:
+            self.cand_acq_funcs_ = [self.acq_func]
+        if acq_func_kwargs is None:
+            acq_func_kwargs = dict()
+        self.eta = acq_func_kwargs.get("eta", 1.0)
+
+        if n_random_starts is not None:
+            warnings.warn("n_random_starts will be removed in favour of n_initial_points.", DeprecationWarning)
+            n_initial_points = n_random_starts
+        if n_initial_points < 0:
+            raise ValueError("Expected `n_initial_points` >= 0, got %d" % n_initial_points)
+        self._n_initial_points = n_initial_points
+        self.n_initial_points_ = n_initial_points
+
+        if isinstance(base_estimator, str):
+            base_estimator = cook_estimator(base_estimator, space=dimensions,
+                                            random_state=self.rng.randint(0, _INT32_MAX), n_jobs=n_jobs)
+        if base_estimator is not None and not is_regressor(base_estimator):
+            raise ValueError("%s has to be a regressor." % base_estimator)
+        self.base_estimator_ = base_estimator
+
+        if acq_optimizer == "auto":
+            acq_optimizer = "lbfgs" if has_gradients(self.base_estimator_) else "sampling"
+        if acq_optimizer not in ["lbfgs", "sampling"]:
+            raise ValueError("Expected acq_optimizer to be 'lbfgs' or 'sampling', got {0}".format(acq_optimizer))
+        if not has_gradients(self.base_estimator_) and acq_optimizer != "sampling":
+            raise ValueError("The regressor {0} should run with acq_optimizer='sampling'.".format(type(base_estimator)))
+        self.acq_optimizer = acq_optimizer
+
+        if acq_optimizer_kwargs is None:
+            acq_optimizer_kwargs = dict()
+        self.n_points = acq_optimizer_kwargs.get("n_points", 10000)
+        self.n_restarts_optimizer = acq_optimizer_kwargs.get("n_restarts_optimizer", 5)
+        self.n_jobs = acq_optimizer_kwargs.get("n_jobs", 1)      # accepted for compatibility; restarts are batched
+        self.acq_optimizer_kwargs = acq_optimizer_kwargs
+
+        if isinstance(self.base_estimator_, GaussianProcessRegressor):
+            dimensions = normalize_dimensions(dimensions)
+        self.space = Space(dimensions)
+
+        if initial_point_generator not in ("random", None):
+            raise NotImplementedError("only the 'random' initial point generator is available on this path "
+                                      "(sobol / lhs / halton / hammersly / grid samplers are out of scope)")
+        self._initial_point_generator = None
+        self._initial_samples = None
+
+        self._cat_inds = [i for i, dim in enumerate(self.space.dimensions) if isinstance(dim, Categorical)]
+        self._non_cat_inds = [i for i, dim in enumerate(self.space.dimensions) if not isinstance(dim, Categorical)]
+
+        if not isinstance(model_queue_size, (int, type(None))):
+            raise TypeError("model_queue_size should be an int or None, got {}".format(type(model_queue_size)))
+        self.max_model_queue_size = model_queue_size
+        self.models = []
+        self.Xi = []
+        self.yi = []
+        self.cache_ = {}
+
+    # ------------------------------------------------------------------------------------------------ copy / ask
+    def copy(self, random_state=None):
+        optimizer = Optimizer(dimensions=self.space.dimensions, base_estimator=self.base_estimator_,
+                              n_initial_points=self.n_initial_points_,
+                              initial_point_generator="random", acq_func=self.acq_func,
+                              acq_optimizer=self.acq_optimizer, acq_func_kwargs=self.acq_func_kwargs,
+                              acq_optimizer_kwargs=self.acq_optimizer_kwargs, random_state=random_state)
+        optimizer._initial_samples = self._initial_samples
+        if hasattr(self, "gains_"):
+            optimizer.gains_ = np.copy(self.gains_)
+        if self.Xi:
+            optimizer._tell(self.Xi, self.yi)
+        return optimizer
+
+    def ask(self, n_points=None, strategy="cl_min"):
+        """One point, or `n_points` points by the constant-liar strategy (cl_min / cl_mean / cl_max)."""
+        if n_points is None:
+            return self._ask()
+        supported = ["cl_min", "cl_mean", "cl_max"]
+        if not (isinstance(n_points, int) and n_points > 0):
+            raise ValueError("n_points should be int > 0, got " + str(n_points))
+        if strategy not in supported:
+            raise ValueError("Expected parallel_strategy to be one of " + str(supported) + ", " + "got %s" % strategy)
+        if (n_points, strategy) in self.cache_:
+            return self.cache_[(n_points, strategy)]
+
+        # the lies are told to a throw-away copy (one rng draw seeds it, as in the reference)
+        opt = self.copy(random_state=self.rng.randint(0, _INT32_MAX))
+        X = []
+        for _ in range(n_points):
+            x = opt.ask()
+            X.append(x)
+            if strategy == "cl_min":
+                y_lie = np.min(opt.yi) if opt.yi else 0.0
+            elif strategy == "cl_mean":
+                y_lie = np.mean(opt.yi) if opt.yi else 0.0
+            else:
+                y_lie = np.max(opt.yi) if opt.yi else 0.0
+            opt._tell(x, y_lie)
+        self.cache_ = {(n_points, strategy): X}
+        return X
+
+    def _ask(self):
+        if self._n_initial_points > 0 or self.base_estimator_ is None:
+            if self._initial_samples is None:
+                return self.space.rvs(random_state=self.rng)[0]
+            return self._initial_samples[len(self._initial_samples) - self._n_initial_points]
+        if not self.models:
+            raise RuntimeError("Random evaluations exhausted and no model has been fit.")
+        next_x = self._next_x
+        min_delta_x = min([self.space.distance(next_x, xi) for xi in self.Xi])
+        if abs(min_delta_x) <= 1e-8:
+            warnings.warn("The objective has been evaluated at this point before.")
+        return next_x
+
+    # ------------------------------------------------------------------------------------------------ tell
+    def tell(self, x, y, fit=True):
+        check_x_in_space(x, self.space)
+        self._check_y_is_valid(x, y)
+        return self._tell(x, y, fit=fit)
+
+    def _tell(self, x, y, fit=True):
+        if is_listlike(y) and is_2Dlistlike(x):
+            self.Xi.extend(x)
+            self.yi.extend(y)
+            self._n_initial_points -= len(y)
+        elif is_listlike(x):
+            self.Xi.append(x)
+            self.yi.append(y)
+            self._n_initial_points -= 1
+        else:
+            raise ValueError("Type of arguments `x` (%s) and `y` (%s) not compatible." % (type(x), type(y)))
+        self.cache_ = {}
+
+        if fit and self._n_initial_points <= 0 and self.base_estimator_ is not None:
+            transformed_bounds = np.array(self.space.transformed_bounds)
+            est = clone(self.base_estimator_)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                est.fit(self.space.transform(self.Xi), self.yi)
+
+            if hasattr(self, "next_xs_") and self.acq_func == "gp_hedge":
+                self.gains_ -= est.predict(np.vstack(self.next_xs_))
+
+            if self.max_model_queue_size is None or len(self.models) < self.max_model_queue_size:
+                self.models.append(est)
+            else:
+                self.models.pop(0)
+                self.models.append(est)
+
+            self.next_xs_ = self._score_and_refine(est, transformed_bounds)
+
+            if self.acq_func == "gp_hedge":
+                logits = np.array(self.gains_)
+                logits -= np.max(logits)
+                exp_logits = np.exp(self.eta * logits)
+                probs = exp_logits / np.sum(exp_logits)
+                next_x = self.next_xs_[np.argmax(self.rng.multinomial(1, probs))]
+            else:
+                next_x = self.next_xs_[0]
+            self._next_x = self.space.inverse_transform(next_x.reshape((1, -1)))[0]
+
+        result = create_result(self.Xi, self.yi, self.space, self.rng, models=self.models)
+        result.specs = self.specs
+        return result
+
+    def _score_and_refine(self, est, transformed_bounds):
+        """The scoring block (optimizer.py:550-594) on the GPU: returns one proposed point per candidate acquisition."""
+        kw = self.acq_func_kwargs or {}
+        xi, kappa = kw.get("xi", 0.01), kw.get("kappa", 1.96)
+        y_opt = np.min(self.yi)
+        acqs = tuple(self.cand_acq_funcs_)
+        X = self.space.rvs_transformed(self.n_points, self.rng)
+        if not hasattr(est, "device_state"):
+            raise TypeError("the GPU scoring path needs this package's GaussianProcessRegressor, got %s" % type(est))
+        dev = est.device_state()
+        k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
+        res = dev.score(X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
+                        want_posterior=False, want_values=False)
+        self._last_scoring = res          # kept for inspection / tests (top-k per acquisition)
+
+        next_xs = []
+        if self.acq_optimizer == "sampling":
+            for acq in acqs:
+                r = res[acq]
+                # np.argmin: the first NaN wins, otherwise the first minimum
+                idx = r["first_nan"] if r["first_nan"] >= 0 else int(r["topk_idx"][0])
+                next_xs.append(X[idx])
+        else:
+            starts, owner = [], []
+            for a_i, acq in enumerate(acqs):
+                for idx in res[acq]["topk_idx"]:
+                    if idx >= 0:
+                        starts.append(X[int(idx)])
+                        owner.append(a_i)
+
+            def evaluate(tasks, Xq):
+                g = dev.score_grad(Xq, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa)
+                f = np.array([g[acqs[owner[t]]]["values"][i] for i, t in enumerate(tasks)])
+                G = np.vstack([g[acqs[owner[t]]]["grad"][i] for i, t in enumerate(tasks)])
+                return f, G
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                results = minimize_batch(starts, evaluate, self.space.transformed_bounds, maxiter=20)
+            for a_i, acq in enumerate(acqs):
+                mine = [r for r, o in zip(results, owner) if o == a_i]
+                cand_xs = np.array([r[0] for r in mine])
+                cand_acqs = np.array([r[1] for r in mine])
+                next_xs.append(cand_xs[np.argmin(cand_acqs)])
+
+        if not self.space.is_categorical:
+            next_xs = [np.clip(x, transformed_bounds[:, 0], transformed_bounds[:, 1]) for x in next_xs]
+        return next_xs
+
+    def _check_y_is_valid(self, x, y):
+        if is_listlike(y) and is_2Dlistlike(x):
+            for y_value in y:
+                if not isinstance(y_value, Number):
+                    raise ValueError("expected y to be a list of scalars")
+        elif is_listlike(x):
+            if not isinstance(y, Number):
+                raise ValueError("`func` should return a scalar")
+        else:
+            raise ValueError("Type of arguments `x` (%s) and `y` (%s) not compatible." % (type(x), type(y)))
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def run(self, func, n_iter=1):
+        for _ in range(n_iter):
+            x = self.ask()
+            self.tell(x, func(x))
+        return self.get_result()
+
+    def update_next(self):
+        self.cache_ = {}
+        if hasattr(self, "_next_x"):
+            opt = self.copy(random_state=self.rng)
+            self._next_x = opt._next_x
+
+    def get_result(self):
+        result = create_result(self.Xi, self.yi, self.space, self.rng, models=self.models)
+        result.specs = self.specs
+        return result
