@@ -1,0 +1,199 @@
+"""CPU tests: C-ABI surface, host-side flattening of fitted models, top-k merge (incl. 2-rank gloo), L-BFGS batching."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from scipy.optimize import fmin_l_bfgs_b
+
+import skopt_b200
+from skopt_b200 import _lib, engine
+from skopt_b200.distributed import merge_topk, shard_bounds
+from skopt_b200.optimizer.lbfgs import minimize_batch
+from oracle import gp_oracle as orc
+from tests._golden import NAMES, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/skb.h is the contract: each declared function must be exported by libskb.so and bound in _lib.py."""
+    header = open(os.path.join(ROOT, "include", "skb.h")).read()
+    declared = set(re.findall(r"\b(skb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound
+    assert _lib.lib().skb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    st = orc.make_synthetic_state(16, 2)
+    hs = engine.HostState(st.X_train, st.alpha, np.eye(16), st.length_scale, 3, 1.0, 0.0, 0.0, 0.0, 1.0)
+    with pytest.raises(_lib.SkbError) as e:
+        engine.DeviceState(hs)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_kernel_flattening_matches_oracle_walker(name):
+    """Two independent walkers (product: engine._flatten_kernel, checker: oracle._reduce_kernel) must agree, and the
+    golden K_trans / diag pin both to the reference."""
+    rec, meta, est = load(name)
+    hs = engine.host_state_from_estimator(est)
+    st = orc.state_from_estimator(est)
+    kind = {(orc.KIND_RBF, np.inf): 0, (orc.KIND_MATERN, 0.5): 1, (orc.KIND_MATERN, 1.5): 2,
+            (orc.KIND_MATERN, 2.5): 3}[(st.kind, st.nu)]
+    assert hs.kernel == kind
+    assert hs.amplitude == pytest.approx(st.amplitude, rel=1e-15) and hs.bias == pytest.approx(st.bias, rel=1e-15)
+    assert hs.white == pytest.approx(st.white, rel=1e-15, abs=1e-300)
+    assert np.array_equal(hs.length_scale, st.length_scale)
+    assert np.allclose(hs.prior_var, rec["diag"], rtol=1e-15)
+    assert np.allclose(hs.L_inv.T @ hs.L_inv, rec["K_inv"], rtol=1e-6, atol=1e-8 * np.abs(rec["K_inv"]).max())
+
+
+def test_unsupported_kernels_raise():
+    from sklearn.gaussian_process import kernels as skk
+
+    class E:
+        pass
+    e = E()
+    e.X_train_ = np.zeros((3, 2)); e.alpha_ = np.zeros(3); e.L_ = np.eye(3)
+    e.y_train_mean_ = 0.0; e.y_train_std_ = 1.0
+    for k in (skk.RationalQuadratic(), skk.RBF() * skk.Matern(), skk.RBF() + skk.Matern(), skk.Matern(nu=3.5),
+              skk.DotProduct()):
+        e.kernel_ = k
+        with pytest.raises(NotImplementedError):
+            engine.host_state_from_estimator(e)
+
+
+def test_product_fit_reproduces_reference_state():
+    """fit() post-processing (gpr.py:182-237): noise_, K_inv_, zeroed WhiteKernel, y statistics."""
+    from skopt_b200.learning import GaussianProcessRegressor
+    from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
+    rec, meta, est = load("matern25_const_noise")
+    c = meta["ctor"]
+    gpr = GaussianProcessRegressor(ConstantKernel(c["amplitude"], "fixed") * Matern(np.array(c["length_scale"]), "fixed",
+                                                                                     nu=c["nu"]),
+                                   normalize_y=c["normalize_y"], noise=c["noise"], optimizer=None)
+    gpr.fit(rec["X_train"], rec["y"])
+    assert gpr.noise_ == float(rec["noise_"])
+    assert np.allclose(gpr.alpha_, rec["alpha"], rtol=1e-9, atol=1e-12 * np.abs(rec["alpha"]).max())
+    assert np.allclose(gpr.K_inv_, rec["K_inv"], rtol=1e-7, atol=1e-9 * np.abs(rec["K_inv"]).max())
+    assert float(gpr.y_train_mean_) == float(rec["y_train_mean"]) and float(gpr.y_train_std_) == float(rec["y_train_std"])
+    hs = engine.host_state_from_estimator(gpr)
+    assert hs.white == 0.0 and hs.amplitude == pytest.approx(c["amplitude"])
+    import pickle
+    from sklearn.base import clone
+    pickle.loads(pickle.dumps(gpr))
+    assert clone(gpr).noise == c["noise"]
+
+
+def test_merge_topk_is_lexicographic():
+    import torch
+    v = torch.tensor([0.5, -1.0, -1.0, float("nan"), 0.0, -0.0, 3.0], dtype=torch.float64)
+    i = torch.tensor([10, 7, 3, 1, 5, 4, -1], dtype=torch.int64)
+    ov, oi = merge_topk(v, i, 5)
+    assert oi.tolist() == [3, 7, 4, 5, 10]
+    ov, oi = merge_topk(v, i, 7)
+    assert oi.tolist()[-2:] == [-1, -1] and torch.isnan(ov[-1])
+    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import skopt_b200
+from skopt_b200.distributed import merge_topk, merge_topk_allgather, shard_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.RandomState(0)
+vals = rng.randn(1001); vals[17] = vals[900] = vals.min() - 1.0          # an exact tie across ranks
+b = shard_bounds(vals.size, world)
+lo, hi = b[rank], b[rank + 1]
+k = 6
+local = np.lexsort((np.arange(lo, hi), vals[lo:hi]))[:k]
+v, i = merge_topk_allgather(torch.from_numpy(vals[lo:hi][local]), torch.from_numpy(local + lo), k)
+expect = np.lexsort((np.arange(vals.size), vals))[:k]
+assert i.tolist() == expect.tolist(), (i.tolist(), expect.tolist())
+assert i[0].item() == int(np.argmin(vals)) == 17
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_topk_allgather_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
+
+
+def test_lockstep_lbfgs_equals_sequential_runs():
+    """Batching must not change any search: same iterates as running fmin_l_bfgs_b one start at a time."""
+    A = np.diag([1.0, 4.0, 9.0])
+    c = np.array([0.3, 0.9, 0.1])
+
+    def f_and_g(x):
+        r = x - c
+        return float(r @ A @ r + np.sin(3 * x[0])), 2 * A @ r + np.array([3 * np.cos(3 * x[0]), 0.0, 0.0])
+
+    calls = []
+
+    def evaluate(tasks, X):
+        calls.append(len(tasks))
+        out = [f_and_g(x) for x in X]
+        return np.array([o[0] for o in out]), np.vstack([o[1] for o in out])
+
+    starts = np.random.RandomState(3).rand(7, 3)
+    bounds = [(0.0, 1.0)] * 3
+    res = minimize_batch(starts, evaluate, bounds, maxiter=20)
+    for x0, (x, f, info) in zip(starts, res):
+        xs, fs, infos = fmin_l_bfgs_b(f_and_g, x0, bounds=bounds, approx_grad=False, maxiter=20)
+        assert np.array_equal(x, xs) and f == fs and info["funcalls"] == infos["funcalls"]
+    assert calls[0] == 7 and max(calls) == 7          # all searches advance together
+
+
+def test_optimizer_host_logic_and_initial_points():
+    """Validation and the random initial phase need no GPU; the points must equal the reference's (same RNG order)."""
+    import json
+    from skopt_b200 import Optimizer
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "traj_gp_minimize.npz")))
+    runs = json.loads(str(gold["runs"]))
+    cfg = runs["hart6_lbfgs_ei"]
+    rng = np.random.RandomState(cfg["random_state"])
+    from skopt_b200.utils import cook_estimator
+    dims = [tuple(d) for d in cfg["dims"]]
+    est = cook_estimator("GP", space=dims, random_state=rng.randint(0, np.iinfo(np.int32).max))   # gp.py:254-257
+    opt = Optimizer(dims, est, n_initial_points=cfg["n_initial_points"], random_state=rng)
+    ref = json.loads(str(gold["hart6_lbfgs_ei_x_iters"]))
+    for i in range(cfg["n_initial_points"] - 1):
+        x = opt.ask()
+        assert x == ref[i]
+        opt.tell(x, float(i))
+    assert opt.acq_optimizer == "lbfgs" and opt.cand_acq_funcs_ == ["EI", "LCB", "PI"] and len(opt.models) == 0
+    with pytest.raises(ValueError):
+        Optimizer([(0.0, 1.0)], "GP", acq_func="nope")
+    with pytest.raises(ValueError):
+        Optimizer([(0.0, 1.0)], "GP", acq_optimizer="newton")
+    with pytest.raises(ValueError):
+        opt.tell([2.0] * 6, 1.0)                         # outside the space
+    with pytest.raises(ValueError):
+        opt.tell([0.5] * 6, "bad")
+    with pytest.raises(ValueError):
+        opt.ask(n_points=0)
+    with pytest.raises(ValueError):
+        opt.ask(n_points=2, strategy="cl_median")
