@@ -103,10 +103,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_CPU_STATE = {}
+
+
 def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
     """Oracle (port of the reference's NumPy/SciPy path) timed on this host on `sample_m` candidates."""
     from oracle import gp_oracle as orc
-    st = orc.make_synthetic_state(n, d, noise=1e-4, seed=seed)
+    key = (n, d, seed)
+    if key not in _CPU_STATE:
+        _CPU_STATE[key] = orc.make_synthetic_state(n, d, noise=1e-4, seed=seed)
+    st = _CPU_STATE[key]
     Xc = np.random.RandomState(seed + 1).rand(sample_m, d)
     y_opt = float(st.meta["y"].min())
     best = None
@@ -278,7 +284,7 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
-                         "kernel": "trmm_sqnorm_acq_kernel (K2)", "peak_source": "measured FP64 DMMA issue peak on this "
+                         "kernel": "trmm_kernel<0> (K2: DMMA triangular contraction + acquisition epilogue)", "peak_source": "measured FP64 DMMA issue peak on this "
                          "pool (tools/microbench/fp64_peaks.cu -> profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json has "
                          "no FP64 entry; cuBLAS DGEMM 8192^3 measured 35.5",
                          "algorithmic_flops_per_candidate": flops_k2(N_TRAIN), "candidates_per_launch": cand_per_k2,

@@ -46,3 +46,32 @@ def shard_bounds(m, world):
     for r in range(world):
         b.append(b[-1] + base + (1 if r < rem else 0))
     return b
+
+
+def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None):
+    """Score the rows of X that belong to this rank and merge the top-k across ranks.
+
+    `X` is the FULL candidate matrix (identical on every rank); the returned dict has, per acquisition, the GLOBAL
+    'topk_val', 'topk_idx' and 'first_nan' -- the same on every rank and the same as a single-GPU run, because a
+    candidate's value does not depend on where it was computed and ties resolve to the lowest global index."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return dev.score(X, y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
+                         want_posterior=False, want_values=False)
+    rank = dist.get_rank(group)
+    b = shard_bounds(X.shape[0], world)
+    lo, hi = b[rank], b[rank + 1]
+    res = dev.score(X[lo:hi], y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k, index_offset=lo,
+                    want_posterior=False, want_values=False)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", dev.device) if backend == "nccl" else torch.device("cpu")
+    for name in acq_funcs:
+        r = res[name]
+        v = torch.from_numpy(r["topk_val"]).to(device)
+        i = torch.from_numpy(r["topk_idx"]).to(device)
+        v, i = merge_topk_allgather(v, i, top_k, group=group)
+        r["topk_val"], r["topk_idx"] = v.cpu().numpy(), i.cpu().numpy()
+        nan = torch.tensor([r["first_nan"] if r["first_nan"] >= 0 else _I64_MAX], dtype=torch.int64, device=device)
+        dist.all_reduce(nan, op=dist.ReduceOp.MIN, group=group)
+        r["first_nan"] = -1 if int(nan) == _I64_MAX else int(nan)
+    return res

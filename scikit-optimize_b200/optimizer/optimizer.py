@@ -27,6 +27,7 @@ from ..learning import GaussianProcessRegressor
 from ..space import Categorical, Space
 from ..utils import (check_x_in_space, cook_estimator, create_result, has_gradients, is_2Dlistlike, is_listlike,
                      normalize_dimensions)
+from ..distributed import sharded_score
 from .lbfgs import minimize_batch
 
 _INT32_MAX = np.iinfo(np.int32).max
@@ -226,8 +227,9 @@ class Optimizer(object):
             raise TypeError("the GPU scoring path needs this package's GaussianProcessRegressor, got %s" % type(est))
         dev = est.device_state()
         k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
-        res = dev.score(X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
-                        want_posterior=False, want_values=False)
+        # one process per GPU: every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
+        # its contiguous block and the per-rank top-k lists are all-gathered (k*16 bytes per acquisition) and merged
+        res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k)
         self._last_scoring = res          # kept for inspection / tests (top-k per acquisition)
 
         next_xs = []

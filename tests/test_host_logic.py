@@ -126,6 +126,23 @@ v, i = merge_topk_allgather(torch.from_numpy(vals[lo:hi][local]), torch.from_num
 expect = np.lexsort((np.arange(vals.size), vals))[:k]
 assert i.tolist() == expect.tolist(), (i.tolist(), expect.tolist())
 assert i[0].item() == int(np.argmin(vals)) == 17
+
+# sharded_score: the N>1 host logic with a stand-in for the device (same interface as engine.DeviceState.score)
+from skopt_b200.distributed import sharded_score
+class FakeDev:
+    device = 0
+    def score(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0, **kw):
+        out = {}
+        for j, a in enumerate(acq_funcs):
+            v = np.sin(7 * X[:, 0] + j) * X[:, 1]
+            order = np.lexsort((np.arange(len(v)), v))[:top_k]
+            out[a] = dict(topk_val=v[order], topk_idx=order + index_offset, first_nan=-1)
+        return out
+X = np.random.RandomState(1).rand(777, 2); X[600] = X[5]
+full = FakeDev().score(X, acq_funcs=("EI", "PI"), top_k=5)
+sh = sharded_score(FakeDev(), X, y_opt=0.0, acq_funcs=("EI", "PI"), xi=0.01, kappa=1.96, top_k=5)
+for a in ("EI", "PI"):
+    assert np.array_equal(full[a]["topk_idx"], sh[a]["topk_idx"]) and np.array_equal(full[a]["topk_val"], sh[a]["topk_val"])
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
