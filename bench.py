@@ -125,6 +125,41 @@ def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
     return sample_m / best, best
 
 
+def branin(x):
+    a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5.0 / np.pi, 6.0, 10.0, 1.0 / (8 * np.pi)
+    return a * (x[1] - b * x[0] ** 2 + c * x[0] - r) ** 2 + s * (1 - t) * np.cos(x[0]) + s
+
+
+def ask_p50_ms(n_tells=30):
+    """Median wall time of the candidate-scoring block (optimizer.py:550-608, fit excluded) over `n_tells` model-based
+    tells of BASELINE.json configs[0]: gp_minimize on Branin, acq_optimizer='sampling', n_points=10000, gp_hedge."""
+    from skopt_b200 import Optimizer
+    opt = Optimizer([(-5.0, 10.0), (0.0, 15.0)], "GP", n_initial_points=10, acq_func="gp_hedge",
+                    acq_optimizer="sampling", acq_optimizer_kwargs=dict(n_points=10000), random_state=0,
+                    acq_func_kwargs=dict(xi=0.01, kappa=1.96))
+    for _ in range(10 + n_tells - 1):
+        x = opt.ask()
+        opt.tell(x, branin(x))
+    t = np.asarray(opt.scoring_times_[1:]) * 1e3          # drop the first (allocations, module load)
+    return float(np.median(t)), int(t.size)
+
+
+def ask_p50_ms_cpu(n_tells=5):
+    """Same block with the oracle port of the reference arithmetic (3 acquisitions, posterior recomputed each time)."""
+    from oracle import gp_oracle as orc
+    st = orc.make_synthetic_state(40, 2, noise=1e-6, seed=0)
+    rng = np.random.RandomState(0)
+    times = []
+    for _ in range(n_tells):
+        X = rng.rand(10000, 2)
+        t0 = time.perf_counter()
+        for acq in ("EI", "LCB", "PI"):
+            v = orc.gaussian_acquisition(X, st, -1.0, acq, acq_func_kwargs=dict(xi=0.01, kappa=1.96), quad="einsum")
+            int(np.argmin(v))
+        times.append(time.perf_counter() - t0)
+    return float(np.median(times)) * 1e3
+
+
 def run_reference(args, rank):
     """Reference arm: the reference algorithm on the host cores (bounded sample per step)."""
     if rank != 0:
@@ -165,6 +200,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=256, help="candidates per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="candidates of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ask", action="store_true", help="skip the ask() p50 latency leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -293,6 +329,12 @@ def main():
                          "whole_path_tflops": flops_value_path(N_TRAIN, N_DIMS) * value / world / 1e12},
             "argmin_index": argmin_idx,
         }
+        if not args.no_ask:
+            p50, cnt = ask_p50_ms()
+            line["ask_p50_ms"] = {"value": p50, "tells": cnt, "config": "BASELINE.json configs[0]: Branin, gp_hedge, "
+                                  "sampling, n_points=10000, n_train 10..39: scoring block of Optimizer._tell, fit "
+                                  "excluded (candidate generation + one fused GPU pass + top-k + inverse transform)",
+                                  "cpu_port_ms": ask_p50_ms_cpu() if not args.no_cpu_baseline else None}
         if not args.no_cpu_baseline:
             evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, args.cpu_sample, quad="einsum")
             evals_s_gemm, _ = cpu_baseline(N_TRAIN, N_DIMS, 4 * args.cpu_sample, quad="gemm")

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, 2) kcross_mean_kernel(const KCrossParams 
 
     const int tid = threadIdx.x, c = tid & (BN - 1), h = tid >> 7;
     const int64_t tile = blockIdx.x;
-    const int nst = p.n_pad / XROWS;
+    const int nst = (p.n + XROWS - 1) / XROWS;      // stages holding real training rows (the rest of n_pad is padding)
 
     if (tid == 0) {
         mbar_init(bars + 0, 1);

@@ -185,10 +185,12 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     const int smem3 = (int)grad_smem_bytes(st->d_pad);
-    CU(cudaFuncSetAttribute(grad_contract_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    CU(cudaFuncSetAttribute(grad_contract_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    CU(cudaFuncSetAttribute(grad_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    CU(cudaFuncSetAttribute(grad_contract_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+#define SKB_GRAD_ATTR(K, M) CU(cudaFuncSetAttribute(grad_contract_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3))
+    SKB_GRAD_ATTR(0, 2); SKB_GRAD_ATTR(0, 4); SKB_GRAD_ATTR(0, 8);
+    SKB_GRAD_ATTR(1, 2); SKB_GRAD_ATTR(1, 4); SKB_GRAD_ATTR(1, 8);
+    SKB_GRAD_ATTR(2, 2); SKB_GRAD_ATTR(2, 4); SKB_GRAD_ATTR(2, 8);
+    SKB_GRAD_ATTR(3, 2); SKB_GRAD_ATTR(3, 4); SKB_GRAD_ATTR(3, 8);
+#undef SKB_GRAD_ATTR
     return SKB_OK;
 }
 
@@ -438,6 +440,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         tp.Kt = st->d_Kt;
         tp.kdot = st->d_kdot;
         tp.n_pad = st->n_pad;
+        tp.n = st->n;
         tp.m = mc;
         tp.a.prior_var = st->amplitude + st->bias + st->white;
         tp.a.y_mean = st->y_mean;
@@ -581,17 +584,28 @@ int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mea
     return SKB_OK;
 }
 
+}  // extern "C"
+
+template <int KIND>
+static void launch_grad_kind(const GradParams& p, int tiles, size_t smem, cudaStream_t s) {
+    if (p.d <= 16) grad_contract_kernel<KIND, 2><<<tiles, GRAD_THREADS, smem, s>>>(p);
+    else if (p.d <= 32) grad_contract_kernel<KIND, 4><<<tiles, GRAD_THREADS, smem, s>>>(p);
+    else grad_contract_kernel<KIND, 8><<<tiles, GRAD_THREADS, smem, s>>>(p);
+}
+
 static int launch_grad(skb_state* st, const GradParams& p, int tiles, cudaStream_t s) {
     const size_t smem = grad_smem_bytes(p.d_pad);
     switch (st->kernel) {
-        case SKB_KERNEL_RBF: grad_contract_kernel<0><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
-        case SKB_KERNEL_MATERN12: grad_contract_kernel<1><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
-        case SKB_KERNEL_MATERN32: grad_contract_kernel<2><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
-        default: grad_contract_kernel<3><<<tiles, GRAD_THREADS, smem, s>>>(p); break;
+        case SKB_KERNEL_RBF: launch_grad_kind<0>(p, tiles, smem, s); break;
+        case SKB_KERNEL_MATERN12: launch_grad_kind<1>(p, tiles, smem, s); break;
+        case SKB_KERNEL_MATERN32: launch_grad_kind<2>(p, tiles, smem, s); break;
+        default: launch_grad_kind<3>(p, tiles, smem, s); break;
     }
     LAUNCHED();
     return SKB_OK;
 }
+
+extern "C" {
 
 static int check_grad_args(skb_state* st, const double* X, int64_t m, const skb_acq_params* params, const skb_grad_out* out) {
     if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
@@ -644,6 +658,7 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
         std::memset(&tp, 0, sizeof(tp));
         tp.Kt = st->d_Kt;
         tp.n_pad = st->n_pad;
+        tp.n = st->n;
         tp.m = mc;
         tp.Ap = st->d_Ap;
         tp.Wt = st->d_Wt;

@@ -15,6 +15,7 @@ the reference so that trajectories stay comparable; the scoring block (:550-608)
   gains_ -= est.predict(next_xs_)                              device mean-only predict
 """
 import sys
+import time
 import warnings
 from math import log
 from numbers import Number
@@ -109,6 +110,7 @@ class Optimizer(object):
         self.Xi = []
         self.yi = []
         self.cache_ = {}
+        self.scoring_times_ = []
 
     # ------------------------------------------------------------------------------------------------ copy / ask
     def copy(self, random_state=None):
@@ -200,7 +202,11 @@ class Optimizer(object):
                 self.models.pop(0)
                 self.models.append(est)
 
+            t_score = time.perf_counter()
             self.next_xs_ = self._score_and_refine(est, transformed_bounds)
+            # wall time of the scoring block alone (fit excluded): the "ask() p50" of BASELINE.json -- in this
+            # version of scikit-optimize the work ask() returns is done here (optimizer.py:550-608)
+            self.scoring_times_.append(time.perf_counter() - t_score)
 
             if self.acq_func == "gp_hedge":
                 logits = np.array(self.gains_)
