@@ -72,7 +72,10 @@ struct skb_state {
     struct Span { int kind; cudaEvent_t a, b; };
     std::vector<Span> spans;
     size_t spans_used = 0;
-    // host entry points
+    // host entry points: candidates are uploaded chunk by chunk on a second stream so that the copy of chunk i+1
+    // overlaps the kernels of chunk i
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ready;
     double* d_X = nullptr;       size_t x_cap = 0;
     double* d_out = nullptr;     size_t out_cap = 0;
     unsigned long long* d_clamp = nullptr;
@@ -238,6 +241,8 @@ void skb_state_destroy(skb_state* st) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
     }
+    for (auto& ev : st->chunk_ready) cudaEventDestroy(ev);
+    if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     if (st->stream) cudaStreamDestroy(st->stream);
     delete st;
 }
@@ -289,6 +294,7 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
     int rc = SKB_OK;
     auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&st->d_ls, d * sizeof(double)));
         CU(cudaMalloc(&st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double)));
         CU(cudaMalloc(&st->d_alpha_p, (size_t)st->n_pad * sizeof(double)));
@@ -369,15 +375,42 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
     return SKB_OK;
 }
 
+// candidate tiles processed per K1/K2 launch pair: as many as the scratch limit allows, in whole waves of SMs
+static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile) {
+    const int64_t tiles = (m + BN - 1) / BN;
+    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / bytes_per_tile));
+    if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
+    return std::min(tiles, cap);
+}
+
+// Upload X in the same chunks the kernels will consume, on the copy stream, one event per chunk.
+static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chunk_tiles) {
+    const int64_t tiles = (m + BN - 1) / BN;
+    const size_t n_chunks = (size_t)((tiles + chunk_tiles - 1) / chunk_tiles);
+    while (st->chunk_ready.size() < n_chunks) {
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        st->chunk_ready.push_back(ev);
+    }
+    size_t ci = 0;
+    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++ci) {
+        const int64_t c0 = t0 * BN;
+        const int64_t mc = std::min<int64_t>(m - c0, chunk_tiles * BN);
+        CU(cudaMemcpyAsync(st->d_X + c0 * st->d, X + c0 * st->d, (size_t)mc * st->d * sizeof(double),
+                           cudaMemcpyHostToDevice, st->copy_stream));
+        CU(cudaEventRecord(st->chunk_ready[ci], st->copy_stream));
+    }
+    return SKB_OK;
+}
+
 static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
-                          const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out) {
+                          const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out,
+                          bool wait_chunk_events = false) {
     CU(cudaSetDevice(st->device));
     if (m == 0) return SKB_OK;
     const int64_t tiles = (m + BN - 1) / BN;
     const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
-    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / tile_bytes));
-    if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;   // whole waves per chunk
-    const int64_t chunk_tiles = std::min(tiles, cap);
+    const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes);
 
     int rc;
     if (!mean_only) {
@@ -408,7 +441,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     }
 
     if (!mean_only && out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
-    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles) {
+    size_t chunk_index = 0;
+    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++chunk_index) {
+        if (wait_chunk_events) CU(cudaStreamWaitEvent(s, st->chunk_ready[chunk_index], 0));
         const int64_t nt = std::min(chunk_tiles, tiles - t0);
         const int64_t c0 = t0 * BN;
         const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
@@ -546,8 +581,8 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         }
     }
     if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
-    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, s));
-    if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr)) != SKB_OK) return rc;
+    if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double)))) != SKB_OK) return rc;
+    if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) return rc;
     if (out->n_var_clamped)
         CU(cudaMemcpyAsync(out->n_var_clamped, st->d_clamp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     if (out->mean) CU(cudaMemcpyAsync(out->mean, dout.mean, m * sizeof(double), cudaMemcpyDeviceToHost, s));
