@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -84,13 +86,92 @@ struct skb_state {
 namespace {
 constexpr int TOPK_BLOCKS_PER_SM = 2;
 
+// ---------------- per-device caching allocator ----------------
+// A BO loop creates one GP state per tell() and drops the previous one; cudaMalloc / cudaFree cost far more than the
+// kernels at small problem sizes, so freed blocks are parked per device and handed back to the next state.
+struct Block { void* ptr; size_t bytes; };
+struct DevicePool {
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t cached_bytes = 0;
+};
+constexpr size_t POOL_MAX_CACHED = 6ull << 30;
+DevicePool g_pools[64];
+
+int pool_alloc(int device, void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~size_t(255);
+    DevicePool& pool = g_pools[device & 63];
+    {
+        std::lock_guard<std::mutex> lock(pool.mu);
+        int best = -1;
+        for (int i = 0; i < (int)pool.free_blocks.size(); ++i) {
+            const size_t b = pool.free_blocks[i].bytes;
+            if (b >= bytes && b <= 2 * bytes + (1u << 20) && (best < 0 || b < pool.free_blocks[best].bytes)) best = i;
+        }
+        if (best >= 0) {
+            Block blk = pool.free_blocks[best];
+            pool.free_blocks.erase(pool.free_blocks.begin() + best);
+            pool.cached_bytes -= blk.bytes;
+            pool.live[blk.ptr] = blk.bytes;
+            *out = blk.ptr;
+            return SKB_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // give the cache back and retry once
+        cudaGetLastError();
+        std::vector<Block> drop;
+        {
+            std::lock_guard<std::mutex> lock(pool.mu);
+            drop.swap(pool.free_blocks);
+            pool.cached_bytes = 0;
+        }
+        for (auto& b : drop) cudaFree(b.ptr);
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? SKB_ERR_NOMEM : SKB_ERR_CUDA, "cudaMalloc(%zu bytes) -> %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lock(pool.mu);
+    pool.live[*out] = bytes;
+    return SKB_OK;
+}
+
+void pool_free(int device, void* ptr) {
+    if (!ptr) return;
+    DevicePool& pool = g_pools[device & 63];
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(pool.mu);
+        auto it = pool.live.find(ptr);
+        if (it != pool.live.end()) {
+            bytes = it->second;
+            pool.live.erase(it);
+            if (pool.cached_bytes + bytes <= POOL_MAX_CACHED) {
+                pool.free_blocks.push_back({ptr, bytes});
+                pool.cached_bytes += bytes;
+                return;
+            }
+        }
+    }
+    cudaFree(ptr);
+}
+
 template <typename T>
-int grow(T** ptr, size_t* cap, size_t need) {
+int grow(int device, T** ptr, size_t* cap, size_t need) {
     if (need <= *cap) return SKB_OK;
-    if (*ptr) CU(cudaFree(*ptr));
+    pool_free(device, *ptr);
     *ptr = nullptr;
     *cap = 0;
-    CU(cudaMalloc(reinterpret_cast<void**>(ptr), need * sizeof(T)));
+    void* p = nullptr;
+    int rc = pool_alloc(device, &p, need * sizeof(T));
+    if (rc != SKB_OK) return rc;
+    *ptr = static_cast<T*>(p);
     *cap = need;
     return SKB_OK;
 }
@@ -180,6 +261,14 @@ int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t 
 }
 
 int set_kernel_attributes(skb_state* st) {
+    // dynamic shared memory limits only ever need to grow: remember the largest d_pad configured per device
+    static std::mutex mu;
+    static int configured_d_pad[64] = {0};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (configured_d_pad[st->device & 63] >= st->d_pad) return SKB_OK;
+        configured_d_pad[st->device & 63] = st->d_pad;
+    }
     const int smem1 = (int)kcross_smem_bytes(st->d_pad);
     CU(cudaFuncSetAttribute(kcross_mean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
@@ -231,12 +320,11 @@ int skb_device_count(void) {
 void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
-    if (st->stream) cudaStreamSynchronize(st->stream);
+    cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
     void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    for (void* p : ptrs) pool_free(st->device, p);
     for (auto& sp : st->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -295,13 +383,15 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
     auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-        CU(cudaMalloc(&st->d_ls, d * sizeof(double)));
-        CU(cudaMalloc(&st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double)));
-        CU(cudaMalloc(&st->d_alpha_p, (size_t)st->n_pad * sizeof(double)));
-        CU(cudaMalloc(&st->d_Vp, vp_elems * sizeof(double)));
-        CU(cudaMalloc(&st->d_clamp, sizeof(unsigned long long)));
-        CU(cudaMalloc(&dX, n * d * sizeof(double)));
-        CU(cudaMalloc(&dV, n * n * sizeof(double)));
+        int prc;
+#define SKB_PALLOC(ptr, bytes) if ((prc = pool_alloc(device, reinterpret_cast<void**>(&(ptr)), (bytes))) != SKB_OK) return prc
+        SKB_PALLOC(st->d_ls, d * sizeof(double));
+        SKB_PALLOC(st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double));
+        SKB_PALLOC(st->d_alpha_p, (size_t)st->n_pad * sizeof(double));
+        SKB_PALLOC(st->d_Vp, vp_elems * sizeof(double));
+        SKB_PALLOC(st->d_clamp, sizeof(unsigned long long));
+        SKB_PALLOC(dX, n * d * sizeof(double));
+        SKB_PALLOC(dV, n * n * sizeof(double));
         CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
         CU(cudaMemcpyAsync(dX, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
         CU(cudaMemcpyAsync(dV, desc->L_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
@@ -313,7 +403,8 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
         if (desc->K_inv) {
-            CU(cudaMalloc(&st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double)));
+            SKB_PALLOC(st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double));
+#undef SKB_PALLOC
             CU(cudaMemcpyAsync(dV, desc->K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
             pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dV, st->d_Ap, st->n, st->n_pad);
             LAUNCHED();
@@ -322,8 +413,8 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         return set_kernel_attributes(st);
     };
     rc = body();
-    if (dX) cudaFree(dX);
-    if (dV) cudaFree(dV);
+    pool_free(device, dX);
+    pool_free(device, dV);
     if (rc != SKB_OK) {
         skb_state_destroy(st);
         return rc;
@@ -414,9 +505,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
 
     int rc;
     if (!mean_only) {
-        if ((rc = grow(&st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
     }
-    if ((rc = grow(&st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
 
     const int top_k = (!mean_only && prm) ? prm->top_k : 0;
     double* acq_ptr[3] = {nullptr, nullptr, nullptr};
@@ -431,7 +522,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             if ((size_t)m > st->acq_cap) {
                 for (int a = 0; a < 3; ++a) {
                     size_t cap_a = st->acq_cap;
-                    if ((rc = grow(&st->d_acq[a], &cap_a, (size_t)m)) != SKB_OK) return rc;
+                    if ((rc = grow(st->device, &st->d_acq[a], &cap_a, (size_t)m)) != SKB_OK) return rc;
                 }
                 st->acq_cap = (size_t)m;
             }
@@ -503,9 +594,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         const int64_t slice = (m + nblk - 1) / nblk;
         if ((size_t)nblk * top_k > st->part_cap) {
             size_t c1 = st->part_cap, c2 = st->part_cap, c3 = st->part_cap;
-            if ((rc = grow(&st->d_part_v, &c1, (size_t)nblk * top_k)) != SKB_OK) return rc;
-            if ((rc = grow(&st->d_part_i, &c2, (size_t)nblk * top_k)) != SKB_OK) return rc;
-            if ((rc = grow(&st->d_part_nan, &c3, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            if ((rc = grow(st->device, &st->d_part_v, &c1, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            if ((rc = grow(st->device, &st->d_part_i, &c2, (size_t)nblk * top_k)) != SKB_OK) return rc;
+            if ((rc = grow(st->device, &st->d_part_nan, &c3, (size_t)nblk * top_k)) != SKB_OK) return rc;
             st->part_cap = (size_t)nblk * top_k;
         }
         for (int a = 0; a < 3; ++a) {
@@ -552,18 +643,18 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
     CU(cudaSetDevice(st->device));
     if (m == 0) return SKB_OK;
     cudaStream_t s = st->stream;
-    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
     // device mirror of the requested outputs: [mean][std][acq0][acq1][acq2] (m each, only those requested)
     int n_vec = (out->mean ? 1 : 0) + (out->std ? 1 : 0);
     for (int a = 0; a < 3; ++a)
         if (((params->acq_mask >> a) & 1) && out->acq[a]) ++n_vec;
     const int k = params->top_k;
-    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)n_vec * m + 1)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)n_vec * m + 1)) != SKB_OK) return rc;
     if ((size_t)3 * std::max(k, 1) > st->topk_cap) {
         size_t c1 = st->topk_cap, c2 = st->topk_cap, c3 = st->topk_cap;
-        if ((rc = grow(&st->d_topk_v, &c1, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
-        if ((rc = grow(&st->d_topk_i, &c2, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
-        if ((rc = grow(&st->d_topk_nan, &c3, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_topk_v, &c1, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_topk_i, &c2, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_topk_nan, &c3, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
         st->topk_cap = (size_t)3 * std::max(k, 1);
     }
     skb_score_out dout;
@@ -610,8 +701,8 @@ int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mea
     CU(cudaSetDevice(st->device));
     if (m == 0) return SKB_OK;
     int rc;
-    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
-    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)m)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)m)) != SKB_OK) return rc;
     CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
     if ((rc = score_dev_impl(st, st->d_X, m, 0, nullptr, nullptr, st->stream, true, st->d_out)) != SKB_OK) return rc;
     CU(cudaMemcpyAsync(mean, st->d_out, m * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
@@ -662,9 +753,9 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
     int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / tile_bytes));
     if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
     const int64_t chunk_tiles = std::min(tiles, cap);
-    if ((rc = grow(&st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
-    if ((rc = grow(&st->d_Wt, &st->wt_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
-    if ((rc = grow(&st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_Wt, &st->wt_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
     const int nI = st->n_pad / BM;
 
     for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles) {
@@ -747,8 +838,8 @@ int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq
     cudaStream_t s = st->stream;
     const size_t d = st->d;
     // device mirror: [mean][std][acq x3] (m each) then [mean_grad][std_grad][acq_grad x3] (m*d each)
-    if ((rc = grow(&st->d_X, &st->x_cap, (size_t)m * d)) != SKB_OK) return rc;
-    if ((rc = grow(&st->d_out, &st->out_cap, (size_t)m * 5 + (size_t)m * d * 5)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_X, &st->x_cap, (size_t)m * d)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)m * 5 + (size_t)m * d * 5)) != SKB_OK) return rc;
     skb_grad_out dout;
     std::memset(&dout, 0, sizeof(dout));
     double* cur = st->d_out;

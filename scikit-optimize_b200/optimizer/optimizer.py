@@ -202,6 +202,10 @@ class Optimizer(object):
                 self.models.pop(0)
                 self.models.append(est)
 
+            # only the newest model needs to stay resident on the GPU; older ones re-upload lazily if predict()ed
+            for old in self.models[:-1]:
+                old.__dict__.pop("_skb_device_state", None)
+
             t_score = time.perf_counter()
             self.next_xs_ = self._score_and_refine(est, transformed_bounds)
             # wall time of the scoring block alone (fit excluded): the "ask() p50" of BASELINE.json -- in this
