@@ -51,25 +51,25 @@ __device__ __forceinline__ void kernel_and_gcoef(double sq, double amplitude, do
                                                  bool& at_zero) {
     at_zero = false;
     if (KIND == 0) {
-        const double e = exp(-0.5 * sq);
+        const double e = exp_nonpos(-0.5 * sq);
         kval = fma(amplitude, e, bias);
         gcoef = -amplitude * e;
         return;
     }
-    const double r = sqrt(sq);
+    const double r = sqrt_nonneg(sq);
     if (KIND == 1) {
-        const double e = exp(-r);
+        const double e = exp_nonpos(-r);
         kval = fma(amplitude, e, bias);
         at_zero = (r == 0.0);                       // reference: gradient row = -1/length_scale (kernels.py:118-128)
         gcoef = at_zero ? 0.0 : -amplitude * e / r;
     } else if (KIND == 2) {
         const double K = r * 1.7320508075688772;
-        const double e = exp(-K);
+        const double e = exp_nonpos(-K);
         kval = fma(amplitude, (1.0 + K) * e, bias);
         gcoef = -3.0 * amplitude * e;
     } else {
         const double K = r * 2.23606797749979;
-        const double e = exp(-K);
+        const double e = exp_nonpos(-K);
         kval = fma(amplitude, (1.0 + K + K * K * (1.0 / 3.0)) * e, bias);
         gcoef = -(5.0 / 3.0) * amplitude * (1.0 + K) * e;
     }

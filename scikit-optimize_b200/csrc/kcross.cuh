@@ -7,6 +7,7 @@
 // form and never leaves the GPU.  Training rows are staged through shared memory with 1-D bulk copies (TMA),
 // double buffered on mbarriers.
 #pragma once
+#include "fastmath.cuh"
 #include "layout.cuh"
 #include "ptx.cuh"
 
@@ -26,12 +27,12 @@ struct KCrossParams {
 
 template <int KIND>
 __device__ __forceinline__ double base_kernel(double sq) {
-    if (KIND == 0) return exp(-0.5 * sq);                         // RBF: exp(-sqeuclidean/2)
-    const double r = sqrt(sq);
-    if (KIND == 1) return exp(-r);                                // Matern 1/2
-    if (KIND == 2) { const double K = r * 1.7320508075688772; return (1.0 + K) * exp(-K); }
+    if (KIND == 0) return exp_nonpos(-0.5 * sq);                  // RBF: exp(-sqeuclidean/2)
+    const double r = sqrt_nonneg(sq);
+    if (KIND == 1) return exp_nonpos(-r);                         // Matern 1/2
+    if (KIND == 2) { const double K = r * 1.7320508075688772; return (1.0 + K) * exp_nonpos(-K); }
     const double K = r * 2.23606797749979;                        // Matern 5/2
-    return (1.0 + K + K * K * (1.0 / 3.0)) * exp(-K);
+    return (1.0 + K + K * K * (1.0 / 3.0)) * exp_nonpos(-K);
 }
 
 constexpr size_t kcross_smem_bytes(int d_pad) {
