@@ -45,7 +45,8 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     p = fma(p, r, c_exp[16]);                               // ... + r/1! + 1/0!
     const int ni = __double2loint(fn);                      // low word of (1.5*2^52 + n) holds n in two's complement
     const double scaled = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
-    return x < c_exp[17] ? 0.0 : scaled;
+    const double y = x < c_exp[17] ? 0.0 : scaled;
+    return x != x ? x : y;                                  // NaN in, NaN out (the exponent patch could hide it)
 }
 
 // sqrt(s) for finite s >= 0: hardware rsqrt seed (about 22 bits), two coupled Newton (Goldschmidt) steps and a final
@@ -63,7 +64,8 @@ __device__ __forceinline__ double sqrt_nonneg(double s) {
     h = fma(h, r, h);
     const double d = fma(-g, g, s);
     g = fma(d, h, g);
-    return s > 0.0 ? g : 0.0;         // s == 0 (or a flushed denormal): the seed is inf and g is NaN
+    // s == 0 or a (flushed) denormal: the seed is inf and g is NaN -> the root is 0 to 1e-145; NaN stays NaN
+    return s > 1e-290 ? g : (s != s ? s : 0.0);
 }
 
 }  // namespace skb

@@ -249,3 +249,79 @@ def test_gradient_matches_finite_differences():
             fd = (f[a]["values"][2 * k] - f[a]["values"][2 * k + 1]) / (2 * eps)
             assert abs(fd - g[a]["grad"][0, k]) < 1e-5, (a, k)
     dev.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# edge cases (ragged / minimal / maximal sizes, NaN, ties, degenerate posteriors)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,m", [(1, 1, 1), (2, 3, 127), (128, 2, 128), (129, 5, 129), (5, 64, 3), (257, 1, 1000)])
+def test_ragged_and_minimal_shapes(n, d, m):
+    st = orc.make_synthetic_state(n, d, noise=1e-2, seed=n * 7 + d, normalize_y=n > 1)
+    Xc = np.random.RandomState(m).rand(m, d)
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    k = min(5, m + 2)                                   # top_k may exceed m: the tail is padded with (nan, -1)
+    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=k)
+    mu, sd = orc.predict(st, Xc, return_std=True)
+    acq_ref = {a: orc.gaussian_acquisition(Xc, st, y_opt, a, acq_func_kwargs=dict(xi=0.01, kappa=1.96)) for a in ACQS}
+    assert np.max(np.abs(res["mean"] - mu)) <= 1e-9 * max(np.max(np.abs(mu)), st.y_std)
+    assert np.max(np.abs(res["std"] ** 2 - sd ** 2)) <= var_tol(st) * st.prior_var * st.y_std ** 2
+    z2 = ((y_opt - 0.01 - mu) / np.maximum(sd, 1e-300)) ** 2
+    for a in ACQS:
+        # normwise 1e-9, plus the pointwise (1 + z^2) allowance for deep-tail EI / PI values (SURVEY 8d iii)
+        tol = 1e-9 * np.max(np.abs(acq_ref[a])) + 1e-9 * (1.0 + z2) * np.abs(acq_ref[a])
+        assert np.all(np.abs(res[a]["values"] - acq_ref[a]) <= tol), a
+        order = np.lexsort((np.arange(m), res[a]["values"]))[:k]
+        assert np.array_equal(res[a]["topk_idx"][:len(order)], order)
+        assert np.all(res[a]["topk_idx"][len(order):] == -1) and np.all(np.isnan(res[a]["topk_val"][len(order):]))
+    g = dev.score_grad(Xc[: min(m, 40)], y_opt=y_opt, acq_funcs=ACQS)
+    _, _, gm, gs = orc.predict_with_grads_batched(st, Xc[: min(m, 40)])
+    assert np.max(np.abs(g["mean_grad"] - gm)) <= 1e-9 * max(np.max(np.abs(gm)), 1e-300)
+    assert np.max(np.abs((g["std_grad"] - gs) * sd[: min(m, 40), None])) <= \
+        10 * var_tol(st) * st.prior_var * st.y_std ** 2 / np.min(st.length_scale)
+    dev.close()
+
+
+def test_empty_candidate_set_and_bad_arguments():
+    st = orc.make_synthetic_state(10, 2, noise=1e-2, seed=1)
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(np.empty((0, 2)), y_opt=0.0, acq_funcs=("EI",), top_k=0)
+    assert res["mean"].shape == (0,) and res["EI"]["values"].shape == (0,)
+    with pytest.raises(ValueError):
+        dev.score(np.zeros((3, 5)), acq_funcs=("EI",))              # wrong number of features
+    with pytest.raises(ValueError):
+        dev.score(np.zeros(3), acq_funcs=("EI",))                   # not 2-D
+    with pytest.raises(ValueError):
+        dev.score(np.zeros((3, 2)), acq_funcs=("UCB",))             # unknown acquisition
+    with pytest.raises(skopt_b200._lib.SkbError):
+        engine.DeviceState(engine.HostState(np.zeros((4, 65)), np.zeros(4), np.eye(4), np.ones(65), 3, 1, 0, 0, 0, 1))
+    dev.close()
+
+
+def test_nan_candidates_follow_numpy_argmin_and_argsort_rules():
+    st = orc.make_synthetic_state(50, 3, noise=1e-2, seed=2)
+    Xc = np.random.RandomState(0).rand(400, 3)
+    Xc[77, 1] = np.nan
+    Xc[300, 0] = np.nan
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(Xc, y_opt=0.0, acq_funcs=("LCB",), top_k=4)
+    v = res["LCB"]["values"]
+    assert np.isnan(v[77]) and np.isnan(v[300]) and np.isfinite(np.delete(v, [77, 300])).all()
+    assert res["LCB"]["first_nan"] == 77 == int(np.argmin(v))                       # np.argmin: first NaN wins
+    assert np.array_equal(res["LCB"]["topk_idx"], np.argsort(v, kind="stable")[:4])  # np.argsort: NaN last
+    dev.close()
+
+
+def test_zero_variance_posterior_gives_zero_ei_and_pi():
+    """Noise-free GP evaluated AT a training point: variance cancels to ~0 and may be clamped; EI/PI must follow the
+    std > 0 mask of acquisition.py:213,296 (value exactly 0 -> -0.0 after the sign flip) without NaN."""
+    st = orc.make_synthetic_state(30, 2, noise=1e-12, seed=3)
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(st.X_train[:10], y_opt=float(st.meta["y"].min()), acq_funcs=ACQS)
+    assert np.all(np.isfinite(res["std"])) and np.all(res["std"] >= 0)
+    for a in ACQS:
+        assert np.all(np.isfinite(res[a]["values"]))
+    z = res["std"] == 0
+    assert np.all(res["EI"]["values"][z] == 0) and np.all(res["PI"]["values"][z] == 0)
+    assert res["clamped"] >= 0
+    dev.close()
