@@ -154,6 +154,18 @@ int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const dou
                                 const double* mu_grad, const double* std_grad, const skb_acq_params* params,
                                 double* const acq[3], double* const acq_grad[3]);
 
+/* Replaces: the per-second composition of _gaussian_acquisition for "EIps" / "PIps" (acquisition.py:61-80):
+ * out = acq * exp(-mu_t + std_t^2/2) and its gradient, given the objective model's acquisition and the log-time
+ * model's posterior.  Host pointers; pass out_grad == NULL to skip gradients. */
+int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq, const double* acq_grad,
+                        const double* mu_t, const double* std_t, const double* mu_t_grad, const double* std_t_grad,
+                        double* out, double* out_grad);
+
+/* Replaces: np.argmin(values) / np.argsort(values)[:k] (optimizer.py:564,570) for a value vector that lives on the
+ * host (used after skb_ps_combine_host).  Same ordering rules as skb_score_out.topk_*. */
+int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
+                  int64_t* topk_idx, int64_t* first_nan);
+
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind
  * (0 = K1 cross-kernel + mean, 1 = K2 triangular contraction + acquisition, 2 = top-k, 3 = gradient kernels),

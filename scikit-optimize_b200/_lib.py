@@ -63,6 +63,10 @@ SYMBOLS = [
     ("skb_score_grad_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AcqParams), C.POINTER(GradOut)]),
     ("skb_acq_from_posterior_host", C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.POINTER(AcqParams), C.c_void_p * 3, C.c_void_p * 3]),
+    ("skb_ps_combine_host", C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

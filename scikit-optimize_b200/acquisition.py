@@ -117,10 +117,68 @@ def _gaussian_acquisition(X, model, y_opt=None, acq_func="LCB", return_grad=Fals
     xi = acq_func_kwargs.get("xi", 0.01)
     kappa = acq_func_kwargs.get("kappa", 1.96)
     if acq_func in ("EIps", "PIps"):
-        raise NotImplementedError("per-second acquisitions (EIps / PIps) are not on the GPU path yet")
+        return _per_second(X, model, acq_func[:2], y_opt, xi, kappa, return_grad)
     if acq_func not in ("LCB", "EI", "PI"):
         raise ValueError("Acquisition function not implemented.")
     return _evaluate(X, model, acq_func, y_opt, xi, kappa, return_grad)
+
+
+def _time_posterior(X, time_model, return_grad):
+    """(mu, std[, mu_grad, std_grad]) of the log-time model, batched."""
+    if _is_device_model(time_model):
+        dev = time_model.device_state()
+        if return_grad:
+            g = dev.score_grad(X, acq_funcs=())
+            return g["mean"], g["std"], g["mean_grad"], g["std_grad"]
+        r = dev.score(X, acq_funcs=(), want_posterior=True)
+        return r["mean"], r["std"], None, None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if return_grad:
+            mu, std, gm, gs = time_model.predict(X, return_std=True, return_mean_grad=True, return_std_grad=True)
+            m, d = X.shape
+            return (np.asarray(mu, dtype=np.float64).ravel(), np.asarray(std, dtype=np.float64).ravel(),
+                    np.asarray(gm, dtype=np.float64).reshape(m, d), np.asarray(gs, dtype=np.float64).reshape(m, d))
+        mu, std = time_model.predict(X, return_std=True)
+        return np.asarray(mu, dtype=np.float64).ravel(), np.asarray(std, dtype=np.float64).ravel(), None, None
+
+
+def _per_second(X, model, base_acq, y_opt, xi, kappa, return_grad):
+    """EIps / PIps (acquisition.py:38-40, 61-80): `model.estimators_` = (objective model, log-time model); the
+    acquisition of the first is divided by the expected evaluation time exp(mu_t - std_t^2/2) of the second.  Both
+    posteriors and the composition (value and chain rule) are evaluated on the GPU."""
+    obj_model, time_model = model.estimators_
+    out = _evaluate(X, obj_model, base_acq, y_opt, xi, kappa, return_grad)
+    m, d = X.shape
+    if return_grad:
+        vals, grad = out
+        grad = np.ascontiguousarray(np.asarray(grad, dtype=np.float64).reshape(m, d))
+    else:
+        vals, grad = out, None
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    mu_t, sd_t, gm_t, gs_t = _time_posterior(np.ascontiguousarray(X, dtype=np.float64), time_model, return_grad)
+    mu_t, sd_t = np.ascontiguousarray(mu_t), np.ascontiguousarray(sd_t)
+    res = np.empty(m)
+    res_grad = np.empty((m, d)) if return_grad else None
+    if return_grad:
+        gm_t, gs_t = np.ascontiguousarray(gm_t), np.ascontiguousarray(gs_t)
+    _lib.check(_lib.lib().skb_ps_combine_host(
+        _default_device(), m, d, vals.ctypes.data, grad.ctypes.data if return_grad else None,
+        mu_t.ctypes.data, sd_t.ctypes.data, gm_t.ctypes.data if return_grad else None,
+        gs_t.ctypes.data if return_grad else None, res.ctypes.data, res_grad.ctypes.data if return_grad else None))
+    if return_grad:
+        return res, (res_grad[0] if m == 1 else res_grad)
+    return res
+
+
+def device_topk(values, k, index_offset=0):
+    """(values, indices, first_nan) of the k smallest entries by (value, index) -- np.argmin / np.argsort[:k] on
+    the GPU for a value vector that is already on the host (per-second acquisitions)."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    tv, ti, nan = np.empty(k), np.empty(k, dtype=np.int64), np.full(1, -1, dtype=np.int64)
+    _lib.check(_lib.lib().skb_topk_host(_default_device(), values.ctypes.data, values.shape[0], int(index_offset), int(k),
+                                        tv.ctypes.data, ti.ctypes.data, nan.ctypes.data))
+    return tv, ti, int(nan[0])
 
 
 def gaussian_acquisition_1D(X, model, y_opt=None, acq_func="LCB", acq_func_kwargs=None, return_grad=True):

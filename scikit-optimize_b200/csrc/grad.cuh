@@ -363,4 +363,33 @@ __global__ void acq_from_posterior_kernel(const AcqOnlyParams p) {
     }
 }
 
+// Per-second acquisitions EIps / PIps (acquisition.py:61-80): acq / E[t] with a log-normal time model,
+//   inv_t = exp(-mu_t + std_t^2 / 2),  acq' = acq * inv_t,  grad' = grad * inv_t + acq' * (-grad mu_t + std_t grad std_t).
+struct PsParams {
+    const double* acq;        // [m]   values to minimise of the objective model (-EI or -PI)
+    const double* acq_grad;   // [m][d] or nullptr
+    const double* mu_t;       // [m]   posterior of the log-time model
+    const double* sd_t;       // [m]
+    const double* mu_t_grad;  // [m][d] or nullptr
+    const double* sd_t_grad;  // [m][d] or nullptr
+    int64_t m;
+    int d;
+    double* out;              // [m]
+    double* out_grad;         // [m][d] or nullptr
+};
+
+__global__ void ps_combine_kernel(const PsParams p) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    const double sd = p.sd_t[i];
+    const double inv_t = exp(-p.mu_t[i] + 0.5 * (sd * sd));
+    const double v = p.acq[i] * inv_t;
+    p.out[i] = v;
+    if (!p.out_grad) return;
+    for (int k = 0; k < p.d; ++k) {
+        const int64_t o = i * p.d + k;
+        p.out_grad[o] = p.acq_grad[o] * inv_t + v * (-p.mu_t_grad[o] + sd * p.sd_t_grad[o]);
+    }
+}
+
 }  // namespace skb

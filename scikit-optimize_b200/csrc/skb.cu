@@ -932,4 +932,99 @@ int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const dou
     return rc;
 }
 
+int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq, const double* acq_grad,
+                        const double* mu_t, const double* std_t, const double* mu_t_grad, const double* std_t_grad,
+                        double* out, double* out_grad) {
+    if (m < 0 || n_dims < 0) return fail(SKB_ERR_INVALID, "negative size");
+    if (m > 0 && (!acq || !mu_t || !std_t || !out)) return fail(SKB_ERR_INVALID, "NULL argument");
+    const bool grads = out_grad != nullptr;
+    if (grads && (!acq_grad || !mu_t_grad || !std_t_grad)) return fail(SKB_ERR_INVALID, "gradient inputs are NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKB_ERR_NO_DEVICE, "device %d not in [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    if (m == 0) return SKB_OK;
+    const size_t md = (size_t)m * (size_t)n_dims;
+    void* raw = nullptr;
+    int rc = pool_alloc(device, &raw, (4 * (size_t)m + (grads ? 4 * md : 0)) * sizeof(double));
+    if (rc != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        double* cur = static_cast<double*>(raw);
+        auto up = [&](const double* host, size_t count) -> double* {
+            double* d = cur;
+            cur += count;
+            return cudaMemcpy(d, host, count * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess ? d : nullptr;
+        };
+        PsParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.m = m;
+        p.d = n_dims;
+        if (!(p.acq = up(acq, m)) || !(p.mu_t = up(mu_t, m)) || !(p.sd_t = up(std_t, m)))
+            return fail(SKB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        p.out = cur;
+        cur += m;
+        if (grads) {
+            if (!(p.acq_grad = up(acq_grad, md)) || !(p.mu_t_grad = up(mu_t_grad, md)) || !(p.sd_t_grad = up(std_t_grad, md)))
+                return fail(SKB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            p.out_grad = cur;
+            cur += md;
+        }
+        ps_combine_kernel<<<(unsigned)((m + 255) / 256), 256>>>(p);
+        LAUNCHED();
+        CU(cudaMemcpy(out, p.out, m * sizeof(double), cudaMemcpyDeviceToHost));
+        if (grads) CU(cudaMemcpy(out_grad, p.out_grad, md * sizeof(double), cudaMemcpyDeviceToHost));
+        return SKB_OK;
+    };
+    rc = body();
+    cudaDeviceSynchronize();
+    pool_free(device, raw);
+    return rc;
+}
+
+int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
+                  int64_t* topk_idx, int64_t* first_nan) {
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (top_k <= 0 || top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [1, 4096]", top_k);
+    if ((m > 0 && !values) || !topk_val || !topk_idx) return fail(SKB_ERR_INVALID, "NULL argument");
+    int ndev = 0, sms = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKB_ERR_NO_DEVICE, "device %d not in [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * TOPK_BLOCKS_PER_SM, (m + 1023) / 1024));
+    const int64_t slice = (m + nblk - 1) / nblk;
+    const size_t words = (size_t)std::max<int64_t>(m, 1) + 2 * (size_t)nblk * top_k + nblk + 2 * (size_t)top_k + 1;
+    void* raw = nullptr;
+    int rc = pool_alloc(device, &raw, words * sizeof(double));
+    if (rc != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        double* d_vals = static_cast<double*>(raw);
+        double* part_v = d_vals + std::max<int64_t>(m, 1);
+        int64_t* part_i = reinterpret_cast<int64_t*>(part_v + (size_t)nblk * top_k);
+        int64_t* part_nan = part_i + (size_t)nblk * top_k;
+        double* out_v = reinterpret_cast<double*>(part_nan + nblk);
+        int64_t* out_i = reinterpret_cast<int64_t*>(out_v + top_k);
+        int64_t* out_nan = out_i + top_k;
+        if (m > 0) CU(cudaMemcpy(d_vals, values, m * sizeof(double), cudaMemcpyHostToDevice));
+        topk_partial_kernel<<<nblk, TOPK_THREADS>>>(d_vals, m, slice, index_offset, top_k, part_v, part_i, part_nan);
+        LAUNCHED();
+        topk_merge_kernel<<<1, TOPK_THREADS>>>(part_v, part_i, part_nan, nblk, top_k, out_v, out_i, out_nan);
+        LAUNCHED();
+        CU(cudaMemcpy(topk_val, out_v, top_k * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(topk_idx, out_i, top_k * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (first_nan) CU(cudaMemcpy(first_nan, out_nan, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        return SKB_OK;
+    };
+    rc = body();
+    cudaDeviceSynchronize();
+    pool_free(device, raw);
+    return rc;
+}
+
 }  // extern "C"

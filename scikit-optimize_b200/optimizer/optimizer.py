@@ -22,12 +22,14 @@ from numbers import Number
 
 import numpy as np
 from sklearn.base import clone, is_regressor
+from sklearn.multioutput import MultiOutputRegressor
 from sklearn.utils import check_random_state
 
 from ..learning import GaussianProcessRegressor
 from ..space import Categorical, Space
 from ..utils import (check_x_in_space, cook_estimator, create_result, has_gradients, is_2Dlistlike, is_listlike,
                      normalize_dimensions)
+from ..acquisition import _gaussian_acquisition, device_topk
 from ..distributed import sharded_score
 from .lbfgs import minimize_batch
 
@@ -48,9 +50,6 @@ class Optimizer(object):
         allowed = ["gp_hedge", "EI", "LCB", "PI", "EIps", "PIps"]
         if self.acq_func not in allowed:
             raise ValueError("expected acq_func to be in %s, got %s" % (",".join(allowed), self.acq_func))
-        if "ps" in self.acq_func:
-            raise NotImplementedError("per-second acquisitions (EIps / PIps) need a second surrogate for the "
-                                      "evaluation time; they are not on the GPU path yet")
         if self.acq_func == "gp_hedge":
             self.cand_acq_funcs_ = ["EI", "LCB", "PI"]
             self.gains_ = np.zeros(3)
@@ -73,7 +72,11 @@ class Optimizer(object):
                                             random_state=self.rng.randint(0, _INT32_MAX), n_jobs=n_jobs)
         if base_estimator is not None and not is_regressor(base_estimator):
             raise ValueError("%s has to be a regressor." % base_estimator)
-        self.base_estimator_ = base_estimator
+        # per-second acquisitions model (objective, log time) with one surrogate each (optimizer.py:230-234)
+        if "ps" in self.acq_func and base_estimator is not None and not isinstance(base_estimator, MultiOutputRegressor):
+            self.base_estimator_ = MultiOutputRegressor(base_estimator)
+        else:
+            self.base_estimator_ = base_estimator
 
         if acq_optimizer == "auto":
             acq_optimizer = "lbfgs" if has_gradients(self.base_estimator_) else "sampling"
@@ -144,13 +147,21 @@ class Optimizer(object):
         for _ in range(n_points):
             x = opt.ask()
             X.append(x)
+            ti_available = "ps" in self.acq_func and len(opt.yi) > 0
+            ti = [t for (_, t) in opt.yi] if ti_available else None
             if strategy == "cl_min":
                 y_lie = np.min(opt.yi) if opt.yi else 0.0
+                t_lie = np.min(ti) if ti is not None else log(sys.float_info.max)
             elif strategy == "cl_mean":
                 y_lie = np.mean(opt.yi) if opt.yi else 0.0
+                t_lie = np.mean(ti) if ti is not None else log(sys.float_info.max)
             else:
                 y_lie = np.max(opt.yi) if opt.yi else 0.0
-            opt._tell(x, y_lie)
+                t_lie = np.max(ti) if ti is not None else log(sys.float_info.max)
+            if "ps" in self.acq_func:
+                opt._tell(x, (y_lie, t_lie))       # _tell: the time is already a logarithm
+            else:
+                opt._tell(x, y_lie)
         self.cache_ = {(n_points, strategy): X}
         return X
 
@@ -171,10 +182,25 @@ class Optimizer(object):
     def tell(self, x, y, fit=True):
         check_x_in_space(x, self.space)
         self._check_y_is_valid(x, y)
+        if "ps" in self.acq_func:                  # (value, seconds) -> (value, log seconds), optimizer.py:485-491
+            if is_2Dlistlike(x):
+                y = [[val, log(t)] for (val, t) in y]
+            elif is_listlike(x):
+                y = list(y)
+                y[1] = log(y[1])
         return self._tell(x, y, fit=fit)
 
     def _tell(self, x, y, fit=True):
-        if is_listlike(y) and is_2Dlistlike(x):
+        if "ps" in self.acq_func:
+            if is_2Dlistlike(x):
+                self.Xi.extend(x)
+                self.yi.extend(y)
+                self._n_initial_points -= len(y)
+            elif is_listlike(x):
+                self.Xi.append(x)
+                self.yi.append(y)
+                self._n_initial_points -= 1
+        elif is_listlike(y) and is_2Dlistlike(x):
             self.Xi.extend(x)
             self.yi.extend(y)
             self._n_initial_points -= len(y)
@@ -233,6 +259,8 @@ class Optimizer(object):
         y_opt = np.min(self.yi)
         acqs = tuple(self.cand_acq_funcs_)
         X = self.space.rvs_transformed(self.n_points, self.rng)
+        if "ps" in self.acq_func:
+            return self._score_and_refine_per_second(est, X, y_opt, transformed_bounds)
         if not hasattr(est, "device_state"):
             raise TypeError("the GPU scoring path needs this package's GaussianProcessRegressor, got %s" % type(est))
         dev = est.device_state()
@@ -276,8 +304,41 @@ class Optimizer(object):
             next_xs = [np.clip(x, transformed_bounds[:, 0], transformed_bounds[:, 1]) for x in next_xs]
         return next_xs
 
+    def _score_and_refine_per_second(self, est, X, y_opt, transformed_bounds):
+        """EIps / PIps: two resident GPs (objective, log time); values are composed on the GPU
+        (acquisition._per_second) and ranked on the GPU (acquisition.device_topk)."""
+        acq = self.cand_acq_funcs_[0]
+        k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
+        values = _gaussian_acquisition(X, est, y_opt, acq, acq_func_kwargs=self.acq_func_kwargs)
+        tv, ti, first_nan = device_topk(values, k)
+        if self.acq_optimizer == "sampling":
+            next_x = X[first_nan if first_nan >= 0 else int(ti[0])]
+        else:
+            starts = [X[int(i)] for i in ti if i >= 0]
+
+            def evaluate(tasks, Xq):
+                f, G = _gaussian_acquisition(Xq, est, y_opt, acq, return_grad=True, acq_func_kwargs=self.acq_func_kwargs)
+                return f, np.asarray(G).reshape(len(tasks), -1)
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                results = minimize_batch(starts, evaluate, self.space.transformed_bounds, maxiter=20)
+            cand_xs = np.array([r[0] for r in results])
+            cand_acqs = np.array([r[1] for r in results])
+            next_x = cand_xs[np.argmin(cand_acqs)]
+        if not self.space.is_categorical:
+            next_x = np.clip(next_x, transformed_bounds[:, 0], transformed_bounds[:, 1])
+        return [next_x]
+
     def _check_y_is_valid(self, x, y):
-        if is_listlike(y) and is_2Dlistlike(x):
+        if "ps" in self.acq_func:
+            if is_2Dlistlike(x):
+                if not (np.ndim(y) == 2 and np.shape(y)[1] == 2):
+                    raise TypeError("expected y to be a list of (func_val, t)")
+            elif is_listlike(x):
+                if not (np.ndim(y) == 1 and len(y) == 2):
+                    raise TypeError("expected y to be (func_val, t)")
+        elif is_listlike(y) and is_2Dlistlike(x):
             for y_value in y:
                 if not isinstance(y_value, Number):
                     raise ValueError("expected y to be a list of scalars")

@@ -138,3 +138,53 @@ def test_estimator_api_on_device():
     assert abs(gaussian_pi(one, ConstSurrogate(), -0.5, xi=0.)[0] - 0.308538) < 1e-6
     assert gaussian_lcb(one, ConstSurrogate(), kappa="inf")[0] == -1.0
     assert abs(gaussian_lcb(one, ConstSurrogate(), kappa=0.3)[0] + 0.3) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# per-second acquisitions (EIps / PIps): acquisition.py:38-40, 61-80; optimizer.py:230-234, 485-491
+# ----------------------------------------------------------------------------------------------------------------
+PS = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "traj_per_second.npz")))
+
+
+def _objective_ps(x):
+    return branin(x), 1.0 + 0.1 * (x[0] + 5.0) + 0.05 * x[1]
+
+
+@pytest.mark.parametrize("acq,optm", [("EIps", "sampling"), ("PIps", "sampling"), ("EIps", "lbfgs")])
+def test_per_second_acquisition(acq, optm):
+    from skopt_b200.acquisition import _gaussian_acquisition, gaussian_acquisition_1D
+    key = "%s_%s" % (acq, optm)
+    opt = Optimizer([(-5.0, 10.0), (0.0, 15.0)], "GP", n_initial_points=5, acq_func=acq, acq_optimizer=optm,
+                    acq_optimizer_kwargs=dict(n_points=1500, n_restarts_optimizer=4), random_state=3)
+    for _ in range(10):
+        x = opt.ask()
+        opt.tell(x, _objective_ps(x))
+    Xi = np.asarray(opt.Xi, dtype=float)
+    if optm == "sampling":
+        assert np.array_equal(Xi, PS[key + "_Xi"])                 # every suggested point, bit for bit
+        assert np.allclose(np.asarray(opt.yi, dtype=float), PS[key + "_yi"], rtol=0, atol=0)
+    else:
+        assert np.array_equal(Xi[:5], PS[key + "_Xi"][:5])
+        assert np.max(np.abs(Xi[5] - PS[key + "_Xi"][5])) <= 1e-5
+    # values and single-point gradients on a model pair refitted from the REFERENCE's own trajectory
+    from sklearn.base import clone
+    est = clone(opt.base_estimator_)
+    est.fit(opt.space.transform(PS[key + "_Xi"].tolist()), PS[key + "_yi"].tolist())
+    y_opt = np.min(PS[key + "_yi"])
+    vals = _gaussian_acquisition(PS[key + "_Xc"], est, y_opt, acq)
+    # the LML fit of these tiny data sets is ill-conditioned; the reference's own values move by ~eps*cond(K)
+    cond = max(np.linalg.cond(e.K_inv_) for e in est.estimators_)
+    rtol = max(1e-8, 1e-11 * cond)
+    assert np.max(np.abs(vals - PS[key + "_vals"])) <= rtol * np.max(np.abs(PS[key + "_vals"]))
+    assert int(np.argmin(vals)) == int(np.argmin(PS[key + "_vals"]))
+    for i in range(8):
+        v, g = gaussian_acquisition_1D(PS[key + "_Xc"][i], est, y_opt, acq)
+        assert v.shape == (1,) and g.shape == (2,)
+        assert abs(v[0] - PS[key + "_v1d"][i]) <= 10 * rtol * np.max(np.abs(PS[key + "_v1d"])) + 1e-300
+        assert np.max(np.abs(g - PS[key + "_g1d"][i])) <= 100 * rtol * np.max(np.abs(PS[key + "_g1d"])) + 1e-300
+    # batched gradients (extension) agree with the one-row calls
+    vb, gb = _gaussian_acquisition(PS[key + "_Xc"][:8], est, y_opt, acq, return_grad=True)
+    v0, g0 = gaussian_acquisition_1D(PS[key + "_Xc"][3], est, y_opt, acq)
+    assert vb[3] == v0[0] and np.array_equal(gb[3], g0)
+    pts = opt.ask(n_points=2)                                       # constant liar with (value, log-time) lies
+    assert len(pts) == 2 and pts[0] != pts[1]
