@@ -325,3 +325,68 @@ def test_zero_variance_posterior_gives_zero_ei_and_pi():
     assert np.all(res["EI"]["values"][z] == 0) and np.all(res["PI"]["values"][z] == 0)
     assert res["clamped"] >= 0
     dev.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: spot checks against the oracle + size-independent properties
+# ----------------------------------------------------------------------------------------------------------------
+def test_full_size_c3_value_path():
+    """configs[2]: n_train=2048, d=20, 1,000,000 candidates.  (a) a random sample of 1,500 candidates against the
+    oracle at the 1e-9 gate; (b) the device top-k equals the (value, index) sort of the returned values, i.e. the
+    argmin is np.argmin; (c) duplicated rows anywhere in the million give bit-equal results; (d) splitting the work
+    into different scratch chunks does not change a single bit."""
+    n, d, m = 2048, 20, 1_000_000
+    st = orc.make_synthetic_state(n, d, noise=1e-4, seed=0)
+    rng = np.random.RandomState(123)
+    Xc = rng.rand(m, d)
+    Xc[999_999] = Xc[17]
+    Xc[500_000] = Xc[17]
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=20)
+    sample = rng.choice(m, 1500, replace=False)
+    mu, sd = orc.predict(st, Xc[sample], return_std=True)
+    assert np.max(np.abs(res["mean"][sample] - mu)) <= 1e-9 * max(np.max(np.abs(mu)), st.y_std)
+    assert np.max(np.abs(res["std"][sample] ** 2 - sd ** 2)) <= 1e-9 * st.prior_var * st.y_std ** 2
+    assert np.max(np.abs(res["std"][sample] - sd) / sd) <= 1e-9
+    for a in ACQS:
+        ref = orc.gaussian_acquisition(Xc[sample], st, y_opt, a, acq_func_kwargs=dict(xi=0.01, kappa=1.96))
+        z2 = ((y_opt - 0.01 - mu) / sd) ** 2
+        assert np.max(np.abs(res[a]["values"][sample] - ref)) <= 1e-9 * np.max(np.abs(ref))
+        assert np.all(np.abs(res[a]["values"][sample] - ref) <= 1e-9 * (1 + z2) * np.abs(ref) + 1e-300)
+        v = res[a]["values"]
+        order = np.lexsort((np.arange(m), v))[:20]
+        assert np.array_equal(res[a]["topk_idx"], order) and res[a]["topk_idx"][0] == int(np.argmin(v))
+        assert v[17] == v[500_000] == v[999_999]
+    dev.set_scratch_limit(300 * 2048 * 128 * 8)          # 296 tiles per chunk instead of 888
+    res2 = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=20)
+    assert np.array_equal(res2["EI"]["values"], res["EI"]["values"]) and np.array_equal(res2["std"], res["std"])
+    assert np.array_equal(res2["EI"]["topk_idx"], res["EI"]["topk_idx"])
+    dev.close()
+
+
+def test_full_size_c4_gradient_path():
+    """configs[3] sizes: n_train=4096, d=50 with gradients, a slice of 20,000 candidates: spot check of batched
+    gradients against single-point oracle calls, and value-path / gradient-path consistency (two formulations of the
+    same posterior: triangular L_inv contraction vs dense K_inv contraction)."""
+    n, d, m = 4096, 50, 20_000
+    st = orc.make_synthetic_state(n, d, noise=1e-4, seed=0)
+    rng = np.random.RandomState(5)
+    Xc = rng.rand(m, d)
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    g = dev.score_grad(Xc, y_opt=y_opt, acq_funcs=("EI", "LCB"))
+    v = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI", "LCB"))
+    assert np.max(np.abs(g["mean"] - v["mean"])) <= 1e-12 * max(np.max(np.abs(v["mean"])), st.y_std)
+    assert np.max(np.abs(g["std"] ** 2 - v["std"] ** 2)) <= 1e-9 * st.prior_var * st.y_std ** 2
+    idx = rng.choice(m, 4, replace=False)
+    mu, sd, gm, gs = orc.predict_with_grads_batched(st, Xc[idx])
+    assert np.max(np.abs(g["mean_grad"][idx] - gm)) <= 1e-9 * np.max(np.abs(gm))
+    assert np.max(np.abs(g["std_grad"][idx] - gs)) <= 1e-9 * np.max(np.abs(gs))
+    for a in ("EI", "LCB"):
+        for i in idx:
+            val, grad = orc.gaussian_acquisition_1D(Xc[i], st, y_opt, a, dict(xi=0.01, kappa=1.96))
+            z2 = ((y_opt - 0.01 - g["mean"][i]) / g["std"][i]) ** 2
+            assert abs(g[a]["values"][i] - val[0]) <= 1e-9 * (1 + z2) * abs(val[0]) + 1e-300
+            assert np.max(np.abs(g[a]["grad"][i] - grad)) <= 1e-9 * (1 + z2) * np.max(np.abs(grad)) + 1e-300
+    dev.close()
