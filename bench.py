@@ -144,6 +144,28 @@ def ask_p50_ms(n_tells=30):
     return float(np.median(t)), int(t.size)
 
 
+def hart6(x):
+    alpha = np.asarray([1.0, 1.2, 3.0, 3.2])
+    P = 1e-4 * np.asarray([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
+                           [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]])
+    A = np.asarray([[10, 3, 17, 3.50, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14], [3, 3.5, 1.7, 10, 17, 8],
+                    [17, 8, 0.05, 10, 0.1, 14]])
+    return -np.sum(alpha * np.exp(-np.sum(A * (np.array(x) - P) ** 2, axis=1)))
+
+
+def ask_p50_ms_lbfgs(n_tells=20):
+    """Same measurement for BASELINE.json configs[1]: Hartmann-6, gp_hedge, acq_optimizer='lbfgs', 20 restarts
+    (candidate scoring + 60 lock-step L-BFGS-B searches with batched GPU gradients)."""
+    from skopt_b200 import Optimizer
+    opt = Optimizer([(0.0, 1.0)] * 6, "GP", n_initial_points=10, acq_func="gp_hedge", acq_optimizer="lbfgs",
+                    acq_optimizer_kwargs=dict(n_points=10000, n_restarts_optimizer=20), random_state=0)
+    for _ in range(10 + n_tells - 1):
+        x = opt.ask()
+        opt.tell(x, hart6(x))
+    t = np.asarray(opt.scoring_times_[1:]) * 1e3
+    return float(np.median(t)), int(t.size)
+
+
 def ask_p50_ms_cpu(n_tells=5):
     """Same block with the oracle port of the reference arithmetic (3 acquisitions, posterior recomputed each time)."""
     from oracle import gp_oracle as orc
@@ -331,6 +353,11 @@ def main():
         }
         if not args.no_ask:
             p50, cnt = ask_p50_ms()
+            p50_l, cnt_l = ask_p50_ms_lbfgs()
+            line["ask_p50_ms_lbfgs"] = {"value": p50_l, "tells": cnt_l, "config": "BASELINE.json configs[1]: Hartmann-6, "
+                                        "gp_hedge, lbfgs, 20 restarts, n_points=10000: scoring block incl. the 60 "
+                                        "lock-step L-BFGS-B searches (reference, measured in SURVEY.md section 6: "
+                                        "35.0 s / 40 tells = 875 ms)"}
             line["ask_p50_ms"] = {"value": p50, "tells": cnt, "config": "BASELINE.json configs[0]: Branin, gp_hedge, "
                                   "sampling, n_points=10000, n_train 10..39: scoring block of Optimizer._tell, fit "
                                   "excluded (candidate generation + one fused GPU pass + top-k + inverse transform)",

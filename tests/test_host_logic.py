@@ -175,13 +175,21 @@ def test_lockstep_lbfgs_equals_sequential_runs():
         out = [f_and_g(x) for x in X]
         return np.array([o[0] for o in out]), np.vstack([o[1] for o in out])
 
+    from skopt_b200.optimizer import lbfgs
     starts = np.random.RandomState(3).rand(7, 3)
+    starts[2] = [0.0, 1.0, 0.5]                        # a start on the boundary
     bounds = [(0.0, 1.0)] * 3
-    res = minimize_batch(starts, evaluate, bounds, maxiter=20)
-    for x0, (x, f, info) in zip(starts, res):
-        xs, fs, infos = fmin_l_bfgs_b(f_and_g, x0, bounds=bounds, approx_grad=False, maxiter=20)
-        assert np.array_equal(x, xs) and f == fs and info["funcalls"] == infos["funcalls"]
-    assert calls[0] == 7 and max(calls) == 7          # all searches advance together
+    drivers = ["threads"] + (["stepper"] if lbfgs._SETULB is not None else [])
+    assert "stepper" in drivers, "SciPy's compiled stepper should be usable with the SciPy in this image"
+    for driver in drivers:
+        del calls[:]
+        for maxiter in (20, 3):
+            res = minimize_batch(starts, evaluate, bounds, maxiter=maxiter, driver=driver)
+            for x0, (x, f, info) in zip(starts, res):
+                xs, fs, infos = fmin_l_bfgs_b(f_and_g, x0, bounds=bounds, approx_grad=False, maxiter=maxiter)
+                assert np.array_equal(x, xs) and f == fs, driver
+                assert info["funcalls"] == infos["funcalls"] and info["nit"] == infos["nit"], driver
+        assert calls[0] == 7 and max(calls) == 7      # all searches advance together
 
 
 def test_optimizer_host_logic_and_initial_points():
