@@ -48,6 +48,12 @@ typedef enum {
 
 /* Acquisition functions of skopt/acquisition.py: gaussian_ei (:232-321), gaussian_pi (:149-229),
  * gaussian_lcb (:90-146).  Values follow _gaussian_acquisition (:20-87): -EI, -PI, LCB, all to be MINIMISED. */
+/* Arithmetic of the O(n^2)-per-candidate variance contraction of skb_score_*.  Both meet the 1e-9 parity gate.
+ *   FP64       : FP64 tensor-core MMA (DMMA), bit-reproducible reference path of this library (default).
+ *   SPLIT_INT8 : operands split into 7 signed 8-bit digit planes (55-bit fixed point per row / global scale), products
+ *                accumulated exactly in int32 on tcgen05 (kind::i8), recombined in FP64 (csrc/ozaki.cuh). */
+typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1 } skb_precision;
+
 typedef enum { SKB_ACQ_EI = 0, SKB_ACQ_PI = 1, SKB_ACQ_LCB = 2, SKB_NUM_ACQ = 3 } skb_acq_kind;
 
 /* Everything GaussianProcessRegressor.predict reads from a fitted model (skopt gpr.py:315-356), flattened.
@@ -82,7 +88,7 @@ typedef struct {
     int32_t kappa_inf;           /* kappa == "inf": LCB = -std (acquisition.py:138,144) */
     int32_t acq_mask;            /* bit i set -> evaluate skb_acq_kind i */
     int32_t top_k;               /* number of (value, index) pairs to return per requested acquisition, >= 0 */
-    int32_t reserved;
+    int32_t precision;           /* skb_precision: how the variance contraction k^T K^-1 k is evaluated (value path) */
 } skb_acq_params;
 
 /* Outputs of one scoring call over m candidates.  Any pointer may be NULL (that output is skipped).

@@ -12,6 +12,7 @@ SKB_OK = 0
 KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
 ACQ_EI, ACQ_PI, ACQ_LCB = 0, 1, 2
 ACQ_INDEX = {"EI": ACQ_EI, "PI": ACQ_PI, "LCB": ACQ_LCB}
+PRECISION = {"fp64": 0, "split_int8": 1}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
@@ -26,7 +27,7 @@ class StateDesc(C.Structure):
 
 class AcqParams(C.Structure):
     _fields_ = [("y_opt", C.c_double), ("xi", C.c_double), ("kappa", C.c_double), ("kappa_inf", C.c_int32),
-                ("acq_mask", C.c_int32), ("top_k", C.c_int32), ("reserved", C.c_int32)]
+                ("acq_mask", C.c_int32), ("top_k", C.c_int32), ("precision", C.c_int32)]
 
 
 class ScoreOut(C.Structure):

@@ -138,4 +138,135 @@ __global__ void __launch_bounds__(256, 2) kcross_mean_kernel(const KCrossParams 
     if (h == 0) p.kdot[tile * BN + c] = macc + mpart[c];
 }
 
+// K1 for the split-integer contraction (ozaki.cuh): same distances, transform and running k . alpha, but the k-tile is
+// emitted as 7 signed 8-bit digit planes (k = sK 2^-55 sum_q b_q 256^(6-q)) in the canonical K-major shared-memory
+// layout of tcgen05.mma, [tile of 64 candidates][chunk of 32 training points][group of 32][k half][plane][8x16 B cores],
+// so a pipeline stage of the MMA kernel is again one contiguous bulk copy.  Thread (c, h) owns training rows
+// [32 h, 32 h + 32) of every 64-row stage, i.e. one whole 32-point chunk, and stores 16 bytes per plane and k half.
+struct KDigitParams {
+    KCrossParams base;
+    int8_t* Kd;               // [tiles64][n_pad/32][OZ_B_CHUNK]
+    double inv_scale_2p55;    // 2^55 / sK
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParams q) {
+    const KCrossParams& p = q.base;
+    extern __shared__ __align__(16) unsigned char smem_k1[];
+    const int d_pad = p.d_pad;
+    const int xt_stage = XG * d_pad * 4;
+    double* xt = reinterpret_cast<double*>(smem_k1);
+    double* al = xt + 2 * xt_stage;
+    double* xs = al + 2 * XROWS;
+    double* mpart = xs + (size_t)d_pad * XS_LD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mpart + BN);
+
+    const int tid = threadIdx.x, c = tid & (BN - 1), h = tid >> 7;
+    const int64_t tile = blockIdx.x;
+    const int nst = (p.n + XROWS - 1) / XROWS;
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < BN * d_pad; idx += 256) {
+        const int cc = idx / d_pad, k = idx - cc * d_pad;
+        const int64_t row = tile * BN + cc;
+        double v = 0.0;
+        if (k < p.d && row < p.m) v = p.X[row * p.d + k] / p.ls[k];
+        xs[k * XS_LD + cc] = v;
+    }
+    __syncthreads();
+    auto issue = [&](int st) {
+        const int buf = st & 1;
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)(xt_stage + XROWS) * 8u);
+        bulk_g2s(xt + buf * xt_stage, p.Xp + (size_t)st * xt_stage, (uint32_t)xt_stage * 8u, bars + buf);
+        bulk_g2s(al + buf * XROWS, p.alpha_p + (size_t)st * XROWS, XROWS * 8u, bars + buf);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nst > 1) issue(1);
+    }
+
+    double macc = 0.0;
+    const int nkc_all = p.n_pad / 32;
+    // destination of this candidate inside its 64-candidate tile: [sub][k half][plane][cand group][cand % 8][16 B]
+    const int cl = c & 63;
+    int8_t* kd_cand = q.Kd + ((size_t)(tile * 2 + (c >> 6)) * nkc_all) * (2 * 2 * 7 * 4 * 128) +
+                      (cl >> 5) * (2 * 7 * 4 * 128) + ((cl & 31) >> 3) * 128 + (cl & 7) * 16;
+
+    for (int st = 0; st < nst; ++st) {
+        const int buf = st & 1;
+        mbar_wait(bars + buf, (st >> 1) & 1);
+        const double* xtb = xt + buf * xt_stage;
+        const double* alb = al + buf * XROWS;
+
+        double s[XG / 2][4];
+#pragma unroll
+        for (int gi = 0; gi < XG / 2; ++gi) s[gi][0] = s[gi][1] = s[gi][2] = s[gi][3] = 0.0;
+        for (int k0 = 0; k0 < d_pad; k0 += 4) {
+            double x[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) x[kk] = xs[(k0 + kk) * XS_LD + c];
+#pragma unroll
+            for (int gi = 0; gi < XG / 2; ++gi) {
+                const double* t = xtb + ((h * (XG / 2) + gi) * d_pad + k0) * 4;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const double2 t01 = *reinterpret_cast<const double2*>(t + kk * 4);
+                    const double2 t23 = *reinterpret_cast<const double2*>(t + kk * 4 + 2);
+                    const double d0 = x[kk] - t01.x, d1 = x[kk] - t01.y, d2 = x[kk] - t23.x, d3 = x[kk] - t23.y;
+                    s[gi][0] = fma(d0, d0, s[gi][0]);
+                    s[gi][1] = fma(d1, d1, s[gi][1]);
+                    s[gi][2] = fma(d2, d2, s[gi][2]);
+                    s[gi][3] = fma(d3, d3, s[gi][3]);
+                }
+            }
+        }
+        // 32 kernel values of chunk kc = 2 st + h -> digits; lo = bytes 0..3 (planes 6..3), hi = bytes 4..6 (planes 2..0)
+        uint32_t lo[32], hi[32];
+#pragma unroll
+        for (int gi = 0; gi < XG / 2; ++gi) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int rr = gi * 4 + r;
+                const int j = st * XROWS + h * 32 + rr;
+                double val = fma(p.amplitude, base_kernel<KIND>(s[gi][r]), p.bias);
+                if (j >= p.n) val = 0.0;
+                macc = fma(val, alb[h * 32 + rr], macc);
+                const unsigned long long y =
+                    ((unsigned long long)__double2ll_rn(val * q.inv_scale_2p55) + 0x0080808080808080ull) ^ 0x0080808080808080ull;
+                lo[rr] = (uint32_t)y;
+                hi[rr] = (uint32_t)(y >> 32);
+            }
+        }
+        int8_t* dst = kd_cand + (size_t)(st * 2 + h) * (2 * 2 * 7 * 4 * 128);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int pl = 0; pl < 7; ++pl) {
+                const int byte = 6 - pl;                                   // plane 0 = most significant digit = byte 6
+                uint32_t w[4];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int r0 = half * 16 + k4 * 4;
+                    uint32_t a0, a1, a2, a3;
+                    if (byte < 4) { a0 = lo[r0]; a1 = lo[r0 + 1]; a2 = lo[r0 + 2]; a3 = lo[r0 + 3]; }
+                    else          { a0 = hi[r0]; a1 = hi[r0 + 1]; a2 = hi[r0 + 2]; a3 = hi[r0 + 3]; }
+                    const int b = byte & 3;
+                    const uint32_t t0 = __byte_perm(a0, a1, b | ((4 + b) << 4));          // [a0.b, a1.b, -, -]
+                    const uint32_t t1 = __byte_perm(a2, a3, b | ((4 + b) << 4));
+                    w[k4] = __byte_perm(t0, t1, 0x5410);                                  // [a0.b, a1.b, a2.b, a3.b]
+                }
+                *reinterpret_cast<uint4*>(dst + half * (7 * 4 * 128) + pl * (4 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && st + 2 < nst) issue(st + 2);
+    }
+    if (h == 1) mpart[c] = macc;
+    __syncthreads();
+    if (h == 0) p.kdot[tile * BN + c] = macc + mpart[c];
+}
+
 }  // namespace skb

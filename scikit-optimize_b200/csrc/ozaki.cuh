@@ -1,0 +1,300 @@
+// Split-integer ("Ozaki scheme") evaluation of the variance contraction on the 5th-generation tensor cores.
+//
+// tcgen05.mma has no FP64 kind, and the warp-level FP64 MMA (DMMA) runs at the FP64 FMA rate (37 TFLOP/s measured),
+// which is where trmm.cuh sits.  The 8-bit integer kind runs ~60x faster and accumulates EXACTLY in int32, so the FP64
+// contraction U = L_inv . K_trans^T is re-expressed in fixed point:
+//
+//   L_inv[i, j]  = sV_i * 2^-55 * sum_p a_p[i, j] 256^(6-p)      a_p in [-128, 127], sV_i a power of two >= 2 max_j |L_inv[i, j]|
+//   k[j, c]      = sK   * 2^-55 * sum_q b_q[j, c] 256^(6-q)      b_q in [-128, 127], sK   a power of two >= 2 (|amplitude| + |bias|)
+//   U[i, c]      = sV_i sK 2^-14 * sum_t 256^-t G_t[i, c],       G_t = sum_{p+q=t} sum_j a_p[i, j] b_q[j, c]   (exact int32)
+//
+// with the digit pairs p + q <= 6 kept (28 of 49 products; the dropped ones are below 2^-53 of full scale, i.e. the
+// size of an FP64 rounding of one product).  Both operands are quantised to 2^-55 of their row / global scale, the
+// integer sums are exact, and the seven partial sums are combined in FP64 -- so the result carries a few units of
+// 1e-16 * (row scale) * (kernel scale) per term instead of FP64's 1e-16 * |term|: still far inside the 1e-9 parity gate
+// (checked in tests/test_gpu_split.py), while the contraction runs on tcgen05 at several times the DMMA rate.
+//
+// One MMA per digit plane p of L_inv covers ALL admissible planes q of the candidates at once: the B operand is the
+// concatenation of planes 0 .. 6-p (N = 32 (7 - p) rows) and the seven accumulator regions G_0 .. G_6 are laid out
+// side by side in TMEM (32 columns each), so plane p accumulates into columns [32 p, 224) in a single instruction.
+// A CTA owns 64 candidates (two such 224-column groups) and walks the lower-triangular row blocks of L_inv like
+// trmm.cuh; operand tiles arrive through a 5-stage mbarrier ring of 1-D bulk copies (TMA), one thread issues the
+// MMAs, four warps drain TMEM (tcgen05.ld), rebuild U in FP64, square and reduce it.
+#pragma once
+#include <math.h>
+#include "layout.cuh"
+#include "ptx.cuh"
+#include "trmm.cuh"
+
+namespace skb {
+
+constexpr int OZ_P = 7;                       // digit planes per operand
+constexpr int OZ_KC = 32;                     // training points per MMA (UMMA K for 8-bit operands)
+constexpr int OZ_SUB = 32;                    // candidates per accumulator group
+constexpr int OZ_NC = 64;                     // candidates per CTA (two groups)
+constexpr int OZ_STAGES = 5;
+constexpr int OZ_THREADS = 192;               // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int OZ_A_CHUNK = OZ_P * BM * OZ_KC;                      // 28,672 B: [plane][k half][row group 16][8 rows][16 B]
+constexpr int OZ_B_SUB = 2 * OZ_P * (OZ_SUB / 8) * 128;            // 7,168 B:  [k half][plane][cand group 4][8 cands][16 B]
+constexpr int OZ_B_CHUNK = (OZ_NC / OZ_SUB) * OZ_B_SUB;            // 14,336 B
+constexpr int OZ_STAGE_BYTES = OZ_A_CHUNK + OZ_B_CHUNK;            // 43,008 B
+constexpr int OZ_TMEM_COLS = 512;
+constexpr int OZ_GROUP_COLS = OZ_P * OZ_SUB;                       // 224 accumulator columns per candidate group
+constexpr unsigned long long OZ_BIAS = 0x0080808080808080ull;      // +128 in each of the 7 digit bytes
+
+// byte offset of (row, k) inside one canonical K-major, no-swizzle (rows x 32) int8 block: 8-row x 16-byte core matrices
+__host__ __device__ inline int oz_canon(int rows, int row, int k) {
+    return (k >> 4) * (rows >> 3) * 128 + (row >> 3) * 128 + (row & 7) * 16 + (k & 15);
+}
+
+// x (|x| <= 0.5 after scaling) -> 7 balanced base-256 digits in the low 7 bytes (byte 6 = most significant digit)
+__device__ __forceinline__ unsigned long long oz_digits(double scaled_2p55) {
+    const long long v = __double2ll_rn(scaled_2p55);
+    return ((unsigned long long)v + OZ_BIAS) ^ OZ_BIAS;
+}
+
+__host__ __device__ inline double oz_pow2_scale(double maxabs) {      // power of two s with maxabs / s in [0.25, 0.5)
+    if (!(maxabs > 0.0)) return 1.0;
+    int e;
+    frexp(maxabs, &e);                     // maxabs = f * 2^e, f in [0.5, 1)
+    return ldexp(1.0, e + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// state preparation: row scales and digit planes of L_inv (lower-triangular 128 x 32 chunks, as in pack_linv_kernel)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void oz_row_scale_kernel(const double* __restrict__ V, double* __restrict__ sV, int n, int n_pad) {
+    const int row = blockIdx.x;
+    __shared__ double red[256];
+    double m = 0.0;
+    if (row < n)
+        for (int j = threadIdx.x; j <= row; j += blockDim.x) m = fmax(m, fabs(V[(size_t)row * n + j]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sV[row] = oz_pow2_scale(red[0]);
+}
+
+__global__ void oz_pack_linv_kernel(const double* __restrict__ V, const double* __restrict__ sV, int8_t* __restrict__ Vd,
+                                    int n, int n_pad) {
+    const int I = blockIdx.y, kc = blockIdx.x;
+    if (kc >= (I + 1) * (BM / OZ_KC)) return;
+    int8_t* chunk = Vd + (size_t)(vp_tiles_before(I) + kc) * OZ_A_CHUNK;
+    for (int e = threadIdx.x; e < BM * OZ_KC; e += blockDim.x) {
+        const int i = e / OZ_KC, k = e % OZ_KC;
+        const int row = I * BM + i, col = kc * OZ_KC + k;
+        double v = 0.0;
+        if (row < n && col <= row) v = V[(size_t)row * n + col] / sV[row] * 36028797018963968.0;   // * 2^55 (exact)
+        const unsigned long long y = oz_digits(v);
+        const int off = oz_canon(BM, i, k);
+#pragma unroll
+        for (int p = 0; p < OZ_P; ++p) chunk[p * (BM * OZ_KC) + off] = (int8_t)((y >> (8 * (6 - p))) & 0xFF);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2o: the contraction
+// ---------------------------------------------------------------------------------------------------------------
+struct OzakiParams {
+    const int8_t* Vd;         // digit planes of L_inv, chunk (I, kc) at (vp_tiles_before(I) + kc) * OZ_A_CHUNK
+    const double* sV;         // [n_pad] row scales
+    const int8_t* Kd;         // digit planes of K_trans: [tile64][kc][OZ_B_CHUNK]
+    const double* kdot;       // [tiles*64] K_trans . alpha from K1
+    double k_scale;           // sK
+    int n, n_pad;
+    int64_t m;
+    AcqConsts a;
+    double* mean;
+    double* std;
+    double* acq[3];
+    unsigned long long* clamp_count;
+};
+
+constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_NC * sizeof(double) + 256; }
+
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);      // version 1, SWIZZLE_NONE
+}
+// kind::i8, S8 x S8 -> S32, K-major operands, M = 128
+__device__ __forceinline__ uint32_t oz_idesc(int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(const OzakiParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_oz[];
+    unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
+    double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][OZ_NC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 4 * OZ_NC);
+    uint64_t* empty = full + OZ_STAGES;
+    uint64_t* tmem_full = empty + OZ_STAGES;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+
+    const int nI = p.n_pad / BM;
+    const int nkc_used = (p.n + OZ_KC - 1) / OZ_KC;
+    const int nkc_all = p.n_pad / OZ_KC;
+    const int8_t* kd_tile = p.Kd + (size_t)blockIdx.x * nkc_all * OZ_B_CHUNK;
+
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int I = 0; I < nI; ++I) {
+                const int nkc = min((I + 1) * (BM / OZ_KC), nkc_used);
+                const int8_t* vrow = p.Vd + (size_t)vp_tiles_before(I) * OZ_A_CHUNK;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int s = it % OZ_STAGES;
+                    const uint32_t ph = (it / OZ_STAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_arrive_expect_tx(full + s, OZ_STAGE_BYTES);
+                    unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
+                    bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, OZ_A_CHUNK, full + s);
+                    bulk_g2s(dst + OZ_A_CHUNK, kd_tile + (size_t)kc * OZ_B_CHUNK, OZ_B_CHUNK, full + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int I = 0; I < nI; ++I) {
+                const int nkc = min((I + 1) * (BM / OZ_KC), nkc_used);
+                if (I > 0) {
+                    mbar_wait(tmem_empty, (uint32_t)((I - 1) & 1));         // epilogue of the previous row block drained TMEM
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                }
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int s = it % OZ_STAGES;
+                    const uint32_t ph = (it / OZ_STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t a_base = smem_u32(stages + (size_t)s * OZ_STAGE_BYTES);
+                    const uint32_t b_base = a_base + OZ_A_CHUNK;
+                    const uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int pl = 0; pl < OZ_P; ++pl) {
+                        const uint64_t da = oz_smem_desc(a_base + pl * (BM * OZ_KC), (BM / 8) * 128, 128);
+                        const int N = OZ_SUB * (OZ_P - pl);
+                        const uint32_t idesc = oz_idesc(N);
+#pragma unroll
+                        for (int sub = 0; sub < OZ_NC / OZ_SUB; ++sub) {
+                            const uint64_t db = oz_smem_desc(b_base + sub * OZ_B_SUB, OZ_P * (OZ_SUB / 8) * 128, 128);
+                            // plane pl contributes to G_pl .. G_6: columns [32 pl, 224) of this candidate group.
+                            // Columns [32 pl, 32 (pl+1)) see their FIRST product of the chunk here; the accumulate flag
+                            // is per instruction, so region t is zeroed by plane 0's MMA of the first chunk only.
+                            oz_mma(tmem + sub * OZ_GROUP_COLS + OZ_SUB * pl, da, db, idesc, (acc | (pl > 0 ? 1u : 0u)));
+                        }
+                    }
+                    oz_commit(empty + s);                   // smem slot is free once these MMAs have read it
+                }
+                oz_commit(tmem_full);                       // all MMAs of row block I retired -> epilogue may read
+            }
+        }
+    } else {
+        // ---------------- epilogue: 4 warps, warp w reads TMEM lanes [32 (w % 4), +32) = rows of the row block ----------------
+        const int quarter = warp & 3;
+        const double cK = p.k_scale * 6.103515625e-05;       // sK * 2^-14
+        double qcol[OZ_NC / OZ_SUB] = {0.0, 0.0};            // lane c holds the running column sum of candidate sub*32 + c
+        for (int I = 0; I < nI; ++I) {
+            mbar_wait(tmem_full, (uint32_t)(I & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
+#pragma unroll
+            for (int sub = 0; sub < OZ_NC / OZ_SUB; ++sub) {
+                double u[OZ_SUB];
+#pragma unroll
+                for (int c = 0; c < OZ_SUB; ++c) u[c] = 0.0;
+                double w = 1.0;
+#pragma unroll
+                for (int t = 0; t < OZ_P; ++t) {
+                    uint32_t g[32];
+                    oz_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + sub * OZ_GROUP_COLS + OZ_SUB * t, g);
+#pragma unroll
+                    for (int c = 0; c < OZ_SUB; ++c) u[c] = fma((double)(int)g[c], w, u[c]);
+                    w *= 0.00390625;                          // 256^-t
+                }
+#pragma unroll
+                for (int c = 0; c < OZ_SUB; ++c) {
+                    const double uu = u[c] * rs;
+                    double sq = uu * uu;
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    if (lane == c) qcol[sub] += sq;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        sRed[quarter * OZ_NC + lane] = qcol[0];
+        sRed[quarter * OZ_NC + OZ_SUB + lane] = qcol[1];
+        named_bar_sync(1, 128);
+        const int t = threadIdx.x - 64;                       // 0 .. 127 over the epilogue warps
+        if (t < OZ_NC) {
+            const int64_t cand = (int64_t)blockIdx.x * OZ_NC + t;
+            if (cand < p.m) {
+                const double q = ((sRed[t] + sRed[OZ_NC + t]) + sRed[2 * OZ_NC + t]) + sRed[3 * OZ_NC + t];
+                double mu, sd, acq[3];
+                if (posterior_from_q(p.a, p.kdot[cand], q, mu, sd) && p.clamp_count) atomicAdd(p.clamp_count, 1ull);
+                acquisition_values(p.a, mu, sd, acq);
+                if (p.mean) p.mean[cand] = mu;
+                if (p.std) p.std[cand] = sd;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (((p.a.acq_mask >> a) & 1) && p.acq[a]) p.acq[a][cand] = acq[a];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace skb

@@ -17,6 +17,7 @@
 #include "grad.cuh"
 #include "kcross.cuh"
 #include "layout.cuh"
+#include "ozaki.cuh"
 #include "topk.cuh"
 #include "trmm.cuh"
 
@@ -61,6 +62,9 @@ struct skb_state {
     double* d_alpha_p = nullptr;
     double* d_Vp = nullptr;
     double* d_Ap = nullptr;      // packed dense K_inv (gradient path), nullptr when the caller gave no K_inv
+    int8_t* d_Vd = nullptr;      // digit planes of L_inv for the split-integer tensor-core contraction (ozaki.cuh)
+    double* d_sV = nullptr;      // [n_pad] power-of-two row scales of L_inv
+    double k_scale = 1.0;        // power-of-two scale of the kernel values
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
@@ -260,6 +264,18 @@ int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t 
     return SKB_OK;
 }
 
+int launch_kcross_digits(skb_state* st, const KDigitParams& p, int tiles, cudaStream_t s) {
+    const size_t smem = kcross_smem_bytes(p.base.d_pad);
+    switch (st->kernel) {
+        case SKB_KERNEL_RBF: kcross_digits_kernel<0><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN12: kcross_digits_kernel<1><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN32: kcross_digits_kernel<2><<<tiles, 256, smem, s>>>(p); break;
+        default: kcross_digits_kernel<3><<<tiles, 256, smem, s>>>(p); break;
+    }
+    LAUNCHED();
+    return SKB_OK;
+}
+
 int set_kernel_attributes(skb_state* st) {
     // dynamic shared memory limits only ever need to grow: remember the largest d_pad configured per device
     static std::mutex mu;
@@ -274,6 +290,11 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     const int smem3 = (int)grad_smem_bytes(st->d_pad);
@@ -290,6 +311,8 @@ int check_params(const skb_acq_params* p) {
     if (!p) return fail(SKB_ERR_INVALID, "params is NULL");
     if (p->acq_mask < 0 || p->acq_mask > 7) return fail(SKB_ERR_INVALID, "acq_mask %d out of range", p->acq_mask);
     if (p->top_k < 0 || p->top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [0, 4096]", p->top_k);
+    if (p->precision != SKB_PRECISION_FP64 && p->precision != SKB_PRECISION_SPLIT_INT8)
+        return fail(SKB_ERR_INVALID, "precision %d is not one of SKB_PRECISION_FP64 / SKB_PRECISION_SPLIT_INT8", p->precision);
     return SKB_OK;
 }
 }  // namespace
@@ -321,7 +344,7 @@ void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
-    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
+    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp};
     for (void* p : ptrs) pool_free(st->device, p);
@@ -402,6 +425,14 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         LAUNCHED();
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
+        // split-integer operands: row scales, then 7 signed 8-bit digit planes per lower-triangular 128 x 32 chunk
+        SKB_PALLOC(st->d_sV, (size_t)st->n_pad * sizeof(double));
+        SKB_PALLOC(st->d_Vd, (size_t)vp_tiles_before(nI) * OZ_A_CHUNK);
+        oz_row_scale_kernel<<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sV, st->n, st->n_pad);
+        LAUNCHED();
+        oz_pack_linv_kernel<<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(dV, st->d_sV, st->d_Vd, st->n, st->n_pad);
+        LAUNCHED();
+        st->k_scale = oz_pow2_scale(std::fabs(desc->amplitude) + std::fabs(desc->bias));
         if (desc->K_inv) {
             SKB_PALLOC(st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double));
 #undef SKB_PALLOC
@@ -552,6 +583,44 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         kp.d_pad = st->d_pad;
         kp.amplitude = st->amplitude;
         kp.bias = st->bias;
+        const bool split = !mean_only && prm->precision == SKB_PRECISION_SPLIT_INT8;
+        if (split) {
+            // ---- split-integer path: K1 emits int8 digit planes, the contraction runs on tcgen05 (ozaki.cuh) ----
+            KDigitParams dp;
+            dp.base = kp;
+            dp.base.Kt = nullptr;
+            dp.Kd = reinterpret_cast<int8_t*>(st->d_Kt);          // 7 bytes per (training point, candidate) <= the FP64 tile
+            dp.inv_scale_2p55 = 36028797018963968.0 / st->k_scale;
+            if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, (int)nt, s)) != SKB_OK) return rc;
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            OzakiParams op;
+            op.Vd = st->d_Vd;
+            op.sV = st->d_sV;
+            op.Kd = dp.Kd;
+            op.kdot = st->d_kdot;
+            op.k_scale = st->k_scale;
+            op.n = st->n;
+            op.n_pad = st->n_pad;
+            op.m = mc;
+            op.a.prior_var = st->amplitude + st->bias + st->white;
+            op.a.y_mean = st->y_mean;
+            op.a.y_std = st->y_std;
+            op.a.y_opt = prm->y_opt;
+            op.a.xi = prm->xi;
+            op.a.kappa = prm->kappa;
+            op.a.kappa_inf = prm->kappa_inf;
+            op.a.acq_mask = prm->acq_mask;
+            op.mean = out->mean ? out->mean + c0 : nullptr;
+            op.std = out->std ? out->std + c0 : nullptr;
+            for (int a = 0; a < 3; ++a) op.acq[a] = acq_ptr[a] ? acq_ptr[a] + c0 : nullptr;
+            op.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
+            if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
+            ozaki_trmm_kernel<<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(), s>>>(op);
+            LAUNCHED();
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            continue;
+        }
         if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
         if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
         if ((rc = span_end(st, s)) != SKB_OK) return rc;

@@ -122,8 +122,11 @@ def _mask(acq_funcs):
     return m
 
 
-def _acq_params(y_opt, xi, kappa, acq_funcs, top_k):
+def _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision="fp64"):
     p = _lib.AcqParams()
+    if precision not in _lib.PRECISION:
+        raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
+    p.precision = _lib.PRECISION[precision]
     p.y_opt = 0.0 if y_opt is None else float(y_opt)
     p.xi = float(xi)
     p.kappa_inf = 1 if isinstance(kappa, str) and kappa == "inf" else 0
@@ -201,7 +204,7 @@ class DeviceState:
         return mean
 
     def score(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0,
-              want_posterior=True, want_values=True):
+              want_posterior=True, want_values=True, precision="fp64"):
         """One pass over the candidates: posterior, every requested acquisition, and their top-k.
 
         Returns a dict with 'mean', 'std' (if want_posterior), per acquisition name 'values' (if want_values),
@@ -209,7 +212,7 @@ class DeviceState:
         """
         X = self._check_X(X)
         m = X.shape[0]
-        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k)
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision)
         out = _lib.ScoreOut()
         res = {}
         clamped = np.zeros(1, dtype=np.int64)
@@ -258,7 +261,7 @@ class DeviceState:
 
     # ---------------------------------------------------------------- device (torch tensor) entry points
     def score_tensors(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0,
-                      want_posterior=False, want_values=False, stream=None):
+                      want_posterior=False, want_values=False, stream=None, precision="fp64"):
         """Same as score() for a CUDA float64 tensor already resident on this state's GPU.  Asynchronous:
         work is enqueued on `stream` (a torch.cuda.Stream; default: torch's current stream)."""
         import torch
@@ -268,7 +271,7 @@ class DeviceState:
             raise ValueError("X is on the wrong device or has the wrong number of features")
         m = X.shape[0]
         dev = X.device
-        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k)
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision)
         out = _lib.ScoreOut()
         res = {}
         if want_posterior:

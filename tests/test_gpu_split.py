@@ -1,0 +1,83 @@
+"""Split-integer (int8 digit planes on tcgen05) evaluation of the variance contraction: same parity gates as the FP64
+DMMA path, checked against the reference fixtures, the oracle and the FP64 path itself."""
+import numpy as np
+import pytest
+
+import skopt_b200
+from skopt_b200 import engine
+from oracle import gp_oracle as orc
+from tests._golden import NAMES, load, load_state, var_tol
+from tests.test_gpu_parity import ACQS, check_against, host_state_from_oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_split_golden_fixture(name):
+    rec, meta, est = load(name)
+    _, _, ost = load_state(name)
+    dev = engine.DeviceState.from_estimator(est)
+    res = dev.score(rec["Xc"], y_opt=float(rec["y_opt"]), acq_funcs=ACQS, xi=float(rec["xi"]), kappa=float(rec["kappa"]),
+                    top_k=10, precision="split_int8")
+    vtol = var_tol(ost)
+    acq_ref = {a: rec["acq_" + a] for a in ACQS}
+    check_against(ost, res, rec["mean"], rec["std"], acq_ref, vtol, float(rec["y_opt"]), float(rec["xi"]),
+                  float(rec["kappa"]), check_argmin=vtol <= 1e-9)
+    dev.close()
+
+
+@pytest.mark.parametrize("n,d,m,kind,nu", [
+    (300, 7, 5000, orc.KIND_MATERN, 2.5),
+    (129, 3, 1000, orc.KIND_MATERN, 1.5),
+    (64, 1, 257, orc.KIND_MATERN, 0.5),
+    (512, 20, 4096, orc.KIND_RBF, np.inf),
+    (1024, 10, 3000, orc.KIND_MATERN, 2.5),
+    (37, 50, 200, orc.KIND_MATERN, 2.5),
+    (1, 1, 1, orc.KIND_MATERN, 2.5),
+])
+def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu):
+    st = orc.make_synthetic_state(n, d, noise=1e-3, seed=n + d, kind=kind, nu=nu, normalize_y=n > 1)
+    rng = np.random.RandomState(7)
+    Xc = rng.rand(m, d)
+    Xc[0] = st.X_train[0]
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision="split_int8")
+    ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision="fp64")
+    mu, sd = orc.predict(st, Xc, return_std=True)
+    acq_ref = {a: orc.gaussian_acquisition(Xc, st, y_opt, a, acq_func_kwargs=dict(xi=0.01, kappa=1.96)) for a in ACQS}
+    check_against(st, res, mu, sd, acq_ref, var_tol(st), y_opt, k=min(10, m))
+    # the two device formulations agree far tighter than the gate
+    scale = st.prior_var * st.y_std ** 2
+    print("split vs fp64: max |d var| / prior = %.2e" % (np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / scale))
+    assert np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) <= 2e-10 * scale
+    for a in ACQS:
+        assert res[a]["topk_idx"][0] == ref[a]["topk_idx"][0]
+    dev.close()
+
+
+def test_split_full_size_c3():
+    n, d, m = 2048, 20, 200_000
+    st = orc.make_synthetic_state(n, d, noise=1e-4, seed=0)
+    rng = np.random.RandomState(123)
+    Xc = rng.rand(m, d)
+    Xc[150_000] = Xc[17]
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=20, precision="split_int8")
+    ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=20, precision="fp64")
+    sample = rng.choice(m, 1000, replace=False)
+    mu, sd = orc.predict(st, Xc[sample], return_std=True)
+    assert np.max(np.abs(res["mean"][sample] - mu)) <= 1e-9 * max(np.max(np.abs(mu)), st.y_std)
+    assert np.max(np.abs(res["std"][sample] ** 2 - sd ** 2)) <= 1e-9 * st.prior_var * st.y_std ** 2
+    assert np.max(np.abs(res["std"][sample] - sd) / sd) <= 1e-9
+    err = np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / (st.prior_var * st.y_std ** 2)
+    print("C3 split vs fp64: max |d var| / prior = %.2e, max rel d std = %.2e" % (err, np.max(np.abs(res["std"] / ref["std"] - 1))))
+    assert err <= 2e-10
+    for a in ACQS:
+        v = res[a]["values"]
+        assert np.array_equal(res[a]["topk_idx"], np.lexsort((np.arange(m), v))[:20])
+        assert res[a]["topk_idx"][0] == ref[a]["topk_idx"][0]
+        assert v[17] == v[150_000]
+        assert np.max(np.abs(v - ref[a]["values"])) <= 1e-9 * np.max(np.abs(ref[a]["values"]))
+    dev.close()
