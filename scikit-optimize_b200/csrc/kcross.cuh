@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 2) kcross_mean_kernel(const KCrossParams 
 
 // K1 for the split-integer contraction (ozaki.cuh): same distances, transform and running k . alpha, but the k-tile is
 // emitted as 7 signed 8-bit digit planes (k = sK 2^-55 sum_q b_q 256^(6-q)) in the canonical K-major shared-memory
-// layout of tcgen05.mma, [tile of 64 candidates][chunk of 32 training points][group of 32][k half][plane][8x16 B cores],
+// layout of tcgen05.mma, [tile of 64 candidates][chunk of 32 training points][k half][plane][8 cand groups][8x16 B core],
 // so a pipeline stage of the MMA kernel is again one contiguous bulk copy.  Thread (c, h) owns training rows
 // [32 h, 32 h + 32) of every 64-row stage, i.e. one whole 32-point chunk, and stores 16 bytes per plane and k half.
 struct KDigitParams {
@@ -190,10 +190,9 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
 
     double macc = 0.0;
     const int nkc_all = p.n_pad / 32;
-    // destination of this candidate inside its 64-candidate tile: [sub][k half][plane][cand group][cand % 8][16 B]
+    // destination of this candidate inside its 64-candidate tile: [k half][plane][cand group (8)][cand % 8][16 B]
     const int cl = c & 63;
-    int8_t* kd_cand = q.Kd + ((size_t)(tile * 2 + (c >> 6)) * nkc_all) * (2 * 2 * 7 * 4 * 128) +
-                      (cl >> 5) * (2 * 7 * 4 * 128) + ((cl & 31) >> 3) * 128 + (cl & 7) * 16;
+    int8_t* kd_cand = q.Kd + ((size_t)(tile * 2 + (c >> 6)) * nkc_all) * (2 * 7 * 8 * 128) + (cl >> 3) * 128 + (cl & 7) * 16;
 
     for (int st = 0; st < nst; ++st) {
         const int buf = st & 1;
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                 hi[rr] = (uint32_t)(y >> 32);
             }
         }
-        int8_t* dst = kd_cand + (size_t)(st * 2 + h) * (2 * 2 * 7 * 4 * 128);
+        int8_t* dst = kd_cand + (size_t)(st * 2 + h) * (2 * 7 * 8 * 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                     const uint32_t t1 = __byte_perm(a2, a3, b | ((4 + b) << 4));
                     w[k4] = __byte_perm(t0, t1, 0x5410);                                  // [a0.b, a1.b, a2.b, a3.b]
                 }
-                *reinterpret_cast<uint4*>(dst + half * (7 * 4 * 128) + pl * (4 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + half * (7 * 8 * 128) + pl * (8 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         __syncthreads();

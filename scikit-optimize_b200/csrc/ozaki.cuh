@@ -14,11 +14,11 @@
 // 1e-16 * (row scale) * (kernel scale) per term instead of FP64's 1e-16 * |term|: still far inside the 1e-9 parity gate
 // (checked in tests/test_gpu_split.py), while the contraction runs on tcgen05 at several times the DMMA rate.
 //
-// One MMA per digit plane p of L_inv covers ALL admissible planes q of the candidates at once: the B operand is the
-// concatenation of planes 0 .. 6-p (N = 32 (7 - p) rows) and the seven accumulator regions G_0 .. G_6 are laid out
-// side by side in TMEM (32 columns each), so plane p accumulates into columns [32 p, 224) in a single instruction.
-// A CTA owns 64 candidates (two such 224-column groups) and walks the lower-triangular row blocks of L_inv like
-// trmm.cuh; operand tiles arrive through a 5-stage mbarrier ring of 1-D bulk copies (TMA), one thread issues the
+// One digit plane p of L_inv is multiplied with ALL admissible planes q of the candidates at once: the B operand rows
+// are ordered [plane q][candidate] (64 candidates per CTA), the seven accumulator regions G_0 .. G_6 sit side by side
+// in TMEM (64 columns each), so plane p accumulates into columns [64 p, 448) -- a contiguous range, issued as one or
+// two MMAs of N <= 256 (10 instructions per 32 training points instead of 28).  The CTA walks the lower-triangular
+// row blocks of L_inv like trmm.cuh; operand tiles arrive through a 5-stage mbarrier ring of 1-D bulk copies (TMA), one thread issues the
 // MMAs, four warps drain TMEM (tcgen05.ld), rebuild U in FP64, square and reduce it.
 #pragma once
 #include <math.h>
@@ -35,11 +35,11 @@ constexpr int OZ_NC = 64;                     // candidates per CTA (two groups)
 constexpr int OZ_STAGES = 5;
 constexpr int OZ_THREADS = 192;               // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int OZ_A_CHUNK = OZ_P * BM * OZ_KC;                      // 28,672 B: [plane][k half][row group 16][8 rows][16 B]
-constexpr int OZ_B_SUB = 2 * OZ_P * (OZ_SUB / 8) * 128;            // 7,168 B:  [k half][plane][cand group 4][8 cands][16 B]
-constexpr int OZ_B_CHUNK = (OZ_NC / OZ_SUB) * OZ_B_SUB;            // 14,336 B
+constexpr int OZ_B_HALF = OZ_P * (OZ_NC / 8) * 128;                // 7,168 B:  [plane][cand group 8][8 cands][16 B] per k half
+constexpr int OZ_B_CHUNK = 2 * OZ_B_HALF;                          // 14,336 B
 constexpr int OZ_STAGE_BYTES = OZ_A_CHUNK + OZ_B_CHUNK;            // 43,008 B
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_GROUP_COLS = OZ_P * OZ_SUB;                       // 224 accumulator columns per candidate group
+constexpr int OZ_ACC_COLS = OZ_P * OZ_NC;                          // 448 accumulator columns: region G_t at [64 t, 64 t + 64)
 constexpr unsigned long long OZ_BIAS = 0x0080808080808080ull;      // +128 in each of the 7 digit bytes
 
 // byte offset of (row, k) inside one canonical K-major, no-swizzle (rows x 32) int8 block: 8-row x 16-byte core matrices
@@ -218,15 +218,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(const OzakiPa
 #pragma unroll
                     for (int pl = 0; pl < OZ_P; ++pl) {
                         const uint64_t da = oz_smem_desc(a_base + pl * (BM * OZ_KC), (BM / 8) * 128, 128);
-                        const int N = OZ_SUB * (OZ_P - pl);
-                        const uint32_t idesc = oz_idesc(N);
+                        // B rows [0, 64 (7 - pl)) = planes 0 .. 6-pl of all 64 candidates -> accumulator columns
+                        // [64 pl, 448); split so that every instruction has N <= 256 (and N a multiple of 16).
+                        const int rows = OZ_NC * (OZ_P - pl);
+                        const int n0 = rows <= 256 ? rows : (pl == 0 ? 256 : rows / 2);
 #pragma unroll
-                        for (int sub = 0; sub < OZ_NC / OZ_SUB; ++sub) {
-                            const uint64_t db = oz_smem_desc(b_base + sub * OZ_B_SUB, OZ_P * (OZ_SUB / 8) * 128, 128);
-                            // plane pl contributes to G_pl .. G_6: columns [32 pl, 224) of this candidate group.
-                            // Columns [32 pl, 32 (pl+1)) see their FIRST product of the chunk here; the accumulate flag
-                            // is per instruction, so region t is zeroed by plane 0's MMA of the first chunk only.
-                            oz_mma(tmem + sub * OZ_GROUP_COLS + OZ_SUB * pl, da, db, idesc, (acc | (pl > 0 ? 1u : 0u)));
+                        for (int piece = 0; piece < 2; ++piece) {
+                            const int r0 = piece == 0 ? 0 : n0;
+                            const int N = piece == 0 ? n0 : rows - n0;
+                            if (N <= 0) continue;
+                            const uint64_t db = oz_smem_desc(b_base + (r0 >> 3) * 128, OZ_B_HALF, 128);
+                            // plane 0 touches every column first: it clears the accumulators on the first chunk
+                            oz_mma(tmem + OZ_NC * pl + r0, da, db, oz_idesc(N), (acc | (pl > 0 ? 1u : 0u)));
                         }
                     }
                     oz_commit(empty + s);                   // smem slot is free once these MMAs have read it
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(const OzakiPa
 #pragma unroll
                 for (int t = 0; t < OZ_P; ++t) {
                     uint32_t g[32];
-                    oz_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + sub * OZ_GROUP_COLS + OZ_SUB * t, g);
+                    oz_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + OZ_SUB * sub, g);
 #pragma unroll
                     for (int c = 0; c < OZ_SUB; ++c) u[c] = fma((double)(int)g[c], w, u[c]);
                     w *= 0.00390625;                          // 256^-t

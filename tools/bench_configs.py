@@ -50,6 +50,7 @@ def timed(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--precision", default="fp64")
     args = ap.parse_args()
     cfgs = [("C1-like", 50, 2, 10000, 10000), ("C2-like", 200, 6, 10000, 60), ("C5", 1032, 10, 1000000, 4096),
             ("C3", 2048, 20, 1000000, 65536), ("C4", 4096, 50, 400000 if not args.quick else 100000, 100000)]
@@ -60,7 +61,7 @@ def main():
         t_state = time.time() - t0
         X = torch.from_numpy(np.random.RandomState(1).rand(m_val, d)).cuda()
         def val():
-            dev.score_tensors(X, y_opt=y_opt, acq_funcs=("EI", "LCB"), top_k=16)
+            dev.score_tensors(X, y_opt=y_opt, acq_funcs=("EI", "LCB"), top_k=16, precision=args.precision)
         dev.set_timing(True); dev.get_timing()
         ms = timed(val, 2)
         tm = dev.get_timing()
