@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, N_DIMS, M_PER_GPU, TOP_K = 2048, 20, 1_000_000, 16
 FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue peak on this pool's B200 (profiles/r01_fp64_peaks.txt); cuBLAS DGEMM: 35.5
+SPLIT_PRODUCTS = 28       # digit-plane products kept by the split-integer contraction (p + q <= 6 of 7 x 7), csrc/ozaki.cuh
 METRIC = "GP-EI candidate evals/sec at n_train=2048,d=20"
 
 
@@ -38,6 +39,20 @@ def flops_value_path(n, d):
 
 def flops_k2(n):
     return n * n + 2 * n + 40
+
+
+def int8_ops_k2(n):
+    """int8 operations (2 per MAC) the split-integer scheme needs per candidate: 28 plane products over the
+    lower-triangular n(n+1)/2 entries of L_inv."""
+    return SPLIT_PRODUCTS * n * (n + 1)
+
+
+def measured_bf16_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst)"
+    except Exception:
+        return 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
 def make_problem(n, d, seed=0):
@@ -261,15 +276,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev():
+    def step_dev(precision="auto"):
         res = dev.score_tensors(Xc_dev, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
-                                index_offset=offset)
+                                index_offset=offset, precision=precision)
         return merge_topk_allgather(res["EI"]["topk_val"], res["EI"]["topk_idx"], TOP_K) if world > 1 else \
             (res["EI"]["topk_val"], res["EI"]["topk_idx"])
 
-    def step_host():
+    def step_host(precision="auto"):
         res = dev.score(Xc_host.numpy(), y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
-                        index_offset=offset, want_posterior=False, want_values=False)
+                        index_offset=offset, want_posterior=False, want_values=False, precision=precision)
         if world > 1:
             v = torch.from_numpy(res["EI"]["topk_val"]).cuda()
             i = torch.from_numpy(res["EI"]["topk_idx"]).cuda()
@@ -278,77 +293,122 @@ def main():
         return res["EI"]["topk_val"], res["EI"]["topk_idx"]
 
     # ---------------------------------------------------------------- device-resident throughput
-    for _ in range(args.warmup):
-        step_dev()
-    dev.set_timing(True)
-    dev.get_timing()
-    barrier()
-    launches0 = engine.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            best = step_dev()
-        e1.record(stream)
+    def timed_dev(precision):
+        for _ in range(args.warmup):
+            step_dev(precision)
+        dev.set_timing(True)
+        dev.get_timing()
         barrier()
-    launches = engine.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    timing = dev.get_timing()
-    dev.set_timing(False)
-    argmin_idx = int(best[1][0].item())
+        l0 = engine.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            a.record(stream)
+            for _ in range(args.steps):
+                best_ = step_dev(precision)
+            b.record(stream)
+            barrier()
+        n_launch = engine.launch_count() - l0
+        tm = dev.get_timing()
+        dev.set_timing(False)
+        return a.elapsed_time(b), tm, n_launch, clk.summary(), int(best_[1][0].item())
 
-    # ---------------------------------------------------------------- end to end through host buffers
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    def timed_host(precision):
+        for _ in range(2):
+            step_host(precision)
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(args.steps):
+            step_host(precision)
+        barrier()
+        return time.perf_counter() - t0_
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    headline = engine.resolve_precision("auto", N_TRAIN, m)          # what the product picks for this workload
+    ms_total, timing, launches, clocks_summary, argmin_idx = timed_dev(headline)
+    e2e_s = timed_host(headline)
+    ms_fp64, timing_fp64, _, _, argmin_fp64 = timed_dev("fp64") if headline != "fp64" else (ms_total, timing, 0, None, argmin_idx)
+    e2e_fp64_s = timed_host("fp64") if headline != "fp64" else e2e_s
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, ms_fp64, e2e_fp64_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, ms_fp64, e2e_fp64_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ms_per_step = ms_total / args.steps
     value = world * m / (ms_per_step / 1e3)
     e2e_value = world * m * args.steps / (e2e_ms / 1e3)
 
     if rank == 0:
-        k2_ms, k2_launches = timing["k2"]
-        k1_ms, _ = timing["k1"]
-        cand_per_k2 = m * args.steps / max(k2_launches, 1)
-        k2_avg_ms = k2_ms / max(k2_launches, 1)
-        achieved = flops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+        def k2_stats(tm, total_ms):
+            k2_ms_, k2_n = tm["k2"]
+            cand = m * args.steps / max(k2_n, 1)
+            avg = k2_ms_ / max(k2_n, 1)
+            return cand, avg, k2_ms_ / total_ms, tm["k1"][0] / total_ms
+
+        cand_per_k2, k2_avg_ms, k2_share, k1_share = k2_stats(timing, ms_total)
+        fp64_equiv = flops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+        if headline == "split_int8":
+            bf16_peak, bf16_src = measured_bf16_peak()
+            peak = 2.0 * bf16_peak
+            achieved = int8_ops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
+                        "traffic": None,
+                        "kernel": "ozaki_trmm_kernel (K2o: tcgen05.mma kind::i8 over 7 s8 digit planes, exact s32 "
+                                  "accumulation in TMEM, FP64 recombination)",
+                        "peak_source": "int8 dense = 2 x " + bf16_src + "; MEASURED_PEAKS.json has no int8 entry, the 2:1 "
+                                       "int8:bf16 issue ratio is measured in profiles/r01_umma_i8_rates.txt",
+                        "algorithmic_ops_per_candidate": int8_ops_k2(N_TRAIN),
+                        "algorithmic_ops_definition": "2 x 28 digit-plane products x n(n+1)/2 (the scheme's own minimum)",
+                        "issue_peak": 2 * 8175 * 148 * (clocks_summary.get("sm_mhz") or 1965.0) / 1e6,
+                        "issue_peak_definition": "2 x 8175 MAC/clk/SM (measured kind::i8 issue rate at N=256, "
+                                                 "profiles/r01_umma_i8_rates.txt) x 148 SMs x SM clock during the run",
+                        "fp64_equivalent_tflops": fp64_equiv,
+                        "fp64_equivalent_vs_dmma_peak": fp64_equiv / FP64_PEAK_TFLOPS,
+                        "candidates_per_launch": cand_per_k2, "avg_launch_ms": k2_avg_ms,
+                        "k2_share_of_step": k2_share, "k1_share_of_step": k1_share,
+                        "whole_path_fp64_equivalent_tflops": flops_value_path(N_TRAIN, N_DIMS) * world * m /
+                                                              (ms_total / args.steps / 1e3) / world / 1e12}
+            roofline["frac_of_issue_peak"] = roofline["achieved"] / roofline["issue_peak"]
+        else:
+            roofline = None
+        c2, a2, s2, s1 = k2_stats(timing_fp64, ms_fp64)
+        achieved64 = flops_k2(N_TRAIN) * c2 / (a2 / 1e3) / 1e12
         traffic = None
         prof = os.path.join(ROOT, "profiles", "k2_dram_bytes_per_launch.json")
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("dram_bytes_per_candidate", 0.0) * cand_per_k2
+            traffic = json.load(open(prof)).get("dram_bytes_per_candidate", 0.0) * c2
+        roofline_fp64 = {"bound": "tensor", "achieved": achieved64, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved64 / FP64_PEAK_TFLOPS, "traffic": traffic,
+                         "kernel": "trmm_kernel<0> (K2: DMMA triangular contraction + acquisition epilogue)",
+                         "peak_source": "measured FP64 DMMA issue peak on this pool (tools/microbench/fp64_peaks.cu -> "
+                                        "profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM "
+                                        "8192^3 measured 35.5",
+                         "algorithmic_flops_per_candidate": flops_k2(N_TRAIN), "candidates_per_launch": c2,
+                         "avg_launch_ms": a2, "k2_share_of_step": s2, "k1_share_of_step": s1}
+        if roofline is None:
+            roofline = roofline_fp64
+        fp64_value = world * m / (ms_fp64 / args.steps / 1e3)
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic GP posterior + EI: n_train=2048, d=20, %d candidates per GPU, FP64 "
+            "vs_baseline": None,
+            "dtype": "f64" if headline == "fp64" else "f64 (variance contraction: 7 s8 digit planes -> exact s32 on tcgen05 -> f64)",
+            "data": "synthetic",
+            "config": {"workload": "synthetic GP posterior + EI: n_train=2048, d=20, %d candidates per GPU, FP64 results "
                                    "(BASELINE.json configs[2])" % m,
                        "n_train": N_TRAIN, "n_dims": N_DIMS, "candidates_per_gpu": m, "top_k": TOP_K,
+                       "precision": headline + " (engine.resolve_precision('auto'); 1e-9 parity gate: tests/test_gpu_split.py)",
                        "kernel": "1.3 * Matern(nu=2.5, length_scale=1.5) + noise 1e-4, normalize_y",
                        "sharding": "candidates sharded across ranks, GP state replicated, NCCL all-gather of top-k",
-                       "l2_policy": "inputs larger than L2 (candidates %.0f MB + 1 GiB cross-covariance scratch per "
+                       "l2_policy": "inputs larger than L2 (candidates %.0f MB + ~1 GiB cross-covariance scratch per "
                                     "chunk vs 126 MB L2)" % (m * N_DIMS * 8 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": m * N_DIMS * 8,
                     "d2h_bytes_per_step": TOP_K * 16 + 16},
             "gpu_launches": launches,
-            "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
-                         "kernel": "trmm_kernel<0> (K2: DMMA triangular contraction + acquisition epilogue)", "peak_source": "measured FP64 DMMA issue peak on this "
-                         "pool (tools/microbench/fp64_peaks.cu -> profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json has "
-                         "no FP64 entry; cuBLAS DGEMM 8192^3 measured 35.5",
-                         "algorithmic_flops_per_candidate": flops_k2(N_TRAIN), "candidates_per_launch": cand_per_k2,
-                         "avg_launch_ms": k2_avg_ms, "k2_share_of_step": k2_ms / ms_total,
-                         "k1_share_of_step": k1_ms / ms_total,
-                         "whole_path_tflops": flops_value_path(N_TRAIN, N_DIMS) * value / world / 1e12},
+            "clocks": clocks_summary,
+            "roofline": roofline,
+            "fp64_dmma_path": {"value": fp64_value, "unit": "evals/s", "ms_per_step": ms_fp64 / args.steps,
+                               "e2e": world * m * args.steps / (e2e_fp64_ms / 1e3), "roofline": roofline_fp64,
+                               "whole_path_tflops": flops_value_path(N_TRAIN, N_DIMS) * fp64_value / world / 1e12,
+                               "argmin_index": argmin_fp64},
             "argmin_index": argmin_idx,
         }
         if not args.no_ask:

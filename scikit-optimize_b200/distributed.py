@@ -48,7 +48,7 @@ def shard_bounds(m, world):
     return b
 
 
-def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None):
+def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64"):
     """Score the rows of X that belong to this rank and merge the top-k across ranks.
 
     `X` is the FULL candidate matrix (identical on every rank); the returned dict has, per acquisition, the GLOBAL
@@ -57,12 +57,15 @@ def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None):
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     if world == 1:
         return dev.score(X, y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
-                         want_posterior=False, want_values=False)
+                         want_posterior=False, want_values=False, precision=precision)
     rank = dist.get_rank(group)
     b = shard_bounds(X.shape[0], world)
     lo, hi = b[rank], b[rank + 1]
+    # the precision is resolved on the FULL problem size so that every rank takes the same path
+    from .engine import resolve_precision
+    precision = resolve_precision(precision, dev.host.n_train, X.shape[0]) if hasattr(dev, "host") else precision
     res = dev.score(X[lo:hi], y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k, index_offset=lo,
-                    want_posterior=False, want_values=False)
+                    want_posterior=False, want_values=False, precision=precision)
     backend = dist.get_backend(group)
     device = torch.device("cuda", dev.device) if backend == "nccl" else torch.device("cpu")
     for name in acq_funcs:

@@ -122,6 +122,20 @@ def _mask(acq_funcs):
     return m
 
 
+# "auto": the split-integer tensor-core contraction pays off once the O(n^2)-per-candidate term dominates; below these
+# sizes the FP64 DMMA path is used (it is also the path whose small-n trajectories are pinned bit-for-bit to the reference)
+AUTO_SPLIT_MIN_TRAIN = 512
+AUTO_SPLIT_MIN_CANDIDATES = 8192
+
+
+def resolve_precision(precision, n_train, m):
+    if precision == "auto":
+        return "split_int8" if (n_train >= AUTO_SPLIT_MIN_TRAIN and m >= AUTO_SPLIT_MIN_CANDIDATES) else "fp64"
+    if precision not in _lib.PRECISION:
+        raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISION))
+    return precision
+
+
 def _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision="fp64"):
     p = _lib.AcqParams()
     if precision not in _lib.PRECISION:
@@ -212,9 +226,10 @@ class DeviceState:
         """
         X = self._check_X(X)
         m = X.shape[0]
+        precision = resolve_precision(precision, self.host.n_train, m)
         prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision)
         out = _lib.ScoreOut()
-        res = {}
+        res = {"precision": precision}
         clamped = np.zeros(1, dtype=np.int64)
         out.n_var_clamped = clamped.ctypes.data
         if want_posterior:
@@ -271,6 +286,7 @@ class DeviceState:
             raise ValueError("X is on the wrong device or has the wrong number of features")
         m = X.shape[0]
         dev = X.device
+        precision = resolve_precision(precision, self.host.n_train, m)
         prm = _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision)
         out = _lib.ScoreOut()
         res = {}

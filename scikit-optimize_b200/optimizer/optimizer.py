@@ -91,6 +91,8 @@ class Optimizer(object):
         self.n_points = acq_optimizer_kwargs.get("n_points", 10000)
         self.n_restarts_optimizer = acq_optimizer_kwargs.get("n_restarts_optimizer", 5)
         self.n_jobs = acq_optimizer_kwargs.get("n_jobs", 1)      # accepted for compatibility; restarts are batched
+        # arithmetic of the variance contraction: "auto" (default), "fp64" or "split_int8" (see engine.resolve_precision)
+        self.precision = acq_optimizer_kwargs.get("precision", "auto")
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
 
         if isinstance(self.base_estimator_, GaussianProcessRegressor):
@@ -267,7 +269,7 @@ class Optimizer(object):
         k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
         # one process per GPU: every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
         # its contiguous block and the per-rank top-k lists are all-gathered (k*16 bytes per acquisition) and merged
-        res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k)
+        res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k, precision=self.precision)
         self._last_scoring = res          # kept for inspection / tests (top-k per acquisition)
 
         next_xs = []

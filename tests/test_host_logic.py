@@ -132,6 +132,7 @@ from skopt_b200.distributed import sharded_score
 class FakeDev:
     device = 0
     def score(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0, **kw):
+        assert kw.get("precision", "fp64") in ("fp64", "split_int8", "auto")
         out = {}
         for j, a in enumerate(acq_funcs):
             v = np.sin(7 * X[:, 0] + j) * X[:, 1]
