@@ -32,7 +32,7 @@ constexpr int OZ_P = 7;                       // digit planes per operand
 constexpr int OZ_KC = 32;                     // training points per MMA (UMMA K for 8-bit operands)
 constexpr int OZ_SUB = 32;                    // candidates per accumulator group
 constexpr int OZ_NC = 64;                     // candidates per CTA (two groups)
-constexpr int OZ_STAGES = 5;
+constexpr int OZ_STAGES = 4;
 constexpr int OZ_THREADS = 192;               // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int OZ_A_CHUNK = OZ_P * BM * OZ_KC;                      // 28,672 B: [plane][k half][row group 16][8 rows][16 B]
 constexpr int OZ_B_HALF = OZ_P * (OZ_NC / 8) * 128;                // 7,168 B:  [plane][cand group 8][8 cands][16 B] per k half
@@ -145,7 +145,59 @@ __device__ __forceinline__ void oz_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(const OzakiParams p) {
+__device__ __forceinline__ void oz_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// issue (no wait) a load of 8 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void oz_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void oz_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Column sums over the 32 lanes of a warp for 8 columns held as v[0..7] in every lane (transposing butterfly: 4 + 2 + 1
+// exchanges, then two closing steps).  Afterwards lane l holds the total of column (l & 7).
+__device__ __forceinline__ double oz_colsum8(double (&v)[8], int lane) {
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int c = 0; c < o; ++c) {
+            const double send = upper ? v[c] : v[c + o];
+            const double keep = upper ? v[c + o] : v[c];
+            v[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    double r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
+    return r + __shfl_xor_sync(0xffffffffu, r, 16);
+}
+
+// Column sums over the 32 lanes of a warp for 16 columns held as v[0..15] in every lane: a transposing butterfly
+// (8 + 4 + 2 + 1 exchanges halve the live columns while doubling the lanes summed, one more closes the 32 lanes).
+// Afterwards lane l holds the total of column (l & 15).  Fixed order -> deterministic.
+__device__ __forceinline__ double oz_colsum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int c = 0; c < o; ++c) {
+            const double send = upper ? v[c] : v[c + o];
+            const double keep = upper ? v[c + o] : v[c];
+            v[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+__global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
     extern __shared__ __align__(1024) unsigned char smem_oz[];
     unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
     double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][OZ_NC]
@@ -241,43 +293,39 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_trmm_kernel(const OzakiPa
         // ---------------- epilogue: 4 warps, warp w reads TMEM lanes [32 (w % 4), +32) = rows of the row block ----------------
         const int quarter = warp & 3;
         const double cK = p.k_scale * 6.103515625e-05;       // sK * 2^-14
-        double qcol[OZ_NC / OZ_SUB] = {0.0, 0.0};            // lane c holds the running column sum of candidate sub*32 + c
+        double qcol[OZ_NC / 8];                              // lane l: running sum of candidate 8 j + (l & 7)
+#pragma unroll
+        for (int j = 0; j < OZ_NC / 8; ++j) qcol[j] = 0.0;
         for (int I = 0; I < nI; ++I) {
             mbar_wait(tmem_full, (uint32_t)(I & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
 #pragma unroll
-            for (int sub = 0; sub < OZ_NC / OZ_SUB; ++sub) {
-                double u[OZ_SUB];
+            for (int j = 0; j < OZ_NC / 8; ++j) {
+                // all seven regions of these 8 candidates are requested before the single wait: one TMEM round trip
+                uint32_t g[OZ_P][8];
 #pragma unroll
-                for (int c = 0; c < OZ_SUB; ++c) u[c] = 0.0;
-                double w = 1.0;
+                for (int t = 0; t < OZ_P; ++t) oz_ld8_issue(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + 8 * j, g[t]);
+                oz_ld_wait();
+                double u[8];
 #pragma unroll
-                for (int t = 0; t < OZ_P; ++t) {
-                    uint32_t g[32];
-                    oz_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + OZ_SUB * sub, g);
+                for (int c = 0; c < 8; ++c) {
+                    double acc = (double)(int)g[OZ_P - 1][c];
 #pragma unroll
-                    for (int c = 0; c < OZ_SUB; ++c) u[c] = fma((double)(int)g[c], w, u[c]);
-                    w *= 0.00390625;                          // 256^-t
+                    for (int t = OZ_P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, (double)(int)g[t][c]);   // Horner in 256^-1
+                    const double uu = acc * rs;
+                    u[c] = uu * uu;
                 }
-#pragma unroll
-                for (int c = 0; c < OZ_SUB; ++c) {
-                    const double uu = u[c] * rs;
-                    double sq = uu * uu;
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    if (lane == c) qcol[sub] += sq;
-                }
+                qcol[j] += oz_colsum8(u, lane);
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
         }
-        sRed[quarter * OZ_NC + lane] = qcol[0];
-        sRed[quarter * OZ_NC + OZ_SUB + lane] = qcol[1];
+        if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < OZ_NC / 8; ++j) sRed[quarter * OZ_NC + 8 * j + lane] = qcol[j];
+        }
         named_bar_sync(1, 128);
         const int t = threadIdx.x - 64;                       // 0 .. 127 over the epilogue warps
         if (t < OZ_NC) {

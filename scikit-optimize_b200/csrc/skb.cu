@@ -82,6 +82,13 @@ struct skb_state {
     // overlaps the kernels of chunk i
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready;
+    // split-integer path: K1 of chunk i+1 runs on a second stream while the tensor-core contraction of chunk i runs on
+    // the caller's stream (different pipes of the same SMs); the digit-plane scratch is double buffered
+    cudaStream_t aux_stream = nullptr;
+    std::vector<cudaEvent_t> ev_k1, ev_k2;
+    cudaEvent_t ev_enter = nullptr;
+    double* d_Kt2 = nullptr;     size_t kt2_cap = 0;
+    double* d_kdot2 = nullptr;   size_t kdot2_cap = 0;
     double* d_X = nullptr;       size_t x_cap = 0;
     double* d_out = nullptr;     size_t out_cap = 0;
     unsigned long long* d_clamp = nullptr;
@@ -346,13 +353,17 @@ void skb_state_destroy(skb_state* st) {
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
     void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
-                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp};
+                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2};
     for (void* p : ptrs) pool_free(st->device, p);
     for (auto& sp : st->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
     }
     for (auto& ev : st->chunk_ready) cudaEventDestroy(ev);
+    for (auto& ev : st->ev_k1) cudaEventDestroy(ev);
+    for (auto& ev : st->ev_k2) cudaEventDestroy(ev);
+    if (st->ev_enter) cudaEventDestroy(st->ev_enter);
+    if (st->aux_stream) cudaStreamDestroy(st->aux_stream);
     if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     if (st->stream) cudaStreamDestroy(st->stream);
     delete st;
@@ -406,6 +417,8 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
     auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&st->aux_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&st->ev_enter, cudaEventDisableTiming));
         int prc;
 #define SKB_PALLOC(ptr, bytes) if ((prc = pool_alloc(device, reinterpret_cast<void**>(&(ptr)), (bytes))) != SKB_OK) return prc
         SKB_PALLOC(st->d_ls, d * sizeof(double));
@@ -498,9 +511,17 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
 }
 
 // candidate tiles processed per K1/K2 launch pair: as many as the scratch limit allows, in whole waves of SMs
-static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile) {
+static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
     const int64_t tiles = (m + BN - 1) / BN;
     int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / bytes_per_tile));
+    // split-integer path: two scratch buffers (half the budget each).  When a K1 CTA fits on an SM next to a contraction
+    // CTA (shared memory permitting: small n_dims), chunks are kept to two K1 waves so that K1 of the next chunk runs
+    // under the contraction of the current one even for moderate candidate counts.
+    if (split) {
+        cap = std::max<int64_t>(1, cap / 2);
+        const bool co_resident = kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
+        if (co_resident) cap = std::min<int64_t>(cap, 2 * (int64_t)st->sm_count);
+    }
     if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
     return std::min(tiles, cap);
 }
@@ -532,9 +553,24 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (m == 0) return SKB_OK;
     const int64_t tiles = (m + BN - 1) / BN;
     const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
-    const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes);
+    const bool split_mode = !mean_only && prm && prm->precision == SKB_PRECISION_SPLIT_INT8;
+    const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes, split_mode);
 
     int rc;
+    if (split_mode) {
+        if ((rc = grow(st->device, &st->d_Kt2, &st->kt2_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_kdot2, &st->kdot2_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
+        const size_t n_chunks = (size_t)((tiles + chunk_tiles - 1) / chunk_tiles);
+        while (st->ev_k1.size() < n_chunks) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            st->ev_k1.push_back(a);
+            st->ev_k2.push_back(b);
+        }
+        CU(cudaEventRecord(st->ev_enter, s));                 // everything already queued on the caller's stream
+        CU(cudaStreamWaitEvent(st->aux_stream, st->ev_enter, 0));
+    }
     if (!mean_only) {
         if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
     }
@@ -565,7 +601,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (!mean_only && out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
     size_t chunk_index = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++chunk_index) {
-        if (wait_chunk_events) CU(cudaStreamWaitEvent(s, st->chunk_ready[chunk_index], 0));
+        if (wait_chunk_events) CU(cudaStreamWaitEvent(split_mode ? st->aux_stream : s, st->chunk_ready[chunk_index], 0));
         const int64_t nt = std::min(chunk_tiles, tiles - t0);
         const int64_t c0 = t0 * BN;
         const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
@@ -583,22 +619,28 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         kp.d_pad = st->d_pad;
         kp.amplitude = st->amplitude;
         kp.bias = st->bias;
-        const bool split = !mean_only && prm->precision == SKB_PRECISION_SPLIT_INT8;
+        const bool split = split_mode;
         if (split) {
-            // ---- split-integer path: K1 emits int8 digit planes, the contraction runs on tcgen05 (ozaki.cuh) ----
+            // ---- split-integer path: K1 emits int8 digit planes (aux stream), the contraction runs on tcgen05 ----
+            const int buf = (int)(chunk_index & 1);
+            cudaStream_t s1 = st->aux_stream;
+            if (chunk_index >= 2) CU(cudaStreamWaitEvent(s1, st->ev_k2[chunk_index - 2], 0));   // scratch `buf` is free again
             KDigitParams dp;
             dp.base = kp;
             dp.base.Kt = nullptr;
-            dp.Kd = reinterpret_cast<int8_t*>(st->d_Kt);          // 7 bytes per (training point, candidate) <= the FP64 tile
+            dp.base.kdot = buf ? st->d_kdot2 : st->d_kdot;
+            dp.Kd = reinterpret_cast<int8_t*>(buf ? st->d_Kt2 : st->d_Kt);   // 7 bytes per (training point, candidate)
             dp.inv_scale_2p55 = 36028797018963968.0 / st->k_scale;
-            if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
-            if ((rc = launch_kcross_digits(st, dp, (int)nt, s)) != SKB_OK) return rc;
-            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            if ((rc = span_begin(st, 0, s1)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, (int)nt, s1)) != SKB_OK) return rc;
+            if ((rc = span_end(st, s1)) != SKB_OK) return rc;
+            CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
+            CU(cudaStreamWaitEvent(s, st->ev_k1[chunk_index], 0));
             OzakiParams op;
             op.Vd = st->d_Vd;
             op.sV = st->d_sV;
             op.Kd = dp.Kd;
-            op.kdot = st->d_kdot;
+            op.kdot = dp.base.kdot;
             op.k_scale = st->k_scale;
             op.n = st->n;
             op.n_pad = st->n_pad;
@@ -619,6 +661,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             ozaki_trmm_kernel<<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(), s>>>(op);
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            CU(cudaEventRecord(st->ev_k2[chunk_index], s));
             continue;
         }
         if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
@@ -741,7 +784,8 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         }
     }
     if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
-    if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double)))) != SKB_OK) return rc;
+    if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double),
+                                                       params->precision == SKB_PRECISION_SPLIT_INT8))) != SKB_OK) return rc;
     if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) return rc;
     if (out->n_var_clamped)
         CU(cudaMemcpyAsync(out->n_var_clamped, st->d_clamp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
