@@ -63,12 +63,14 @@ __host__ __device__ inline double oz_pow2_scale(double maxabs) {      // power o
 // ---------------------------------------------------------------------------------------------------------------
 // state preparation: row scales and digit planes of L_inv (lower-triangular 128 x 32 chunks, as in pack_linv_kernel)
 // ---------------------------------------------------------------------------------------------------------------
+// DENSE = false: lower-triangular L_inv (entries above the diagonal ignored); DENSE = true: full symmetric K_inv
+template <bool DENSE>
 __global__ void oz_row_scale_kernel(const double* __restrict__ V, double* __restrict__ sV, int n, int n_pad) {
     const int row = blockIdx.x;
     __shared__ double red[256];
     double m = 0.0;
     if (row < n)
-        for (int j = threadIdx.x; j <= row; j += blockDim.x) m = fmax(m, fabs(V[(size_t)row * n + j]));
+        for (int j = threadIdx.x; j <= (DENSE ? n - 1 : row); j += blockDim.x) m = fmax(m, fabs(V[(size_t)row * n + j]));
     red[threadIdx.x] = m;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -78,16 +80,17 @@ __global__ void oz_row_scale_kernel(const double* __restrict__ V, double* __rest
     if (threadIdx.x == 0) sV[row] = oz_pow2_scale(red[0]);
 }
 
+template <bool DENSE>
 __global__ void oz_pack_linv_kernel(const double* __restrict__ V, const double* __restrict__ sV, int8_t* __restrict__ Vd,
                                     int n, int n_pad) {
     const int I = blockIdx.y, kc = blockIdx.x;
-    if (kc >= (I + 1) * (BM / OZ_KC)) return;
-    int8_t* chunk = Vd + (size_t)(vp_tiles_before(I) + kc) * OZ_A_CHUNK;
+    if (!DENSE && kc >= (I + 1) * (BM / OZ_KC)) return;
+    int8_t* chunk = Vd + (size_t)(DENSE ? (int64_t)I * (n_pad / OZ_KC) + kc : vp_tiles_before(I) + kc) * OZ_A_CHUNK;
     for (int e = threadIdx.x; e < BM * OZ_KC; e += blockDim.x) {
         const int i = e / OZ_KC, k = e % OZ_KC;
         const int row = I * BM + i, col = kc * OZ_KC + k;
         double v = 0.0;
-        if (row < n && col <= row) v = V[(size_t)row * n + col] / sV[row] * 36028797018963968.0;   // * 2^55 (exact)
+        if (row < n && (DENSE ? col < n : col <= row)) v = V[(size_t)row * n + col] / sV[row] * 36028797018963968.0;   // * 2^55 (exact)
         const unsigned long long y = oz_digits(v);
         const int off = oz_canon(BM, i, k);
 #pragma unroll
@@ -111,6 +114,7 @@ struct OzakiParams {
     double* std;
     double* acq[3];
     unsigned long long* clamp_count;
+    double* Wt;               // MODE 1: [tiles128][n_pad][BN] = K_inv . K_trans^T in FP64 for the gradient kernel
 };
 
 constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_NC * sizeof(double) + 256; }
@@ -197,6 +201,9 @@ __device__ __forceinline__ double oz_colsum16(double (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
+// MODE 0: triangular L_inv, U squared and reduced, posterior + acquisition epilogue; grid.x = 64-candidate tile.
+// MODE 1: dense K_inv, W = K_inv . K_trans^T stored in FP64; grid = (row block, 64-candidate tile).
+template <int MODE>
 __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
     extern __shared__ __align__(1024) unsigned char smem_oz[];
     unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
@@ -226,18 +233,20 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
-    const int nI = p.n_pad / BM;
+    const int tile_id = MODE == 0 ? blockIdx.x : blockIdx.y;
+    const int I_begin = MODE == 0 ? 0 : blockIdx.x;
+    const int I_end = MODE == 0 ? p.n_pad / BM : blockIdx.x + 1;
     const int nkc_used = (p.n + OZ_KC - 1) / OZ_KC;
     const int nkc_all = p.n_pad / OZ_KC;
-    const int8_t* kd_tile = p.Kd + (size_t)blockIdx.x * nkc_all * OZ_B_CHUNK;
+    const int8_t* kd_tile = p.Kd + (size_t)tile_id * nkc_all * OZ_B_CHUNK;
 
     if (warp == 0) {
         // ---------------- producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int I = 0; I < nI; ++I) {
-                const int nkc = min((I + 1) * (BM / OZ_KC), nkc_used);
-                const int8_t* vrow = p.Vd + (size_t)vp_tiles_before(I) * OZ_A_CHUNK;
+            for (int I = I_begin; I < I_end; ++I) {
+                const int nkc = MODE == 0 ? min((I + 1) * (BM / OZ_KC), nkc_used) : nkc_used;
+                const int8_t* vrow = p.Vd + (size_t)(MODE == 0 ? vp_tiles_before(I) : (int64_t)I * nkc_all) * OZ_A_CHUNK;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int s = it % OZ_STAGES;
                     const uint32_t ph = (it / OZ_STAGES) & 1;
@@ -253,10 +262,10 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int I = 0; I < nI; ++I) {
-                const int nkc = min((I + 1) * (BM / OZ_KC), nkc_used);
-                if (I > 0) {
-                    mbar_wait(tmem_empty, (uint32_t)((I - 1) & 1));         // epilogue of the previous row block drained TMEM
+            for (int I = I_begin; I < I_end; ++I) {
+                const int nkc = MODE == 0 ? min((I + 1) * (BM / OZ_KC), nkc_used) : nkc_used;
+                if (I > I_begin) {
+                    mbar_wait(tmem_empty, (uint32_t)((I - I_begin - 1) & 1));   // epilogue of the previous row block drained TMEM
                     asm volatile("tcgen05.fence::after_thread_sync;");
                 }
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
@@ -296,8 +305,8 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
         double qcol[OZ_NC / 8];                              // lane l: running sum of candidate 8 j + (l & 7)
 #pragma unroll
         for (int j = 0; j < OZ_NC / 8; ++j) qcol[j] = 0.0;
-        for (int I = 0; I < nI; ++I) {
-            mbar_wait(tmem_full, (uint32_t)(I & 1));
+        for (int I = I_begin; I < I_end; ++I) {
+            mbar_wait(tmem_full, (uint32_t)((I - I_begin) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
 #pragma unroll
@@ -314,21 +323,29 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
 #pragma unroll
                     for (int t = OZ_P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, (double)(int)g[t][c]);   // Horner in 256^-1
                     const double uu = acc * rs;
-                    u[c] = uu * uu;
+                    u[c] = MODE == 0 ? uu * uu : uu;
                 }
-                qcol[j] += oz_colsum8(u, lane);
+                if (MODE == 0) {
+                    qcol[j] += oz_colsum8(u, lane);
+                } else {
+                    // row of W owned by this lane, 8 consecutive candidates: one 64-byte store
+                    double* w = p.Wt + ((size_t)(tile_id >> 1) * p.n_pad + I * BM + quarter * 32 + lane) * BN +
+                                (tile_id & 1) * OZ_NC + 8 * j;
+                    *reinterpret_cast<double4*>(w) = make_double4(u[0], u[1], u[2], u[3]);
+                    *reinterpret_cast<double4*>(w + 4) = make_double4(u[4], u[5], u[6], u[7]);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
         }
-        if (lane < 8) {
+        if (MODE == 0 && lane < 8) {
 #pragma unroll
             for (int j = 0; j < OZ_NC / 8; ++j) sRed[quarter * OZ_NC + 8 * j + lane] = qcol[j];
         }
         named_bar_sync(1, 128);
         const int t = threadIdx.x - 64;                       // 0 .. 127 over the epilogue warps
-        if (t < OZ_NC) {
+        if (MODE == 0 && t < OZ_NC) {
             const int64_t cand = (int64_t)blockIdx.x * OZ_NC + t;
             if (cand < p.m) {
                 const double q = ((sRed[t] + sRed[OZ_NC + t]) + sRed[2 * OZ_NC + t]) + sRed[3 * OZ_NC + t];

@@ -64,6 +64,8 @@ struct skb_state {
     double* d_Ap = nullptr;      // packed dense K_inv (gradient path), nullptr when the caller gave no K_inv
     int8_t* d_Vd = nullptr;      // digit planes of L_inv for the split-integer tensor-core contraction (ozaki.cuh)
     double* d_sV = nullptr;      // [n_pad] power-of-two row scales of L_inv
+    int8_t* d_Ad = nullptr;      // digit planes of the dense K_inv (split-integer gradient path)
+    double* d_sA = nullptr;      // [n_pad] row scales of K_inv
     double k_scale = 1.0;        // power-of-two scale of the kernel values
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
@@ -301,7 +303,8 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(ozaki_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     const int smem3 = (int)grad_smem_bytes(st->d_pad);
@@ -351,7 +354,7 @@ void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
-    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
+    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2};
     for (void* p : ptrs) pool_free(st->device, p);
@@ -441,17 +444,23 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         // split-integer operands: row scales, then 7 signed 8-bit digit planes per lower-triangular 128 x 32 chunk
         SKB_PALLOC(st->d_sV, (size_t)st->n_pad * sizeof(double));
         SKB_PALLOC(st->d_Vd, (size_t)vp_tiles_before(nI) * OZ_A_CHUNK);
-        oz_row_scale_kernel<<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sV, st->n, st->n_pad);
+        oz_row_scale_kernel<false><<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sV, st->n, st->n_pad);
         LAUNCHED();
-        oz_pack_linv_kernel<<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(dV, st->d_sV, st->d_Vd, st->n, st->n_pad);
+        oz_pack_linv_kernel<false><<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(dV, st->d_sV, st->d_Vd, st->n, st->n_pad);
         LAUNCHED();
         st->k_scale = oz_pow2_scale(std::fabs(desc->amplitude) + std::fabs(desc->bias));
         if (desc->K_inv) {
             SKB_PALLOC(st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double));
-#undef SKB_PALLOC
             CU(cudaMemcpyAsync(dV, desc->K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
             pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dV, st->d_Ap, st->n, st->n_pad);
             LAUNCHED();
+            SKB_PALLOC(st->d_sA, (size_t)st->n_pad * sizeof(double));
+            SKB_PALLOC(st->d_Ad, (size_t)nI * (st->n_pad / OZ_KC) * OZ_A_CHUNK);
+            oz_row_scale_kernel<true><<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sA, st->n, st->n_pad);
+            LAUNCHED();
+            oz_pack_linv_kernel<true><<<dim3(st->n_pad / OZ_KC, nI), 256, 0, st->stream>>>(dV, st->d_sA, st->d_Ad, st->n, st->n_pad);
+            LAUNCHED();
+#undef SKB_PALLOC
         }
         CU(cudaStreamSynchronize(st->stream));
         return set_kernel_attributes(st);
@@ -511,17 +520,17 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
 }
 
 // candidate tiles processed per K1/K2 launch pair: as many as the scratch limit allows, in whole waves of SMs
+// can a K1 CTA sit on an SM next to a split-integer contraction CTA?  (shared memory decides: small n_dims only)
+static bool split_overlaps(const skb_state* st) {
+    return kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
+}
+
 static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
     const int64_t tiles = (m + BN - 1) / BN;
     int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / bytes_per_tile));
-    // split-integer path: two scratch buffers (half the budget each).  When a K1 CTA fits on an SM next to a contraction
-    // CTA (shared memory permitting: small n_dims), chunks are kept to two K1 waves so that K1 of the next chunk runs
-    // under the contraction of the current one even for moderate candidate counts.
-    if (split) {
-        cap = std::max<int64_t>(1, cap / 2);
-        const bool co_resident = kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
-        if (co_resident) cap = std::min<int64_t>(cap, 2 * (int64_t)st->sm_count);
-    }
+    // split-integer path with overlap: two scratch buffers (half the budget each) and chunks of two K1 waves, so that
+    // K1 of the next chunk runs under the contraction of the current one even for moderate candidate counts
+    if (split && split_overlaps(st)) cap = std::min<int64_t>(std::max<int64_t>(1, cap / 2), 2 * (int64_t)st->sm_count);
     if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
     return std::min(tiles, cap);
 }
@@ -556,8 +565,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     const bool split_mode = !mean_only && prm && prm->precision == SKB_PRECISION_SPLIT_INT8;
     const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes, split_mode);
 
+    const bool overlap = split_mode && split_overlaps(st);
     int rc;
-    if (split_mode) {
+    if (overlap) {
         if ((rc = grow(st->device, &st->d_Kt2, &st->kt2_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
         if ((rc = grow(st->device, &st->d_kdot2, &st->kdot2_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
         const size_t n_chunks = (size_t)((tiles + chunk_tiles - 1) / chunk_tiles);
@@ -601,7 +611,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (!mean_only && out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
     size_t chunk_index = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++chunk_index) {
-        if (wait_chunk_events) CU(cudaStreamWaitEvent(split_mode ? st->aux_stream : s, st->chunk_ready[chunk_index], 0));
+        if (wait_chunk_events) CU(cudaStreamWaitEvent(overlap ? st->aux_stream : s, st->chunk_ready[chunk_index], 0));
         const int64_t nt = std::min(chunk_tiles, tiles - t0);
         const int64_t c0 = t0 * BN;
         const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
@@ -622,9 +632,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         const bool split = split_mode;
         if (split) {
             // ---- split-integer path: K1 emits int8 digit planes (aux stream), the contraction runs on tcgen05 ----
-            const int buf = (int)(chunk_index & 1);
-            cudaStream_t s1 = st->aux_stream;
-            if (chunk_index >= 2) CU(cudaStreamWaitEvent(s1, st->ev_k2[chunk_index - 2], 0));   // scratch `buf` is free again
+            const int buf = overlap ? (int)(chunk_index & 1) : 0;
+            cudaStream_t s1 = overlap ? st->aux_stream : s;
+            if (overlap && chunk_index >= 2) CU(cudaStreamWaitEvent(s1, st->ev_k2[chunk_index - 2], 0));   // scratch `buf` free
             KDigitParams dp;
             dp.base = kp;
             dp.base.Kt = nullptr;
@@ -634,8 +644,10 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             if ((rc = span_begin(st, 0, s1)) != SKB_OK) return rc;
             if ((rc = launch_kcross_digits(st, dp, (int)nt, s1)) != SKB_OK) return rc;
             if ((rc = span_end(st, s1)) != SKB_OK) return rc;
-            CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
-            CU(cudaStreamWaitEvent(s, st->ev_k1[chunk_index], 0));
+            if (overlap) {
+                CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
+                CU(cudaStreamWaitEvent(s, st->ev_k1[chunk_index], 0));
+            }
             OzakiParams op;
             op.Vd = st->d_Vd;
             op.sV = st->d_sV;
@@ -658,10 +670,11 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             for (int a = 0; a < 3; ++a) op.acq[a] = acq_ptr[a] ? acq_ptr[a] + c0 : nullptr;
             op.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
             if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
-            ozaki_trmm_kernel<<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(), s>>>(op);
+            op.Wt = nullptr;
+            ozaki_trmm_kernel<0><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(), s>>>(op);
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
-            CU(cudaEventRecord(st->ev_k2[chunk_index], s));
+            if (overlap) CU(cudaEventRecord(st->ev_k2[chunk_index], s));
             continue;
         }
         if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
@@ -889,22 +902,48 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
         kp.d_pad = st->d_pad;
         kp.amplitude = st->amplitude;
         kp.bias = st->bias;
-        if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
-        if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
-        if ((rc = span_end(st, s)) != SKB_OK) return rc;
+        if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
+            // W = K_inv . K_trans^T on tcgen05 from int8 digit planes (dense variant of ozaki.cuh), stored in FP64
+            KDigitParams dp;
+            dp.base = kp;
+            dp.base.Kt = nullptr;
+            dp.Kd = reinterpret_cast<int8_t*>(st->d_Kt);
+            dp.inv_scale_2p55 = 36028797018963968.0 / st->k_scale;
+            if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, (int)nt, s)) != SKB_OK) return rc;
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            OzakiParams op;
+            std::memset(&op, 0, sizeof(op));
+            op.Vd = st->d_Ad;
+            op.sV = st->d_sA;
+            op.Kd = dp.Kd;
+            op.k_scale = st->k_scale;
+            op.n = st->n;
+            op.n_pad = st->n_pad;
+            op.m = mc;
+            op.Wt = st->d_Wt;
+            if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
+            ozaki_trmm_kernel<1><<<dim3(nI, (unsigned)(2 * nt)), OZ_THREADS, oz_smem_bytes(), s>>>(op);
+            LAUNCHED();
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+        } else {
+            if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
+            if ((rc = launch_kcross(st, kp, (int)nt, s)) != SKB_OK) return rc;
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
 
-        TrmmParams tp;
-        std::memset(&tp, 0, sizeof(tp));
-        tp.Kt = st->d_Kt;
-        tp.n_pad = st->n_pad;
-        tp.n = st->n;
-        tp.m = mc;
-        tp.Ap = st->d_Ap;
-        tp.Wt = st->d_Wt;
-        if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
-        trmm_kernel<1><<<dim3(nI, (unsigned)nt), TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
-        LAUNCHED();
-        if ((rc = span_end(st, s)) != SKB_OK) return rc;
+            TrmmParams tp;
+            std::memset(&tp, 0, sizeof(tp));
+            tp.Kt = st->d_Kt;
+            tp.n_pad = st->n_pad;
+            tp.n = st->n;
+            tp.m = mc;
+            tp.Ap = st->d_Ap;
+            tp.Wt = st->d_Wt;
+            if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
+            trmm_kernel<1><<<dim3(nI, (unsigned)nt), TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
+            LAUNCHED();
+            if ((rc = span_end(st, s)) != SKB_OK) return rc;
+        }
 
         GradParams gp;
         std::memset(&gp, 0, sizeof(gp));

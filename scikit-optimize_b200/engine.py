@@ -256,12 +256,12 @@ class DeviceState:
         res["clamped"] = int(clamped[0])
         return res
 
-    def score_grad(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96):
+    def score_grad(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, precision="fp64"):
         """Posterior, acquisition values and their input gradients for every row of X (batched extension of
         gaussian_acquisition_1D / predict(..., return_mean_grad, return_std_grad); the reference takes one row)."""
         X = self._check_X(X)
         m, d = X.shape
-        prm = _acq_params(y_opt, xi, kappa, acq_funcs, 0)
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, 0, resolve_precision(precision, self.host.n_train, m))
         out = _lib.GradOut()
         res = {"mean": np.empty(m), "std": np.empty(m), "mean_grad": np.empty((m, d)), "std_grad": np.empty((m, d))}
         out.mean, out.std = res["mean"].ctypes.data, res["std"].ctypes.data

@@ -81,3 +81,42 @@ def test_split_full_size_c3():
         assert v[17] == v[150_000]
         assert np.max(np.abs(v - ref[a]["values"])) <= 1e-9 * np.max(np.abs(ref[a]["values"]))
     dev.close()
+
+
+@pytest.mark.parametrize("n,d,m,kind,nu", [
+    (300, 7, 200, orc.KIND_MATERN, 2.5),
+    (129, 3, 130, orc.KIND_MATERN, 1.5),
+    (200, 50, 100, orc.KIND_MATERN, 2.5),
+    (256, 20, 150, orc.KIND_RBF, np.inf),
+    (1024, 10, 300, orc.KIND_MATERN, 2.5),
+])
+def test_split_gradient_path(n, d, m, kind, nu):
+    """Gradient path with the dense split-integer contraction W = K_inv K_trans^T: same gates as the FP64 path."""
+    from tests.test_gpu_parity import check_grads
+    st = orc.make_synthetic_state(n, d, noise=1e-3, seed=n + d, kind=kind, nu=nu)
+    rng = np.random.RandomState(11)
+    Xc = rng.rand(m, d)
+    Xc[3] = st.X_train[0]
+    y_opt = float(st.meta["y"].min())
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    g = dev.score_grad(Xc, y_opt=y_opt, acq_funcs=ACQS, precision="split_int8")
+    g64 = dev.score_grad(Xc, y_opt=y_opt, acq_funcs=ACQS, precision="fp64")
+    k = min(m, 60)
+    mu, sd, gm, gs = orc.predict_with_grads_batched(st, Xc[:k])
+    acq_ref = {}
+    z2 = ((y_opt - 0.01 - mu) / np.maximum(sd, 1e-300)) ** 2
+    for a in ACQS:
+        vs, grads = np.empty(k), np.empty((k, d))
+        for i in range(k):
+            v, gr = orc.gaussian_acquisition_1D(Xc[i], st, y_opt, a, dict(xi=0.01, kappa=1.96))
+            vs[i], grads[i] = v[0], gr
+        acq_ref[a] = (vs, grads, z2)
+    # K_inv (entries up to ~1/noise) is quantised to 2^-55 of its row maximum: the variance-scale noise floor of this
+    # formulation is ~1e-11 of the prior instead of the FP64 path's ~1e-12 (both far below the 1e-9 gate)
+    check_grads(st, g, mu, sd, gm, gs, acq_ref, var_tol(st), floor=2e-11)
+    scale = st.prior_var * st.y_std ** 2
+    assert np.max(np.abs(g["std"] ** 2 - g64["std"] ** 2)) <= 1e-9 * scale
+    assert np.max(np.abs(g["mean_grad"] - g64["mean_grad"])) <= 1e-12 * np.max(np.abs(g64["mean_grad"]))
+    gv = np.abs((g["std_grad"] - g64["std_grad"]) * g64["std"][:, None])
+    assert np.max(gv) <= 1e-9 * scale / np.min(st.length_scale)
+    dev.close()

@@ -20,9 +20,9 @@ def flops_grad_path(n, d):
     return n * (3 * d + 12) + (2 * n * n + 2 * n) + 6 * n * d + 60 * d
 
 
-def grad_dev(dev, X, y_opt, acqs):
+def grad_dev(dev, X, y_opt, acqs, precision="fp64"):
     m, d = X.shape
-    prm = engine._acq_params(y_opt, 0.01, 1.96, acqs, 0)
+    prm = engine._acq_params(y_opt, 0.01, 1.96, acqs, 0, precision)
     out = _lib.GradOut()
     keep = []
     def buf(*shape):
@@ -70,7 +70,7 @@ def main():
             "tflops": flops_value_path(n, d) * m_val / ms / 1e9,
             "k1_ms": tm["k1"][0] / 3, "k2_ms": tm["k2"][0] / 3, "topk_ms": tm["topk"][0] / 3}}
         Xg = X[:m_grad].contiguous()
-        run, keep = grad_dev(dev, Xg, y_opt, ("EI", "LCB"))
+        run, keep = grad_dev(dev, Xg, y_opt, ("EI", "LCB"), args.precision)
         dev.get_timing()
         ms = timed(run, 2)
         tm = dev.get_timing()
