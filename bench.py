@@ -349,8 +349,12 @@ def main():
             bf16_peak, bf16_src = measured_bf16_peak()
             peak = 2.0 * bf16_peak
             achieved = int8_ops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+            traffic_o = None
+            prof_o = os.path.join(ROOT, "profiles", "k2o_dram_bytes_per_launch.json")
+            if os.path.exists(prof_o):
+                traffic_o = json.load(open(prof_o)).get("dram_bytes_per_candidate", 0.0) * cand_per_k2
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
-                        "traffic": None,
+                        "traffic": traffic_o,
                         "kernel": "ozaki_trmm_kernel (K2o: tcgen05.mma kind::i8 over 7 s8 digit planes, exact s32 "
                                   "accumulation in TMEM, FP64 recombination)",
                         "peak_source": "int8 dense = 2 x " + bf16_src + "; MEASURED_PEAKS.json has no int8 entry, the 2:1 "
