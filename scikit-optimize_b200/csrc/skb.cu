@@ -555,10 +555,16 @@ static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chu
     return SKB_OK;
 }
 
+// exact int32 accumulation of the split-integer path: 7 digit-pair sums of at most n products of magnitude <= 2^14
+constexpr int SPLIT_MAX_TRAIN = 16384;
+
 static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
                           const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out,
                           bool wait_chunk_events = false) {
     CU(cudaSetDevice(st->device));
+    if (!mean_only && prm && prm->precision == SKB_PRECISION_SPLIT_INT8 && st->n > SPLIT_MAX_TRAIN)
+        return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= %d (int32 accumulators), got %d",
+                    SPLIT_MAX_TRAIN, st->n);
     if (m == 0) return SKB_OK;
     const int64_t tiles = (m + BN - 1) / BN;
     const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
@@ -864,7 +870,10 @@ static int check_grad_args(skb_state* st, const double* X, int64_t m, const skb_
     if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
     if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
     if (!st->d_Ap) return fail(SKB_ERR_UNSUPPORTED, "state was created without K_inv: gradient entry points are unavailable");
-    return check_params(params);
+    int rc = check_params(params);
+    if (rc == SKB_OK && params->precision == SKB_PRECISION_SPLIT_INT8 && st->n > 16384)
+        return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= 16384 (int32 accumulators), got %d", st->n);
+    return rc;
 }
 
 int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_params* prm, const skb_grad_out* out,

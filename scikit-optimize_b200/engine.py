@@ -125,12 +125,14 @@ def _mask(acq_funcs):
 # "auto": the split-integer tensor-core contraction pays off once the O(n^2)-per-candidate term dominates; below these
 # sizes the FP64 DMMA path is used (it is also the path whose small-n trajectories are pinned bit-for-bit to the reference)
 AUTO_SPLIT_MIN_TRAIN = 512
+AUTO_SPLIT_MAX_TRAIN = 16384          # exact int32 accumulation bound of the split-integer path
 AUTO_SPLIT_MIN_CANDIDATES = 8192
 
 
 def resolve_precision(precision, n_train, m):
     if precision == "auto":
-        return "split_int8" if (n_train >= AUTO_SPLIT_MIN_TRAIN and m >= AUTO_SPLIT_MIN_CANDIDATES) else "fp64"
+        return "split_int8" if (AUTO_SPLIT_MIN_TRAIN <= n_train <= AUTO_SPLIT_MAX_TRAIN and
+                                m >= AUTO_SPLIT_MIN_CANDIDATES) else "fp64"
     if precision not in _lib.PRECISION:
         raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISION))
     return precision

@@ -120,3 +120,33 @@ def test_split_gradient_path(n, d, m, kind, nu):
     gv = np.abs((g["std_grad"] - g64["std_grad"]) * g64["std"][:, None])
     assert np.max(gv) <= 1e-9 * scale / np.min(st.length_scale)
     dev.close()
+
+
+def test_split_extreme_scales():
+    """Operands spanning many orders of magnitude: large amplitude, short and long length scales, tiny noise
+    (large entries in L_inv / K_inv).  The split path must stay inside the same conditioning-aware gate."""
+    rng = np.random.RandomState(3)
+    n, d, m = 400, 4, 3000
+    X = rng.rand(n, d)
+    y = 50.0 * np.sin(6 * X[:, 0]) + 1e3 * X[:, 1] - 3.0
+    from skopt_b200.learning import GaussianProcessRegressor
+    from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
+    for amp, ls, noise in ((900.0, [0.05, 0.3, 5.0, 80.0], 1e-6), (1e-3, [0.2] * 4, 1e-8), (3.0, [2.0] * 4, 1e-2)):
+        gpr = GaussianProcessRegressor(ConstantKernel(amp, "fixed") * Matern(np.array(ls), "fixed", nu=2.5) + 0.25,
+                                       normalize_y=True, noise=noise, optimizer=None).fit(X, y)
+        ost = orc.state_from_estimator(gpr)
+        Xc = rng.rand(m, d)
+        Xc[:5] = X[:5]
+        dev = gpr.device_state()
+        y_opt = float(y.min())
+        res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="split_int8")
+        ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="fp64")
+        mu, sd = orc.predict(ost, Xc, return_std=True)
+        vtol = var_tol(ost)
+        scale = ost.prior_var * ost.y_std ** 2
+        assert np.max(np.abs(res["mean"] - mu)) <= 1e-9 * max(np.max(np.abs(mu)), ost.y_std)
+        assert np.max(np.abs(res["std"] ** 2 - sd ** 2)) <= vtol * scale
+        assert np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) <= max(1e-10, 0.1 * vtol) * scale
+        print("amp=%g noise=%g cond tol %.1e: split-fp64 %.2e, split-oracle %.2e" % (
+            amp, noise, vtol, np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / scale,
+            np.max(np.abs(res["std"] ** 2 - sd ** 2)) / scale))
