@@ -149,6 +149,10 @@ struct KDigitParams {
     double inv_scale_2p55;    // 2^55 / sK
 };
 
+// Thread (cp, rq): candidates cp and cp + 64 of the 128-candidate tile (one in each 64-candidate MMA tile) x training
+// rows [16 rq, 16 rq + 16) of every 64-row stage, i.e. one k-half of a 32-point chunk.  Two candidates share every
+// broadcast read of a training row, which halves this kernel's shared-memory traffic -- it runs next to the
+// shared-memory-bound contraction kernel (second stream), so that is what decides how much of it is hidden.
 template <int KIND>
 __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParams q) {
     const KCrossParams& p = q.base;
@@ -158,10 +162,10 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     double* xt = reinterpret_cast<double*>(smem_k1);
     double* al = xt + 2 * xt_stage;
     double* xs = al + 2 * XROWS;
-    double* mpart = xs + (size_t)d_pad * XS_LD;
+    double* mpart = xs + (size_t)d_pad * XS_LD;              // [BN]; reused as [4][BN] staging through xt after the loop
     uint64_t* bars = reinterpret_cast<uint64_t*>(mpart + BN);
 
-    const int tid = threadIdx.x, c = tid & (BN - 1), h = tid >> 7;
+    const int tid = threadIdx.x, cp = tid & 63, rq = tid >> 6;
     const int64_t tile = blockIdx.x;
     const int nst = (p.n + XROWS - 1) / XROWS;
     if (tid == 0) {
@@ -188,11 +192,12 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
         if (nst > 1) issue(1);
     }
 
-    double macc = 0.0;
+    double macc[2] = {0.0, 0.0};
     const int nkc_all = p.n_pad / 32;
-    // destination of this candidate inside its 64-candidate tile: [k half][plane][cand group (8)][cand % 8][16 B]
-    const int cl = c & 63;
-    int8_t* kd_cand = q.Kd + ((size_t)(tile * 2 + (c >> 6)) * nkc_all) * (2 * 7 * 8 * 128) + (cl >> 3) * 128 + (cl & 7) * 16;
+    // candidate e (0/1) lives in MMA tile 2*tile + e at position cp: [k half][plane][cand group (8)][cand % 8][16 B]
+    int8_t* kd_base = q.Kd + ((size_t)(tile * 2) * nkc_all) * (2 * 7 * 8 * 128) + (cp >> 3) * 128 + (cp & 7) * 16 +
+                      (rq & 1) * (7 * 8 * 128);
+    const size_t tile64_stride = (size_t)nkc_all * (2 * 7 * 8 * 128);
 
     for (int st = 0; st < nst; ++st) {
         const int buf = st & 1;
@@ -200,55 +205,60 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
         const double* xtb = xt + buf * xt_stage;
         const double* alb = al + buf * XROWS;
 
-        double s[XG / 2][4];
+        double s[2][16];
 #pragma unroll
-        for (int gi = 0; gi < XG / 2; ++gi) s[gi][0] = s[gi][1] = s[gi][2] = s[gi][3] = 0.0;
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int r = 0; r < 16; ++r) s[e][r] = 0.0;
         for (int k0 = 0; k0 < d_pad; k0 += 4) {
-            double x[4];
+            double x0[4], x1[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) x[kk] = xs[(k0 + kk) * XS_LD + c];
+            for (int kk = 0; kk < 4; ++kk) {
+                x0[kk] = xs[(k0 + kk) * XS_LD + cp];
+                x1[kk] = xs[(k0 + kk) * XS_LD + cp + 64];
+            }
 #pragma unroll
-            for (int gi = 0; gi < XG / 2; ++gi) {
-                const double* t = xtb + ((h * (XG / 2) + gi) * d_pad + k0) * 4;
+            for (int g = 0; g < 4; ++g) {
+                const double* t = xtb + ((rq * 4 + g) * d_pad + k0) * 4;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const double2 t01 = *reinterpret_cast<const double2*>(t + kk * 4);
                     const double2 t23 = *reinterpret_cast<const double2*>(t + kk * 4 + 2);
-                    const double d0 = x[kk] - t01.x, d1 = x[kk] - t01.y, d2 = x[kk] - t23.x, d3 = x[kk] - t23.y;
-                    s[gi][0] = fma(d0, d0, s[gi][0]);
-                    s[gi][1] = fma(d1, d1, s[gi][1]);
-                    s[gi][2] = fma(d2, d2, s[gi][2]);
-                    s[gi][3] = fma(d3, d3, s[gi][3]);
+                    double a;
+                    a = x0[kk] - t01.x; s[0][g * 4 + 0] = fma(a, a, s[0][g * 4 + 0]);
+                    a = x0[kk] - t01.y; s[0][g * 4 + 1] = fma(a, a, s[0][g * 4 + 1]);
+                    a = x0[kk] - t23.x; s[0][g * 4 + 2] = fma(a, a, s[0][g * 4 + 2]);
+                    a = x0[kk] - t23.y; s[0][g * 4 + 3] = fma(a, a, s[0][g * 4 + 3]);
+                    a = x1[kk] - t01.x; s[1][g * 4 + 0] = fma(a, a, s[1][g * 4 + 0]);
+                    a = x1[kk] - t01.y; s[1][g * 4 + 1] = fma(a, a, s[1][g * 4 + 1]);
+                    a = x1[kk] - t23.x; s[1][g * 4 + 2] = fma(a, a, s[1][g * 4 + 2]);
+                    a = x1[kk] - t23.y; s[1][g * 4 + 3] = fma(a, a, s[1][g * 4 + 3]);
                 }
             }
         }
-        // 32 kernel values of chunk kc = 2 st + h -> digits; lo = bytes 0..3 (planes 6..3), hi = bytes 4..6 (planes 2..0)
-        uint32_t lo[32], hi[32];
 #pragma unroll
-        for (int gi = 0; gi < XG / 2; ++gi) {
+        for (int e = 0; e < 2; ++e) {
+            // 16 kernel values -> digits; lo = bytes 0..3 (planes 6..3), hi = bytes 4..6 (planes 2..0)
+            uint32_t lo[16], hi[16];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int rr = gi * 4 + r;
-                const int j = st * XROWS + h * 32 + rr;
-                double val = fma(p.amplitude, base_kernel<KIND>(s[gi][r]), p.bias);
+            for (int r = 0; r < 16; ++r) {
+                const int j = st * XROWS + rq * 16 + r;
+                double val = fma(p.amplitude, base_kernel<KIND>(s[e][r]), p.bias);
                 if (j >= p.n) val = 0.0;
-                macc = fma(val, alb[h * 32 + rr], macc);
+                macc[e] = fma(val, alb[rq * 16 + r], macc[e]);
                 const unsigned long long y =
                     ((unsigned long long)__double2ll_rn(val * q.inv_scale_2p55) + 0x0080808080808080ull) ^ 0x0080808080808080ull;
-                lo[rr] = (uint32_t)y;
-                hi[rr] = (uint32_t)(y >> 32);
+                lo[r] = (uint32_t)y;
+                hi[r] = (uint32_t)(y >> 32);
             }
-        }
-        int8_t* dst = kd_cand + (size_t)(st * 2 + h) * (2 * 7 * 8 * 128);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+            int8_t* dst = kd_base + e * tile64_stride + (size_t)(st * 2 + (rq >> 1)) * (2 * 7 * 8 * 128);
 #pragma unroll
             for (int pl = 0; pl < 7; ++pl) {
                 const int byte = 6 - pl;                                   // plane 0 = most significant digit = byte 6
                 uint32_t w[4];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                    const int r0 = half * 16 + k4 * 4;
+                    const int r0 = k4 * 4;
                     uint32_t a0, a1, a2, a3;
                     if (byte < 4) { a0 = lo[r0]; a1 = lo[r0 + 1]; a2 = lo[r0 + 2]; a3 = lo[r0 + 3]; }
                     else          { a0 = hi[r0]; a1 = hi[r0 + 1]; a2 = hi[r0 + 2]; a3 = hi[r0 + 3]; }
@@ -257,15 +267,19 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                     const uint32_t t1 = __byte_perm(a2, a3, b | ((4 + b) << 4));
                     w[k4] = __byte_perm(t0, t1, 0x5410);                                  // [a0.b, a1.b, a2.b, a3.b]
                 }
-                *reinterpret_cast<uint4*>(dst + half * (7 * 8 * 128) + pl * (8 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + pl * (8 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         __syncthreads();
         if (tid == 0 && st + 2 < nst) issue(st + 2);
     }
-    if (h == 1) mpart[c] = macc;
+    // k . alpha: the four row quarters of a candidate are combined in a fixed order (staged through the xt buffers)
+    double* stage = xt;                                       // [4][BN], free after the loop
+    stage[rq * BN + cp] = macc[0];
+    stage[rq * BN + cp + 64] = macc[1];
     __syncthreads();
-    if (h == 0) p.kdot[tile * BN + c] = macc + mpart[c];
+    if (tid < BN)
+        p.kdot[tile * BN + tid] = ((stage[tid] + stage[BN + tid]) + stage[2 * BN + tid]) + stage[3 * BN + tid];
 }
 
 }  // namespace skb

@@ -72,9 +72,13 @@ struct skb_state {
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
     double* d_kdot = nullptr;    size_t kdot_cap = 0;
     double* d_Wt = nullptr;      size_t wt_cap = 0;
-    double* d_acq[3] = {nullptr, nullptr, nullptr};  size_t acq_cap = 0;
-    double* d_part_v = nullptr;  int64_t* d_part_i = nullptr;  int64_t* d_part_nan = nullptr;  size_t part_cap = 0;
-    double* d_topk_v = nullptr;  int64_t* d_topk_i = nullptr;  int64_t* d_topk_nan = nullptr;  size_t topk_cap = 0;
+    double* d_acq[3] = {nullptr, nullptr, nullptr};  size_t acq_cap[3] = {0, 0, 0};
+    double* d_part_v = nullptr;    size_t part_v_cap = 0;
+    int64_t* d_part_i = nullptr;   size_t part_i_cap = 0;
+    int64_t* d_part_nan = nullptr; size_t part_nan_cap = 0;
+    double* d_topk_v = nullptr;    size_t topk_v_cap = 0;
+    int64_t* d_topk_i = nullptr;   size_t topk_i_cap = 0;
+    int64_t* d_topk_nan = nullptr; size_t topk_nan_cap = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
     struct Span { int kind; cudaEvent_t a, b; };
@@ -303,6 +307,13 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    // the digit kernels are meant to share an SM with the contraction kernel (which needs the maximum shared-memory
+    // carve-out): ask for the same carve-out so that the SM does not have to be reconfigured between them
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
@@ -602,13 +613,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             if (!acq_ptr[a] && top_k > 0) need_internal = true;
         }
         if (need_internal) {
-            if ((size_t)m > st->acq_cap) {
-                for (int a = 0; a < 3; ++a) {
-                    size_t cap_a = st->acq_cap;
-                    if ((rc = grow(st->device, &st->d_acq[a], &cap_a, (size_t)m)) != SKB_OK) return rc;
-                }
-                st->acq_cap = (size_t)m;
-            }
+            for (int a = 0; a < 3; ++a)
+                if (((prm->acq_mask >> a) & 1) && !acq_ptr[a])
+                    if ((rc = grow(st->device, &st->d_acq[a], &st->acq_cap[a], (size_t)m)) != SKB_OK) return rc;
             for (int a = 0; a < 3; ++a)
                 if (((prm->acq_mask >> a) & 1) && !acq_ptr[a]) acq_ptr[a] = st->d_acq[a];
         }
@@ -723,13 +730,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (top_k > 0) {
         const int nblk = (int)std::min<int64_t>((int64_t)st->sm_count * TOPK_BLOCKS_PER_SM, (m + 1023) / 1024);
         const int64_t slice = (m + nblk - 1) / nblk;
-        if ((size_t)nblk * top_k > st->part_cap) {
-            size_t c1 = st->part_cap, c2 = st->part_cap, c3 = st->part_cap;
-            if ((rc = grow(st->device, &st->d_part_v, &c1, (size_t)nblk * top_k)) != SKB_OK) return rc;
-            if ((rc = grow(st->device, &st->d_part_i, &c2, (size_t)nblk * top_k)) != SKB_OK) return rc;
-            if ((rc = grow(st->device, &st->d_part_nan, &c3, (size_t)nblk * top_k)) != SKB_OK) return rc;
-            st->part_cap = (size_t)nblk * top_k;
-        }
+        if ((rc = grow(st->device, &st->d_part_v, &st->part_v_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_part_i, &st->part_i_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_part_nan, &st->part_nan_cap, (size_t)nblk)) != SKB_OK) return rc;
         for (int a = 0; a < 3; ++a) {
             if (!((prm->acq_mask >> a) & 1)) continue;
             if (!out->topk_val[a] || !out->topk_idx[a])
@@ -781,13 +784,10 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         if (((params->acq_mask >> a) & 1) && out->acq[a]) ++n_vec;
     const int k = params->top_k;
     if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)n_vec * m + 1)) != SKB_OK) return rc;
-    if ((size_t)3 * std::max(k, 1) > st->topk_cap) {
-        size_t c1 = st->topk_cap, c2 = st->topk_cap, c3 = st->topk_cap;
-        if ((rc = grow(st->device, &st->d_topk_v, &c1, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
-        if ((rc = grow(st->device, &st->d_topk_i, &c2, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
-        if ((rc = grow(st->device, &st->d_topk_nan, &c3, (size_t)3 * std::max(k, 1))) != SKB_OK) return rc;
-        st->topk_cap = (size_t)3 * std::max(k, 1);
-    }
+    const size_t kk = (size_t)3 * std::max(k, 1);
+    if ((rc = grow(st->device, &st->d_topk_v, &st->topk_v_cap, kk)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_topk_i, &st->topk_i_cap, kk)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_topk_nan, &st->topk_nan_cap, 3)) != SKB_OK) return rc;
     skb_score_out dout;
     std::memset(&dout, 0, sizeof(dout));
     double* cur = st->d_out;

@@ -1,0 +1,41 @@
+"""CPU pin of the split-integer scheme's arithmetic (oracle/split_emulation.py restates csrc/ozaki.cuh in NumPy)."""
+import numpy as np
+
+from oracle import split_emulation as se
+from oracle import gp_oracle as orc
+
+
+def test_digit_trick_reconstructs_the_integer():
+    rng = np.random.RandomState(0)
+    x = (rng.rand(10000) - 0.5) * 2.0 ** 55          # |x| <= 2^54, the range the kernel guarantees
+    x[:4] = [0.0, 2.0 ** 54, -2.0 ** 54, 1.0]
+    planes, v = se.digits(x)
+    rebuilt = sum(planes[p] * 256 ** (6 - p) for p in range(se.P))
+    assert np.array_equal(rebuilt, v)
+    assert all(pl.min() >= -128 and pl.max() <= 127 for pl in planes)
+
+
+def test_scale_puts_values_in_quarter_to_half():
+    for m in (1e-300, 3e-9, 0.24, 0.25, 0.5, 1.0, 7.3, 1e12):
+        s = se.pow2_scale(m)
+        assert 0.25 <= m / s < 0.5 and np.log2(s) == np.round(np.log2(s))
+    assert se.pow2_scale(0.0) == 1.0
+
+
+def test_split_product_matches_extended_precision():
+    """Error of the scheme relative to (row scale x kernel scale): a few 1e-16 per term, like an FP64 product."""
+    st = orc.make_synthetic_state(96, 5, noise=1e-4, seed=1)
+    from scipy.linalg import solve_triangular
+    V = solve_triangular(st.L, np.eye(st.n), lower=True)
+    Xc = np.random.RandomState(2).rand(40, 5)
+    K = orc.kernel_cross(st, Xc).T                                   # (n, c)
+    U = se.split_matmul(V, K)
+    exact = (V.astype(np.longdouble) @ K.astype(np.longdouble)).astype(np.float64)
+    fp64 = V @ K
+    scale = np.max(np.abs(V), axis=1, keepdims=True) * np.max(np.abs(K))
+    err_split = np.max(np.abs(U - exact) / scale)
+    err_fp64 = np.max(np.abs(fp64 - exact) / scale)
+    assert err_split <= 96 * 2.0 ** -52 and err_split <= 50 * max(err_fp64, 2.0 ** -53)
+    q = np.sum(U * U, axis=0)
+    q_ref = np.einsum("ci,ci->c", K.T @ st.K_inv, K.T)
+    assert np.max(np.abs(q - q_ref)) <= 1e-11 * st.prior_var
