@@ -172,6 +172,28 @@ int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq
 int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
                   int64_t* topk_idx, int64_t* first_nan);
 
+/* ---- candidate generation on the device (the step that feeds the path: optimizer.py:552-553) ----
+ * Replaces: `space.rvs(n_points, random_state=rng)` + `space.transform(...)` (skopt/space/space.py:874-903, 942-974;
+ * transformers.py:243-276) for "normalize"-warped Real (uniform prior), Integer and Categorical dimensions.
+ *
+ * skb_mt19937_uniform_dev continues NumPy's legacy MT19937 stream: `key` / `pos` are RandomState.get_state()[1:3]
+ * (host, in/out); `count` doubles are written to DEVICE memory d_out in exactly the order and with exactly the bits
+ * of `rng.uniform(0, 1, count)`, and key / pos come back advanced (feed them to RandomState.set_state).
+ * skb_candidates_transform_dev maps d_U [n_dims][m] (dimension by dimension, the reference's draw order) to the
+ * candidate matrix d_X [m][n_dims] with the reference's floating-point operations, bit for bit.
+ * skb_gather_rows_dev copies the k rows idx[] of d_X to the host (arg-min row / L-BFGS starts). */
+typedef enum { SKB_DIM_REAL_UNIFORM = 0, SKB_DIM_INTEGER_UNIFORM = 1 } skb_dim_kind;
+typedef struct {
+    int32_t kind;                /* skb_dim_kind; Categorical dimensions are INTEGER_UNIFORM over [0, n_categories-1] */
+    int32_t reserved;
+    double low, high;            /* bounds in the original space */
+} skb_dim_desc;
+int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream);
+int skb_candidates_transform_dev(int device, const double* d_U, int64_t m, int32_t n_dims, const skb_dim_desc* dims,
+                                 double* d_X, void* stream);
+int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
+                        void* stream);
+
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind
  * (0 = K1 cross-kernel + mean, 1 = K2 triangular contraction + acquisition, 2 = top-k, 3 = gradient kernels),

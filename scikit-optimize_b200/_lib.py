@@ -36,6 +36,10 @@ class ScoreOut(C.Structure):
                 ("n_var_clamped", C.c_void_p)]
 
 
+class DimDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("low", C.c_double), ("high", C.c_double)]
+
+
 class GradOut(C.Structure):
     _fields_ = [("mean", C.c_void_p), ("std", C.c_void_p), ("mean_grad", C.c_void_p), ("std_grad", C.c_void_p),
                 ("acq", C.c_void_p * 3), ("acq_grad", C.c_void_p * 3)]
@@ -68,6 +72,10 @@ SYMBOLS = [
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
+    ("skb_candidates_transform_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(DimDesc), C.c_void_p,
+                                               C.c_void_p]),
+    ("skb_gather_rows_dev", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

@@ -1,0 +1,147 @@
+// Candidate generation on the device, bit-identical to the host path it replaces.
+//
+// Optimizer._tell draws its candidate set with `space.transform(space.rvs(n_points, rng))` (optimizer.py:552-553): for
+// every dimension, n_points doubles from NumPy's legacy MT19937 stream (`RandomState.uniform`, two 32-bit outputs per
+// double, genrand_res53), pushed through the dimension's un-warp / clip / warp arithmetic (space.py:205-209, 302-346,
+// transformers.py:243-276).  On the host this costs more than scoring the candidates on the GPU.  Here
+//   * mt19937_fill_kernel continues the SAME stream from the RandomState's own 624-word state (one CTA: the state
+//     recurrence is sequential across regenerations but its 624 words regenerate in four parallel phases), and hands
+//     the advanced state back so the host generator stays in step;
+//   * candidates_transform_kernel applies the per-dimension arithmetic with IEEE round-to-nearest operations in the
+//     host's order (no FMA contraction), so every coordinate has exactly the bits NumPy produces.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace skb {
+
+constexpr int MT_N = 624, MT_M = 397;
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
+    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+// genrand_res53: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53, every step exact in FP64
+__device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+// key: the generator's 624 state words (in/out), pos_io: its position (in/out), out[count] uniforms in [0, 1)
+__global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* __restrict__ key, int* __restrict__ pos_io,
+                                                           int64_t count, double* __restrict__ out) {
+    __shared__ uint32_t mt[MT_N];
+    __shared__ uint32_t tw[MT_N];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < MT_N; i += 256) mt[i] = key[i];
+    int pos = *pos_io;
+    __syncthreads();
+    const int64_t words_needed = 2 * count;
+    int64_t produced = 0;
+    while (produced < words_needed) {
+        if (pos == MT_N) {
+            // regenerate the 624 words: each phase only reads words that earlier phases (or the old state) finalised
+            uint32_t v0 = 0, v1 = 0, v2 = 0;
+            // phase 1: i in [0, 227)
+            if (tid < MT_N - MT_M) v0 = mt[tid + MT_M] ^ mt_twist(mt[tid], mt[tid + 1]);
+            __syncthreads();
+            if (tid < MT_N - MT_M) mt[tid] = v0;
+            __syncthreads();
+            // phase 2: i in [227, 454)
+            if (tid < 227) v1 = mt[tid] ^ mt_twist(mt[tid + 227], mt[tid + 228]);
+            __syncthreads();
+            if (tid < 227) mt[tid + 227] = v1;
+            __syncthreads();
+            // phase 3: i in [454, 623)
+            if (tid < 169) v2 = mt[tid + 227] ^ mt_twist(mt[tid + 454], mt[tid + 455]);
+            __syncthreads();
+            if (tid < 169) mt[tid + 454] = v2;
+            __syncthreads();
+            // phase 4: i = 623
+            if (tid == 0) mt[623] = mt[396] ^ mt_twist(mt[623], mt[0]);
+            __syncthreads();
+            pos = 0;
+        }
+        const int64_t left = words_needed - produced;
+        const int take = (int)((MT_N - pos) < left ? (MT_N - pos) : left);
+        for (int i = tid; i < take; i += 256) tw[i] = mt_temper(mt[pos + i]);
+        __syncthreads();
+        uint32_t new_carry = 0;
+        bool set_carry = false;
+        for (int i = tid; i < take; i += 256) {
+            const int64_t g = produced + i;                     // index of this word in the requested stream
+            if ((g & 1) == 0) {
+                if (i + 1 < take) out[g >> 1] = mt_double(tw[i], tw[i + 1]);
+                else { new_carry = tw[i]; set_carry = true; }   // its partner is the first word after regeneration
+            } else if (i == 0) {
+                out[g >> 1] = mt_double(carry, tw[0]);
+            }
+        }
+        __syncthreads();
+        if (set_carry) carry = new_carry;
+        __syncthreads();
+        produced += take;
+        pos += take;
+    }
+    for (int i = tid; i < MT_N; i += 256) key[i] = mt[i];
+    if (tid == 0) *pos_io = pos;
+}
+
+// Per-dimension arithmetic of the "normalize" warping (every GP run), kinds the device reproduces bit for bit:
+//   0  Real, uniform prior:      v = u*(1+eps) + 0;  x = clip(v*(hi-lo)+lo, lo, hi);                t = (x-lo)/(hi-lo)
+//   1  Integer / Categorical:    v as above;         x = rint(clip(rint(v*(hi-lo)+lo), lo, hi));    t = (rint(x)-lo)/(hi-lo)
+// (log-uniform priors need pow()/log10(), which differ in the last bit between libm and CUDA: those stay on the host)
+struct DimDesc {
+    int32_t kind;
+    int32_t pad;
+    double lo, hi;
+};
+
+// U: [d][m] uniforms in stream order (dimension by dimension), X: [m][d] row-major candidates
+__global__ void __launch_bounds__(256) candidates_transform_kernel(const double* __restrict__ U, const DimDesc* __restrict__ dims,
+                                                                   int64_t m, int d, double* __restrict__ X) {
+    __shared__ double tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int jj = ty; jj < 32; jj += 8) {
+        const int j = j0 + jj;
+        const int64_t i = i0 + tx;
+        double t = 0.0;
+        if (j < d && i < m) {
+            const DimDesc dd = dims[j];
+            const double width = __dsub_rn(dd.hi, dd.lo);
+            const double v = __dadd_rn(__dmul_rn(U[(int64_t)j * m + i], 1.0000000000000002), 0.0);
+            double x = __dadd_rn(__dmul_rn(v, width), dd.lo);
+            if (dd.kind == 1) x = rint(x);
+            x = fmin(fmax(x, dd.lo), dd.hi);
+            if (dd.kind == 1) x = rint(x);
+            t = __ddiv_rn(__dsub_rn(x, dd.lo), width);
+        }
+        tile[jj][tx] = t;
+    }
+    __syncthreads();
+    for (int ii = ty; ii < 32; ii += 8) {
+        const int64_t i = i0 + ii;
+        const int j = j0 + tx;
+        if (i < m && j < d) X[i * d + j] = tile[tx][ii];
+    }
+}
+
+// rows[k] = X[idx[k]]  (the few candidates the host needs back: the arg-min / the L-BFGS starts)
+__global__ void gather_rows_kernel(const double* __restrict__ X, const int64_t* __restrict__ idx, int k, int d,
+                                   double* __restrict__ rows) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < k * d) {
+        const int r = t / d, c = t - r * d;
+        rows[t] = idx[r] >= 0 ? X[idx[r] * d + c] : nan("");
+    }
+}
+
+}  // namespace skb

@@ -18,6 +18,7 @@
 #include "kcross.cuh"
 #include "layout.cuh"
 #include "ozaki.cuh"
+#include "rng.cuh"
 #include "topk.cuh"
 #include "trmm.cuh"
 
@@ -1184,6 +1185,98 @@ int skb_topk_host(int device, const double* values, int64_t m, int64_t index_off
     };
     rc = body();
     cudaDeviceSynchronize();
+    pool_free(device, raw);
+    return rc;
+}
+
+static int check_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SKB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SKB_ERR_NO_DEVICE, "device %d not in [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    return SKB_OK;
+}
+
+int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream) {
+    if (!key || !pos || count < 0 || (count > 0 && !d_out)) return fail(SKB_ERR_INVALID, "bad argument");
+    if (*pos < 0 || *pos > MT_N) return fail(SKB_ERR_INVALID, "MT19937 position %d out of range [0, 624]", *pos);
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    if (count == 0) return SKB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    void* raw = nullptr;
+    if ((rc = pool_alloc(device, &raw, (MT_N + 1) * sizeof(uint32_t))) != SKB_OK) return rc;
+    uint32_t* d_key = static_cast<uint32_t*>(raw);
+    int* d_pos = reinterpret_cast<int*>(d_key + MT_N);
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(d_key, key, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_pos, pos, sizeof(int), cudaMemcpyHostToDevice, s));
+        mt19937_fill_kernel<<<1, 256, 0, s>>>(d_key, d_pos, count, d_out);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(key, d_key, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(pos, d_pos, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return SKB_OK;
+    };
+    rc = body();
+    pool_free(device, raw);
+    return rc;
+}
+
+int skb_candidates_transform_dev(int device, const double* d_U, int64_t m, int32_t n_dims, const skb_dim_desc* dims,
+                                 double* d_X, void* stream) {
+    if (m < 0 || n_dims <= 0 || !dims || (m > 0 && (!d_U || !d_X))) return fail(SKB_ERR_INVALID, "bad argument");
+    for (int j = 0; j < n_dims; ++j) {
+        if (dims[j].kind != SKB_DIM_REAL_UNIFORM && dims[j].kind != SKB_DIM_INTEGER_UNIFORM)
+            return fail(SKB_ERR_UNSUPPORTED, "dimension %d: kind %d has no bit-exact device transform", j, dims[j].kind);
+        if (!(dims[j].high > dims[j].low)) return fail(SKB_ERR_INVALID, "dimension %d: high must exceed low", j);
+    }
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    if (m == 0) return SKB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    void* raw = nullptr;
+    if ((rc = pool_alloc(device, &raw, (size_t)n_dims * sizeof(DimDesc))) != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        std::vector<DimDesc> h(n_dims);
+        for (int j = 0; j < n_dims; ++j) { h[j].kind = dims[j].kind; h[j].pad = 0; h[j].lo = dims[j].low; h[j].hi = dims[j].high; }
+        CU(cudaMemcpyAsync(raw, h.data(), (size_t)n_dims * sizeof(DimDesc), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));            // `h` is a stack-lifetime staging buffer
+        candidates_transform_kernel<<<dim3((unsigned)((m + 31) / 32), (unsigned)((n_dims + 31) / 32)), 256, 0, s>>>(
+            d_U, static_cast<const DimDesc*>(raw), m, n_dims, d_X);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s));
+        return SKB_OK;
+    };
+    rc = body();
+    pool_free(device, raw);
+    return rc;
+}
+
+int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
+                        void* stream) {
+    if (k < 0 || n_dims <= 0 || (k > 0 && (!d_X || !idx || !rows))) return fail(SKB_ERR_INVALID, "bad argument");
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    if (k == 0) return SKB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    void* raw = nullptr;
+    const size_t bytes = (size_t)k * sizeof(int64_t) + (size_t)k * n_dims * sizeof(double);
+    if ((rc = pool_alloc(device, &raw, bytes)) != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        double* d_rows = static_cast<double*>(raw);
+        int64_t* d_idx = reinterpret_cast<int64_t*>(d_rows + (size_t)k * n_dims);
+        CU(cudaMemcpyAsync(d_idx, idx, (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        gather_rows_kernel<<<(k * n_dims + 255) / 256, 256, 0, s>>>(d_X, d_idx, k, n_dims, d_rows);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(rows, d_rows, (size_t)k * n_dims * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return SKB_OK;
+    };
+    rc = body();
     pool_free(device, raw);
     return rc;
 }

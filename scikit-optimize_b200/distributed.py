@@ -78,3 +78,28 @@ def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precis
         dist.all_reduce(nan, op=dist.ReduceOp.MIN, group=group)
         r["first_nan"] = -1 if int(nan) == _I64_MAX else int(nan)
     return res
+
+
+def sharded_score_tensor(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64"):
+    """sharded_score for a candidate matrix that already lives on this rank's GPU (a CUDA tensor, identical on every
+    rank): no host copy of the candidates at all; only the k (value, index) pairs per acquisition come back."""
+    from .engine import resolve_precision
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    m = X.shape[0]
+    precision = resolve_precision(precision, dev.host.n_train, m)
+    b = shard_bounds(m, world)
+    lo, hi = b[rank], b[rank + 1]
+    part = X[lo:hi] if world > 1 else X
+    res = dev.score_tensors(part.contiguous(), y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
+                            index_offset=lo, precision=precision)
+    out = {"precision": precision}
+    for name in acq_funcs:
+        v, i, nan = res[name]["topk_val"], res[name]["topk_idx"], res[name]["first_nan"]
+        if world > 1:
+            v, i = merge_topk_allgather(v, i, top_k, group=group)
+            nan = torch.where(nan < 0, torch.full_like(nan, _I64_MAX), nan)
+            dist.all_reduce(nan, op=dist.ReduceOp.MIN, group=group)
+            nan = torch.where(nan == _I64_MAX, torch.full_like(nan, -1), nan)
+        out[name] = {"topk_val": v.cpu().numpy(), "topk_idx": i.cpu().numpy(), "first_nan": int(nan.cpu()[0])}
+    return out

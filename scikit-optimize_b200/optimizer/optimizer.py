@@ -30,10 +30,23 @@ from ..space import Categorical, Space
 from ..utils import (check_x_in_space, cook_estimator, create_result, has_gradients, is_2Dlistlike, is_listlike,
                      normalize_dimensions)
 from ..acquisition import _gaussian_acquisition, device_topk
-from ..distributed import sharded_score
+from ..distributed import sharded_score, sharded_score_tensor
+from ..engine import device_candidates
+from ..space import device_dim_descs
 from .lbfgs import minimize_batch
 
 _INT32_MAX = np.iinfo(np.int32).max
+
+
+class _DeviceRows(object):
+    """Candidate matrix living on the GPU; `X[i]` brings one row to the host (NumPy), as the scoring block needs."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.shape = tuple(tensor.shape)
+
+    def __getitem__(self, i):
+        return self.tensor[int(i)].cpu().numpy()
 
 
 class Optimizer(object):
@@ -93,6 +106,8 @@ class Optimizer(object):
         self.n_jobs = acq_optimizer_kwargs.get("n_jobs", 1)      # accepted for compatibility; restarts are batched
         # arithmetic of the variance contraction: "auto" (default), "fp64" or "split_int8" (see engine.resolve_precision)
         self.precision = acq_optimizer_kwargs.get("precision", "auto")
+        # draw the candidate set on the GPU when the space allows a bit-exact device version (engine.device_candidates)
+        self.device_candidates = acq_optimizer_kwargs.get("device_candidates", True)
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
 
         if isinstance(self.base_estimator_, GaussianProcessRegressor):
@@ -260,16 +275,26 @@ class Optimizer(object):
         xi, kappa = kw.get("xi", 0.01), kw.get("kappa", 1.96)
         y_opt = np.min(self.yi)
         acqs = tuple(self.cand_acq_funcs_)
-        X = self.space.rvs_transformed(self.n_points, self.rng)
         if "ps" in self.acq_func:
+            X = self.space.rvs_transformed(self.n_points, self.rng)
             return self._score_and_refine_per_second(est, X, y_opt, transformed_bounds)
         if not hasattr(est, "device_state"):
             raise TypeError("the GPU scoring path needs this package's GaussianProcessRegressor, got %s" % type(est))
         dev = est.device_state()
-        k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
-        # one process per GPU: every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
-        # its contiguous block and the per-rank top-k lists are all-gathered (k*16 bytes per acquisition) and merged
-        res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k, precision=self.precision)
+        k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), self.n_points))
+        # candidate matrix: generated ON the GPU (same MT19937 stream, same arithmetic, same bits as the host path) when
+        # every dimension allows it, so neither the draw nor the upload of n_points x n_dims doubles happens on the host
+        descs = device_dim_descs(self.space) if self.device_candidates else None
+        if descs is not None and isinstance(self.rng, np.random.RandomState):
+            X = _DeviceRows(device_candidates(descs, self.n_points, self.rng, dev.device))
+            res = sharded_score_tensor(dev, X.tensor, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
+                                       precision=self.precision)
+        else:
+            X = self.space.rvs_transformed(self.n_points, self.rng)
+            # one process per GPU: every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
+            # its contiguous block and the per-rank top-k lists are all-gathered (k*16 bytes per acquisition) and merged
+            res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
+                                precision=self.precision)
         self._last_scoring = res          # kept for inspection / tests (top-k per acquisition)
 
         next_xs = []

@@ -517,6 +517,24 @@ class Space(object):
         return np.ascontiguousarray(np.hstack(cols))
 
 
+def device_dim_descs(space):
+    """(kind, low, high) per dimension if every dimension's "normalize" arithmetic has a bit-exact device version
+    (Real with a uniform prior, Integer with a uniform prior, Categorical with >= 2 categories), else None."""
+    descs = []
+    for dim in space.dimensions:
+        if dim.transform_ != "normalize":
+            return None
+        if isinstance(dim, Real) and dim.prior == "uniform" and dim.dtype in (float, "float"):
+            descs.append((0, float(dim.low), float(dim.high)))
+        elif isinstance(dim, Integer) and dim.prior == "uniform":
+            descs.append((1, float(dim.low), float(dim.high)))
+        elif isinstance(dim, Categorical) and len(dim.categories) >= 2:
+            descs.append((1, 0.0, float(len(dim.categories) - 1)))
+        else:
+            return None
+    return descs
+
+
 def normalize_dimensions(dimensions):
     """Space whose dimensions all use the "normalize" warping (skopt/utils.py:569-607)."""
     space = Space(dimensions)
