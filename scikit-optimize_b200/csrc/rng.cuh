@@ -32,64 +32,61 @@ __device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-// key: the generator's 624 state words (in/out), pos_io: its position (in/out), out[count] uniforms in [0, 1)
+// key: the generator's 624 state words (in/out), pos_io: its position (in/out), out[count] uniforms in [0, 1).
+// The stream is inherently serial across regenerations of the 624-word state, so one CTA walks it; inside a
+// regeneration the words depend only on the previous state and on words at distance 227, which gives three parallel
+// phases (the last word joins the third).  With two state buffers no phase reads what it writes, so a regeneration
+// costs three barriers, and the tempering / conversion of the current block overlaps the first phase of the next.
 __global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* __restrict__ key, int* __restrict__ pos_io,
                                                            int64_t count, double* __restrict__ out) {
-    __shared__ uint32_t mt[MT_N];
-    __shared__ uint32_t tw[MT_N];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t buf[2][MT_N];
+    __shared__ uint32_t carry[2];           // alternates per block: written for block b, read while emitting block b + 1
+    int blk = 0;
     const int tid = threadIdx.x;
-    for (int i = tid; i < MT_N; i += 256) mt[i] = key[i];
+    for (int i = tid; i < MT_N; i += 256) buf[0][i] = key[i];
     int pos = *pos_io;
+    int cur = 0;
     __syncthreads();
     const int64_t words_needed = 2 * count;
     int64_t produced = 0;
     while (produced < words_needed) {
         if (pos == MT_N) {
-            // regenerate the 624 words: each phase only reads words that earlier phases (or the old state) finalised
-            uint32_t v0 = 0, v1 = 0, v2 = 0;
-            // phase 1: i in [0, 227)
-            if (tid < MT_N - MT_M) v0 = mt[tid + MT_M] ^ mt_twist(mt[tid], mt[tid + 1]);
+            const uint32_t* o = buf[cur];
+            uint32_t* n = buf[cur ^ 1];
+            if (tid < 227) n[tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);                       // i in [0, 227)
             __syncthreads();
-            if (tid < MT_N - MT_M) mt[tid] = v0;
+            if (tid < 227) n[tid + 227] = n[tid] ^ mt_twist(o[tid + 227], o[tid + 228]);                // i in [227, 454)
             __syncthreads();
-            // phase 2: i in [227, 454)
-            if (tid < 227) v1 = mt[tid] ^ mt_twist(mt[tid + 227], mt[tid + 228]);
+            if (tid < 169) n[tid + 454] = n[tid + 227] ^ mt_twist(o[tid + 454], o[tid + 455]);          // i in [454, 623)
+            else if (tid == 255) n[623] = n[396] ^ mt_twist(o[623], n[0]);                              // i = 623
             __syncthreads();
-            if (tid < 227) mt[tid + 227] = v1;
-            __syncthreads();
-            // phase 3: i in [454, 623)
-            if (tid < 169) v2 = mt[tid + 227] ^ mt_twist(mt[tid + 454], mt[tid + 455]);
-            __syncthreads();
-            if (tid < 169) mt[tid + 454] = v2;
-            __syncthreads();
-            // phase 4: i = 623
-            if (tid == 0) mt[623] = mt[396] ^ mt_twist(mt[623], mt[0]);
-            __syncthreads();
+            cur ^= 1;
             pos = 0;
         }
+        const uint32_t* mt = buf[cur];
         const int64_t left = words_needed - produced;
         const int take = (int)((MT_N - pos) < left ? (MT_N - pos) : left);
-        for (int i = tid; i < take; i += 256) tw[i] = mt_temper(mt[pos + i]);
-        __syncthreads();
         uint32_t new_carry = 0;
         bool set_carry = false;
         for (int i = tid; i < take; i += 256) {
             const int64_t g = produced + i;                     // index of this word in the requested stream
             if ((g & 1) == 0) {
-                if (i + 1 < take) out[g >> 1] = mt_double(tw[i], tw[i + 1]);
-                else { new_carry = tw[i]; set_carry = true; }   // its partner is the first word after regeneration
+                if (i + 1 < take) out[g >> 1] = mt_double(mt_temper(mt[pos + i]), mt_temper(mt[pos + i + 1]));
+                else { new_carry = mt_temper(mt[pos + i]); set_carry = true; }   // partner: first word of the next block
             } else if (i == 0) {
-                out[g >> 1] = mt_double(carry, tw[0]);
+                out[g >> 1] = mt_double(carry[(blk ^ 1) & 1], mt_temper(mt[pos]));
             }
         }
-        __syncthreads();
-        if (set_carry) carry = new_carry;
-        __syncthreads();
+        // written by the thread that owns the block's last word, read by thread 0 while it emits the NEXT block (the
+        // regeneration barriers in between order the two); the other slot is the one thread 0 may still be reading
+        if (set_carry) carry[blk & 1] = new_carry;
+        ++blk;
         produced += take;
         pos += take;
+        if (pos != MT_N) __syncthreads();
     }
-    for (int i = tid; i < MT_N; i += 256) key[i] = mt[i];
+    __syncthreads();
+    for (int i = tid; i < MT_N; i += 256) key[i] = buf[cur][i];
     if (tid == 0) *pos_io = pos;
 }
 
