@@ -179,8 +179,9 @@ int skb_topk_host(int device, const double* values, int64_t m, int64_t index_off
  * skb_mt19937_uniform_dev continues NumPy's legacy MT19937 stream: `key` / `pos` are RandomState.get_state()[1:3]
  * (host, in/out); `count` doubles are written to DEVICE memory d_out in exactly the order and with exactly the bits
  * of `rng.uniform(0, 1, count)`, and key / pos come back advanced (feed them to RandomState.set_state).
- * skb_candidates_transform_dev maps d_U [n_dims][m] (dimension by dimension, the reference's draw order) to the
- * candidate matrix d_X [m][n_dims] with the reference's floating-point operations, bit for bit.
+ * skb_candidates_generate_dev draws m * n_dims uniforms from the same stream (dimension by dimension, the reference's
+ * draw order) and maps them to the candidate matrix d_X [m][n_dims] with the reference's floating-point operations,
+ * bit for bit; key / pos come back advanced.
  * skb_gather_rows_dev copies the k rows idx[] of d_X to the host (arg-min row / L-BFGS starts). */
 typedef enum { SKB_DIM_REAL_UNIFORM = 0, SKB_DIM_INTEGER_UNIFORM = 1 } skb_dim_kind;
 typedef struct {
@@ -189,8 +190,8 @@ typedef struct {
     double low, high;            /* bounds in the original space */
 } skb_dim_desc;
 int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream);
-int skb_candidates_transform_dev(int device, const double* d_U, int64_t m, int32_t n_dims, const skb_dim_desc* dims,
-                                 double* d_X, void* stream);
+int skb_candidates_generate_dev(int device, uint32_t* key, int32_t* pos, int64_t m, int32_t n_dims,
+                                const skb_dim_desc* dims, double* d_X, void* stream);
 int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
                         void* stream);
 

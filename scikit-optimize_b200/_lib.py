@@ -73,8 +73,8 @@ SYMBOLS = [
     ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
     ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
-    ("skb_candidates_transform_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(DimDesc), C.c_void_p,
-                                               C.c_void_p]),
+    ("skb_candidates_generate_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32,
+                                              C.POINTER(DimDesc), C.c_void_p, C.c_void_p]),
     ("skb_gather_rows_dev", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_launch_count", C.c_int64, []),
 ]

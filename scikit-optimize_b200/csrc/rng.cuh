@@ -32,24 +32,22 @@ __device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-// key: the generator's 624 state words (in/out), pos_io: its position (in/out), out[count] uniforms in [0, 1).
-// The stream is inherently serial across regenerations of the 624-word state, so one CTA walks it; inside a
-// regeneration the words depend only on the previous state and on words at distance 227, which gives three parallel
-// phases (the last word joins the third).  With two state buffers no phase reads what it writes, so a regeneration
-// costs three barriers, and the tempering / conversion of the current block overlaps the first phase of the next.
-__global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* __restrict__ key, int* __restrict__ pos_io,
-                                                           int64_t count, double* __restrict__ out) {
+// key: the generator's 624 state words (in/out), pos_io: its position (in/out), words[n_words]: the next n_words RAW
+// (untempered) outputs of the generator.  The stream is inherently serial across regenerations of the 624-word state,
+// so one CTA walks it and does nothing else: inside a regeneration the words depend only on the previous state and on
+// words at distance 227, which gives three parallel phases (the last word joins the third); with two state buffers no
+// phase reads what it writes, so a regeneration costs three barriers.  Tempering, the 53-bit conversion and the
+// per-dimension arithmetic are embarrassingly parallel and run in a second, full-grid kernel.
+__global__ void __launch_bounds__(256) mt19937_words_kernel(uint32_t* __restrict__ key, int* __restrict__ pos_io,
+                                                            int64_t n_words, uint32_t* __restrict__ words) {
     __shared__ uint32_t buf[2][MT_N];
-    __shared__ uint32_t carry[2];           // alternates per block: written for block b, read while emitting block b + 1
-    int blk = 0;
     const int tid = threadIdx.x;
     for (int i = tid; i < MT_N; i += 256) buf[0][i] = key[i];
     int pos = *pos_io;
     int cur = 0;
     __syncthreads();
-    const int64_t words_needed = 2 * count;
     int64_t produced = 0;
-    while (produced < words_needed) {
+    while (produced < n_words) {
         if (pos == MT_N) {
             const uint32_t* o = buf[cur];
             uint32_t* n = buf[cur ^ 1];
@@ -63,31 +61,25 @@ __global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* __restrict_
             cur ^= 1;
             pos = 0;
         }
-        const uint32_t* mt = buf[cur];
-        const int64_t left = words_needed - produced;
+        const int64_t left = n_words - produced;
         const int take = (int)((MT_N - pos) < left ? (MT_N - pos) : left);
-        uint32_t new_carry = 0;
-        bool set_carry = false;
-        for (int i = tid; i < take; i += 256) {
-            const int64_t g = produced + i;                     // index of this word in the requested stream
-            if ((g & 1) == 0) {
-                if (i + 1 < take) out[g >> 1] = mt_double(mt_temper(mt[pos + i]), mt_temper(mt[pos + i + 1]));
-                else { new_carry = mt_temper(mt[pos + i]); set_carry = true; }   // partner: first word of the next block
-            } else if (i == 0) {
-                out[g >> 1] = mt_double(carry[(blk ^ 1) & 1], mt_temper(mt[pos]));
-            }
-        }
-        // written by the thread that owns the block's last word, read by thread 0 while it emits the NEXT block (the
-        // regeneration barriers in between order the two); the other slot is the one thread 0 may still be reading
-        if (set_carry) carry[blk & 1] = new_carry;
-        ++blk;
+        // the next regeneration only READS this buffer, so no barrier is needed before it starts
+        for (int i = tid; i < take; i += 256) words[produced + i] = buf[cur][pos + i];
         produced += take;
         pos += take;
-        if (pos != MT_N) __syncthreads();
     }
     __syncthreads();
     for (int i = tid; i < MT_N; i += 256) key[i] = buf[cur][i];
     if (tid == 0) *pos_io = pos;
+}
+
+// out[k] = genrand_res53(words[2k], words[2k+1])  ==  RandomState.uniform(0, 1)
+__global__ void mt_words_to_uniform_kernel(const uint32_t* __restrict__ words, int64_t count, double* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < count) {
+        const uint2 w = reinterpret_cast<const uint2*>(words)[k];
+        out[k] = mt_double(mt_temper(w.x), mt_temper(w.y));
+    }
 }
 
 // Per-dimension arithmetic of the "normalize" warping (every GP run), kinds the device reproduces bit for bit:
@@ -100,8 +92,9 @@ struct DimDesc {
     double lo, hi;
 };
 
-// U: [d][m] uniforms in stream order (dimension by dimension), X: [m][d] row-major candidates
-__global__ void __launch_bounds__(256) candidates_transform_kernel(const double* __restrict__ U, const DimDesc* __restrict__ dims,
+// W: raw generator words, two per uniform, uniforms in stream order [d][m] (dimension by dimension);
+// X: [m][d] row-major candidates
+__global__ void __launch_bounds__(256) candidates_transform_kernel(const uint32_t* __restrict__ W, const DimDesc* __restrict__ dims,
                                                                    int64_t m, int d, double* __restrict__ X) {
     __shared__ double tile[32][33];
     const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -114,7 +107,9 @@ __global__ void __launch_bounds__(256) candidates_transform_kernel(const double*
         if (j < d && i < m) {
             const DimDesc dd = dims[j];
             const double width = __dsub_rn(dd.hi, dd.lo);
-            const double v = __dadd_rn(__dmul_rn(U[(int64_t)j * m + i], 1.0000000000000002), 0.0);
+            const uint2 w2 = reinterpret_cast<const uint2*>(W)[(int64_t)j * m + i];
+            const double u = mt_double(mt_temper(w2.x), mt_temper(w2.y));
+            const double v = __dadd_rn(__dmul_rn(u, 1.0000000000000002), 0.0);
             double x = __dadd_rn(__dmul_rn(v, width), dd.lo);
             if (dd.kind == 1) x = rint(x);
             x = fmin(fmax(x, dd.lo), dd.hi);

@@ -1200,21 +1200,17 @@ static int check_device(int device) {
     return SKB_OK;
 }
 
-int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream) {
-    if (!key || !pos || count < 0 || (count > 0 && !d_out)) return fail(SKB_ERR_INVALID, "bad argument");
-    if (*pos < 0 || *pos > MT_N) return fail(SKB_ERR_INVALID, "MT19937 position %d out of range [0, 624]", *pos);
-    int rc = check_device(device);
-    if (rc != SKB_OK) return rc;
-    if (count == 0) return SKB_OK;
-    cudaStream_t s = (cudaStream_t)stream;
+// raw words of the stream into d_words (device), generator state advanced on the host side
+static int mt_words(int device, uint32_t* key, int32_t* pos, int64_t n_words, uint32_t* d_words, cudaStream_t s) {
     void* raw = nullptr;
-    if ((rc = pool_alloc(device, &raw, (MT_N + 1) * sizeof(uint32_t))) != SKB_OK) return rc;
+    int rc = pool_alloc(device, &raw, (MT_N + 1) * sizeof(uint32_t));
+    if (rc != SKB_OK) return rc;
     uint32_t* d_key = static_cast<uint32_t*>(raw);
     int* d_pos = reinterpret_cast<int*>(d_key + MT_N);
     auto body = [&]() -> int {
         CU(cudaMemcpyAsync(d_key, key, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(d_pos, pos, sizeof(int), cudaMemcpyHostToDevice, s));
-        mt19937_fill_kernel<<<1, 256, 0, s>>>(d_key, d_pos, count, d_out);
+        mt19937_words_kernel<<<1, 256, 0, s>>>(d_key, d_pos, n_words, d_words);
         LAUNCHED();
         CU(cudaMemcpyAsync(key, d_key, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(pos, d_pos, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1226,9 +1222,32 @@ int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t cou
     return rc;
 }
 
-int skb_candidates_transform_dev(int device, const double* d_U, int64_t m, int32_t n_dims, const skb_dim_desc* dims,
-                                 double* d_X, void* stream) {
-    if (m < 0 || n_dims <= 0 || !dims || (m > 0 && (!d_U || !d_X))) return fail(SKB_ERR_INVALID, "bad argument");
+int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream) {
+    if (!key || !pos || count < 0 || (count > 0 && !d_out)) return fail(SKB_ERR_INVALID, "bad argument");
+    if (*pos < 0 || *pos > MT_N) return fail(SKB_ERR_INVALID, "MT19937 position %d out of range [0, 624]", *pos);
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    if (count == 0) return SKB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    void* words = nullptr;
+    if ((rc = pool_alloc(device, &words, (size_t)2 * count * sizeof(uint32_t))) != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        int r2 = mt_words(device, key, pos, 2 * count, static_cast<uint32_t*>(words), s);
+        if (r2 != SKB_OK) return r2;
+        mt_words_to_uniform_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(static_cast<const uint32_t*>(words), count, d_out);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s));
+        return SKB_OK;
+    };
+    rc = body();
+    pool_free(device, words);
+    return rc;
+}
+
+int skb_candidates_generate_dev(int device, uint32_t* key, int32_t* pos, int64_t m, int32_t n_dims, const skb_dim_desc* dims,
+                                double* d_X, void* stream) {
+    if (!key || !pos || m < 0 || n_dims <= 0 || !dims || (m > 0 && !d_X)) return fail(SKB_ERR_INVALID, "bad argument");
+    if (*pos < 0 || *pos > MT_N) return fail(SKB_ERR_INVALID, "MT19937 position %d out of range [0, 624]", *pos);
     for (int j = 0; j < n_dims; ++j) {
         if (dims[j].kind != SKB_DIM_REAL_UNIFORM && dims[j].kind != SKB_DIM_INTEGER_UNIFORM)
             return fail(SKB_ERR_UNSUPPORTED, "dimension %d: kind %d has no bit-exact device transform", j, dims[j].kind);
@@ -1238,15 +1257,19 @@ int skb_candidates_transform_dev(int device, const double* d_U, int64_t m, int32
     if (rc != SKB_OK) return rc;
     if (m == 0) return SKB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t count = m * n_dims;
     void* raw = nullptr;
-    if ((rc = pool_alloc(device, &raw, (size_t)n_dims * sizeof(DimDesc))) != SKB_OK) return rc;
+    if ((rc = pool_alloc(device, &raw, (size_t)2 * count * sizeof(uint32_t) + (size_t)n_dims * sizeof(DimDesc))) != SKB_OK) return rc;
     auto body = [&]() -> int {
+        uint32_t* d_words = static_cast<uint32_t*>(raw);
+        DimDesc* d_dims = reinterpret_cast<DimDesc*>(d_words + 2 * count);
         std::vector<DimDesc> h(n_dims);
         for (int j = 0; j < n_dims; ++j) { h[j].kind = dims[j].kind; h[j].pad = 0; h[j].lo = dims[j].low; h[j].hi = dims[j].high; }
-        CU(cudaMemcpyAsync(raw, h.data(), (size_t)n_dims * sizeof(DimDesc), cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));            // `h` is a stack-lifetime staging buffer
+        CU(cudaMemcpyAsync(d_dims, h.data(), (size_t)n_dims * sizeof(DimDesc), cudaMemcpyHostToDevice, s));
+        int r2 = mt_words(device, key, pos, 2 * count, d_words, s);        // synchronises: `h` may go out of scope after it
+        if (r2 != SKB_OK) return r2;
         candidates_transform_kernel<<<dim3((unsigned)((m + 31) / 32), (unsigned)((n_dims + 31) / 32)), 256, 0, s>>>(
-            d_U, static_cast<const DimDesc*>(raw), m, n_dims, d_X);
+            d_words, d_dims, m, n_dims, d_X);
         LAUNCHED();
         CU(cudaStreamSynchronize(s));
         return SKB_OK;

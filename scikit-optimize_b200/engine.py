@@ -341,15 +341,20 @@ def device_uniform(rng, count, device=0):
 
 def device_candidates(dim_descs, n_samples, rng, device=0):
     """Candidate matrix (n_samples x n_dims, CUDA float64) for dimensions described as (kind, low, high) triples, with
-    the draw order and arithmetic of `space.transform(space.rvs(n, rng))`."""
+    the draw order and arithmetic of `space.transform(space.rvs(n, rng))`; `rng` is advanced as the host call would."""
     import torch
+    name, key, pos, has_gauss, cached = rng.get_state()
+    if name != "MT19937":
+        raise ValueError("device candidate generation needs a legacy MT19937 RandomState, got %s" % name)
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    pos_c = C.c_int32(int(pos))
     d = len(dim_descs)
-    U = device_uniform(rng, int(n_samples) * d, device)
-    X = torch.empty((int(n_samples), d), dtype=torch.float64, device=U.device)
+    X = torch.empty((int(n_samples), d), dtype=torch.float64, device=torch.device("cuda", device))
     arr = (_lib.DimDesc * d)()
     for j, (kind, lo, hi) in enumerate(dim_descs):
         arr[j].kind, arr[j].low, arr[j].high = int(kind), float(lo), float(hi)
-    s = torch.cuda.current_stream(U.device)
-    _lib.check(_lib.lib().skb_candidates_transform_dev(int(device), U.data_ptr(), int(n_samples), d, arr, X.data_ptr(),
-                                                       C.c_void_p(s.cuda_stream)))
+    s = torch.cuda.current_stream(X.device)
+    _lib.check(_lib.lib().skb_candidates_generate_dev(int(device), key.ctypes.data, C.byref(pos_c), int(n_samples), d, arr,
+                                                      X.data_ptr(), C.c_void_p(s.cuda_stream)))
+    rng.set_state((name, key, int(pos_c.value), has_gauss, cached))
     return X
