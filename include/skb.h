@@ -128,6 +128,9 @@ int skb_device_count(void);
 /* Replaces: the attribute reads est.X_train_/alpha_/K_inv_/kernel_/y_train_mean_/y_train_std_ at gpr.py:315-356. */
 int skb_state_create(const skb_state_desc* desc, int device, skb_state** out);
 void skb_state_destroy(skb_state* st);
+/* Add est.K_inv_ ([n_train * n_train], host) to a state created without it: enables the gradient entry points.
+ * (A BO loop in 'sampling' mode never needs it; the Python mirror attaches it on the first gradient call.) */
+int skb_state_attach_kinv(skb_state* st, const double* K_inv);
 /* cudaStream_t owned by the state (so callers can record events on it). */
 void* skb_state_stream(skb_state* st);
 int skb_state_sync(skb_state* st);

@@ -52,6 +52,7 @@ SYMBOLS = [
     ("skb_device_count", C.c_int, []),
     ("skb_state_create", C.c_int, [C.POINTER(StateDesc), C.c_int, C.POINTER(C.c_void_p)]),
     ("skb_state_destroy", None, [C.c_void_p]),
+    ("skb_state_attach_kinv", C.c_int, [C.c_void_p, C.c_void_p]),
     ("skb_state_stream", C.c_void_p, [C.c_void_p]),
     ("skb_state_sync", C.c_int, [C.c_void_p]),
     ("skb_state_set_scratch_limit", C.c_int, [C.c_void_p, C.c_uint64]),

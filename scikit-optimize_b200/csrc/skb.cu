@@ -461,31 +461,59 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         oz_pack_linv_kernel<false><<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(dV, st->d_sV, st->d_Vd, st->n, st->n_pad);
         LAUNCHED();
         st->k_scale = oz_pow2_scale(std::fabs(desc->amplitude) + std::fabs(desc->bias));
-        if (desc->K_inv) {
-            SKB_PALLOC(st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double));
-            CU(cudaMemcpyAsync(dV, desc->K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-            pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dV, st->d_Ap, st->n, st->n_pad);
-            LAUNCHED();
-            SKB_PALLOC(st->d_sA, (size_t)st->n_pad * sizeof(double));
-            SKB_PALLOC(st->d_Ad, (size_t)nI * (st->n_pad / OZ_KC) * OZ_A_CHUNK);
-            oz_row_scale_kernel<true><<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sA, st->n, st->n_pad);
-            LAUNCHED();
-            oz_pack_linv_kernel<true><<<dim3(st->n_pad / OZ_KC, nI), 256, 0, st->stream>>>(dV, st->d_sA, st->d_Ad, st->n, st->n_pad);
-            LAUNCHED();
 #undef SKB_PALLOC
-        }
         CU(cudaStreamSynchronize(st->stream));
         return set_kernel_attributes(st);
     };
     rc = body();
     pool_free(device, dX);
     pool_free(device, dV);
+    if (rc == SKB_OK && desc->K_inv) rc = skb_state_attach_kinv(st, desc->K_inv);
     if (rc != SKB_OK) {
         skb_state_destroy(st);
         return rc;
     }
     *out = st;
     return SKB_OK;
+}
+
+int skb_state_attach_kinv(skb_state* st, const double* K_inv) {
+    if (!st || !K_inv) return fail(SKB_ERR_INVALID, "state/K_inv is NULL");
+    if (st->d_Ap) return SKB_OK;                      // already attached
+    CU(cudaSetDevice(st->device));
+    const size_t n = st->n;
+    const int nI = st->n_pad / BM;
+    double* dK = nullptr;
+    int rc;
+    auto body = [&]() -> int {
+        int prc;
+#define SKB_PALLOC(ptr, bytes) if ((prc = pool_alloc(st->device, reinterpret_cast<void**>(&(ptr)), (bytes))) != SKB_OK) return prc
+        SKB_PALLOC(dK, n * n * sizeof(double));
+        SKB_PALLOC(st->d_Ap, (size_t)st->n_pad * st->n_pad * sizeof(double));
+        SKB_PALLOC(st->d_sA, (size_t)st->n_pad * sizeof(double));
+        SKB_PALLOC(st->d_Ad, (size_t)nI * (st->n_pad / OZ_KC) * OZ_A_CHUNK);
+#undef SKB_PALLOC
+        CU(cudaMemcpyAsync(dK, K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dK, st->d_Ap, st->n, st->n_pad);
+        LAUNCHED();
+        oz_row_scale_kernel<true><<<st->n_pad, 256, 0, st->stream>>>(dK, st->d_sA, st->n, st->n_pad);
+        LAUNCHED();
+        oz_pack_linv_kernel<true><<<dim3(st->n_pad / OZ_KC, nI), 256, 0, st->stream>>>(dK, st->d_sA, st->d_Ad, st->n, st->n_pad);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(st->stream));
+        return SKB_OK;
+    };
+    rc = body();
+    pool_free(st->device, dK);
+    if (rc != SKB_OK) {                               // leave the state usable for the value path
+        pool_free(st->device, st->d_Ap);
+        pool_free(st->device, st->d_sA);
+        pool_free(st->device, st->d_Ad);
+        st->d_Ap = nullptr;
+        st->d_sA = nullptr;
+        st->d_Ad = nullptr;
+    }
+    return rc;
 }
 
 void* skb_state_stream(skb_state* st) { return st ? (void*)st->stream : nullptr; }

@@ -167,7 +167,8 @@ class DeviceState:
         desc.X_train = host_state.X_train.ctypes.data
         desc.alpha = host_state.alpha.ctypes.data
         desc.L_inv = host_state.L_inv.ctypes.data
-        desc.K_inv = host_state.K_inv.ctypes.data if host_state.K_inv is not None else None
+        desc.K_inv = None                       # attached lazily: only the gradient entry points read it
+        self._kinv_attached = False
         handle = C.c_void_p()
         _lib.check(L.skb_state_create(C.byref(desc), self.device, C.byref(handle)))
         self._h = handle
@@ -193,6 +194,14 @@ class DeviceState:
 
     def set_scratch_limit(self, nbytes):
         _lib.check(_lib.lib().skb_state_set_scratch_limit(self._h, int(nbytes)))
+
+    def _attach_kinv(self):
+        """Upload K_inv (and pack its FP64 tiles / digit planes) the first time a gradient is requested."""
+        if not self._kinv_attached:
+            if self.host.K_inv is None:
+                raise ValueError("this state was built without K_inv: gradients are unavailable")
+            _lib.check(_lib.lib().skb_state_attach_kinv(self._h, self.host.K_inv.ctypes.data))
+            self._kinv_attached = True
 
     def set_timing(self, enabled):
         _lib.check(_lib.lib().skb_state_set_timing(self._h, 1 if enabled else 0))
@@ -263,6 +272,7 @@ class DeviceState:
         gaussian_acquisition_1D / predict(..., return_mean_grad, return_std_grad); the reference takes one row)."""
         X = self._check_X(X)
         m, d = X.shape
+        self._attach_kinv()
         prm = _acq_params(y_opt, xi, kappa, acq_funcs, 0, resolve_precision(precision, self.host.n_train, m))
         out = _lib.GradOut()
         res = {"mean": np.empty(m), "std": np.empty(m), "mean_grad": np.empty((m, d)), "std_grad": np.empty((m, d))}

@@ -284,7 +284,9 @@ class Optimizer(object):
         k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), self.n_points))
         # candidate matrix: generated ON the GPU (same MT19937 stream, same arithmetic, same bits as the host path) when
         # every dimension allows it, so neither the draw nor the upload of n_points x n_dims doubles happens on the host
-        descs = device_dim_descs(self.space) if self.device_candidates else None
+        # (tiny candidate sets are cheaper to draw on the host than the device round trip of the generator state)
+        big_enough = self.n_points * self.space.transformed_n_dims >= 30000 or self.device_candidates == "always"
+        descs = device_dim_descs(self.space) if (self.device_candidates and big_enough) else None
         if descs is not None and isinstance(self.rng, np.random.RandomState):
             X = _DeviceRows(device_candidates(descs, self.n_points, self.rng, dev.device))
             res = sharded_score_tensor(dev, X.tensor, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,

@@ -56,7 +56,7 @@ def test_unsupported_dimensions_fall_back_to_the_host():
 def test_optimizer_same_points_with_and_without_device_candidates():
     from skopt_b200 import Optimizer
     pts = {}
-    for flag in (True, False):
+    for flag in ("always", False):
         opt = Optimizer([(-5.0, 10.0), (0, 7), ["x", "y", "z"]], "GP", n_initial_points=5, acq_func="gp_hedge",
                         acq_optimizer="sampling", random_state=3,
                         acq_optimizer_kwargs=dict(n_points=4000, device_candidates=flag))
@@ -64,4 +64,4 @@ def test_optimizer_same_points_with_and_without_device_candidates():
             x = opt.ask()
             opt.tell(x, float((x[0] - 1.0) ** 2 + 0.1 * x[1] + {"x": 0.0, "y": 1.0, "z": -1.0}[x[2]]))
         pts[flag] = opt.Xi
-    assert pts[True] == pts[False]
+    assert pts["always"] == pts[False]

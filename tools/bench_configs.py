@@ -22,6 +22,7 @@ def flops_grad_path(n, d):
 
 def grad_dev(dev, X, y_opt, acqs, precision="fp64"):
     m, d = X.shape
+    dev._attach_kinv()
     prm = engine._acq_params(y_opt, 0.01, 1.96, acqs, 0, precision)
     out = _lib.GradOut()
     keep = []
