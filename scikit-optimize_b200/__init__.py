@@ -12,5 +12,6 @@ from .engine import DeviceState, HostState, host_state_from_estimator, launch_co
 from .learning.gaussian_process.gpr import set_default_device  # noqa: F401
 from .optimizer import Optimizer, base_minimize, gp_minimize  # noqa: F401
 from .space import Space  # noqa: F401
+from .utils import dump, expected_minimum, expected_minimum_random_sampling, load  # noqa: F401
 
 __version__ = "0.1.0"

@@ -188,3 +188,47 @@ def test_per_second_acquisition(acq, optm):
     assert vb[3] == v0[0] and np.array_equal(gb[3], g0)
     pts = opt.ask(n_points=2)                                       # constant liar with (value, log-time) lies
     assert len(pts) == 2 and pts[0] != pts[1]
+
+
+@pytest.mark.gpu
+def test_expected_minimum_and_persistence(tmp_path):
+    """utils.expected_minimum / expected_minimum_random_sampling / dump / load on a finished run (reference
+    tests/test_utils.py::test_expected_minimum, test_dump_and_load)."""
+    import skopt_b200
+    from skopt_b200 import gp_minimize
+
+    def branin(x):
+        a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5.0 / np.pi, 6.0, 10.0, 1.0 / (8 * np.pi)
+        return a * (x[1] - b * x[0] ** 2 + c * x[0] - r) ** 2 + s * (1 - t) * np.cos(x[0]) + s
+
+    res = gp_minimize(branin, [(-5.0, 10.0), (0.0, 15.0)], n_calls=20, n_initial_points=10, random_state=1,
+                      acq_optimizer="sampling", n_points=2000, noise=1e-10)
+    x_min, f_min = skopt_b200.expected_minimum(res, n_random_starts=20, random_state=1)
+    x_min2, f_min2 = skopt_b200.expected_minimum(res, n_random_starts=20, random_state=1)
+    assert x_min == x_min2 and f_min == f_min2
+    assert all(lo <= v <= hi for v, (lo, hi) in zip(x_min, res.space.bounds))
+    model = res.models[-1]
+    assert f_min == pytest.approx(model.predict(res.space.transform([x_min]))[0], rel=1e-9, abs=1e-9)
+    x_rs, f_rs = skopt_b200.expected_minimum_random_sampling(res, n_random_starts=100000, random_state=1)
+    assert f_min <= f_rs + 1e-6 * max(1.0, abs(f_rs))          # local refinement beats dense random sampling
+    assert f_rs == pytest.approx(model.predict(res.space.transform([x_rs]))[0], rel=1e-9, abs=1e-9)
+    # the gradient handed to L-BFGS is the derivative of the function it minimises
+    x0 = np.array([2.5, 7.0])
+    h = 1e-3           # alpha is large at noise=1e-10: smaller steps drown in the rounding of k . alpha
+    def mean_at(x):
+        return model.predict(res.space.transform([list(x)]))[0]
+    dev = model.device_state()
+    g = dev.score_grad(res.space.transform([list(x0)]), acq_funcs=())["mean_grad"][0]
+    slopes = np.array([skopt_b200.utils._transform_slope(d, v) for d, v in zip(res.space.dimensions, x0)])
+    for j in range(2):
+        e = np.zeros(2); e[j] = h
+        fd = (mean_at(x0 + e) - mean_at(x0 - e)) / (2 * h)
+        assert g[j] * slopes[j] == pytest.approx(fd, rel=1e-3, abs=1e-5)
+
+    path = tmp_path / "res.pkl"
+    skopt_b200.dump(res, path, store_objective=False)
+    back = skopt_b200.load(path)
+    assert "func" not in back.specs["args"] and "func" in res.specs["args"]
+    assert back.x == res.x and back.fun == res.fun
+    Xq = np.random.RandomState(0).rand(50, 2)
+    np.testing.assert_array_equal(back.models[-1].predict(Xq), model.predict(Xq))
