@@ -203,6 +203,11 @@ def run_reference(args, rank):
         return
     sample = args.ref_sample
     cores = os.cpu_count() or 1
+    try:                                  # torchrun exports OMP_NUM_THREADS=1: give the BLAS parts the host's threads back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:                     # noqa: BLE001 - the einsum contraction dominates and is single-threaded anyway
+        pass
     times = []
     for i in range(args.warmup + args.steps):
         evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, sample, quad="einsum", seed=0)
@@ -415,7 +420,8 @@ def main():
                                "argmin_index": argmin_fp64},
             "argmin_index": argmin_idx,
         }
-        if not args.no_ask:
+        # the ask-latency and CPU legs are single-GPU context for the headline: rank 0 at N=1 only
+        if not args.no_ask and world == 1:
             p50, cnt = ask_p50_ms()
             p50_l, cnt_l = ask_p50_ms_lbfgs()
             line["ask_p50_ms_lbfgs"] = {"value": p50_l, "tells": cnt_l, "config": "BASELINE.json configs[1]: Hartmann-6, "
@@ -426,7 +432,7 @@ def main():
                                   "sampling, n_points=10000, n_train 10..39: scoring block of Optimizer._tell, fit "
                                   "excluded (candidate generation + one fused GPU pass + top-k + inverse transform)",
                                   "cpu_port_ms": ask_p50_ms_cpu() if not args.no_cpu_baseline else None}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, args.cpu_sample, quad="einsum")
             evals_s_gemm, _ = cpu_baseline(N_TRAIN, N_DIMS, 4 * args.cpu_sample, quad="gemm")
             line["cpu_baseline"] = {

@@ -48,13 +48,21 @@ def shard_bounds(m, world):
     return b
 
 
+def _world(group):
+    """Ranks the candidates are sharded over: `group=False` keeps the call local even inside an initialised process
+    group (the Optimizer's default - collectives are opt-in), None is the default group."""
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
 def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64"):
     """Score the rows of X that belong to this rank and merge the top-k across ranks.
 
     `X` is the FULL candidate matrix (identical on every rank); the returned dict has, per acquisition, the GLOBAL
     'topk_val', 'topk_idx' and 'first_nan' -- the same on every rank and the same as a single-GPU run, because a
     candidate's value does not depend on where it was computed and ties resolve to the lowest global index."""
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    world = _world(group)
     if world == 1:
         return dev.score(X, y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
                          want_posterior=False, want_values=False, precision=precision)
@@ -84,7 +92,7 @@ def sharded_score_tensor(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None,
     """sharded_score for a candidate matrix that already lives on this rank's GPU (a CUDA tensor, identical on every
     rank): no host copy of the candidates at all; only the k (value, index) pairs per acquisition come back."""
     from .engine import resolve_precision
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    world = _world(group)
     rank = dist.get_rank(group) if world > 1 else 0
     m = X.shape[0]
     precision = resolve_precision(precision, dev.host.n_train, m)

@@ -108,6 +108,11 @@ class Optimizer(object):
         self.precision = acq_optimizer_kwargs.get("precision", "auto")
         # draw the candidate set on the GPU when the space allows a bit-exact device version (engine.device_candidates)
         self.device_candidates = acq_optimizer_kwargs.get("device_candidates", True)
+        # multi-GPU scoring is opt-in: shard_group=True (default process group) or a torch.distributed group makes
+        # every tell() a collective that ALL ranks of the group must enter with identical Optimizer state; the default
+        # keeps tell() local so independent optimisers can live inside an initialised process group
+        shard = acq_optimizer_kwargs.get("shard_group", None)
+        self._shard_group = False if shard is None or shard is False else (None if shard is True else shard)
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
 
         if isinstance(self.base_estimator_, GaussianProcessRegressor):
@@ -290,13 +295,13 @@ class Optimizer(object):
         if descs is not None and isinstance(self.rng, np.random.RandomState):
             X = _DeviceRows(device_candidates(descs, self.n_points, self.rng, dev.device))
             res = sharded_score_tensor(dev, X.tensor, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
-                                       precision=self.precision)
+                                       group=self._shard_group, precision=self.precision)
         else:
             X = self.space.rvs_transformed(self.n_points, self.rng)
-            # one process per GPU: every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
+            # with shard_group set (one process per GPU): every rank holds the same RNG stream, hence the same candidate matrix; rank r scores
             # its contiguous block and the per-rank top-k lists are all-gathered (k*16 bytes per acquisition) and merged
             res = sharded_score(dev, X, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa, top_k=k,
-                                precision=self.precision)
+                                group=self._shard_group, precision=self.precision)
         self._last_scoring = res          # kept for inspection / tests (top-k per acquisition)
 
         next_xs = []

@@ -34,13 +34,20 @@ for a in ("EI", "LCB", "PI"):
     assert np.array_equal(full[a]["topk_val"], shard[a]["topk_val"]), a
 # an Optimizer driven identically on every rank proposes identical points
 opt = Optimizer([(0.0, 1.0)] * 3, "GP", n_initial_points=4, acq_func="gp_hedge", acq_optimizer="sampling",
-                acq_optimizer_kwargs=dict(n_points=3000), random_state=5)
+                acq_optimizer_kwargs=dict(n_points=3000, shard_group=True), random_state=5)
 for _ in range(7):
     x = opt.ask(); opt.tell(x, float(np.sum((np.array(x) - 0.3) ** 2)))
 pts = torch.tensor(opt.Xi, dtype=torch.float64, device="cuda")
 ref = pts.clone(); dist.broadcast(ref, 0)
 assert torch.equal(pts, ref)
 rank = dist.get_rank()
+# without shard_group a tell() is local even inside the process group: only rank 0 runs it here, and it must not hang
+if rank == 0:
+    solo = Optimizer([(0.0, 1.0)] * 3, "GP", n_initial_points=4, acq_func="EI", acq_optimizer="sampling",
+                     acq_optimizer_kwargs=dict(n_points=3000), random_state=5)
+    for _ in range(6):
+        x = solo.ask(); solo.tell(x, float(np.sum((np.array(x) - 0.3) ** 2)))
+dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
