@@ -18,8 +18,8 @@
 // are ordered [plane q][candidate] (64 candidates per CTA), the seven accumulator regions G_0 .. G_6 sit side by side
 // in TMEM (64 columns each), so plane p accumulates into columns [64 p, 448) -- a contiguous range, issued as one or
 // two MMAs of N <= 256 (10 instructions per 32 training points instead of 28).  The CTA walks the lower-triangular
-// row blocks of L_inv like trmm.cuh; operand tiles arrive through a 5-stage mbarrier ring of 1-D bulk copies (TMA), one thread issues the
-// MMAs, four warps drain TMEM (tcgen05.ld), rebuild U in FP64, square and reduce it.
+// row blocks of L_inv like trmm.cuh; operand tiles arrive through a 4-stage mbarrier ring of 1-D bulk copies (TMA), one thread issues the
+// MMAs, eight warps drain TMEM (tcgen05.ld), rebuild U in FP64, square and reduce it.
 #pragma once
 #include <math.h>
 #include "layout.cuh"
@@ -33,7 +33,8 @@ constexpr int OZ_KC = 32;                     // training points per MMA (UMMA K
 constexpr int OZ_SUB = 32;                    // candidates per accumulator group
 constexpr int OZ_NC = 64;                     // candidates per CTA (two groups)
 constexpr int OZ_STAGES = 4;
-constexpr int OZ_THREADS = 192;               // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int OZ_EPI_WARPS = 8;                // two warps per TMEM lane quarter, each owning 32 of the 64 candidates
+constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;   // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int OZ_A_CHUNK = OZ_P * BM * OZ_KC;                      // 28,672 B: [plane][k half][row group 16][8 rows][16 B]
 constexpr int OZ_B_HALF = OZ_P * (OZ_NC / 8) * 128;                // 7,168 B:  [plane][cand group 8][8 cands][16 B] per k half
 constexpr int OZ_B_CHUNK = 2 * OZ_B_HALF;                          // 14,336 B
@@ -136,29 +137,6 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void oz_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void oz_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // issue (no wait) a load of 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void oz_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -167,29 +145,17 @@ __device__ __forceinline__ void oz_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void oz_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Column sums over the 32 lanes of a warp for 8 columns held as v[0..7] in every lane (transposing butterfly: 4 + 2 + 1
-// exchanges, then two closing steps).  Afterwards lane l holds the total of column (l & 7).
-__device__ __forceinline__ double oz_colsum8(double (&v)[8], int lane) {
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) {
-        const bool upper = (lane & o) != 0;
-#pragma unroll
-        for (int c = 0; c < o; ++c) {
-            const double send = upper ? v[c] : v[c + o];
-            const double keep = upper ? v[c + o] : v[c];
-            v[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    double r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
-    return r + __shfl_xor_sync(0xffffffffu, r, 16);
+// exact (double)(int32) on the FP64 pipe: the mantissa of 2^52 + 2^31 + x is x ^ 0x80000000, one subtraction removes the
+// offset.  The I2F conversion unit runs at a quarter of the FP64 rate and was the epilogue's bottleneck.
+__device__ __forceinline__ double oz_i2d(uint32_t g) {
+    return __hiloint2double(0x43300000, (int)(g ^ 0x80000000u)) - 4503601774854144.0;
 }
 
-// Column sums over the 32 lanes of a warp for 16 columns held as v[0..15] in every lane: a transposing butterfly
-// (8 + 4 + 2 + 1 exchanges halve the live columns while doubling the lanes summed, one more closes the 32 lanes).
-// Afterwards lane l holds the total of column (l & 15).  Fixed order -> deterministic.
-__device__ __forceinline__ double oz_colsum16(double (&v)[16], int lane) {
+// Column sums over the 32 lanes of a warp for 32 columns held as v[0..31] in every lane (transposing butterfly,
+// 16 + 8 + 4 + 2 + 1 exchanges); afterwards lane l holds the total of column l.  Fixed order -> deterministic.
+__device__ __forceinline__ double oz_colsum32(double (&v)[32], int lane) {
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {
+    for (int o = 16; o >= 1; o >>= 1) {
         const bool upper = (lane & o) != 0;
 #pragma unroll
         for (int c = 0; c < o; ++c) {
@@ -198,13 +164,13 @@ __device__ __forceinline__ double oz_colsum16(double (&v)[16], int lane) {
             v[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+    return v[0];
 }
 
 // MODE 0: triangular L_inv, U squared and reduced, posterior + acquisition epilogue; grid.x = 64-candidate tile.
 // MODE 1: dense K_inv, W = K_inv . K_trans^T stored in FP64; grid = (row block, 64-candidate tile).
 template <int MODE>
-__global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
+__global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
     extern __shared__ __align__(1024) unsigned char smem_oz[];
     unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
     double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][OZ_NC]
@@ -221,7 +187,7 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
             mbar_init(empty + s, 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, OZ_EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -299,18 +265,21 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
             }
         }
     } else {
-        // ---------------- epilogue: 4 warps, warp w reads TMEM lanes [32 (w % 4), +32) = rows of the row block ----------------
-        const int quarter = warp & 3;
+        // ---------------- epilogue: 8 warps; warp w reads TMEM lanes [32 (w % 4), +32) = rows of the row block, and the
+        // candidate half (w - 2) / 4.  Each thread keeps the running sum of squares of ITS row for its 32 candidates
+        // (no cross-lane traffic per row block); lanes and quarters are combined once at the end. ----------------
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const double cK = p.k_scale * 6.103515625e-05;       // sK * 2^-14
-        double qcol[OZ_NC / 8];                              // lane l: running sum of candidate 8 j + (l & 7)
+        double qacc[OZ_NC / 2];
 #pragma unroll
-        for (int j = 0; j < OZ_NC / 8; ++j) qcol[j] = 0.0;
+        for (int c = 0; c < OZ_NC / 2; ++c) qacc[c] = 0.0;
         for (int I = I_begin; I < I_end; ++I) {
             mbar_wait(tmem_full, (uint32_t)((I - I_begin) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
 #pragma unroll
-            for (int j = 0; j < OZ_NC / 8; ++j) {
+            for (int jj = 0; jj < OZ_NC / 16; ++jj) {
+                const int j = half * (OZ_NC / 16) + jj;
                 // all seven regions of these 8 candidates are requested before the single wait: one TMEM round trip
                 uint32_t g[OZ_P][8];
 #pragma unroll
@@ -319,15 +288,13 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
                 double u[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double acc = (double)(int)g[OZ_P - 1][c];
+                    double acc = oz_i2d(g[OZ_P - 1][c]);
 #pragma unroll
-                    for (int t = OZ_P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, (double)(int)g[t][c]);   // Horner in 256^-1
-                    const double uu = acc * rs;
-                    u[c] = MODE == 0 ? uu * uu : uu;
+                    for (int t = OZ_P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, oz_i2d(g[t][c]));   // Horner in 256^-1
+                    u[c] = acc * rs;
+                    if (MODE == 0) qacc[8 * jj + c] = fma(u[c], u[c], qacc[8 * jj + c]);
                 }
-                if (MODE == 0) {
-                    qcol[j] += oz_colsum8(u, lane);
-                } else {
+                if (MODE == 1) {
                     // row of W owned by this lane, 8 consecutive candidates: one 64-byte store
                     double* w = p.Wt + ((size_t)(tile_id >> 1) * p.n_pad + I * BM + quarter * 32 + lane) * BN +
                                 (tile_id & 1) * OZ_NC + 8 * j;
@@ -339,12 +306,9 @@ __global__ void __maxnreg__(128) ozaki_trmm_kernel(const OzakiParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
         }
-        if (MODE == 0 && lane < 8) {
-#pragma unroll
-            for (int j = 0; j < OZ_NC / 8; ++j) sRed[quarter * OZ_NC + 8 * j + lane] = qcol[j];
-        }
-        named_bar_sync(1, 128);
-        const int t = threadIdx.x - 64;                       // 0 .. 127 over the epilogue warps
+        if (MODE == 0) sRed[quarter * OZ_NC + half * (OZ_NC / 2) + lane] = oz_colsum32(qacc, lane);
+        named_bar_sync(1, 32 * OZ_EPI_WARPS);
+        const int t = threadIdx.x - 64;                       // 0 .. 255 over the epilogue warps
         if (MODE == 0 && t < OZ_NC) {
             const int64_t cand = (int64_t)blockIdx.x * OZ_NC + t;
             if (cand < p.m) {
