@@ -198,6 +198,30 @@ int skb_candidates_generate_dev(int device, uint32_t* key, int32_t* pos, int64_t
 int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
                         void* stream);
 
+/* ---- GP fit objective on the device (opt-in, the default fit stays on the host) ----
+ * Replaces: sklearn GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True) (_gpr.py:541-657), the
+ * function the L-BFGS-B hyper-parameter search of `fit` evaluates (reached from skopt gpr.py:195), for the kernel
+ * grammar  amplitude * {RBF | Matern}(length_scale[n_dims]) + WhiteKernel(noise):
+ *   theta = [log amplitude, log length_scale[0..n_dims), log noise]   (natural logs; log noise = -inf means no noise)
+ *   lml   = -1/2 y.K^-1 y - sum log diag chol(K) - n/2 log 2 pi,  K = kernel(X) + alpha I
+ *   grad  = d lml / d theta, [n_dims + 2] in the order of theta (the caller drops fixed hyper-parameters and sums the
+ *           length-scale entries of an isotropic kernel).
+ * A K that is not positive definite gives lml = -inf and a zero gradient, like the reference.  The dK/dtheta tensor
+ * of the reference (n x n x (n_dims + 2)) is never formed.  Cholesky / solve / inverse are cuSOLVER calls (loaded on
+ * first use); the kernel matrix and the gradient contraction are this library's kernels. */
+typedef struct skb_fit skb_fit;
+typedef struct {
+    int32_t n_train, n_dims;
+    int32_t kernel;            /* skb_kernel_kind */
+    int32_t reserved;
+    double alpha;              /* GaussianProcessRegressor.alpha: jitter added to the diagonal of K */
+    const double* X_train;     /* [n_train * n_dims] host, row-major */
+    const double* y_train;     /* [n_train] host, already normalised (y_train_ of the estimator) */
+} skb_fit_desc;
+int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out);
+void skb_fit_destroy(skb_fit* fit);
+int skb_fit_lml_host(skb_fit* fit, const double* theta, int32_t want_grad, double* lml, double* grad);
+
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind
  * (0 = K1 cross-kernel + mean, 1 = K2 triangular contraction + acquisition, 2 = top-k, 3 = gradient kernels),

@@ -380,3 +380,59 @@ def make_synthetic_state(n, d, noise=1e-4, seed=0, nu=2.5, amplitude=1.3, length
     st.L = L
     st.meta = dict(y=y, noise=noise, seed=seed, rng=rng)
     return st
+
+
+# --------------------------------------------------------------------------
+# fit objective: log marginal likelihood and gradient
+# --------------------------------------------------------------------------
+def log_marginal_likelihood(X_train, y_train, nu, theta_full, alpha=1e-10):
+    """sklearn GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True) (_gpr.py:541-657) for the
+    kernel  amplitude * {RBF (nu=inf) | Matern(nu)}(length_scale[d]) + WhiteKernel(noise)  with
+    theta_full = [log amplitude, log length_scale[d], log noise] (log noise = -inf: no noise term).
+
+    Kernel gradients follow sklearn kernels.py: ConstantKernel :1296-1307 (dK/dlog c = c), Product :975-983,
+    Sum :876-880, WhiteKernel :1406-1416 (noise * I), RBF :1578-1589 (K * D), Matern :1737-1763
+    (nu=1/2: K * D / r with 0 where r = 0; 3/2: 3 D exp(-sqrt(3) r); 5/2: 5/3 D (sqrt(5) r + 1) exp(-sqrt(5) r)),
+    D = (x_i - x_j)^2 / l^2 per dimension.  Returns (lml, grad[d + 2]); (-inf, zeros) when K is not positive definite.
+    The n x n x (d + 2) gradient tensor of the reference is formed here too (small cases only)."""
+    from scipy.linalg import cho_solve, cholesky
+    X = np.asarray(X_train, dtype=np.float64)
+    y = np.asarray(y_train, dtype=np.float64)
+    theta_full = np.asarray(theta_full, dtype=np.float64)
+    n, d = X.shape
+    amplitude, ls, noise = np.exp(theta_full[0]), np.exp(theta_full[1:d + 1]), np.exp(theta_full[d + 1])
+    Xs = X / ls
+    sq = _scaled_sqdist(Xs, Xs)
+    D = (X[:, None, :] - X[None, :, :]) ** 2 / (ls ** 2)              # kernels.py:1738-1741
+    if nu == math.inf:
+        base = np.exp(-0.5 * sq)
+        G = base[..., None] * D
+    else:
+        r = np.sqrt(sq)
+        if nu == 0.5:
+            base = np.exp(-r)
+            G = np.zeros_like(D)
+            np.divide(D, r[..., None], out=G, where=r[..., None] != 0)
+            G = base[..., None] * G
+        elif nu == 1.5:
+            t = r * _SQRT3
+            base = (1.0 + t) * np.exp(-t)
+            G = 3.0 * D * np.exp(-t)[..., None]
+        elif nu == 2.5:
+            t = r * _SQRT5
+            base = (1.0 + t + t ** 2 / 3.0) * np.exp(-t)
+            G = 5.0 / 3.0 * D * ((t + 1.0) * np.exp(-t))[..., None]
+        else:
+            raise NotImplementedError("Matern nu=%r" % nu)
+    K = amplitude * base + noise * np.eye(n)
+    K_gradient = np.dstack([(amplitude * base)[..., None], amplitude * G, (noise * np.eye(n))[..., None]])
+    K[np.diag_indices_from(K)] += alpha
+    try:
+        L = cholesky(K, lower=True, check_finite=False)
+    except np.linalg.LinAlgError:
+        return -np.inf, np.zeros(d + 2)
+    a = cho_solve((L, True), y, check_finite=False)
+    lml = -0.5 * y.dot(a) - np.log(np.diag(L)).sum() - n / 2.0 * np.log(2.0 * np.pi)
+    inner = np.outer(a, a) - cho_solve((L, True), np.eye(n), check_finite=False)
+    grad = 0.5 * np.einsum("ij,jik->k", inner, K_gradient)
+    return lml, grad

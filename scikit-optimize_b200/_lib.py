@@ -40,6 +40,11 @@ class DimDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("low", C.c_double), ("high", C.c_double)]
 
 
+class FitDesc(C.Structure):
+    _fields_ = [("n_train", C.c_int32), ("n_dims", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32),
+                ("alpha", C.c_double), ("X_train", C.c_void_p), ("y_train", C.c_void_p)]
+
+
 class GradOut(C.Structure):
     _fields_ = [("mean", C.c_void_p), ("std", C.c_void_p), ("mean_grad", C.c_void_p), ("std_grad", C.c_void_p),
                 ("acq", C.c_void_p * 3), ("acq_grad", C.c_void_p * 3)]
@@ -77,6 +82,9 @@ SYMBOLS = [
     ("skb_candidates_generate_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32,
                                               C.POINTER(DimDesc), C.c_void_p, C.c_void_p]),
     ("skb_gather_rows_dev", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("skb_fit_create", C.c_int, [C.POINTER(FitDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    ("skb_fit_destroy", None, [C.c_void_p]),
+    ("skb_fit_lml_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

@@ -12,8 +12,11 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cusolverDn.h>      // declarations only: the library is opened lazily with dlopen (fit objective)
+#include <dlfcn.h>
 
 #include "../../include/skb.h"
+#include "fit.cuh"
 #include "grad.cuh"
 #include "kcross.cuh"
 #include "layout.cuh"
@@ -1330,6 +1333,223 @@ int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32
     rc = body();
     pool_free(device, raw);
     return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// GP fit objective (log marginal likelihood + gradient), fit.cuh
+// ------------------------------------------------------------------------------------------------
+namespace {
+// cuSOLVER is only needed by the fit objective; it is opened on first use so that the scoring path neither links nor
+// loads it.
+struct SolverApi {
+    void* lib = nullptr;
+    decltype(&cusolverDnCreate) create = nullptr;
+    decltype(&cusolverDnDestroy) destroy = nullptr;
+    decltype(&cusolverDnSetStream) set_stream = nullptr;
+    decltype(&cusolverDnDpotrf_bufferSize) potrf_size = nullptr;
+    decltype(&cusolverDnDpotrf) potrf = nullptr;
+    decltype(&cusolverDnDpotrs) potrs = nullptr;
+    decltype(&cusolverDnDpotri_bufferSize) potri_size = nullptr;
+    decltype(&cusolverDnDpotri) potri = nullptr;
+    bool ok = false;
+};
+SolverApi g_solver;
+std::mutex g_solver_mu;
+
+int load_solver() {
+    std::lock_guard<std::mutex> lock(g_solver_mu);
+    if (g_solver.ok) return SKB_OK;
+    const char* names[] = {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"};
+    for (const char* nm : names) {
+        g_solver.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_solver.lib) break;
+    }
+    if (!g_solver.lib) return fail(SKB_ERR_UNSUPPORTED, "cuSOLVER (libcusolver.so) could not be loaded: %s", dlerror());
+#define SKB_SYM(field, name)                                                                          \
+    g_solver.field = reinterpret_cast<decltype(g_solver.field)>(dlsym(g_solver.lib, name));           \
+    if (!g_solver.field) return fail(SKB_ERR_UNSUPPORTED, "cuSOLVER symbol %s not found", name)
+    SKB_SYM(create, "cusolverDnCreate");
+    SKB_SYM(destroy, "cusolverDnDestroy");
+    SKB_SYM(set_stream, "cusolverDnSetStream");
+    SKB_SYM(potrf_size, "cusolverDnDpotrf_bufferSize");
+    SKB_SYM(potrf, "cusolverDnDpotrf");
+    SKB_SYM(potrs, "cusolverDnDpotrs");
+    SKB_SYM(potri_size, "cusolverDnDpotri_bufferSize");
+    SKB_SYM(potri, "cusolverDnDpotri");
+#undef SKB_SYM
+    g_solver.ok = true;
+    return SKB_OK;
+}
+
+#define SOLVER(call)                                                                                      \
+    do {                                                                                                  \
+        cusolverStatus_t s_ = (call);                                                                     \
+        if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ERR_CUDA, "%s -> cusolver status %d", #call, (int)s_); \
+    } while (0)
+}  // namespace
+
+struct skb_fit {
+    int device = 0, n = 0, d = 0, kernel = 0, n_blocks = 0, lwork = 0;
+    double alpha = 0;
+    cudaStream_t stream = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    std::vector<void*> ptrs;
+    double *d_X = nullptr, *d_y = nullptr, *d_Xs = nullptr, *d_ls = nullptr, *d_K = nullptr, *d_a = nullptr;
+    double *d_partial = nullptr, *d_out = nullptr, *d_work = nullptr;
+    int* d_info = nullptr;
+};
+
+extern "C" {
+
+void skb_fit_destroy(skb_fit* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    if (f->solver && g_solver.ok) g_solver.destroy(f->solver);
+    for (void* p : f->ptrs) pool_free(f->device, p);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out) {
+    if (!desc || !out) return fail(SKB_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (desc->n_train <= 0 || desc->n_dims <= 0 || !desc->X_train || !desc->y_train)
+        return fail(SKB_ERR_INVALID, "bad skb_fit_desc");
+    if (desc->n_dims > MAX_DIMS) return fail(SKB_ERR_UNSUPPORTED, "n_dims %d > %d", desc->n_dims, MAX_DIMS);
+    if (desc->kernel < SKB_KERNEL_RBF || desc->kernel > SKB_KERNEL_MATERN52) return fail(SKB_ERR_INVALID, "unknown kernel");
+    if (!(desc->alpha >= 0.0)) return fail(SKB_ERR_INVALID, "alpha must be >= 0");
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    if ((rc = load_solver()) != SKB_OK) return rc;
+    skb_fit* f = new (std::nothrow) skb_fit();
+    if (!f) return fail(SKB_ERR_NOMEM, "host allocation failed");
+    f->device = device;
+    f->n = desc->n_train;
+    f->d = desc->n_dims;
+    f->kernel = desc->kernel;
+    f->alpha = desc->alpha;
+    const int T = (f->n + FIT_TILE - 1) / FIT_TILE;
+    f->n_blocks = T * (T + 1) / 2;
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+        SOLVER(g_solver.create(&f->solver));
+        SOLVER(g_solver.set_stream(f->solver, f->stream));
+        const size_t n = (size_t)f->n, d = (size_t)f->d;
+        auto alloc = [&](double** ptr, size_t count) -> int {
+            void* raw = nullptr;
+            int r = pool_alloc(f->device, &raw, count * sizeof(double));
+            if (r != SKB_OK) return r;
+            f->ptrs.push_back(raw);
+            *ptr = static_cast<double*>(raw);
+            return SKB_OK;
+        };
+        int r;
+        if ((r = alloc(&f->d_X, n * d)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_Xs, n * d)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_y, n)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_a, n)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_ls, d)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_K, n * n)) != SKB_OK) return r;
+        if ((r = alloc(&f->d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
+        if ((r = alloc(&f->d_out, d + 4)) != SKB_OK) return r;
+        int lw1 = 0, lw2 = 0;
+        SOLVER(g_solver.potrf_size(f->solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_K, f->n, &lw1));
+        SOLVER(g_solver.potri_size(f->solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_K, f->n, &lw2));
+        f->lwork = std::max(std::max(lw1, lw2), 1);
+        if ((r = alloc(&f->d_work, (size_t)f->lwork)) != SKB_OK) return r;
+        double* info_raw = nullptr;
+        if ((r = alloc(&info_raw, 4)) != SKB_OK) return r;
+        f->d_info = reinterpret_cast<int*>(info_raw);
+        CU(cudaMemcpyAsync(f->d_X, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+        CU(cudaMemcpyAsync(f->d_y, desc->y_train, n * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+        CU(cudaStreamSynchronize(f->stream));
+        return SKB_OK;
+    };
+    rc = body();
+    if (rc != SKB_OK) {
+        skb_fit_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return SKB_OK;
+}
+
+int skb_fit_lml_host(skb_fit* f, const double* theta, int32_t want_grad, double* lml, double* grad) {
+    if (!f || !theta || !lml || (want_grad && !grad)) return fail(SKB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(f->device));
+    cudaStream_t s = f->stream;
+    const int n = f->n, d = f->d;
+    double ls[MAX_DIMS];
+    const double amplitude = exp(theta[0]), noise = exp(theta[d + 1]);      // exp(-inf) = 0: no noise term
+    for (int k = 0; k < d; ++k) ls[k] = exp(theta[1 + k]);
+    if (!(amplitude >= 0.0) || !(noise >= 0.0) || std::isinf(amplitude) || std::isinf(noise))
+        return fail(SKB_ERR_INVALID, "non-finite hyper-parameter");
+    CU(cudaMemcpyAsync(f->d_ls, ls, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s));
+    fit_scale_kernel<<<(unsigned)(((size_t)n * d + 255) / 256), 256, 0, s>>>(f->d_X, f->d_ls, f->d_Xs, n, d);
+    LAUNCHED();
+    FitParams kp;
+    kp.Xs = f->d_Xs;
+    kp.n = n;
+    kp.d = d;
+    kp.amplitude = amplitude;
+    kp.noise = noise;
+    kp.alpha = f->alpha;
+    kp.diag_add = noise + f->alpha;
+    kp.K = f->d_K;
+    const int T = (n + FIT_TILE - 1) / FIT_TILE;
+    const size_t smem_k = 2 * (size_t)FIT_TILE * (d + 1) * sizeof(double);
+    switch (f->kernel) {
+        case SKB_KERNEL_RBF: fit_kbuild_kernel<0><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        case SKB_KERNEL_MATERN12: fit_kbuild_kernel<1><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        case SKB_KERNEL_MATERN32: fit_kbuild_kernel<2><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        default: fit_kbuild_kernel<3><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+    }
+    LAUNCHED();
+    CU(cudaMemsetAsync(f->d_info, 0, 4 * sizeof(int), s));
+    SOLVER(g_solver.potrf(f->solver, CUBLAS_FILL_MODE_LOWER, n, f->d_K, n, f->d_work, f->lwork, f->d_info));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, f->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (info != 0) {                       // not positive definite: sklearn returns -inf and a zero gradient (_gpr.py:586-589)
+        *lml = -INFINITY;
+        if (want_grad) std::memset(grad, 0, (size_t)(d + 2) * sizeof(double));
+        return SKB_OK;
+    }
+    CU(cudaMemcpyAsync(f->d_a, f->d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SOLVER(g_solver.potrs(f->solver, CUBLAS_FILL_MODE_LOWER, n, 1, f->d_K, n, f->d_a, n, f->d_info + 1));
+    fit_lml_kernel<<<1, 256, 0, s>>>(f->d_K, f->d_y, f->d_a, n, f->d_out);
+    LAUNCHED();
+    if (want_grad) {
+        SOLVER(g_solver.potri(f->solver, CUBLAS_FILL_MODE_LOWER, n, f->d_K, n, f->d_work, f->lwork, f->d_info + 2));
+        FitGradParams gp;
+        gp.Xs = f->d_Xs;
+        gp.Kinv = f->d_K;
+        gp.a = f->d_a;
+        gp.n = n;
+        gp.d = d;
+        gp.amplitude = amplitude;
+        gp.noise = noise;
+        gp.partial = f->d_partial;
+        const size_t smem_g = smem_k + 8 * (size_t)(d + 2) * sizeof(double);
+        switch (f->kernel) {
+            case SKB_KERNEL_RBF: fit_grad_kernel<0><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            case SKB_KERNEL_MATERN12: fit_grad_kernel<1><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            case SKB_KERNEL_MATERN32: fit_grad_kernel<2><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            default: fit_grad_kernel<3><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+        }
+        LAUNCHED();
+        fit_grad_reduce_kernel<<<d + 2, 256, 0, s>>>(f->d_partial, f->n_blocks, d + 2, f->d_out + 1);
+        LAUNCHED();
+    }
+    double host_out[MAX_DIMS + 4];
+    CU(cudaMemcpyAsync(host_out, f->d_out, (size_t)(want_grad ? d + 3 : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *lml = host_out[0];
+    if (want_grad) std::memcpy(grad, host_out + 1, (size_t)(d + 2) * sizeof(double));
+    return SKB_OK;
 }
 
 }  // extern "C"

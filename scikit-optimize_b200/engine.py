@@ -368,3 +368,113 @@ def device_candidates(dim_descs, n_samples, rng, device=0):
                                                       X.data_ptr(), C.c_void_p(s.cuda_stream)))
     rng.set_state((name, key, int(pos_c.value), has_gauss, cached))
     return X
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GP fit objective on the device (opt-in): log marginal likelihood + gradient, include/skb.h skb_fit_*
+# ---------------------------------------------------------------------------------------------------------------
+class FitLayout:
+    """How sklearn's `theta` (the log of the NON-fixed hyper-parameters, in `kernel.hyperparameters` order) maps onto
+    the device objective's full vector [log amplitude, log length_scale[d], log noise]."""
+
+    def __init__(self, kernel, n_dims):
+        self.kind = None
+        self.n_dims = n_dims
+        self.full = np.empty(n_dims + 2)            # fixed entries keep their value, free ones are overwritten
+        self.full[0], self.full[1:n_dims + 1], self.full[n_dims + 1] = 0.0, 0.0, -np.inf
+        self.slots = []                             # per theta entry: indices of `full` it drives
+        self._walk(kernel)
+        if self.kind is None:
+            raise NotImplementedError("no stationary base kernel")
+        params = kernel.get_params()
+        for hp in kernel.hyperparameters:
+            leaf = hp.name.rsplit("__", 1)[-1]
+            value = np.atleast_1d(np.asarray(params[hp.name], dtype=np.float64))
+            if leaf == "constant_value":
+                idx = [[0]]
+            elif leaf == "length_scale":
+                idx = [[1 + k] for k in range(n_dims)] if value.size == n_dims and hp.n_elements == n_dims \
+                    else [list(range(1, n_dims + 1))]
+                if value.size not in (1, n_dims):
+                    raise NotImplementedError("length_scale with %d entries for %d dimensions" % (value.size, n_dims))
+            elif leaf == "noise_level":
+                idx = [[n_dims + 1]]
+            else:
+                raise NotImplementedError("hyper-parameter %s" % hp.name)
+            with np.errstate(divide="ignore"):
+                logs = np.log(value)
+            for j, group in enumerate(idx):
+                self.full[group] = logs[j] if logs.size > 1 else logs[0]
+            if not hp.fixed:
+                self.slots.extend(idx)
+        self.n_theta = len(self.slots)
+
+    def _walk(self, kernel):
+        """Accept exactly  [Constant *] {RBF | Matern} [+ White]  (either operand order)."""
+        cls = type(kernel).__name__
+        if cls == "Sum":
+            kinds = sorted([type(kernel.k1).__name__, type(kernel.k2).__name__])
+            if "WhiteKernel" not in kinds or kinds.count("WhiteKernel") != 1:
+                raise NotImplementedError("Sum without exactly one WhiteKernel")
+            self._walk(kernel.k2 if type(kernel.k1).__name__ == "WhiteKernel" else kernel.k1)
+        elif cls == "Product":
+            kinds = [type(kernel.k1).__name__, type(kernel.k2).__name__]
+            if kinds.count("ConstantKernel") != 1:
+                raise NotImplementedError("Product without exactly one ConstantKernel")
+            self._walk(kernel.k2 if kinds[0] == "ConstantKernel" else kernel.k1)
+        elif cls in ("RBF", "Matern"):
+            if self.kind is not None:
+                raise NotImplementedError("more than one stationary kernel")
+            self.kind = _flatten_kernel(kernel).base[0]
+        else:
+            raise NotImplementedError("kernel %s" % cls)
+
+    def expand(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.shape != (self.n_theta,):
+            raise ValueError("theta has %s entries, the kernel has %d free hyper-parameters" % (theta.shape, self.n_theta))
+        full = self.full.copy()
+        for t, group in zip(theta, self.slots):
+            full[group] = t
+        return full
+
+    def select(self, grad_full):
+        return np.array([grad_full[group].sum() for group in self.slots], dtype=np.float64)
+
+
+class DeviceFit:
+    """Training set resident on the GPU for the duration of one hyper-parameter search."""
+
+    def __init__(self, X_train, y_train, kernel_kind, alpha, device=0):
+        self.X = np.ascontiguousarray(X_train, dtype=np.float64)
+        self.y = np.ascontiguousarray(y_train, dtype=np.float64)
+        if self.y.shape != (self.X.shape[0],):
+            raise ValueError("y_train must be 1-D with one entry per training row")
+        desc = _lib.FitDesc(self.X.shape[0], self.X.shape[1], int(kernel_kind), 0, float(alpha),
+                            self.X.ctypes.data, self.y.ctypes.data)
+        self._h = C.c_void_p()
+        self.device = int(device)
+        _lib.check(_lib.lib().skb_fit_create(C.byref(desc), self.device, C.byref(self._h)))
+        self.n_evals = 0
+
+    def lml(self, theta_full, eval_gradient=True):
+        theta_full = np.ascontiguousarray(theta_full, dtype=np.float64)
+        if theta_full.shape != (self.X.shape[1] + 2,):
+            raise ValueError("theta_full must have n_dims + 2 entries")
+        value = C.c_double()
+        grad = np.zeros(theta_full.shape[0])
+        _lib.check(_lib.lib().skb_fit_lml_host(self._h, theta_full.ctypes.data, 1 if eval_gradient else 0,
+                                               C.byref(value), grad.ctypes.data))
+        self.n_evals += 1
+        return (value.value, grad) if eval_gradient else value.value
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _lib.lib().skb_fit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:     # noqa: BLE001 - interpreter shutdown
+            pass

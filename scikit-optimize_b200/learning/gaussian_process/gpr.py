@@ -24,6 +24,19 @@ def set_default_device(index):
     _DEFAULT_DEVICE[0] = int(index)
 
 
+_FIT_DEVICE = ["host"]
+
+
+def set_fit_device(where):
+    """Where the hyper-parameter search evaluates the log marginal likelihood: "host" (default: scikit-learn's own
+    code, bit-identical hyper-parameters and hence trajectories to the reference) or "gpu" (skb_fit_lml_host: same
+    objective within ~1e-12, hundreds of times faster at n >= 1000; the optimiser may then stop at hyper-parameters that
+    differ in the last digits).  An estimator attribute `_skb_fit_device` overrides the global setting."""
+    if where not in ("host", "gpu"):
+        raise ValueError("fit device must be 'host' or 'gpu', got %r" % (where,))
+    _FIT_DEVICE[0] = where
+
+
 def _white_kernel_key(kernel, prefix=""):
     """get_params() key of the first WhiteKernel that is a direct operand in a tree of Sums (gpr.py:17-36)."""
     if isinstance(kernel, Sum):
@@ -49,7 +62,41 @@ class GaussianProcessRegressor(_SkGPR):
         state = super().__getstate__()
         state = dict(state)
         state.pop("_skb_device_state", None)
+        state.pop("_skb_device_fit", None)
         return state
+
+    def _close_device_fit(self):
+        cached = self.__dict__.pop("_skb_device_fit", None)
+        if cached is not None:
+            cached[1].close()
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """sklearn _gpr.py:541-657.  With the fit device set to "gpu" (set_fit_device / `_skb_fit_device`) and a kernel
+        of the form [Constant *] {RBF | Matern} [+ White], the value and gradient come from the GPU objective; any
+        other kernel, multi-output targets or an array-valued alpha use scikit-learn's host code."""
+        where = self.__dict__.get("_skb_fit_device", _FIT_DEVICE[0])
+        if theta is None or where != "gpu" or np.ndim(self.alpha) != 0 or np.ndim(self.y_train_) != 1:
+            return super().log_marginal_likelihood(theta, eval_gradient=eval_gradient, clone_kernel=clone_kernel)
+        cached = self.__dict__.get("_skb_device_fit")
+        if cached is None or cached[0] is not self.X_train_:
+            self._close_device_fit()
+            try:
+                layout = engine.FitLayout(self.kernel_, self.X_train_.shape[1])
+            except NotImplementedError:
+                layout = None
+            fit = None if layout is None else engine.DeviceFit(self.X_train_, self.y_train_, layout.kind, self.alpha,
+                                                               _DEFAULT_DEVICE[0])
+            cached = (self.X_train_, fit, layout)
+            self.__dict__["_skb_device_fit"] = cached
+        _, fit, layout = cached
+        if fit is None:
+            return super().log_marginal_likelihood(theta, eval_gradient=eval_gradient, clone_kernel=clone_kernel)
+        if not clone_kernel:
+            self.kernel_.theta = theta              # the side effect sklearn's fit relies on (_gpr.py:568-572)
+        out = fit.lml(layout.expand(theta), eval_gradient=eval_gradient)
+        if eval_gradient:
+            return out[0], layout.select(out[1])
+        return out
 
     def fit(self, X, y):
         """gpr.py:166-237: add the noise kernel, fit with scikit-learn, silence the noise for prediction,
@@ -63,7 +110,10 @@ class GaussianProcessRegressor(_SkGPR):
         elif self.noise:
             self.kernel = self.kernel + WhiteKernel(noise_level=self.noise, noise_level_bounds="fixed")
         self.__dict__.pop("_skb_device_state", None)
-        super().fit(X, y)
+        try:
+            super().fit(X, y)
+        finally:
+            self._close_device_fit()            # the training set only stays on the GPU during the search
 
         self.noise_ = None
         if self.noise:

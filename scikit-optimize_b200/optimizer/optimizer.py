@@ -111,6 +111,11 @@ class Optimizer(object):
         # multi-GPU scoring is opt-in: shard_group=True (default process group) or a torch.distributed group makes
         # every tell() a collective that ALL ranks of the group must enter with identical Optimizer state; the default
         # keeps tell() local so independent optimisers can live inside an initialised process group
+        # where the GP hyper-parameter search evaluates its objective: None = the package setting
+        # (learning.gaussian_process.gpr.set_fit_device, default "host"), or "host" / "gpu" for this optimizer
+        self.fit_device = acq_optimizer_kwargs.get("fit_device", None)
+        if self.fit_device not in (None, "host", "gpu"):
+            raise ValueError("fit_device must be None, 'host' or 'gpu', got %r" % (self.fit_device,))
         shard = acq_optimizer_kwargs.get("shard_group", None)
         self._shard_group = False if shard is None or shard is False else (None if shard is True else shard)
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
@@ -237,6 +242,8 @@ class Optimizer(object):
         if fit and self._n_initial_points <= 0 and self.base_estimator_ is not None:
             transformed_bounds = np.array(self.space.transformed_bounds)
             est = clone(self.base_estimator_)
+            if self.fit_device is not None and hasattr(est, "log_marginal_likelihood"):
+                est._skb_fit_device = self.fit_device
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 est.fit(self.space.transform(self.Xi), self.yi)

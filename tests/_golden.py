@@ -10,7 +10,7 @@ from oracle import gp_oracle as orc
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-               if not os.path.basename(p).startswith("traj_"))
+               if not os.path.basename(p).startswith(("traj_", "fit_")))
 
 
 def _build_kernel(params, cls, prefix=""):
