@@ -563,9 +563,14 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
 }
 
 // candidate tiles processed per K1/K2 launch pair: as many as the scratch limit allows, in whole waves of SMs
-// can a K1 CTA sit on an SM next to a split-integer contraction CTA?  (shared memory decides: small n_dims only)
+// Split-integer path: K1 of chunk i+1 CAN run on a second stream under the contraction of chunk i when a K1 CTA fits on
+// an SM next to a contraction CTA (shared memory decides: small n_dims only).  Measured at (2048, 20), 10^6 candidates:
+// the overlapped schedule is 1 % SLOWER than running the two kernels back to back (18.6 vs 18.8 M evals/s) - the board
+// is at its power cap under the contraction, so co-running FP64 work only lowers the clock - and it needs twice the
+// scratch and three times the launches.  It therefore stays off unless SKB_SPLIT_OVERLAP=1 is exported.
 static bool split_overlaps(const skb_state* st) {
-    return kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
+    static const bool enabled = [] { const char* e = getenv("SKB_SPLIT_OVERLAP"); return e && e[0] == '1'; }();
+    return enabled && kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
 }
 
 static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
