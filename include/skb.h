@@ -221,6 +221,11 @@ typedef struct {
 int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out);
 void skb_fit_destroy(skb_fit* fit);
 int skb_fit_lml_host(skb_fit* fit, const double* theta, int32_t want_grad, double* lml, double* grad);
+/* `count` hyper-parameter vectors at once (thetas [count][n_dims + 2], lml [count], grad [count][n_dims + 2]): the
+ * evaluations run concurrently on separate streams, each bit-identical to a skb_fit_lml_host call.  Used to advance the
+ * L-BFGS-B restarts of one fit (sklearn _gpr.py:316-337 runs them one after the other) in lock step. */
+int skb_fit_lml_batch_host(skb_fit* fit, int32_t count, const double* thetas, int32_t want_grad, double* lml,
+                           double* grad);
 
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind

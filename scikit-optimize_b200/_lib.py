@@ -85,6 +85,7 @@ SYMBOLS = [
     ("skb_fit_create", C.c_int, [C.POINTER(FitDesc), C.c_int, C.POINTER(C.c_void_p)]),
     ("skb_fit_destroy", None, [C.c_void_p]),
     ("skb_fit_lml_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("skb_fit_lml_batch_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

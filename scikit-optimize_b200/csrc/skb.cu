@@ -1395,26 +1395,162 @@ int load_solver() {
     } while (0)
 }  // namespace
 
+// One evaluation in flight: its own stream, solver handle and n x n workspace, so that several hyper-parameter vectors
+// (the L-BFGS-B restarts of a fit advance in lock step) are evaluated concurrently - a single evaluation at n ~ 1000 is
+// a chain of ~100 small launches that leaves most SMs idle.
+struct FitSlot {
+    cudaStream_t stream = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    double *d_Xs = nullptr, *d_ls = nullptr, *d_K = nullptr, *d_a = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    double* d_work = nullptr;
+    int* d_info = nullptr;
+    double* h_pinned = nullptr;      // [MAX_DIMS] length scales in | [MAX_DIMS + 4] results out | 4 ints info
+    bool want_grad = false;
+};
+constexpr int FIT_MAX_SLOTS = 8;
+
 struct skb_fit {
     int device = 0, n = 0, d = 0, kernel = 0, n_blocks = 0, lwork = 0;
     double alpha = 0;
-    cudaStream_t stream = nullptr;
-    cusolverDnHandle_t solver = nullptr;
     std::vector<void*> ptrs;
-    double *d_X = nullptr, *d_y = nullptr, *d_Xs = nullptr, *d_ls = nullptr, *d_K = nullptr, *d_a = nullptr;
-    double *d_partial = nullptr, *d_out = nullptr, *d_work = nullptr;
-    int* d_info = nullptr;
+    double *d_X = nullptr, *d_y = nullptr;
+    std::vector<FitSlot> slots;
 };
+
+namespace {
+double* slot_h_ls(FitSlot& sl) { return sl.h_pinned; }
+double* slot_h_out(FitSlot& sl) { return sl.h_pinned + MAX_DIMS; }
+int* slot_h_info(FitSlot& sl) { return reinterpret_cast<int*>(sl.h_pinned + 2 * MAX_DIMS + 4); }
+
+int fit_alloc(skb_fit* f, double** ptr, size_t count) {
+    void* raw = nullptr;
+    int r = pool_alloc(f->device, &raw, count * sizeof(double));
+    if (r != SKB_OK) return r;
+    f->ptrs.push_back(raw);
+    *ptr = static_cast<double*>(raw);
+    return SKB_OK;
+}
+
+int fit_add_slot(skb_fit* f) {
+    f->slots.emplace_back();
+    FitSlot& sl = f->slots.back();
+    const size_t n = (size_t)f->n, d = (size_t)f->d;
+    CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    SOLVER(g_solver.create(&sl.solver));
+    SOLVER(g_solver.set_stream(sl.solver, sl.stream));
+    int r;
+    if ((r = fit_alloc(f, &sl.d_Xs, n * d)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_a, n)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_ls, d)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_K, n * n)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_out, d + 4)) != SKB_OK) return r;
+    if (f->lwork == 0) {
+        int lw1 = 0, lw2 = 0;
+        SOLVER(g_solver.potrf_size(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, sl.d_K, f->n, &lw1));
+        SOLVER(g_solver.potri_size(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, sl.d_K, f->n, &lw2));
+        f->lwork = std::max(std::max(lw1, lw2), 1);
+    }
+    if ((r = fit_alloc(f, &sl.d_work, (size_t)f->lwork)) != SKB_OK) return r;
+    double* info_raw = nullptr;
+    if ((r = fit_alloc(f, &info_raw, 4)) != SKB_OK) return r;
+    sl.d_info = reinterpret_cast<int*>(info_raw);
+    CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
+    return SKB_OK;
+}
+
+// queue one evaluation on the slot's stream; nothing here waits for the GPU
+int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
+    cudaStream_t s = sl.stream;
+    const int n = f->n, d = f->d;
+    const double amplitude = exp(theta[0]), noise = exp(theta[d + 1]);      // exp(-inf) = 0: no noise term
+    double* ls = slot_h_ls(sl);
+    for (int k = 0; k < d; ++k) ls[k] = exp(theta[1 + k]);
+    if (!(amplitude >= 0.0) || !(noise >= 0.0) || std::isinf(amplitude) || std::isinf(noise))
+        return fail(SKB_ERR_INVALID, "non-finite hyper-parameter");
+    sl.want_grad = want_grad;
+    CU(cudaMemcpyAsync(sl.d_ls, ls, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s));
+    fit_scale_kernel<<<(unsigned)(((size_t)n * d + 255) / 256), 256, 0, s>>>(f->d_X, sl.d_ls, sl.d_Xs, n, d);
+    LAUNCHED();
+    FitParams kp;
+    kp.Xs = sl.d_Xs;
+    kp.n = n;
+    kp.d = d;
+    kp.amplitude = amplitude;
+    kp.noise = noise;
+    kp.alpha = f->alpha;
+    kp.diag_add = noise + f->alpha;
+    kp.K = sl.d_K;
+    const int T = (n + FIT_TILE - 1) / FIT_TILE;
+    const size_t smem_k = 2 * (size_t)FIT_TILE * (d + 1) * sizeof(double);
+    switch (f->kernel) {
+        case SKB_KERNEL_RBF: fit_kbuild_kernel<0><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        case SKB_KERNEL_MATERN12: fit_kbuild_kernel<1><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        case SKB_KERNEL_MATERN32: fit_kbuild_kernel<2><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+        default: fit_kbuild_kernel<3><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
+    }
+    LAUNCHED();
+    CU(cudaMemsetAsync(sl.d_info, 0, 4 * sizeof(int), s));
+    // a failed factorisation (info > 0) is only looked at after the whole chain: the later steps then work on garbage
+    // but stay inside the workspace, and the result is replaced by (-inf, 0)
+    SOLVER(g_solver.potrf(sl.solver, CUBLAS_FILL_MODE_LOWER, n, sl.d_K, n, sl.d_work, f->lwork, sl.d_info));
+    CU(cudaMemcpyAsync(sl.d_a, f->d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SOLVER(g_solver.potrs(sl.solver, CUBLAS_FILL_MODE_LOWER, n, 1, sl.d_K, n, sl.d_a, n, sl.d_info + 1));
+    fit_lml_kernel<<<1, 256, 0, s>>>(sl.d_K, f->d_y, sl.d_a, n, sl.d_out);
+    LAUNCHED();
+    if (want_grad) {
+        SOLVER(g_solver.potri(sl.solver, CUBLAS_FILL_MODE_LOWER, n, sl.d_K, n, sl.d_work, f->lwork, sl.d_info + 2));
+        FitGradParams gp;
+        gp.Xs = sl.d_Xs;
+        gp.Kinv = sl.d_K;
+        gp.a = sl.d_a;
+        gp.n = n;
+        gp.d = d;
+        gp.amplitude = amplitude;
+        gp.noise = noise;
+        gp.partial = sl.d_partial;
+        const size_t smem_g = smem_k + 8 * (size_t)(d + 2) * sizeof(double);
+        switch (f->kernel) {
+            case SKB_KERNEL_RBF: fit_grad_kernel<0><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            case SKB_KERNEL_MATERN12: fit_grad_kernel<1><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            case SKB_KERNEL_MATERN32: fit_grad_kernel<2><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+            default: fit_grad_kernel<3><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+        }
+        LAUNCHED();
+        fit_grad_reduce_kernel<<<d + 2, 256, 0, s>>>(sl.d_partial, f->n_blocks, d + 2, sl.d_out + 1);
+        LAUNCHED();
+    }
+    CU(cudaMemcpyAsync(slot_h_out(sl), sl.d_out, (size_t)(want_grad ? d + 3 : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(slot_h_info(sl), sl.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return SKB_OK;
+}
+
+int fit_collect(skb_fit* f, FitSlot& sl, double* lml, double* grad) {
+    CU(cudaStreamSynchronize(sl.stream));
+    const int d = f->d;
+    if (*slot_h_info(sl) != 0) {           // not positive definite: sklearn returns -inf and a zero gradient (_gpr.py:586-589)
+        *lml = -INFINITY;
+        if (sl.want_grad) std::memset(grad, 0, (size_t)(d + 2) * sizeof(double));
+        return SKB_OK;
+    }
+    *lml = slot_h_out(sl)[0];
+    if (sl.want_grad) std::memcpy(grad, slot_h_out(sl) + 1, (size_t)(d + 2) * sizeof(double));
+    return SKB_OK;
+}
+}  // namespace
 
 extern "C" {
 
 void skb_fit_destroy(skb_fit* f) {
     if (!f) return;
     cudaSetDevice(f->device);
-    if (f->stream) cudaStreamSynchronize(f->stream);
-    if (f->solver && g_solver.ok) g_solver.destroy(f->solver);
+    for (FitSlot& sl : f->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.solver && g_solver.ok) g_solver.destroy(sl.solver);
+        if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     for (void* p : f->ptrs) pool_free(f->device, p);
-    if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
 }
 
@@ -1438,39 +1574,17 @@ int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out) {
     f->alpha = desc->alpha;
     const int T = (f->n + FIT_TILE - 1) / FIT_TILE;
     f->n_blocks = T * (T + 1) / 2;
+    f->slots.reserve(FIT_MAX_SLOTS);
     auto body = [&]() -> int {
-        CU(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-        SOLVER(g_solver.create(&f->solver));
-        SOLVER(g_solver.set_stream(f->solver, f->stream));
         const size_t n = (size_t)f->n, d = (size_t)f->d;
-        auto alloc = [&](double** ptr, size_t count) -> int {
-            void* raw = nullptr;
-            int r = pool_alloc(f->device, &raw, count * sizeof(double));
-            if (r != SKB_OK) return r;
-            f->ptrs.push_back(raw);
-            *ptr = static_cast<double*>(raw);
-            return SKB_OK;
-        };
         int r;
-        if ((r = alloc(&f->d_X, n * d)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_Xs, n * d)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_y, n)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_a, n)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_ls, d)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_K, n * n)) != SKB_OK) return r;
-        if ((r = alloc(&f->d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
-        if ((r = alloc(&f->d_out, d + 4)) != SKB_OK) return r;
-        int lw1 = 0, lw2 = 0;
-        SOLVER(g_solver.potrf_size(f->solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_K, f->n, &lw1));
-        SOLVER(g_solver.potri_size(f->solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_K, f->n, &lw2));
-        f->lwork = std::max(std::max(lw1, lw2), 1);
-        if ((r = alloc(&f->d_work, (size_t)f->lwork)) != SKB_OK) return r;
-        double* info_raw = nullptr;
-        if ((r = alloc(&info_raw, 4)) != SKB_OK) return r;
-        f->d_info = reinterpret_cast<int*>(info_raw);
-        CU(cudaMemcpyAsync(f->d_X, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-        CU(cudaMemcpyAsync(f->d_y, desc->y_train, n * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-        CU(cudaStreamSynchronize(f->stream));
+        if ((r = fit_alloc(f, &f->d_X, n * d)) != SKB_OK) return r;
+        if ((r = fit_alloc(f, &f->d_y, n)) != SKB_OK) return r;
+        if ((r = fit_add_slot(f)) != SKB_OK) return r;
+        cudaStream_t s = f->slots[0].stream;
+        CU(cudaMemcpyAsync(f->d_X, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(f->d_y, desc->y_train, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
         return SKB_OK;
     };
     rc = body();
@@ -1482,79 +1596,31 @@ int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out) {
     return SKB_OK;
 }
 
-int skb_fit_lml_host(skb_fit* f, const double* theta, int32_t want_grad, double* lml, double* grad) {
-    if (!f || !theta || !lml || (want_grad && !grad)) return fail(SKB_ERR_INVALID, "NULL argument");
+int skb_fit_lml_batch_host(skb_fit* f, int32_t count, const double* thetas, int32_t want_grad, double* lml, double* grad) {
+    if (!f || count < 0 || (count > 0 && (!thetas || !lml || (want_grad && !grad)))) return fail(SKB_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(f->device));
-    cudaStream_t s = f->stream;
-    const int n = f->n, d = f->d;
-    double ls[MAX_DIMS];
-    const double amplitude = exp(theta[0]), noise = exp(theta[d + 1]);      // exp(-inf) = 0: no noise term
-    for (int k = 0; k < d; ++k) ls[k] = exp(theta[1 + k]);
-    if (!(amplitude >= 0.0) || !(noise >= 0.0) || std::isinf(amplitude) || std::isinf(noise))
-        return fail(SKB_ERR_INVALID, "non-finite hyper-parameter");
-    CU(cudaMemcpyAsync(f->d_ls, ls, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s));
-    fit_scale_kernel<<<(unsigned)(((size_t)n * d + 255) / 256), 256, 0, s>>>(f->d_X, f->d_ls, f->d_Xs, n, d);
-    LAUNCHED();
-    FitParams kp;
-    kp.Xs = f->d_Xs;
-    kp.n = n;
-    kp.d = d;
-    kp.amplitude = amplitude;
-    kp.noise = noise;
-    kp.alpha = f->alpha;
-    kp.diag_add = noise + f->alpha;
-    kp.K = f->d_K;
-    const int T = (n + FIT_TILE - 1) / FIT_TILE;
-    const size_t smem_k = 2 * (size_t)FIT_TILE * (d + 1) * sizeof(double);
-    switch (f->kernel) {
-        case SKB_KERNEL_RBF: fit_kbuild_kernel<0><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
-        case SKB_KERNEL_MATERN12: fit_kbuild_kernel<1><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
-        case SKB_KERNEL_MATERN32: fit_kbuild_kernel<2><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
-        default: fit_kbuild_kernel<3><<<dim3(T, T), FIT_THREADS, smem_k, s>>>(kp); break;
-    }
-    LAUNCHED();
-    CU(cudaMemsetAsync(f->d_info, 0, 4 * sizeof(int), s));
-    SOLVER(g_solver.potrf(f->solver, CUBLAS_FILL_MODE_LOWER, n, f->d_K, n, f->d_work, f->lwork, f->d_info));
-    int info = 0;
-    CU(cudaMemcpyAsync(&info, f->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (info != 0) {                       // not positive definite: sklearn returns -inf and a zero gradient (_gpr.py:586-589)
-        *lml = -INFINITY;
-        if (want_grad) std::memset(grad, 0, (size_t)(d + 2) * sizeof(double));
-        return SKB_OK;
-    }
-    CU(cudaMemcpyAsync(f->d_a, f->d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SOLVER(g_solver.potrs(f->solver, CUBLAS_FILL_MODE_LOWER, n, 1, f->d_K, n, f->d_a, n, f->d_info + 1));
-    fit_lml_kernel<<<1, 256, 0, s>>>(f->d_K, f->d_y, f->d_a, n, f->d_out);
-    LAUNCHED();
-    if (want_grad) {
-        SOLVER(g_solver.potri(f->solver, CUBLAS_FILL_MODE_LOWER, n, f->d_K, n, f->d_work, f->lwork, f->d_info + 2));
-        FitGradParams gp;
-        gp.Xs = f->d_Xs;
-        gp.Kinv = f->d_K;
-        gp.a = f->d_a;
-        gp.n = n;
-        gp.d = d;
-        gp.amplitude = amplitude;
-        gp.noise = noise;
-        gp.partial = f->d_partial;
-        const size_t smem_g = smem_k + 8 * (size_t)(d + 2) * sizeof(double);
-        switch (f->kernel) {
-            case SKB_KERNEL_RBF: fit_grad_kernel<0><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
-            case SKB_KERNEL_MATERN12: fit_grad_kernel<1><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
-            case SKB_KERNEL_MATERN32: fit_grad_kernel<2><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
-            default: fit_grad_kernel<3><<<f->n_blocks, FIT_THREADS, smem_g, s>>>(gp); break;
+    const int stride = f->d + 2;
+    for (int base = 0; base < count; base += FIT_MAX_SLOTS) {
+        const int group = std::min(FIT_MAX_SLOTS, count - base);
+        while ((int)f->slots.size() < group) {
+            int rc = fit_add_slot(f);
+            if (rc != SKB_OK) return rc;
         }
-        LAUNCHED();
-        fit_grad_reduce_kernel<<<d + 2, 256, 0, s>>>(f->d_partial, f->n_blocks, d + 2, f->d_out + 1);
-        LAUNCHED();
+        int rc = SKB_OK;
+        int issued = 0;
+        for (; issued < group; ++issued)
+            if ((rc = fit_issue(f, f->slots[issued], thetas + (size_t)(base + issued) * stride, want_grad != 0)) != SKB_OK) break;
+        for (int i = 0; i < issued; ++i) {
+            int rc2 = fit_collect(f, f->slots[i], lml + base + i, want_grad ? grad + (size_t)(base + i) * stride : nullptr);
+            if (rc == SKB_OK) rc = rc2;
+        }
+        if (rc != SKB_OK) return rc;
     }
-    double host_out[MAX_DIMS + 4];
-    CU(cudaMemcpyAsync(host_out, f->d_out, (size_t)(want_grad ? d + 3 : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    *lml = host_out[0];
-    if (want_grad) std::memcpy(grad, host_out + 1, (size_t)(d + 2) * sizeof(double));
     return SKB_OK;
+}
+
+int skb_fit_lml_host(skb_fit* f, const double* theta, int32_t want_grad, double* lml, double* grad) {
+    return skb_fit_lml_batch_host(f, 1, theta, want_grad, lml, grad);
 }
 
 }  // extern "C"

@@ -468,6 +468,20 @@ class DeviceFit:
         self.n_evals += 1
         return (value.value, grad) if eval_gradient else value.value
 
+    def lml_batch(self, thetas_full):
+        """Values and gradients for several hyper-parameter vectors, evaluated concurrently on the GPU; row i is
+        bit-identical to lml(thetas_full[i])."""
+        thetas_full = np.ascontiguousarray(thetas_full, dtype=np.float64)
+        if thetas_full.ndim != 2 or thetas_full.shape[1] != self.X.shape[1] + 2:
+            raise ValueError("thetas_full must have shape (count, n_dims + 2)")
+        count = thetas_full.shape[0]
+        values = np.empty(count)
+        grads = np.zeros_like(thetas_full)
+        _lib.check(_lib.lib().skb_fit_lml_batch_host(self._h, count, thetas_full.ctypes.data, 1, values.ctypes.data,
+                                                     grads.ctypes.data))
+        self.n_evals += count
+        return values, grads
+
     def close(self):
         if self._h is not None and self._h.value:
             _lib.lib().skb_fit_destroy(self._h)

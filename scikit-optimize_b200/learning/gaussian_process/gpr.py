@@ -63,20 +63,20 @@ class GaussianProcessRegressor(_SkGPR):
         state = dict(state)
         state.pop("_skb_device_state", None)
         state.pop("_skb_device_fit", None)
+        state.pop("_skb_lockstep", None)
         return state
 
     def _close_device_fit(self):
         cached = self.__dict__.pop("_skb_device_fit", None)
-        if cached is not None:
+        self.__dict__.pop("_skb_lockstep", None)
+        if cached is not None and cached[1] is not None:
             cached[1].close()
 
-    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
-        """sklearn _gpr.py:541-657.  With the fit device set to "gpu" (set_fit_device / `_skb_fit_device`) and a kernel
-        of the form [Constant *] {RBF | Matern} [+ White], the value and gradient come from the GPU objective; any
-        other kernel, multi-output targets or an array-valued alpha use scikit-learn's host code."""
+    def _device_fit(self):
+        """(DeviceFit, FitLayout) for the current training set when the fit objective runs on the GPU, else None."""
         where = self.__dict__.get("_skb_fit_device", _FIT_DEVICE[0])
-        if theta is None or where != "gpu" or np.ndim(self.alpha) != 0 or np.ndim(self.y_train_) != 1:
-            return super().log_marginal_likelihood(theta, eval_gradient=eval_gradient, clone_kernel=clone_kernel)
+        if where != "gpu" or np.ndim(self.alpha) != 0 or np.ndim(self.y_train_) != 1:
+            return None
         cached = self.__dict__.get("_skb_device_fit")
         if cached is None or cached[0] is not self.X_train_:
             self._close_device_fit()
@@ -88,15 +88,62 @@ class GaussianProcessRegressor(_SkGPR):
                                                                _DEFAULT_DEVICE[0])
             cached = (self.X_train_, fit, layout)
             self.__dict__["_skb_device_fit"] = cached
-        _, fit, layout = cached
-        if fit is None:
+            self.__dict__.pop("_skb_lockstep", None)
+        return None if cached[1] is None else (cached[1], cached[2])
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """sklearn _gpr.py:541-657.  With the fit device set to "gpu" (set_fit_device / `_skb_fit_device`) and a kernel
+        of the form [Constant *] {RBF | Matern} [+ White], the value and gradient come from the GPU objective; any
+        other kernel, multi-output targets or an array-valued alpha use scikit-learn's host code."""
+        dev = None if theta is None else self._device_fit()
+        if dev is None:
             return super().log_marginal_likelihood(theta, eval_gradient=eval_gradient, clone_kernel=clone_kernel)
+        fit, layout = dev
         if not clone_kernel:
             self.kernel_.theta = theta              # the side effect sklearn's fit relies on (_gpr.py:568-572)
         out = fit.lml(layout.expand(theta), eval_gradient=eval_gradient)
         if eval_gradient:
             return out[0], layout.select(out[1])
         return out
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        """sklearn _gpr.py:658-677.  scikit-learn runs the L-BFGS-B search from the kernel's theta and then from
+        `n_restarts_optimizer` random starts, one after the other (_gpr.py:316-337).  With the GPU objective all starts
+        advance in lock step instead: the random starts are pre-drawn from a COPY of the estimator's generator (the
+        draws do not depend on the search results, so scikit-learn later draws the very same vectors), every round
+        evaluates the pending points of all searches concurrently (skb_fit_lml_batch_host), and each call returns its
+        search's result.  Each search sees exactly the iterates it would see alone (optimizer/lbfgs.py)."""
+        dev = self._device_fit() if self.optimizer == "fmin_l_bfgs_b" else None
+        if dev is None:
+            return super()._constrained_optimization(obj_func, initial_theta, bounds)
+        fit, layout = dev
+        cache = self.__dict__.get("_skb_lockstep")
+        if cache is None:
+            import copy
+
+            from ...optimizer.lbfgs import minimize_batch
+            rng = copy.deepcopy(self._rng)
+            starts = [np.array(initial_theta, dtype=np.float64)]
+            if np.isfinite(bounds).all():
+                starts += [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(self.n_restarts_optimizer)]
+
+            def evaluate(tasks, thetas):
+                values, grads = fit.lml_batch(np.array([layout.expand(t) for t in thetas]))
+                return -values, -np.array([layout.select(g) for g in grads])
+
+            results = minimize_batch(starts, evaluate, [tuple(b) for b in bounds], maxiter=15000)
+            cache = {"starts": starts, "results": results, "next": 0}
+            self.__dict__["_skb_lockstep"] = cache
+        i = cache["next"]
+        cache["next"] += 1
+        if i >= len(cache["starts"]) or not np.array_equal(cache["starts"][i], initial_theta):
+            return super()._constrained_optimization(obj_func, initial_theta, bounds)      # not the sequence fit() issues
+        theta_opt, func_min, info = cache["results"][i]
+        if info["warnflag"] != 0:
+            from sklearn.exceptions import ConvergenceWarning
+            warnings.warn("lbfgs failed to converge after %d iteration(s) (warnflag=%d)." % (info["nit"], info["warnflag"]),
+                          ConvergenceWarning)
+        return theta_opt, func_min
 
     def fit(self, X, y):
         """gpr.py:166-237: add the noise kernel, fit with scikit-learn, silence the noise for prediction,

@@ -43,3 +43,67 @@ def test_fit_layout_orders_and_fixed_parameters():
         FitLayout(k + ConstantKernel(1.0), d)
     with pytest.raises(NotImplementedError):
         FitLayout(RBF(1.0) * RBF(2.0), d)
+
+
+class _OracleFit:
+    """Stand-in for engine.DeviceFit (same interface) that evaluates the objective with the CPU oracle: lets the
+    lock-step restart logic of GaussianProcessRegressor.fit run without a GPU."""
+
+    def __init__(self, X, y, nu):
+        self.X, self.y, self.nu, self.batches = X, y, nu, []
+
+    def lml(self, theta_full, eval_gradient=True):
+        v, g = orc.log_marginal_likelihood(self.X, self.y, self.nu, theta_full, 1e-10)
+        return (v, g) if eval_gradient else v
+
+    def lml_batch(self, thetas_full):
+        self.batches.append(len(thetas_full))
+        out = [self.lml(t) for t in thetas_full]
+        return np.array([o[0] for o in out]), np.array([o[1] for o in out])
+
+    def close(self):
+        pass
+
+
+def test_lockstep_restarts_equal_sequential_restarts(monkeypatch):
+    """fit() with the device objective advances all L-BFGS-B restarts in lock step; the result must be bit-identical
+    to scikit-learn's one-after-the-other loop over the same objective, and the estimator's RNG must end in the same
+    state."""
+    from sklearn.gaussian_process import GaussianProcessRegressor as SkGPR
+    from skopt_b200 import engine
+    from skopt_b200.learning import GaussianProcessRegressor
+
+    rng = np.random.RandomState(2)
+    X = rng.rand(40, 2)
+    y = np.sin(4 * X[:, 0]) + X[:, 1] + 0.05 * rng.randn(40)
+    kernel = ConstantKernel(1.0, (0.01, 1000.0)) * Matern(length_scale=[1.0, 1.0], length_scale_bounds=[(0.01, 100)] * 2,
+                                                            nu=2.5) + WhiteKernel(1.0, (1e-5, 1e5))
+    fakes = []
+
+    def fake_device_fit(self):
+        cached = self.__dict__.get("_skb_device_fit")
+        if cached is None or cached[0] is not self.X_train_:
+            fakes.append(_OracleFit(self.X_train_, self.y_train_, 2.5))
+            cached = (self.X_train_, fakes[-1], engine.FitLayout(self.kernel_, 2))
+            self.__dict__["_skb_device_fit"] = cached
+            self.__dict__.pop("_skb_lockstep", None)
+        return cached[1], cached[2]
+
+    monkeypatch.setattr(GaussianProcessRegressor, "_device_fit", fake_device_fit)
+
+    class Sequential(GaussianProcessRegressor):          # same objective, scikit-learn's own restart loop
+        def _constrained_optimization(self, obj_func, initial_theta, bounds):
+            return SkGPR._constrained_optimization(self, obj_func, initial_theta, bounds)
+
+    a = GaussianProcessRegressor(kernel=kernel, normalize_y=True, n_restarts_optimizer=3, random_state=5).fit(X, y)
+    assert max(fakes[-1].batches) == 4 and len(fakes[-1].batches) > 5          # four searches really ran together
+    b = Sequential(kernel=kernel, normalize_y=True, n_restarts_optimizer=3, random_state=5).fit(X, y)
+    np.testing.assert_array_equal(a.kernel_.theta, b.kernel_.theta)
+    assert a.log_marginal_likelihood_value_ == b.log_marginal_likelihood_value_
+    np.testing.assert_array_equal(a.alpha_, b.alpha_)
+    assert a._rng.get_state()[2] == b._rng.get_state()[2]
+    np.testing.assert_array_equal(a._rng.get_state()[1], b._rng.get_state()[1])
+    # and both sit at scikit-learn's host optimum up to the optimiser's tolerance
+    monkeypatch.undo()
+    c = GaussianProcessRegressor(kernel=kernel, normalize_y=True, n_restarts_optimizer=3, random_state=5).fit(X, y)
+    assert abs(a.log_marginal_likelihood_value_ - c.log_marginal_likelihood_value_) <= 1e-6 * abs(c.log_marginal_likelihood_value_)

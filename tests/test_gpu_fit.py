@@ -100,3 +100,21 @@ def test_optimizer_with_gpu_fit():
     assert min(runs["gpu"].yi) <= 0.5
     with pytest.raises(ValueError):
         Optimizer([(-2.0, 2.0)], "GP", acq_optimizer_kwargs=dict(fit_device="tpu"))
+
+
+def test_batched_evaluations_are_bit_identical_to_single_ones():
+    from skopt_b200.engine import DeviceFit
+    rng = np.random.RandomState(0)
+    n, d = 300, 6
+    X = rng.rand(n, d)
+    y = np.sin(X.dot(rng.randn(d)))
+    y = (y - y.mean()) / y.std()
+    fit = DeviceFit(X, y, 3, 1e-10)
+    thetas = np.concatenate([rng.randn(11, 1), 0.5 * rng.randn(11, d), np.log(0.01) + rng.randn(11, 1)], axis=1)
+    thetas[4, -1] = -np.inf                                  # no noise, alpha only
+    values, grads = fit.lml_batch(thetas)                    # 11 > 8 slots: two groups
+    for i, th in enumerate(thetas):
+        v, g = fit.lml(th)
+        assert v == values[i]
+        np.testing.assert_array_equal(g, grads[i])
+    fit.close()
