@@ -1408,6 +1408,9 @@ struct FitSlot {
     bool want_grad = false;
 };
 constexpr int FIT_MAX_SLOTS = 8;
+struct SolverCtx { cudaStream_t stream; cusolverDnHandle_t solver; double* h_pinned; };
+static std::vector<SolverCtx> g_ctx_cache[64];
+static std::mutex g_ctx_mu;
 
 struct skb_fit {
     int device = 0, n = 0, d = 0, kernel = 0, n_blocks = 0, lwork = 0;
@@ -1435,9 +1438,24 @@ int fit_add_slot(skb_fit* f) {
     f->slots.emplace_back();
     FitSlot& sl = f->slots.back();
     const size_t n = (size_t)f->n, d = (size_t)f->d;
-    CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    SOLVER(g_solver.create(&sl.solver));
-    SOLVER(g_solver.set_stream(sl.solver, sl.stream));
+    {
+        // stream + solver handle + pinned staging are recycled across fits: creating / destroying a cuSOLVER handle
+        // costs tens of milliseconds, a BO loop builds one skb_fit per tell()
+        std::lock_guard<std::mutex> lock(g_ctx_mu);
+        std::vector<SolverCtx>& cache = g_ctx_cache[f->device & 63];
+        if (!cache.empty()) {
+            sl.stream = cache.back().stream;
+            sl.solver = cache.back().solver;
+            sl.h_pinned = cache.back().h_pinned;
+            cache.pop_back();
+        }
+    }
+    if (!sl.stream) {
+        CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        SOLVER(g_solver.create(&sl.solver));
+        SOLVER(g_solver.set_stream(sl.solver, sl.stream));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
+    }
     int r;
     if ((r = fit_alloc(f, &sl.d_Xs, n * d)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_a, n)) != SKB_OK) return r;
@@ -1455,7 +1473,6 @@ int fit_add_slot(skb_fit* f) {
     double* info_raw = nullptr;
     if ((r = fit_alloc(f, &info_raw, 4)) != SKB_OK) return r;
     sl.d_info = reinterpret_cast<int*>(info_raw);
-    CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
     return SKB_OK;
 }
 
@@ -1546,6 +1563,11 @@ void skb_fit_destroy(skb_fit* f) {
     cudaSetDevice(f->device);
     for (FitSlot& sl : f->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.stream && sl.solver && sl.h_pinned) {
+            std::lock_guard<std::mutex> lock(g_ctx_mu);
+            g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.solver, sl.h_pinned});
+            continue;
+        }
         if (sl.solver && g_solver.ok) g_solver.destroy(sl.solver);
         if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
         if (sl.stream) cudaStreamDestroy(sl.stream);

@@ -200,7 +200,7 @@ class Optimizer(object):
         if not self.models:
             raise RuntimeError("Random evaluations exhausted and no model has been fit.")
         next_x = self._next_x
-        min_delta_x = min([self.space.distance(next_x, xi) for xi in self.Xi])
+        min_delta_x = self.space.min_distance(next_x, self.Xi)
         if abs(min_delta_x) <= 1e-8:
             warnings.warn("The objective has been evaluated at this point before.")
         return next_x

@@ -478,6 +478,29 @@ class Space(object):
     def distance(self, point_a, point_b):
         return sum(dim.distance(a, b) for a, b, dim in zip(point_a, point_b, self.dimensions))
 
+    def min_distance(self, point, points):
+        """min(self.distance(point, p) for p in points) (the duplicate check of Optimizer._ask, optimizer.py:350-353),
+        one NumPy pass per dimension instead of one Python call per (point, dimension): the per-point sums accumulate
+        in dimension order like the reference's sum(), so the result is the same float."""
+        if len(points) == 0:
+            raise ValueError("min_distance needs at least one point")
+        if point not in self or len(point) != len(self.dimensions):
+            return min(self.distance(point, p) for p in points)          # raises the reference's error
+        acc = 0
+        for j, dim in enumerate(self.dimensions):
+            col = [p[j] for p in points]
+            if isinstance(dim, Categorical):
+                if not all(v in dim for v in col):
+                    return min(self.distance(point, p) for p in points)
+                term = np.fromiter((1 if v != point[j] else 0 for v in col), dtype=np.int64, count=len(col))
+            else:
+                arr = np.asarray(col)
+                if arr.dtype == object or not np.all((arr >= dim.low) & (arr <= dim.high)):
+                    return min(self.distance(point, p) for p in points)
+                term = np.abs(point[j] - arr)
+            acc = acc + term
+        return acc.min()
+
     # ------------------------------------------------------------------ sampling and warping
     def rvs(self, n_samples=1, random_state=None):
         """Points in the ORIGINAL space as a list of lists (space.py:874-903): one draw per dimension, in order."""

@@ -56,3 +56,22 @@ def test_dimension_dispatch_and_validation():
     assert sp.distance([0.25, 1], [0.75, 3]) == 2.5
     with pytest.raises(ValueError):
         normalize_dimensions([(0.0, 1.0)]).transform([[1.5]])
+
+
+def test_min_distance_equals_reference_loop():
+    """Space.min_distance (used by Optimizer._ask) returns exactly min(space.distance(x, p) for p in points)."""
+    from skopt_b200.space import Categorical, Integer, Real, Space
+    rng = np.random.RandomState(0)
+    for dims in ([Real(-3.0, 5.0), Real(1e-3, 10.0, prior="log-uniform"), Real(0.0, 1.0)],
+                 [Integer(-5, 50), Real(0.0, 2.0), Categorical(["a", "b", "c"]), Integer(0, 3)]):
+        space = Space(dims)
+        pts = space.rvs(200, random_state=rng)
+        for x in space.rvs(5, random_state=rng) + [pts[17]]:
+            ref = min(space.distance(x, p) for p in pts)
+            got = space.min_distance(x, pts)
+            assert got == ref and type(float(got)) is float
+    space = Space([Real(0.0, 1.0)])
+    with pytest.raises(RuntimeError):
+        space.min_distance([0.5], [[2.0]])
+    with pytest.raises(RuntimeError):
+        space.min_distance([3.0], [[0.5]])
