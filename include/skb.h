@@ -34,7 +34,8 @@ typedef enum {
     SKB_ERR_UNSUPPORTED = -2,   /* outside the supported grammar / size limits */
     SKB_ERR_NO_DEVICE = -3,     /* no CUDA device, or not sm_100 */
     SKB_ERR_CUDA = -4,          /* a CUDA runtime call failed; see skb_last_error() */
-    SKB_ERR_NOMEM = -5
+    SKB_ERR_NOMEM = -5,
+    SKB_ERR_NOT_POSDEF = -6     /* skb_fit_finalize_host: K(theta) has no Cholesky factor */
 } skb_status;
 
 /* Stationary base kernels of the hot path: sklearn RBF.__call__ (sklearn kernels.py:1558-1570) and
@@ -226,6 +227,19 @@ int skb_fit_lml_host(skb_fit* fit, const double* theta, int32_t want_grad, doubl
  * L-BFGS-B restarts of one fit (sklearn _gpr.py:316-337 runs them one after the other) in lock step. */
 int skb_fit_lml_batch_host(skb_fit* fit, int32_t count, const double* thetas, int32_t want_grad, double* lml,
                            double* grad);
+/* End of the search: factorise K(theta*) once more on the device and hand back what `fit` stores on the estimator.
+ * Replaces the tail of sklearn's fit (_gpr.py:341-367: K = kernel_(X_train_) + alpha I, L_ = cholesky(K),
+ * alpha_ = cho_solve(L_, y_train_)).  lml [1], alpha_out [n_train] and L_out [n_train * n_train] (row-major, lower
+ * triangular, zeros above the diagonal like SciPy's) are host arrays; L_out may be NULL.  Returns SKB_ERR_NOT_POSDEF when
+ * K is not positive definite (the reference raises LinAlgError there).  The factor stays on the device for
+ * skb_state_create_from_fit. */
+int skb_fit_finalize_host(skb_fit* fit, const double* theta, double* lml, double* alpha_out, double* L_out);
+/* Scoring state straight from the finalised fit: replaces skopt gpr.py:223-224 (L_inv, K_inv_ = L_inv^T L_inv on the
+ * host) and the upload of skb_state_create - the triangular inverse (cuSOLVER trtri), K^-1 (potri) and their packed
+ * FP64 tiles / digit planes are produced on the device from the resident factor, X_train and alpha.  `desc` supplies
+ * the scalars and length_scale of the PREDICTION kernel (after skopt silenced the noise term, gpr.py:199-220);
+ * its X_train / alpha / L_inv / K_inv pointers are ignored.  Requires a successful skb_fit_finalize_host. */
+int skb_state_create_from_fit(skb_fit* fit, const skb_state_desc* desc, skb_state** out);
 
 /* Per-kernel device timing for roofline reports.  When enabled, every launch group is bracketed by CUDA events on
  * the launching stream.  skb_state_get_timing waits for them, sums the elapsed milliseconds per kind

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libskb.so")
 
 SKB_OK = 0
+SKB_ERR_NOT_POSDEF = -6
 KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
 ACQ_EI, ACQ_PI, ACQ_LCB = 0, 1, 2
 ACQ_INDEX = {"EI": ACQ_EI, "PI": ACQ_PI, "LCB": ACQ_LCB}
@@ -86,6 +87,8 @@ SYMBOLS = [
     ("skb_fit_destroy", None, [C.c_void_p]),
     ("skb_fit_lml_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_fit_lml_batch_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("skb_fit_finalize_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("skb_state_create_from_fit", C.c_int, [C.c_void_p, C.POINTER(StateDesc), C.POINTER(C.c_void_p)]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

@@ -210,4 +210,50 @@ __global__ void fit_grad_reduce_kernel(const double* __restrict__ partial, int n
     if (threadIdx.x == 0) grad[k] = 0.5 * red[0];
 }
 
+// cuSOLVER works on column-major lower triangles; the rest of this library reads row-major matrices.  `src` holds the
+// lower triangle of an n x n matrix in column-major order (entry (i, j), i >= j, at src[j * n + i]; the other triangle
+// is stale).  SYMMETRIC = false: dst = that triangular matrix, row-major, zeros above the diagonal (L_, L^-1).
+// SYMMETRIC = true: dst = the full symmetric matrix (K^-1 after potri).  32 x 32 tiles through shared memory so that
+// both the reads and the writes are coalesced.
+template <bool SYMMETRIC>
+__global__ void __launch_bounds__(256) fit_unpack_lower_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;             // destination tile: rows bi*32.., columns bj*32..
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool mirror = bj > bi;                            // tile lies above the diagonal
+    if (mirror && !SYMMETRIC) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = bi * 32 + ty + 8 * q, j = bj * 32 + tx;
+            if (i < n && j < n) dst[(size_t)i * n + j] = 0.0;
+        }
+        return;
+    }
+    if (!mirror) {
+        // dst(i, j) = src[j * n + i]: read with i fastest, transpose through the tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = bj * 32 + ty + 8 * q, i = bi * 32 + tx;
+            tile[ty + 8 * q][tx] = (i < n && j < n) ? src[(size_t)j * n + i] : 0.0;        // tile[j_local][i_local]
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int il = ty + 8 * q, jl = tx;
+            const int i = bi * 32 + il, j = bj * 32 + jl;
+            if (i >= n || j >= n) continue;
+            double v = tile[jl][il];
+            if (j > i) v = SYMMETRIC ? tile[il][jl] : 0.0;  // only on diagonal tiles: (j, i) is in the same tile
+            dst[(size_t)i * n + j] = v;
+        }
+        return;
+    }
+    // SYMMETRIC and above the diagonal: dst(i, j) = M(j, i) = src[i * n + j] - a straight copy of the stored triangle
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = bi * 32 + ty + 8 * q, j = bj * 32 + tx;
+        if (i < n && j < n) dst[(size_t)i * n + j] = src[(size_t)i * n + j];
+    }
+}
+
 }  // namespace skb

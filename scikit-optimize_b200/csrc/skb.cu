@@ -387,7 +387,12 @@ void skb_state_destroy(skb_state* st) {
     delete st;
 }
 
-int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
+}  // extern "C"
+
+// `kind` = cudaMemcpyHostToDevice for caller-owned host arrays (skb_state_create) or cudaMemcpyDeviceToDevice when
+// X_train / alpha / L_inv / K_inv of `desc` already live on `device` (skb_state_create_from_fit)
+static int attach_kinv_impl(skb_state* st, const double* K_inv, cudaMemcpyKind kind);
+static int state_create_impl(const skb_state_desc* desc, int device, skb_state** out, cudaMemcpyKind kind) {
     if (!desc || !out) return fail(SKB_ERR_INVALID, "desc/out is NULL");
     *out = nullptr;
     if (desc->n_train <= 0 || desc->n_dims <= 0) return fail(SKB_ERR_INVALID, "n_train and n_dims must be positive");
@@ -447,10 +452,10 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
         SKB_PALLOC(dX, n * d * sizeof(double));
         SKB_PALLOC(dV, n * n * sizeof(double));
         CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-        CU(cudaMemcpyAsync(dX, desc->X_train, n * d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-        CU(cudaMemcpyAsync(dV, desc->L_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemcpyAsync(dX, desc->X_train, n * d * sizeof(double), kind, st->stream));
+        CU(cudaMemcpyAsync(dV, desc->L_inv, n * n * sizeof(double), kind, st->stream));
         CU(cudaMemsetAsync(st->d_alpha_p, 0, (size_t)st->n_pad * sizeof(double), st->stream));
-        CU(cudaMemcpyAsync(st->d_alpha_p, desc->alpha, n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemcpyAsync(st->d_alpha_p, desc->alpha, n * sizeof(double), kind, st->stream));
         pack_xtrain_kernel<<<std::min(1024, (st->n_pad * st->d_pad + 255) / 256), 256, 0, st->stream>>>(
             dX, st->d_ls, st->d_Xp, st->n, st->n_pad, st->d, st->d_pad);
         LAUNCHED();
@@ -471,7 +476,7 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
     rc = body();
     pool_free(device, dX);
     pool_free(device, dV);
-    if (rc == SKB_OK && desc->K_inv) rc = skb_state_attach_kinv(st, desc->K_inv);
+    if (rc == SKB_OK && desc->K_inv) rc = attach_kinv_impl(st, desc->K_inv, kind);
     if (rc != SKB_OK) {
         skb_state_destroy(st);
         return rc;
@@ -480,7 +485,17 @@ int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
     return SKB_OK;
 }
 
-int skb_state_attach_kinv(skb_state* st, const double* K_inv) {
+extern "C" {
+
+int skb_state_create(const skb_state_desc* desc, int device, skb_state** out) {
+    return state_create_impl(desc, device, out, cudaMemcpyHostToDevice);
+}
+
+int skb_state_attach_kinv(skb_state* st, const double* K_inv) { return attach_kinv_impl(st, K_inv, cudaMemcpyHostToDevice); }
+
+}  // extern "C"
+
+static int attach_kinv_impl(skb_state* st, const double* K_inv, cudaMemcpyKind kind) {
     if (!st || !K_inv) return fail(SKB_ERR_INVALID, "state/K_inv is NULL");
     if (st->d_Ap) return SKB_OK;                      // already attached
     CU(cudaSetDevice(st->device));
@@ -496,7 +511,7 @@ int skb_state_attach_kinv(skb_state* st, const double* K_inv) {
         SKB_PALLOC(st->d_sA, (size_t)st->n_pad * sizeof(double));
         SKB_PALLOC(st->d_Ad, (size_t)nI * (st->n_pad / OZ_KC) * OZ_A_CHUNK);
 #undef SKB_PALLOC
-        CU(cudaMemcpyAsync(dK, K_inv, n * n * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        CU(cudaMemcpyAsync(dK, K_inv, n * n * sizeof(double), kind, st->stream));
         pack_dense_kernel<<<dim3(st->n_pad / BK, nI), 256, 0, st->stream>>>(dK, st->d_Ap, st->n, st->n_pad);
         LAUNCHED();
         oz_row_scale_kernel<true><<<st->n_pad, 256, 0, st->stream>>>(dK, st->d_sA, st->n, st->n_pad);
@@ -518,6 +533,8 @@ int skb_state_attach_kinv(skb_state* st, const double* K_inv) {
     }
     return rc;
 }
+
+extern "C" {
 
 void* skb_state_stream(skb_state* st) { return st ? (void*)st->stream : nullptr; }
 
@@ -1358,6 +1375,8 @@ struct SolverApi {
     decltype(&cusolverDnDpotrs) potrs = nullptr;
     decltype(&cusolverDnDpotri_bufferSize) potri_size = nullptr;
     decltype(&cusolverDnDpotri) potri = nullptr;
+    decltype(&cusolverDnXtrtri_bufferSize) trtri_size = nullptr;
+    decltype(&cusolverDnXtrtri) trtri = nullptr;
     bool ok = false;
 };
 SolverApi g_solver;
@@ -1383,6 +1402,8 @@ int load_solver() {
     SKB_SYM(potrs, "cusolverDnDpotrs");
     SKB_SYM(potri_size, "cusolverDnDpotri_bufferSize");
     SKB_SYM(potri, "cusolverDnDpotri");
+    SKB_SYM(trtri_size, "cusolverDnXtrtri_bufferSize");
+    SKB_SYM(trtri, "cusolverDnXtrtri");
 #undef SKB_SYM
     g_solver.ok = true;
     return SKB_OK;
@@ -1418,6 +1439,13 @@ struct skb_fit {
     std::vector<void*> ptrs;
     double *d_X = nullptr, *d_y = nullptr;
     std::vector<FitSlot> slots;
+    // skb_fit_finalize_host / skb_state_create_from_fit: slot 0 keeps the factor of K(theta*); two more n x n buffers
+    // hold row-major copies (L_ for the host, then L^-1 and a second copy of the factor that potri turns into K^-1)
+    double *d_T = nullptr, *d_T2 = nullptr;
+    void* d_trtri_work = nullptr;
+    size_t trtri_dev_bytes = 0, trtri_host_bytes = 0;
+    std::vector<char> h_trtri_work;
+    bool finalized = false;
 };
 
 namespace {
@@ -1643,6 +1671,80 @@ int skb_fit_lml_batch_host(skb_fit* f, int32_t count, const double* thetas, int3
 
 int skb_fit_lml_host(skb_fit* f, const double* theta, int32_t want_grad, double* lml, double* grad) {
     return skb_fit_lml_batch_host(f, 1, theta, want_grad, lml, grad);
+}
+
+int skb_fit_finalize_host(skb_fit* f, const double* theta, double* lml, double* alpha_out, double* L_out) {
+    if (!f || !theta || !lml || !alpha_out) return fail(SKB_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(f->device));
+    f->finalized = false;
+    FitSlot& sl = f->slots[0];
+    const size_t n = (size_t)f->n;
+    int rc = fit_issue(f, sl, theta, false);
+    if (rc != SKB_OK) return rc;
+    if ((rc = fit_collect(f, sl, lml, nullptr)) != SKB_OK) return rc;
+    if (*slot_h_info(sl) != 0)
+        return fail(SKB_ERR_NOT_POSDEF, "kernel matrix is not positive definite (potrf info = %d)", *slot_h_info(sl));
+    CU(cudaMemcpyAsync(alpha_out, sl.d_a, n * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    if (L_out) {
+        if (!f->d_T && (rc = fit_alloc(f, &f->d_T, n * n)) != SKB_OK) return rc;
+        const unsigned T = (unsigned)((n + 31) / 32);
+        fit_unpack_lower_kernel<false><<<dim3(T, T), 256, 0, sl.stream>>>(sl.d_K, f->d_T, f->n);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(L_out, f->d_T, n * n * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    f->finalized = true;
+    return SKB_OK;
+}
+
+int skb_state_create_from_fit(skb_fit* f, const skb_state_desc* desc, skb_state** out) {
+    if (!f || !desc || !out) return fail(SKB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (!f->finalized) return fail(SKB_ERR_INVALID, "skb_fit_finalize_host has not succeeded on this fit");
+    if (desc->n_train != f->n || desc->n_dims != f->d || desc->kernel != f->kernel)
+        return fail(SKB_ERR_INVALID, "desc (n_train %d, n_dims %d, kernel %d) does not describe this fit (%d, %d, %d)",
+                    desc->n_train, desc->n_dims, desc->kernel, f->n, f->d, f->kernel);
+    CU(cudaSetDevice(f->device));
+    FitSlot& sl = f->slots[0];
+    const size_t n = (size_t)f->n;
+    int rc;
+    if (!f->d_T && (rc = fit_alloc(f, &f->d_T, n * n)) != SKB_OK) return rc;
+    if (!f->d_T2 && (rc = fit_alloc(f, &f->d_T2, n * n)) != SKB_OK) return rc;
+    if (!f->d_trtri_work) {
+        size_t dev_bytes = 0, host_bytes = 0;
+        SOLVER(g_solver.trtri_size(sl.solver, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)f->n, CUDA_R_64F, sl.d_K,
+                                   (int64_t)f->n, &dev_bytes, &host_bytes));
+        double* raw = nullptr;
+        if ((rc = fit_alloc(f, &raw, (std::max<size_t>(dev_bytes, 8) + 7) / 8)) != SKB_OK) return rc;
+        f->d_trtri_work = raw;
+        f->trtri_dev_bytes = dev_bytes;
+        f->trtri_host_bytes = host_bytes;
+        f->h_trtri_work.resize(std::max<size_t>(host_bytes, 8));
+    }
+    cudaStream_t s = sl.stream;
+    const unsigned T = (unsigned)((n + 31) / 32);
+    // d_K holds the factor L (column-major lower).  Keep a copy for potri, invert the factor in place, bring L^-1 into
+    // the row-major form the pack kernels read, then K^-1 = potri(copy) mirrored into a full symmetric matrix.
+    CU(cudaMemcpyAsync(f->d_T2, sl.d_K, n * n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SOLVER(g_solver.trtri(sl.solver, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)f->n, CUDA_R_64F, sl.d_K, (int64_t)f->n,
+                          f->d_trtri_work, f->trtri_dev_bytes, f->h_trtri_work.data(), f->trtri_host_bytes, sl.d_info + 3));
+    fit_unpack_lower_kernel<false><<<dim3(T, T), 256, 0, s>>>(sl.d_K, f->d_T, f->n);
+    LAUNCHED();
+    SOLVER(g_solver.potri(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_T2, f->n, sl.d_work, f->lwork, sl.d_info + 2));
+    fit_unpack_lower_kernel<true><<<dim3(T, T), 256, 0, s>>>(f->d_T2, sl.d_K, f->n);
+    LAUNCHED();
+    int* h_info = slot_h_info(sl);
+    CU(cudaMemcpyAsync(h_info, sl.d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    f->finalized = false;                             // the factor in slot 0 has been consumed
+    if (h_info[2] != 0 || h_info[3] != 0)
+        return fail(SKB_ERR_CUDA, "triangular inverse failed (potri info = %d, trtri info = %d)", h_info[2], h_info[3]);
+    skb_state_desc full = *desc;
+    full.X_train = f->d_X;
+    full.alpha = sl.d_a;
+    full.L_inv = f->d_T;
+    full.K_inv = sl.d_K;
+    return state_create_impl(&full, f->device, out, cudaMemcpyDeviceToDevice);
 }
 
 }  // extern "C"

@@ -152,25 +152,61 @@ def _acq_params(y_opt, xi, kappa, acq_funcs, top_k, precision="fp64"):
     return p
 
 
+class StateScalars:
+    """The part of a HostState that is not an n-sized array: what skb_state_create_from_fit needs from the host when the
+    training rows, alpha and the Cholesky factor are already on the device."""
+
+    def __init__(self, n_train, n_dims, length_scale, kernel, amplitude, bias, white, y_mean, y_std):
+        self.n_train, self.n_dims = int(n_train), int(n_dims)
+        self.length_scale = np.ascontiguousarray(np.broadcast_to(np.asarray(length_scale, dtype=np.float64), (self.n_dims,)))
+        self.kernel = int(kernel)
+        self.amplitude, self.bias, self.white = float(amplitude), float(bias), float(white)
+        self.y_mean, self.y_std = float(y_mean), float(y_std)
+        self.K_inv = None
+
+    @property
+    def prior_var(self):
+        return self.amplitude + self.bias + self.white
+
+
+def state_scalars_from_estimator(est):
+    """Kernel scalars of the PREDICTION kernel est.kernel_ (after gpr.py:199-220 silenced the noise term)."""
+    aff = _flatten_kernel(est.kernel_)
+    n, d = est.X_train_.shape
+    if aff.base is None:
+        kind, ls, amp = _lib.KERNEL_RBF, np.ones(d), 0.0
+    else:
+        (kind, ls), amp = aff.base, aff.a
+    return StateScalars(n, d, ls, kind, amp, aff.c, aff.w, np.ravel(est.y_train_mean_)[0], np.ravel(est.y_train_std_)[0])
+
+
+def _fill_desc(desc, hs):
+    desc.n_train, desc.n_dims, desc.kernel = hs.n_train, hs.n_dims, hs.kernel
+    desc.amplitude, desc.bias, desc.white = hs.amplitude, hs.bias, hs.white
+    desc.y_mean, desc.y_std = hs.y_mean, hs.y_std
+    desc.length_scale = hs.length_scale.ctypes.data
+
+
 class DeviceState:
     """A fitted GP resident on one B200 (owner of a skb_state handle)."""
 
-    def __init__(self, host_state, device=0):
+    def __init__(self, host_state, device=0, _handle=None):
         L = _lib.lib()
         self.host = host_state
         self.device = int(device)
-        desc = _lib.StateDesc()
-        desc.n_train, desc.n_dims, desc.kernel = host_state.n_train, host_state.n_dims, host_state.kernel
-        desc.amplitude, desc.bias, desc.white = host_state.amplitude, host_state.bias, host_state.white
-        desc.y_mean, desc.y_std = host_state.y_mean, host_state.y_std
-        desc.length_scale = host_state.length_scale.ctypes.data
-        desc.X_train = host_state.X_train.ctypes.data
-        desc.alpha = host_state.alpha.ctypes.data
-        desc.L_inv = host_state.L_inv.ctypes.data
-        desc.K_inv = None                       # attached lazily: only the gradient entry points read it
-        self._kinv_attached = False
-        handle = C.c_void_p()
-        _lib.check(L.skb_state_create(C.byref(desc), self.device, C.byref(handle)))
+        if _handle is None:
+            desc = _lib.StateDesc()
+            _fill_desc(desc, host_state)
+            desc.X_train = host_state.X_train.ctypes.data
+            desc.alpha = host_state.alpha.ctypes.data
+            desc.L_inv = host_state.L_inv.ctypes.data
+            desc.K_inv = None                   # attached lazily: only the gradient entry points read it
+            self._kinv_attached = False
+            handle = C.c_void_p()
+            _lib.check(L.skb_state_create(C.byref(desc), self.device, C.byref(handle)))
+        else:
+            handle = _handle                    # built on the device by skb_state_create_from_fit, K_inv included
+            self._kinv_attached = True
         self._h = handle
         self._finalizer = weakref.finalize(self, L.skb_state_destroy, handle)
 
@@ -481,6 +517,34 @@ class DeviceFit:
                                                      grads.ctypes.data))
         self.n_evals += count
         return values, grads
+
+    def finalize(self, theta_full, want_factor=True):
+        """Tail of sklearn's fit at the chosen hyper-parameters (_gpr.py:341-367) on the device: returns
+        (lml, alpha_, L_) with L_ lower triangular like SciPy's (None unless want_factor).  Raises LinAlgError when K is
+        not positive definite.  The factor stays on the device for make_state()."""
+        theta_full = np.ascontiguousarray(theta_full, dtype=np.float64)
+        n = self.X.shape[0]
+        if theta_full.shape != (self.X.shape[1] + 2,):
+            raise ValueError("theta_full must have n_dims + 2 entries")
+        value = C.c_double()
+        alpha = np.empty(n)
+        factor = np.empty((n, n)) if want_factor else None
+        rc = _lib.lib().skb_fit_finalize_host(self._h, theta_full.ctypes.data, C.byref(value), alpha.ctypes.data,
+                                              factor.ctypes.data if want_factor else None)
+        if rc == _lib.SKB_ERR_NOT_POSDEF:
+            raise np.linalg.LinAlgError(_lib.lib().skb_last_error().decode("utf-8", "replace"))
+        _lib.check(rc)
+        self.n_evals += 1
+        return value.value, alpha, factor
+
+    def make_state(self, scalars):
+        """DeviceState built on the GPU from the finalised factor (skb_state_create_from_fit): L^-1, K^-1 and their
+        packed forms never exist on the host."""
+        desc = _lib.StateDesc()
+        _fill_desc(desc, scalars)
+        handle = C.c_void_p()
+        _lib.check(_lib.lib().skb_state_create_from_fit(self._h, C.byref(desc), C.byref(handle)))
+        return DeviceState(scalars, self.device, _handle=handle)
 
     def close(self):
         if self._h is not None and self._h.value:

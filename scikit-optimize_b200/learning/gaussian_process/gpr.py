@@ -10,8 +10,11 @@ import warnings
 
 import numpy as np
 from scipy.linalg import cho_solve, solve_triangular
+from sklearn.base import clone
 from sklearn.gaussian_process import GaussianProcessRegressor as _SkGPR
-from sklearn.utils import check_array
+from sklearn.preprocessing._data import _handle_zeros_in_scale
+from sklearn.utils import check_array, check_random_state
+from sklearn.utils.validation import validate_data
 
 from ... import engine
 from .kernels import RBF, ConstantKernel, Sum, WhiteKernel
@@ -145,9 +148,90 @@ class GaussianProcessRegressor(_SkGPR):
                           ConvergenceWarning)
         return theta_opt, func_min
 
+    def _search_on_device(self, X, y):
+        """scikit-learn's fit up to the choice of the hyper-parameters (_gpr.py:233-340) with the objective on the GPU.
+        Same sequence of calls as scikit-learn makes - the search from the kernel's theta, then `n_restarts_optimizer`
+        searches from starts drawn from `self._rng`, each through `_constrained_optimization` - so the lock-step
+        machinery (and anything a subclass overrides) sees exactly what it would see under scikit-learn's fit.
+        Returns the full device hyper-parameter vector at the optimum, or None when this model is outside the device
+        objective's grammar (the caller then runs scikit-learn's fit)."""
+        where = self.__dict__.get("_skb_fit_device", _FIT_DEVICE[0])
+        if where != "gpu" or np.ndim(self.alpha) != 0 or self.optimizer not in (None, "fmin_l_bfgs_b"):
+            return None
+        self._validate_params()
+        X, y = validate_data(self, X, y, multi_output=True, y_numeric=True, ensure_2d=True, dtype="numeric")
+        if y.ndim != 1 or (self.n_targets is not None and self.n_targets != 1):
+            return None
+        self.kernel_ = clone(self.kernel)
+        self._rng = check_random_state(self.random_state)
+        if self.normalize_y:
+            self._y_train_mean = np.mean(y, axis=0)
+            self._y_train_std = _handle_zeros_in_scale(np.std(y, axis=0), copy=False)
+            y = (y - self._y_train_mean) / self._y_train_std
+        else:
+            self._y_train_mean = np.zeros(shape=1)
+            self._y_train_std = np.ones(shape=1)
+        self.X_train_ = np.copy(X) if self.copy_X_train else X
+        self.y_train_ = np.copy(y) if self.copy_X_train else y
+        dev = self._device_fit()
+        if dev is None:                         # kernel outside [Constant *] {RBF | Matern} [+ White]
+            return None
+        layout = dev[1]
+        self.__dict__.pop("log_marginal_likelihood_value_", None)
+        if self.optimizer is not None and self.kernel_.n_dims > 0:
+            def obj_func(theta, eval_gradient=True):
+                if eval_gradient:
+                    lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=False)
+                    return -lml, -grad
+                return -self.log_marginal_likelihood(theta, clone_kernel=False)
+
+            bounds = self.kernel_.bounds
+            found = [self._constrained_optimization(obj_func, self.kernel_.theta, bounds)]
+            if self.n_restarts_optimizer > 0:
+                if not np.isfinite(bounds).all():
+                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are "
+                                     "finite.")
+                for _ in range(self.n_restarts_optimizer):
+                    start = self._rng.uniform(bounds[:, 0], bounds[:, 1])
+                    found.append(self._constrained_optimization(obj_func, start, bounds))
+            best = int(np.argmin([f[1] for f in found]))
+            self.kernel_.theta = found[best][0]
+            self.kernel_._check_bounds_params()
+            self.log_marginal_likelihood_value_ = -found[best][1]
+        return layout.expand(self.kernel_.theta)
+
+    def _finalize_on_device(self, theta_full):
+        """Tail of the fit on the GPU: L_, alpha_ (sklearn _gpr.py:341-367) and the scoring state (gpr.py:223-224) from
+        the training set that is still resident from the search."""
+        fit = self._device_fit()[0]
+        lml, self.alpha_, self.L_ = fit.finalize(theta_full)
+        if "log_marginal_likelihood_value_" not in self.__dict__:
+            self.log_marginal_likelihood_value_ = lml
+        self.y_train_std_ = self._y_train_std
+        self.y_train_mean_ = self._y_train_mean
+        state = fit.make_state(engine.state_scalars_from_estimator(self))
+        if state is not None:
+            self.__dict__["_skb_device_state"] = state
+
+    def __getattr__(self, name):
+        # K_inv_ and the triangular inverse are fitted attributes of the reference (gpr.py:223-224).  After a fit that
+        # was finalised on the GPU they only exist there; the host copies are produced from L_ on first access.
+        if name in ("K_inv_", "_L_inv_lower") and "L_" in self.__dict__:
+            L_inv = self.__dict__.get("_L_inv_lower")
+            if L_inv is None:
+                L_inv = solve_triangular(self.L_, np.eye(self.L_.shape[0]), lower=True)
+                self.__dict__["_L_inv_lower"] = L_inv
+            if name == "K_inv_":
+                self.__dict__["K_inv_"] = L_inv.T.dot(L_inv)
+            return self.__dict__[name]
+        raise AttributeError("%r object has no attribute %r" % (type(self).__name__, name))
+
     def fit(self, X, y):
         """gpr.py:166-237: add the noise kernel, fit with scikit-learn, silence the noise for prediction,
-        precompute K_inv_ (here together with the triangular factor the GPU kernels contract with)."""
+        precompute K_inv_ (here together with the triangular factor the GPU kernels contract with).  With the fit
+        device set to "gpu" the whole fit runs on the device: the search (log_marginal_likelihood), the final
+        factorisation and the triangular inverse / K^-1 the scoring kernels read; K_inv_ is then materialised on the
+        host only if somebody reads it."""
         if isinstance(self.noise, str) and self.noise != "gaussian":
             raise ValueError("expected noise to be 'gaussian', got %s" % self.noise)
         if self.kernel is None:
@@ -156,28 +240,34 @@ class GaussianProcessRegressor(_SkGPR):
             self.kernel = self.kernel + WhiteKernel()
         elif self.noise:
             self.kernel = self.kernel + WhiteKernel(noise_level=self.noise, noise_level_bounds="fixed")
-        self.__dict__.pop("_skb_device_state", None)
+        for stale in ("_skb_device_state", "K_inv_", "_L_inv_lower"):
+            self.__dict__.pop(stale, None)
         try:
-            super().fit(X, y)
+            theta_full = self._search_on_device(X, y)
+            if theta_full is None:
+                super().fit(X, y)
+
+            self.noise_ = None
+            if self.noise:
+                # K(X*, X*) must not contain the observation noise (GPML eq. 2.24); alpha_ already has it.
+                if isinstance(self.kernel_, WhiteKernel):
+                    self.kernel_.set_params(noise_level=0.0)
+                else:
+                    key = _white_kernel_key(self.kernel_)
+                    if key is not None:
+                        self.noise_ = self.kernel_.get_params()[key].noise_level
+                        self.kernel_.set_params(**{key: WhiteKernel(noise_level=0.0)})
+            if theta_full is not None:
+                self._finalize_on_device(theta_full)
         finally:
-            self._close_device_fit()            # the training set only stays on the GPU during the search
+            self._close_device_fit()            # the training set only stays on the GPU during the fit
 
-        self.noise_ = None
-        if self.noise:
-            # K(X*, X*) must not contain the observation noise (GPML eq. 2.24); alpha_ already has it.
-            if isinstance(self.kernel_, WhiteKernel):
-                self.kernel_.set_params(noise_level=0.0)
-            else:
-                key = _white_kernel_key(self.kernel_)
-                if key is not None:
-                    self.noise_ = self.kernel_.get_params()[key].noise_level
-                    self.kernel_.set_params(**{key: WhiteKernel(noise_level=0.0)})
-
-        n = self.L_.shape[0]
-        self._L_inv_lower = solve_triangular(self.L_, np.eye(n), lower=True)
-        self.K_inv_ = self._L_inv_lower.T.dot(self._L_inv_lower)
-        self.y_train_std_ = self._y_train_std
-        self.y_train_mean_ = self._y_train_mean
+        if theta_full is None:
+            n = self.L_.shape[0]
+            self._L_inv_lower = solve_triangular(self.L_, np.eye(n), lower=True)
+            self.K_inv_ = self._L_inv_lower.T.dot(self._L_inv_lower)
+            self.y_train_std_ = self._y_train_std
+            self.y_train_mean_ = self._y_train_mean
         return self
 
     def device_state(self, device=None):

@@ -61,6 +61,19 @@ class _OracleFit:
         out = [self.lml(t) for t in thetas_full]
         return np.array([o[0] for o in out]), np.array([o[1] for o in out])
 
+    def finalize(self, theta_full, want_factor=True):
+        from scipy.linalg import cho_solve, cholesky
+        amplitude, ls, noise = np.exp(theta_full[0]), np.exp(theta_full[1:-1]), np.exp(theta_full[-1])
+        K = amplitude * Matern(length_scale=ls, nu=self.nu)(self.X)
+        K[np.diag_indices_from(K)] = (amplitude + noise) + 1e-10
+        L = cholesky(K, lower=True)
+        self.finalized = theta_full.copy()
+        return self.lml(theta_full, eval_gradient=False), cho_solve((L, True), self.y), L
+
+    def make_state(self, scalars):
+        self.scalars = scalars
+        return None                      # no GPU in this test: the estimator then builds its state lazily
+
     def close(self):
         pass
 
@@ -90,6 +103,8 @@ def test_lockstep_restarts_equal_sequential_restarts(monkeypatch):
         return cached[1], cached[2]
 
     monkeypatch.setattr(GaussianProcessRegressor, "_device_fit", fake_device_fit)
+    from skopt_b200.learning.gaussian_process import gpr as gpr_module
+    monkeypatch.setattr(gpr_module, "_FIT_DEVICE", ["gpu"])
 
     class Sequential(GaussianProcessRegressor):          # same objective, scikit-learn's own restart loop
         def _constrained_optimization(self, obj_func, initial_theta, bounds):
@@ -103,6 +118,15 @@ def test_lockstep_restarts_equal_sequential_restarts(monkeypatch):
     np.testing.assert_array_equal(a.alpha_, b.alpha_)
     assert a._rng.get_state()[2] == b._rng.get_state()[2]
     np.testing.assert_array_equal(a._rng.get_state()[1], b._rng.get_state()[1])
+    # the tail of the fit ran through the device objective's finalize at the chosen theta (noise still in it), and the
+    # state scalars describe the prediction kernel (noise silenced: here the user's own WhiteKernel stays, noise=None)
+    lay = engine.FitLayout(kernel, 2)
+    np.testing.assert_array_equal(fakes[0].finalized, lay.expand(a.kernel_.theta))
+    assert fakes[0].scalars.n_train == 40 and fakes[0].scalars.white == a.kernel_.k2.noise_level
+    assert a.L_.shape == (40, 40) and not np.triu(a.L_, 1).any()
+    assert "K_inv_" not in a.__dict__                       # host copy only on demand ...
+    np.testing.assert_allclose(a.K_inv_.dot(a.L_.dot(a.L_.T)), np.eye(40), atol=1e-6)
+    assert "K_inv_" in a.__dict__ and "_L_inv_lower" in a.__dict__
     # and both sit at scikit-learn's host optimum up to the optimiser's tolerance
     monkeypatch.undo()
     c = GaussianProcessRegressor(kernel=kernel, normalize_y=True, n_restarts_optimizer=3, random_state=5).fit(X, y)

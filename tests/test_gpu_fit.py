@@ -118,3 +118,99 @@ def test_batched_evaluations_are_bit_identical_to_single_ones():
         assert v == values[i]
         np.testing.assert_array_equal(g, grads[i])
     fit.close()
+
+
+def _fixed_kernel_problem(n, d, nu, seed):
+    from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, d)
+    y = np.sin(X.dot(rng.randn(d))) + 0.1 * rng.randn(n)
+    kernel = ConstantKernel(1.3, "fixed") * Matern(length_scale=np.full(d, 0.9), length_scale_bounds="fixed", nu=nu)
+    return X, y, kernel, rng
+
+
+@pytest.mark.parametrize("n,d", [(33, 2), (300, 5), (1100, 12)])
+def test_finalize_matches_host_factorisation(n, d):
+    """skb_fit_finalize_host: L_, alpha_ and the lml at theta* against SciPy's Cholesky of the same K."""
+    from scipy.linalg import cho_solve, cholesky
+    from skopt_b200.engine import DeviceFit, FitLayout
+    from skopt_b200.learning.gaussian_process.kernels import WhiteKernel
+    X, y, kernel, _ = _fixed_kernel_problem(n, d, 2.5, n)
+    y = (y - y.mean()) / y.std()
+    full_kernel = kernel + WhiteKernel(1e-3, "fixed")
+    lay = FitLayout(full_kernel, d)
+    fit = DeviceFit(X, y, lay.kind, 1e-10)
+    try:
+        theta_full = lay.expand(full_kernel.theta)
+        lml, alpha, L = fit.finalize(theta_full)
+        assert lml == fit.lml(theta_full, eval_gradient=False)
+        K = full_kernel(X)
+        K[np.diag_indices_from(K)] += 1e-10
+        L_ref = cholesky(K, lower=True)
+        cond = np.linalg.cond(K)
+        assert not np.triu(L, 1).any()
+        assert np.max(np.abs(L - L_ref)) <= 1e-15 * cond * np.max(np.abs(L_ref)) + 1e-12
+        a_ref = cho_solve((L_ref, True), y)
+        assert np.max(np.abs(alpha - a_ref)) <= 1e-15 * cond * np.max(np.abs(a_ref)) + 1e-12
+        lml2, alpha2, none = fit.finalize(theta_full, want_factor=False)
+        assert none is None and lml2 == lml
+        np.testing.assert_array_equal(alpha2, alpha)
+    finally:
+        fit.close()
+
+
+def test_finalize_not_positive_definite_raises():
+    from skopt_b200.engine import DeviceFit
+    fit = DeviceFit(np.zeros((40, 2)), np.arange(40.0), 3, 0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        fit.finalize(np.array([0.0, 0.0, 0.0, -np.inf]))
+    from skopt_b200._lib import SkbError
+    from skopt_b200.engine import StateScalars
+    with pytest.raises(SkbError):                        # no factor, no state
+        fit.make_state(StateScalars(40, 2, 1.0, 3, 1.0, 0.0, 0.0, 0.0, 1.0))
+    fit.close()
+
+
+@pytest.mark.parametrize("n,d,nu", [(33, 2, 2.5), (300, 5, 1.5), (1100, 12, 2.5)])
+def test_state_built_on_device_scores_like_the_host_built_state(n, d, nu):
+    """fit(optimizer=None) finalised on the GPU (skb_state_create_from_fit: trtri, potri, packing on the device) against
+    the same model finalised on the host (SciPy factor, solve_triangular, upload): posterior, acquisition, arg-min and
+    gradients; FP64 and split-integer contraction."""
+    from skopt_b200.learning import GaussianProcessRegressor
+    X, y, kernel, rng = _fixed_kernel_problem(n, d, nu, 7 * n)
+    est = {}
+    for where in ("host", "gpu"):
+        e = GaussianProcessRegressor(kernel=kernel, normalize_y=True, noise=1e-3, optimizer=None)
+        e._skb_fit_device = where
+        est[where] = e.fit(X, y)
+    h, g = est["host"], est["gpu"]
+    assert "_skb_device_state" in g.__dict__ and "K_inv_" not in g.__dict__ and "K_inv_" in h.__dict__
+    assert g.noise_ == h.noise_ and g.kernel_ == h.kernel_
+    cond = np.linalg.cond(h.L_) ** 2
+    assert np.max(np.abs(g.L_ - h.L_)) <= 1e-15 * cond * np.max(np.abs(h.L_)) + 1e-12
+    assert np.max(np.abs(g.alpha_ - h.alpha_)) <= 1e-15 * cond * np.max(np.abs(h.alpha_)) + 1e-12
+    assert abs(g.log_marginal_likelihood_value_ - h.log_marginal_likelihood_value_) <= 1e-9 * abs(h.log_marginal_likelihood_value_)
+    m = 9000
+    Xq = rng.rand(m, d)
+    y_opt = float(y.min())
+    prior = h.device_state().host.prior_var * float(h.y_train_std_) ** 2
+    for precision in ("fp64", "split_int8"):
+        rh = h.device_state().score(Xq, y_opt=y_opt, acq_funcs=("EI", "LCB"), top_k=4, precision=precision)
+        rg = g.device_state().score(Xq, y_opt=y_opt, acq_funcs=("EI", "LCB"), top_k=4, precision=precision)
+        assert np.max(np.abs(rg["mean"] - rh["mean"])) <= 1e-9 * max(np.max(np.abs(rh["mean"])), float(h.y_train_std_))
+        assert np.max(np.abs(rg["std"] ** 2 - rh["std"] ** 2)) <= max(1e-9, 1e-15 * cond) * prior
+        for a in ("EI", "LCB"):
+            assert np.max(np.abs(rg[a]["values"] - rh[a]["values"])) <= 1e-9 * np.max(np.abs(rh[a]["values"]))
+            assert rg[a]["topk_idx"][0] == rh[a]["topk_idx"][0]
+    gh = h.device_state().score_grad(Xq[:200], y_opt=y_opt, acq_funcs=("EI",))
+    gg = g.device_state().score_grad(Xq[:200], y_opt=y_opt, acq_funcs=("EI",))
+    for key in ("mean_grad", "std_grad"):
+        assert np.max(np.abs(gg[key] - gh[key])) <= 1e-8 * np.max(np.abs(gh[key]))
+    assert np.max(np.abs(gg["EI"]["grad"] - gh["EI"]["grad"])) <= 1e-8 * np.max(np.abs(gh["EI"]["grad"]))
+    # the host copies appear on demand and agree with the host-built ones
+    assert np.max(np.abs(g.K_inv_ - h.K_inv_)) <= 1e-15 * cond * np.max(np.abs(h.K_inv_)) + 1e-12
+    # a pickled model comes back without device handles and rebuilds its state from L_
+    import pickle
+    g2 = pickle.loads(pickle.dumps(g))
+    assert "_skb_device_state" not in g2.__dict__
+    np.testing.assert_allclose(g2.predict(Xq[:50]), g.predict(Xq[:50]), rtol=0, atol=1e-9 * float(h.y_train_std_))
