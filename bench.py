@@ -28,7 +28,11 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, N_DIMS, M_PER_GPU, TOP_K = 2048, 20, 1_000_000, 16
 FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue peak on this pool's B200 (profiles/r01_fp64_peaks.txt); cuBLAS DGEMM: 35.5
-SPLIT_PRODUCTS = 28       # digit-plane products kept by the split-integer contraction (p + q <= 6 of 7 x 7), csrc/ozaki.cuh
+
+def split_products(planes):
+    """Digit-plane products the split-integer contraction keeps (p + q <= planes - 1): 28 for 7 planes, 21 for 6."""
+    return planes * (planes + 1) // 2
+
 METRIC = "GP-EI candidate evals/sec at n_train=2048,d=20"
 
 
@@ -41,10 +45,10 @@ def flops_k2(n):
     return n * n + 2 * n + 40
 
 
-def int8_ops_k2(n):
-    """int8 operations (2 per MAC) the split-integer scheme needs per candidate: 28 plane products over the
-    lower-triangular n(n+1)/2 entries of L_inv."""
-    return SPLIT_PRODUCTS * n * (n + 1)
+def int8_ops_k2(n, planes):
+    """int8 operations (2 per MAC) the split-integer scheme needs per candidate: 28 (7 planes) or 21 (6 planes) plane
+    products over the lower-triangular n(n+1)/2 entries of L_inv."""
+    return split_products(planes) * n * (n + 1)
 
 
 def measured_bf16_peak():
@@ -330,6 +334,8 @@ def main():
     headline = engine.resolve_precision("auto", N_TRAIN, m)          # what the product picks for this workload
     ms_total, timing, launches, clocks_summary, argmin_idx = timed_dev(headline)
     e2e_s = timed_host(headline)
+    planes, probe_diff = dev.split_info() if headline == "split_int8" else (0, -1.0)
+    ms_p7 = timed_dev("split_int8_p7")[0] if headline == "split_int8" and planes != 7 else None
     ms_fp64, timing_fp64, _, _, argmin_fp64 = timed_dev("fp64") if headline != "fp64" else (ms_total, timing, 0, None, argmin_idx)
     e2e_fp64_s = timed_host("fp64") if headline != "fp64" else e2e_s
 
@@ -353,19 +359,25 @@ def main():
         if headline == "split_int8":
             bf16_peak, bf16_src = measured_bf16_peak()
             peak = 2.0 * bf16_peak
-            achieved = int8_ops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
+            achieved = int8_ops_k2(N_TRAIN, planes) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
             traffic_o = None
             prof_o = os.path.join(ROOT, "profiles", "k2o_dram_bytes_per_launch.json")
             if os.path.exists(prof_o):
                 traffic_o = json.load(open(prof_o)).get("dram_bytes_per_candidate", 0.0) * cand_per_k2
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
                         "traffic": traffic_o,
-                        "kernel": "ozaki_trmm_kernel (K2o: tcgen05.mma kind::i8 over 7 s8 digit planes, exact s32 "
-                                  "accumulation in TMEM, FP64 recombination)",
+                        "kernel": "ozaki_trmm_kernel<0, %d> (K2o: tcgen05.mma kind::i8 over %d s8 digit planes, exact s32 "
+                                  "accumulation in TMEM, FP64 recombination)" % (planes, planes),
+                        "digit_planes": planes,
+                        "digit_planes_self_check": "6 planes when 256 probe candidates scored with FP64 and with 6 planes "
+                                                   "agree to 1e-10 of the prior variance, else 7 (csrc/skb.cu "
+                                                   "decide_split_planes); measured difference: %.2e" % probe_diff,
+                        "seven_plane_evals_s": (world * m / (ms_p7 / args.steps / 1e3)) if ms_p7 else None,
                         "peak_source": "int8 dense = 2 x " + bf16_src + "; MEASURED_PEAKS.json has no int8 entry, the 2:1 "
                                        "int8:bf16 issue ratio is measured in profiles/r01_umma_i8_rates.txt",
-                        "algorithmic_ops_per_candidate": int8_ops_k2(N_TRAIN),
-                        "algorithmic_ops_definition": "2 x 28 digit-plane products x n(n+1)/2 (the scheme's own minimum)",
+                        "algorithmic_ops_per_candidate": int8_ops_k2(N_TRAIN, planes),
+                        "algorithmic_ops_definition": "2 x %d digit-plane products x n(n+1)/2 (the scheme's own minimum at "
+                                                      "%d planes)" % (split_products(planes), planes),
                         "issue_peak": 2 * 8175 * 148 * (clocks_summary.get("sm_mhz") or 1965.0) / 1e6,
                         "issue_peak_definition": "2 x 8175 MAC/clk/SM (measured kind::i8 issue rate at N=256, "
                                                  "profiles/r01_umma_i8_rates.txt) x 148 SMs x SM clock during the run",
@@ -399,7 +411,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f64" if headline == "fp64" else "f64 (variance contraction: 7 s8 digit planes -> exact s32 on tcgen05 -> f64)",
+            "dtype": "f64" if headline == "fp64" else "f64 (variance contraction: %d s8 digit planes -> exact s32 on tcgen05 "
+                                                      "-> f64)" % planes,
             "data": "synthetic",
             "config": {"workload": "synthetic GP posterior + EI: n_train=2048, d=20, %d candidates per GPU, FP64 results "
                                    "(BASELINE.json configs[2])" % m,

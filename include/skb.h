@@ -51,9 +51,14 @@ typedef enum {
  * gaussian_lcb (:90-146).  Values follow _gaussian_acquisition (:20-87): -EI, -PI, LCB, all to be MINIMISED. */
 /* Arithmetic of the O(n^2)-per-candidate variance contraction of skb_score_*.  Both meet the 1e-9 parity gate.
  *   FP64       : FP64 tensor-core MMA (DMMA), bit-reproducible reference path of this library (default).
- *   SPLIT_INT8 : operands split into 7 signed 8-bit digit planes (55-bit fixed point per row / global scale), products
- *                accumulated exactly in int32 on tcgen05 (kind::i8), recombined in FP64 (csrc/ozaki.cuh). */
-typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1 } skb_precision;
+ *   SPLIT_INT8_P7 : operands split into 7 signed 8-bit digit planes (55-bit fixed point per row / global scale),
+ *                products accumulated exactly in int32 on tcgen05 (kind::i8), recombined in FP64 (csrc/ozaki.cuh);
+ *                2e-14 of the prior variance from the exact contraction.
+ *   SPLIT_INT8 : the same on the leading 6 planes (47-bit operands, 21 instead of 28 digit-plane products; 4e-12 of the
+ *                prior variance) WHEN a self-check run once per state - 256 probe candidates scored with FP64 and with 6
+ *                planes - agrees to 1e-10 of the prior variance; otherwise 7 planes.  skb_state_split_info reports the
+ *                choice.  The gradient entry points always contract 7 planes. */
+typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1, SKB_PRECISION_SPLIT_INT8_P7 = 2 } skb_precision;
 
 typedef enum { SKB_ACQ_EI = 0, SKB_ACQ_PI = 1, SKB_ACQ_LCB = 2, SKB_NUM_ACQ = 3 } skb_acq_kind;
 
@@ -132,6 +137,9 @@ void skb_state_destroy(skb_state* st);
 /* Add est.K_inv_ ([n_train * n_train], host) to a state created without it: enables the gradient entry points.
  * (A BO loop in 'sampling' mode never needs it; the Python mirror attaches it on the first gradient call.) */
 int skb_state_attach_kinv(skb_state* st, const double* K_inv);
+/* Digit planes SKB_PRECISION_SPLIT_INT8 contracts on this state (6 or 7; 0 = not decided yet, the self-check runs on the
+ * first split-integer call) and the relative variance difference the self-check measured (-1 before it ran). */
+int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff);
 /* cudaStream_t owned by the state (so callers can record events on it). */
 void* skb_state_stream(skb_state* st);
 int skb_state_sync(skb_state* st);

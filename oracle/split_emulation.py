@@ -2,8 +2,9 @@
 
 Restates, with exact Python/NumPy integer arithmetic, what the tcgen05 kernel computes: both operands quantised to
 55-bit fixed point (per-row power-of-two scale for L_inv, one global scale for the kernel values), split into 7 balanced
-base-256 digits, digit-plane products with p + q <= 6 accumulated exactly, recombined in float64.  Used by the CPU
-tests to pin the arithmetic of the scheme (digit extraction trick, dropped-term bound, scaling) without a GPU.
+base-256 digits, digit-plane products with p + q <= 6 accumulated exactly, recombined in float64 - or, with
+`planes=6`, the 47-bit variant on the leading 6 digits (p + q <= 5, 21 products).  Used by the CPU tests to pin the
+arithmetic of the scheme (digit extraction trick, leading digits = rounding, dropped-term bound, scaling) without a GPU.
 """
 import numpy as np
 
@@ -19,28 +20,32 @@ def pow2_scale(maxabs):
     return float(np.ldexp(1.0, int(e) + 1))
 
 
-def digits(x_scaled_2p55):
-    """Balanced base-256 digits (most significant first) of round(x): the (v + 0x80..80) ^ 0x80..80 byte trick."""
-    v = np.rint(x_scaled_2p55).astype(np.int64)
-    y = (v + BIAS) ^ BIAS
-    planes = [((y >> (8 * (6 - p))) & 0xFF).astype(np.uint8).view(np.int8).astype(np.int64) for p in range(P)]
-    return planes, v
+def digits(x_scaled, planes=P):
+    """Balanced base-256 digits (most significant first) of round(x): the (v + 0x80..80) ^ 0x80..80 byte trick.
+    `x_scaled` = value / scale * 2^(8 planes - 1)."""
+    v = np.rint(x_scaled).astype(np.int64)
+    bias = sum(0x80 << (8 * i) for i in range(planes))
+    y = (v + bias) ^ bias
+    out = [((y >> (8 * (planes - 1 - p))) & 0xFF).astype(np.uint8).view(np.int8).astype(np.int64) for p in range(planes)]
+    return out, v
 
 
-def split_matmul(V, K):
-    """U = V @ K evaluated like the kernel: V (r x n) row-scaled, K (n x c) globally scaled."""
+def split_matmul(V, K, planes=P, k_scale=None):
+    """U = V @ K evaluated like the kernel: V (r x n) row-scaled, K (n x c) globally scaled (k_scale: the kernel's
+    a-priori scale pow2_scale(|amplitude| + |bias|); default: from the data)."""
     V = np.asarray(V, dtype=np.float64)
     K = np.asarray(K, dtype=np.float64)
     sV = np.array([pow2_scale(np.max(np.abs(row))) for row in V])
-    sK = pow2_scale(np.max(np.abs(K)))
-    a, _ = digits(V / sV[:, None] * 2.0 ** 55)
-    b, _ = digits(K / sK * 2.0 ** 55)
-    G = [np.zeros((V.shape[0], K.shape[1]), dtype=np.int64) for _ in range(P)]
-    for p in range(P):
-        for q in range(P - p):
-            G[p + q] += a[p] @ b[q]
+    sK = pow2_scale(np.max(np.abs(K))) if k_scale is None else k_scale
+    a, _ = digits(V / sV[:, None] * 2.0 ** (8 * planes - 1), planes)
+    b, _ = digits(K / sK * 2.0 ** (8 * planes - 1), planes)
+    G = [np.zeros((V.shape[0], K.shape[1]), dtype=np.int64) for _ in range(planes)]
+    for p in range(planes):
+        for q in range(planes - p):
+            # float64 matmul of small integers is exact (|sum| <= n 2^14 << 2^53) and runs on BLAS
+            G[p + q] += np.rint(a[p].astype(np.float64) @ b[q].astype(np.float64)).astype(np.int64)
     assert all(np.max(np.abs(g)) < 2 ** 31 for g in G), "int32 accumulators would overflow"
-    acc = G[P - 1].astype(np.float64)
-    for t in range(P - 2, -1, -1):                      # Horner in 256^-1, as in the kernel epilogue
+    acc = G[planes - 1].astype(np.float64)
+    for t in range(planes - 2, -1, -1):                 # Horner in 256^-1, as in the kernel epilogue
         acc = acc * 0.00390625 + G[t].astype(np.float64)
-    return acc * (sV[:, None] * (sK * 2.0 ** -14))
+    return acc * (sV[:, None] * (sK * 2.0 ** -14))      # the 2^-14 does not depend on the number of planes

@@ -13,7 +13,7 @@ SKB_ERR_NOT_POSDEF = -6
 KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
 ACQ_EI, ACQ_PI, ACQ_LCB = 0, 1, 2
 ACQ_INDEX = {"EI": ACQ_EI, "PI": ACQ_PI, "LCB": ACQ_LCB}
-PRECISION = {"fp64": 0, "split_int8": 1}
+PRECISION = {"fp64": 0, "split_int8": 1, "split_int8_p7": 2}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
@@ -59,6 +59,7 @@ SYMBOLS = [
     ("skb_state_create", C.c_int, [C.POINTER(StateDesc), C.c_int, C.POINTER(C.c_void_p)]),
     ("skb_state_destroy", None, [C.c_void_p]),
     ("skb_state_attach_kinv", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("skb_state_split_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     ("skb_state_stream", C.c_void_p, [C.c_void_p]),
     ("skb_state_sync", C.c_int, [C.c_void_p]),
     ("skb_state_set_scratch_limit", C.c_int, [C.c_void_p, C.c_uint64]),

@@ -139,22 +139,24 @@ __global__ void __launch_bounds__(256, 2) kcross_mean_kernel(const KCrossParams 
 }
 
 // K1 for the split-integer contraction (ozaki.cuh): same distances, transform and running k . alpha, but the k-tile is
-// emitted as 7 signed 8-bit digit planes (k = sK 2^-55 sum_q b_q 256^(6-q)) in the canonical K-major shared-memory
+// emitted as P signed 8-bit digit planes (k = sK 2^-(8P-1) sum_q b_q 256^(P-1-q)) in the canonical K-major shared-memory
 // layout of tcgen05.mma, [tile of 64 candidates][chunk of 32 training points][k half][plane][8 cand groups][8x16 B core],
 // so a pipeline stage of the MMA kernel is again one contiguous bulk copy.  Thread (c, h) owns training rows
 // [32 h, 32 h + 32) of every 64-row stage, i.e. one whole 32-point chunk, and stores 16 bytes per plane and k half.
 struct KDigitParams {
     KCrossParams base;
-    int8_t* Kd;               // [tiles64][n_pad/32][OZ_B_CHUNK]
-    double inv_scale_2p55;    // 2^55 / sK
+    int8_t* Kd;               // [tiles64][n_pad/32][2 k halves][P planes][8 cand groups][8 cands][16 B]
+    double inv_scale;         // 2^(8P-1) / sK
 };
 
 // Thread (cp, rq): candidates cp and cp + 64 of the 128-candidate tile (one in each 64-candidate MMA tile) x training
 // rows [16 rq, 16 rq + 16) of every 64-row stage, i.e. one k-half of a 32-point chunk.  Two candidates share every
 // broadcast read of a training row, which halves this kernel's shared-memory traffic -- it runs next to the
 // shared-memory-bound contraction kernel (second stream), so that is what decides how much of it is hidden.
-template <int KIND>
+// P = number of digit planes emitted (7: 55-bit values, 6: 47-bit values; ozaki.cuh).
+template <int KIND, int P>
 __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParams q) {
+    constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));     // +128 in each of the P digit bytes
     const KCrossParams& p = q.base;
     extern __shared__ __align__(16) unsigned char smem_k1[];
     const int d_pad = p.d_pad;
@@ -195,9 +197,9 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     double macc[2] = {0.0, 0.0};
     const int nkc_all = p.n_pad / 32;
     // candidate e (0/1) lives in MMA tile 2*tile + e at position cp: [k half][plane][cand group (8)][cand % 8][16 B]
-    int8_t* kd_base = q.Kd + ((size_t)(tile * 2) * nkc_all) * (2 * 7 * 8 * 128) + (cp >> 3) * 128 + (cp & 7) * 16 +
-                      (rq & 1) * (7 * 8 * 128);
-    const size_t tile64_stride = (size_t)nkc_all * (2 * 7 * 8 * 128);
+    int8_t* kd_base = q.Kd + ((size_t)(tile * 2) * nkc_all) * (2 * P * 8 * 128) + (cp >> 3) * 128 + (cp & 7) * 16 +
+                      (rq & 1) * (P * 8 * 128);
+    const size_t tile64_stride = (size_t)nkc_all * (2 * P * 8 * 128);
 
     for (int st = 0; st < nst; ++st) {
         const int buf = st & 1;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            // 16 kernel values -> digits; lo = bytes 0..3 (planes 6..3), hi = bytes 4..6 (planes 2..0)
+            // 16 kernel values -> digits; lo = bytes 0..3 (planes P-1..P-4), hi = bytes 4..P-1 (planes P-5..0)
             uint32_t lo[16], hi[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -246,15 +248,14 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                 double val = fma(p.amplitude, base_kernel<KIND>(s[e][r]), p.bias);
                 if (j >= p.n) val = 0.0;
                 macc[e] = fma(val, alb[rq * 16 + r], macc[e]);
-                const unsigned long long y =
-                    ((unsigned long long)__double2ll_rn(val * q.inv_scale_2p55) + 0x0080808080808080ull) ^ 0x0080808080808080ull;
+                const unsigned long long y = ((unsigned long long)__double2ll_rn(val * q.inv_scale) + DIGIT_BIAS) ^ DIGIT_BIAS;
                 lo[r] = (uint32_t)y;
                 hi[r] = (uint32_t)(y >> 32);
             }
-            int8_t* dst = kd_base + e * tile64_stride + (size_t)(st * 2 + (rq >> 1)) * (2 * 7 * 8 * 128);
+            int8_t* dst = kd_base + e * tile64_stride + (size_t)(st * 2 + (rq >> 1)) * (2 * P * 8 * 128);
 #pragma unroll
-            for (int pl = 0; pl < 7; ++pl) {
-                const int byte = 6 - pl;                                   // plane 0 = most significant digit = byte 6
+            for (int pl = 0; pl < P; ++pl) {
+                const int byte = P - 1 - pl;                               // plane 0 = most significant digit = byte P-1
                 uint32_t w[4];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {

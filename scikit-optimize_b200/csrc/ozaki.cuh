@@ -32,16 +32,22 @@ constexpr int OZ_P = 7;                       // digit planes per operand
 constexpr int OZ_KC = 32;                     // training points per MMA (UMMA K for 8-bit operands)
 constexpr int OZ_SUB = 32;                    // candidates per accumulator group
 constexpr int OZ_NC = 64;                     // candidates per CTA (two groups)
-constexpr int OZ_STAGES = 4;
 constexpr int OZ_EPI_WARPS = 8;                // two warps per TMEM lane quarter, each owning 32 of the 64 candidates
 constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;   // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int OZ_A_CHUNK = OZ_P * BM * OZ_KC;                      // 28,672 B: [plane][k half][row group 16][8 rows][16 B]
-constexpr int OZ_B_HALF = OZ_P * (OZ_NC / 8) * 128;                // 7,168 B:  [plane][cand group 8][8 cands][16 B] per k half
-constexpr int OZ_B_CHUNK = 2 * OZ_B_HALF;                          // 14,336 B
-constexpr int OZ_STAGE_BYTES = OZ_A_CHUNK + OZ_B_CHUNK;            // 43,008 B
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_ACC_COLS = OZ_P * OZ_NC;                          // 448 accumulator columns: region G_t at [64 t, 64 t + 64)
 constexpr unsigned long long OZ_BIAS = 0x0080808080808080ull;      // +128 in each of the 7 digit bytes
+// The contraction can run on the leading P <= OZ_P planes of both operands.  Balanced digits make that a rounding, not
+// a truncation: the first P digits of the 7-digit expansion ARE the P-digit expansion of the value rounded to
+// 2^-(8P-1) of its scale (every dropped digit is at most half a unit of the one before it), so the packed L_inv planes
+// serve every P and only the leading planes are fetched.  P = 6 (47-bit operands, 21 digit-plane products instead of
+// 28): difference to the exact contraction 4e-12 of the prior variance at (2048, 20) - the 1e-9 gate with a factor
+// of 200 to spare - against 2e-14 for P = 7 (oracle/split_emulation.py, tests/test_split_emulation.py).
+__host__ __device__ constexpr int oz_a_bytes(int P) { return P * BM * OZ_KC; }                      // leading planes of one A chunk
+__host__ __device__ constexpr int oz_b_half(int P) { return P * (OZ_NC / 8) * 128; }                // [plane][cand group 8][8 cands][16 B] per k half
+__host__ __device__ constexpr int oz_b_chunk(int P) { return 2 * oz_b_half(P); }                    // 14,336 B (P = 7), 12,288 B (P = 6)
+__host__ __device__ constexpr int oz_stage_bytes(int P) { return oz_a_bytes(P) + oz_b_chunk(P); }   // 43,008 B / 36,864 B
+__host__ __device__ constexpr int oz_stages(int P) { return P >= 7 ? 4 : 5; }
 
 // byte offset of (row, k) inside one canonical K-major, no-swizzle (rows x 32) int8 block: 8-row x 16-byte core matrices
 __host__ __device__ inline int oz_canon(int rows, int row, int k) {
@@ -105,7 +111,7 @@ __global__ void oz_pack_linv_kernel(const double* __restrict__ V, const double* 
 struct OzakiParams {
     const int8_t* Vd;         // digit planes of L_inv, chunk (I, kc) at (vp_tiles_before(I) + kc) * OZ_A_CHUNK
     const double* sV;         // [n_pad] row scales
-    const int8_t* Kd;         // digit planes of K_trans: [tile64][kc][OZ_B_CHUNK]
+    const int8_t* Kd;         // digit planes of K_trans: [tile64][kc][oz_b_chunk(P)]
     const double* kdot;       // [tiles*64] K_trans . alpha from K1
     double k_scale;           // sK
     int n, n_pad;
@@ -118,7 +124,7 @@ struct OzakiParams {
     double* Wt;               // MODE 1: [tiles128][n_pad][BN] = K_inv . K_trans^T in FP64 for the gradient kernel
 };
 
-constexpr size_t oz_smem_bytes() { return (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * OZ_NC * sizeof(double) + 256; }
+constexpr size_t oz_smem_bytes(int P) { return (size_t)oz_stages(P) * oz_stage_bytes(P) + 4 * OZ_NC * sizeof(double) + 256; }
 
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -169,8 +175,13 @@ __device__ __forceinline__ double oz_colsum32(double (&v)[32], int lane) {
 
 // MODE 0: triangular L_inv, U squared and reduced, posterior + acquisition epilogue; grid.x = 64-candidate tile.
 // MODE 1: dense K_inv, W = K_inv . K_trans^T stored in FP64; grid = (row block, 64-candidate tile).
-template <int MODE>
+template <int MODE, int P>
 __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
+    constexpr int OZ_STAGES = oz_stages(P);
+    constexpr int OZ_STAGE_BYTES = oz_stage_bytes(P);
+    constexpr int OZ_B_HALF = oz_b_half(P);
+    constexpr int OZ_B_CHUNK = oz_b_chunk(P);
+    constexpr int A_BYTES = oz_a_bytes(P);
     extern __shared__ __align__(1024) unsigned char smem_oz[];
     unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
     double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][OZ_NC]
@@ -219,8 +230,8 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
                     mbar_wait(empty + s, ph ^ 1);
                     mbar_arrive_expect_tx(full + s, OZ_STAGE_BYTES);
                     unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
-                    bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, OZ_A_CHUNK, full + s);
-                    bulk_g2s(dst + OZ_A_CHUNK, kd_tile + (size_t)kc * OZ_B_CHUNK, OZ_B_CHUNK, full + s);
+                    bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, A_BYTES, full + s);        // leading P of the 7 packed planes
+                    bulk_g2s(dst + A_BYTES, kd_tile + (size_t)kc * OZ_B_CHUNK, OZ_B_CHUNK, full + s);
                 }
             }
         }
@@ -240,14 +251,14 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
                     mbar_wait(full + s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_base = smem_u32(stages + (size_t)s * OZ_STAGE_BYTES);
-                    const uint32_t b_base = a_base + OZ_A_CHUNK;
+                    const uint32_t b_base = a_base + A_BYTES;
                     const uint32_t acc = kc > 0 ? 1u : 0u;
 #pragma unroll
-                    for (int pl = 0; pl < OZ_P; ++pl) {
+                    for (int pl = 0; pl < P; ++pl) {
                         const uint64_t da = oz_smem_desc(a_base + pl * (BM * OZ_KC), (BM / 8) * 128, 128);
-                        // B rows [0, 64 (7 - pl)) = planes 0 .. 6-pl of all 64 candidates -> accumulator columns
-                        // [64 pl, 448); split so that every instruction has N <= 256 (and N a multiple of 16).
-                        const int rows = OZ_NC * (OZ_P - pl);
+                        // B rows [0, 64 (P - pl)) = planes 0 .. P-1-pl of all 64 candidates -> accumulator columns
+                        // [64 pl, 64 P); split so that every instruction has N <= 256 (and N a multiple of 16).
+                        const int rows = OZ_NC * (P - pl);
                         const int n0 = rows <= 256 ? rows : (pl == 0 ? 256 : rows / 2);
 #pragma unroll
                         for (int piece = 0; piece < 2; ++piece) {
@@ -280,17 +291,17 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
 #pragma unroll
             for (int jj = 0; jj < OZ_NC / 16; ++jj) {
                 const int j = half * (OZ_NC / 16) + jj;
-                // all seven regions of these 8 candidates are requested before the single wait: one TMEM round trip
-                uint32_t g[OZ_P][8];
+                // all P regions of these 8 candidates are requested before the single wait: one TMEM round trip
+                uint32_t g[P][8];
 #pragma unroll
-                for (int t = 0; t < OZ_P; ++t) oz_ld8_issue(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + 8 * j, g[t]);
+                for (int t = 0; t < P; ++t) oz_ld8_issue(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + 8 * j, g[t]);
                 oz_ld_wait();
                 double u[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double acc = oz_i2d(g[OZ_P - 1][c]);
+                    double acc = oz_i2d(g[P - 1][c]);
 #pragma unroll
-                    for (int t = OZ_P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, oz_i2d(g[t][c]));   // Horner in 256^-1
+                    for (int t = P - 2; t >= 0; --t) acc = fma(acc, 0.00390625, oz_i2d(g[t][c]));   // Horner in 256^-1
                     u[c] = acc * rs;
                     if (MODE == 0) qacc[8 * jj + c] = fma(u[c], u[c], qacc[8 * jj + c]);
                 }

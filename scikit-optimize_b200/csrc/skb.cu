@@ -55,6 +55,10 @@ static int fail(int code, const char* fmt, ...) {
         CU(cudaGetLastError());      \
     } while (0)
 
+static inline bool is_split(int precision) {
+    return precision == SKB_PRECISION_SPLIT_INT8 || precision == SKB_PRECISION_SPLIT_INT8_P7;
+}
+
 struct skb_state {
     int device = 0;
     int sm_count = 0;
@@ -71,6 +75,12 @@ struct skb_state {
     int8_t* d_Ad = nullptr;      // digit planes of the dense K_inv (split-integer gradient path)
     double* d_sA = nullptr;      // [n_pad] row scales of K_inv
     double k_scale = 1.0;        // power-of-two scale of the kernel values
+    // SKB_PRECISION_SPLIT_INT8 contracts the leading 6 of the 7 digit planes when a self-check on this state allows it:
+    // 0 = not decided yet (decide_split_planes runs on the first split-integer call), else 6 or 7
+    int split_planes = 0;
+    double split_probe_diff = -1.0;   // measured |var(6 planes) - var(FP64)| / prior variance on the probe rows
+    double* d_probe = nullptr;        // [PROBE_ROWS][d] candidates made from the training rows at state creation
+    double* d_probe_out = nullptr;    // [2][PROBE_ROWS] posterior std: FP64 path | 6-plane split path
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
@@ -242,6 +252,25 @@ __global__ void pack_dense_kernel(const double* __restrict__ K, double* __restri
     }
 }
 
+// Probe candidates for the split-integer self-check (decide_split_planes): PROBE_ROWS rows spread over the training set;
+// even rows are the training points themselves (posterior variance at the noise level: prior - q cancels almost
+// completely), odd rows are moved by up to a quarter of a length scale per coordinate (hash of (row, column)).
+constexpr int PROBE_ROWS = 256;
+__global__ void make_probe_kernel(const double* __restrict__ X, const double* __restrict__ ls, double* __restrict__ probe,
+                                  int n, int d) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= PROBE_ROWS * d) return;
+    const int r = idx / d, k = idx - r * d;
+    const int row = (int)(((int64_t)r * n) / PROBE_ROWS);
+    double v = X[(size_t)row * d + k];
+    if (r & 1) {
+        uint32_t h = ((uint32_t)r * 73856093u) ^ ((uint32_t)k * 19349663u) ^ 0x9e3779b9u;
+        h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+        v += ls[k] * 0.5 * ((double)h * (1.0 / 4294967296.0) - 0.5);
+    }
+    probe[idx] = v;
+}
+
 __global__ void mean_affine_kernel(const double* __restrict__ kdot, double* __restrict__ mean, int64_t m, double y_std,
                                    double y_mean) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -281,14 +310,22 @@ int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t 
     return SKB_OK;
 }
 
-int launch_kcross_digits(skb_state* st, const KDigitParams& p, int tiles, cudaStream_t s) {
-    const size_t smem = kcross_smem_bytes(p.base.d_pad);
-    switch (st->kernel) {
-        case SKB_KERNEL_RBF: kcross_digits_kernel<0><<<tiles, 256, smem, s>>>(p); break;
-        case SKB_KERNEL_MATERN12: kcross_digits_kernel<1><<<tiles, 256, smem, s>>>(p); break;
-        case SKB_KERNEL_MATERN32: kcross_digits_kernel<2><<<tiles, 256, smem, s>>>(p); break;
-        default: kcross_digits_kernel<3><<<tiles, 256, smem, s>>>(p); break;
+template <int P>
+void launch_kcross_digits_planes(int kernel, const KDigitParams& p, int tiles, size_t smem, cudaStream_t s) {
+    switch (kernel) {
+        case SKB_KERNEL_RBF: kcross_digits_kernel<0, P><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN12: kcross_digits_kernel<1, P><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_MATERN32: kcross_digits_kernel<2, P><<<tiles, 256, smem, s>>>(p); break;
+        default: kcross_digits_kernel<3, P><<<tiles, 256, smem, s>>>(p); break;
     }
+}
+
+// `planes` digit planes per kernel value (6 or 7); p.inv_scale is set here to 2^(8 planes - 1) / sK
+int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s) {
+    const size_t smem = kcross_smem_bytes(p.base.d_pad);
+    p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
+    if (planes == 6) launch_kcross_digits_planes<6>(st->kernel, p, tiles, smem, s);
+    else launch_kcross_digits_planes<7>(st->kernel, p, tiles, smem, s);
     LAUNCHED();
     return SKB_OK;
 }
@@ -307,19 +344,19 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     // the digit kernels are meant to share an SM with the contraction kernel (which needs the maximum shared-memory
     // carve-out): ask for the same carve-out so that the SM does not have to be reconfigured between them
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(kcross_digits_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
-    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes()));
+#define SKB_DIGIT_ATTR(K, P)                                                                                                  \
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<K, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));                 \
+    CU(cudaFuncSetAttribute(kcross_digits_kernel<K, P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+    SKB_DIGIT_ATTR(0, 6); SKB_DIGIT_ATTR(1, 6); SKB_DIGIT_ATTR(2, 6); SKB_DIGIT_ATTR(3, 6);
+    SKB_DIGIT_ATTR(0, 7); SKB_DIGIT_ATTR(1, 7); SKB_DIGIT_ATTR(2, 7); SKB_DIGIT_ATTR(3, 7);
+#undef SKB_DIGIT_ATTR
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(7)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(7)));
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     const int smem3 = (int)grad_smem_bytes(st->d_pad);
@@ -336,8 +373,8 @@ int check_params(const skb_acq_params* p) {
     if (!p) return fail(SKB_ERR_INVALID, "params is NULL");
     if (p->acq_mask < 0 || p->acq_mask > 7) return fail(SKB_ERR_INVALID, "acq_mask %d out of range", p->acq_mask);
     if (p->top_k < 0 || p->top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [0, 4096]", p->top_k);
-    if (p->precision != SKB_PRECISION_FP64 && p->precision != SKB_PRECISION_SPLIT_INT8)
-        return fail(SKB_ERR_INVALID, "precision %d is not one of SKB_PRECISION_FP64 / SKB_PRECISION_SPLIT_INT8", p->precision);
+    if (p->precision != SKB_PRECISION_FP64 && !is_split(p->precision))
+        return fail(SKB_ERR_INVALID, "precision %d is not one of SKB_PRECISION_FP64 / SPLIT_INT8 / SPLIT_INT8_P7", p->precision);
     return SKB_OK;
 }
 }  // namespace
@@ -371,7 +408,7 @@ void skb_state_destroy(skb_state* st) {
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
     void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
-                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2};
+                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out};
     for (void* p : ptrs) pool_free(st->device, p);
     for (auto& sp : st->spans) {
         cudaEventDestroy(sp.a);
@@ -458,6 +495,9 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
         CU(cudaMemcpyAsync(st->d_alpha_p, desc->alpha, n * sizeof(double), kind, st->stream));
         pack_xtrain_kernel<<<std::min(1024, (st->n_pad * st->d_pad + 255) / 256), 256, 0, st->stream>>>(
             dX, st->d_ls, st->d_Xp, st->n, st->n_pad, st->d, st->d_pad);
+        LAUNCHED();
+        SKB_PALLOC(st->d_probe, (size_t)PROBE_ROWS * d * sizeof(double));
+        make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(dX, st->d_ls, st->d_probe, st->n, st->d);
         LAUNCHED();
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
@@ -587,7 +627,7 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
 // scratch and three times the launches.  It therefore stays off unless SKB_SPLIT_OVERLAP=1 is exported.
 static bool split_overlaps(const skb_state* st) {
     static const bool enabled = [] { const char* e = getenv("SKB_SPLIT_OVERLAP"); return e && e[0] == '1'; }();
-    return enabled && kcross_smem_bytes(st->d_pad) + oz_smem_bytes() + 4096 <= 232448;
+    return enabled && kcross_smem_bytes(st->d_pad) + oz_smem_bytes(7) + 4096 <= 232448;
 }
 
 static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
@@ -623,17 +663,31 @@ static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chu
 // exact int32 accumulation of the split-integer path: 7 digit-pair sums of at most n products of magnitude <= 2^14
 constexpr int SPLIT_MAX_TRAIN = 16384;
 
+static int decide_split_planes(skb_state* st, cudaStream_t s);
+
+// force_planes: 0 = follow the precision mode (SPLIT_INT8_P7: 7; SPLIT_INT8: the state's self-checked choice), 6 / 7 = use that
 static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
                           const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out,
-                          bool wait_chunk_events = false) {
+                          bool wait_chunk_events = false, int force_planes = 0) {
     CU(cudaSetDevice(st->device));
-    if (!mean_only && prm && prm->precision == SKB_PRECISION_SPLIT_INT8 && st->n > SPLIT_MAX_TRAIN)
+    const bool split_mode = !mean_only && prm && is_split(prm->precision);
+    if (split_mode && st->n > SPLIT_MAX_TRAIN)
         return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= %d (int32 accumulators), got %d",
                     SPLIT_MAX_TRAIN, st->n);
     if (m == 0) return SKB_OK;
+    int planes = 7;
+    if (split_mode) {
+        if (force_planes) planes = force_planes;
+        else if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
+            if (st->split_planes == 0) {
+                int prc = decide_split_planes(st, s);
+                if (prc != SKB_OK) return prc;
+            }
+            planes = st->split_planes;
+        }
+    }
     const int64_t tiles = (m + BN - 1) / BN;
     const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
-    const bool split_mode = !mean_only && prm && prm->precision == SKB_PRECISION_SPLIT_INT8;
     const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes, split_mode);
 
     const bool overlap = split_mode && split_overlaps(st);
@@ -706,10 +760,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             dp.base = kp;
             dp.base.Kt = nullptr;
             dp.base.kdot = buf ? st->d_kdot2 : st->d_kdot;
-            dp.Kd = reinterpret_cast<int8_t*>(buf ? st->d_Kt2 : st->d_Kt);   // 7 bytes per (training point, candidate)
-            dp.inv_scale_2p55 = 36028797018963968.0 / st->k_scale;
+            dp.Kd = reinterpret_cast<int8_t*>(buf ? st->d_Kt2 : st->d_Kt);   // `planes` (<= 7) bytes per (training point, candidate)
             if ((rc = span_begin(st, 0, s1)) != SKB_OK) return rc;
-            if ((rc = launch_kcross_digits(st, dp, (int)nt, s1)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, planes, (int)nt, s1)) != SKB_OK) return rc;
             if ((rc = span_end(st, s1)) != SKB_OK) return rc;
             if (overlap) {
                 CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
@@ -738,7 +791,10 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             op.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
             if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
             op.Wt = nullptr;
-            ozaki_trmm_kernel<0><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(), s>>>(op);
+            if (planes == 6)
+                ozaki_trmm_kernel<0, 6><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(6), s>>>(op);
+            else
+                ozaki_trmm_kernel<0, 7><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(7), s>>>(op);
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
             if (overlap) CU(cudaEventRecord(st->ev_k2[chunk_index], s));
@@ -804,6 +860,66 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     return SKB_OK;
 }
 
+}  // extern "C"
+
+// Self-check behind SKB_PRECISION_SPLIT_INT8: score the probe rows of this state with the FP64 DMMA path and with the
+// 6-plane split-integer path; when the posterior variances agree to 1e-10 of the prior variance (a tenth of the 1e-9
+// parity gate; typical: 4e-12) the state contracts 6 planes from now on (21 digit-plane products instead of 28),
+// otherwise all 7.  Runs once per state, on the caller's stream, and waits for it (two 256-candidate passes).
+// SKB_SPLIT_PLANES=6|7 in the environment skips the check.
+static int decide_split_planes(skb_state* st, cudaStream_t s) {
+    static const int forced = [] { const char* e = getenv("SKB_SPLIT_PLANES"); return e ? atoi(e) : 0; }();
+    if (forced == 6 || forced == 7) {
+        st->split_planes = forced;
+        return SKB_OK;
+    }
+    int rc;
+    if (!st->d_probe_out &&
+        (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), 2 * PROBE_ROWS * sizeof(double))) != SKB_OK)
+        return rc;
+    skb_acq_params prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.xi = 0.01;
+    prm.kappa = 1.96;
+    skb_score_out o;
+    std::memset(&o, 0, sizeof(o));
+    const bool timing = st->timing;
+    st->timing = false;                                   // the probe is not part of anybody's roofline
+    prm.precision = SKB_PRECISION_FP64;
+    o.std = st->d_probe_out;
+    rc = score_dev_impl(st, st->d_probe, PROBE_ROWS, 0, &prm, &o, s, false, nullptr, false, 0);
+    if (rc == SKB_OK) {
+        prm.precision = SKB_PRECISION_SPLIT_INT8;
+        o.std = st->d_probe_out + PROBE_ROWS;
+        rc = score_dev_impl(st, st->d_probe, PROBE_ROWS, 0, &prm, &o, s, false, nullptr, false, 6);
+    }
+    st->timing = timing;
+    if (rc != SKB_OK) return rc;
+    double h[2 * PROBE_ROWS];
+    CU(cudaMemcpyAsync(h, st->d_probe_out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    double worst = 0.0;
+    bool finite = true;
+    for (int i = 0; i < PROBE_ROWS; ++i) {
+        const double dv = std::fabs(h[i] * h[i] - h[PROBE_ROWS + i] * h[PROBE_ROWS + i]);
+        if (!(dv == dv)) finite = false;
+        worst = std::max(worst, dv);
+    }
+    const double scale = std::fabs(st->amplitude + st->bias + st->white) * st->y_std * st->y_std;
+    st->split_probe_diff = scale > 0.0 ? worst / scale : worst;
+    st->split_planes = (finite && scale > 0.0 && worst <= 1e-10 * scale) ? 6 : 7;
+    return SKB_OK;
+}
+
+extern "C" {
+
+int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    if (planes) *planes = st->split_planes;
+    if (probe_rel_diff) *probe_rel_diff = st->split_probe_diff;
+    return SKB_OK;
+}
+
 int skb_score_dev(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* params,
                   const skb_score_out* out, void* stream) {
     if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
@@ -858,7 +974,7 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
     }
     if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
     if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double),
-                                                       params->precision == SKB_PRECISION_SPLIT_INT8))) != SKB_OK) return rc;
+                                                       is_split(params->precision)))) != SKB_OK) return rc;
     if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) return rc;
     if (out->n_var_clamped)
         CU(cudaMemcpyAsync(out->n_var_clamped, st->d_clamp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
@@ -925,7 +1041,7 @@ static int check_grad_args(skb_state* st, const double* X, int64_t m, const skb_
     if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
     if (!st->d_Ap) return fail(SKB_ERR_UNSUPPORTED, "state was created without K_inv: gradient entry points are unavailable");
     int rc = check_params(params);
-    if (rc == SKB_OK && params->precision == SKB_PRECISION_SPLIT_INT8 && st->n > 16384)
+    if (rc == SKB_OK && is_split(params->precision) && st->n > 16384)
         return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= 16384 (int32 accumulators), got %d", st->n);
     return rc;
 }
@@ -965,15 +1081,16 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
         kp.d_pad = st->d_pad;
         kp.amplitude = st->amplitude;
         kp.bias = st->bias;
-        if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
+        if (is_split(prm->precision)) {
             // W = K_inv . K_trans^T on tcgen05 from int8 digit planes (dense variant of ozaki.cuh), stored in FP64
             KDigitParams dp;
             dp.base = kp;
             dp.base.Kt = nullptr;
             dp.Kd = reinterpret_cast<int8_t*>(st->d_Kt);
-            dp.inv_scale_2p55 = 36028797018963968.0 / st->k_scale;
+            // always all 7 planes here: the rows of K_inv are scaled like 1 / noise (those of L_inv like its square
+            // root), so the dense contraction has no accuracy to spare for the 6-plane variant
             if ((rc = span_begin(st, 0, s)) != SKB_OK) return rc;
-            if ((rc = launch_kcross_digits(st, dp, (int)nt, s)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, 7, (int)nt, s)) != SKB_OK) return rc;
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
             OzakiParams op;
             std::memset(&op, 0, sizeof(op));
@@ -986,7 +1103,7 @@ int skb_score_grad_dev(skb_state* st, const double* X, int64_t m, const skb_acq_
             op.m = mc;
             op.Wt = st->d_Wt;
             if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
-            ozaki_trmm_kernel<1><<<dim3(nI, (unsigned)(2 * nt)), OZ_THREADS, oz_smem_bytes(), s>>>(op);
+            ozaki_trmm_kernel<1, 7><<<dim3(nI, (unsigned)(2 * nt)), OZ_THREADS, oz_smem_bytes(7), s>>>(op);
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
         } else {

@@ -12,13 +12,17 @@ from tests.test_gpu_parity import ACQS, check_against, host_state_from_oracle_st
 pytestmark = pytest.mark.gpu
 
 
+SPLIT_MODES = ("split_int8", "split_int8_p7")        # self-checked 6-or-7 planes, always 7 planes
+
+
+@pytest.mark.parametrize("precision", SPLIT_MODES)
 @pytest.mark.parametrize("name", NAMES)
-def test_split_golden_fixture(name):
+def test_split_golden_fixture(name, precision):
     rec, meta, est = load(name)
     _, _, ost = load_state(name)
     dev = engine.DeviceState.from_estimator(est)
     res = dev.score(rec["Xc"], y_opt=float(rec["y_opt"]), acq_funcs=ACQS, xi=float(rec["xi"]), kappa=float(rec["kappa"]),
-                    top_k=10, precision="split_int8")
+                    top_k=10, precision=precision)
     vtol = var_tol(ost)
     acq_ref = {a: rec["acq_" + a] for a in ACQS}
     check_against(ost, res, rec["mean"], rec["std"], acq_ref, vtol, float(rec["y_opt"]), float(rec["xi"]),
@@ -35,22 +39,24 @@ def test_split_golden_fixture(name):
     (37, 50, 200, orc.KIND_MATERN, 2.5),
     (1, 1, 1, orc.KIND_MATERN, 2.5),
 ])
-def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu):
+@pytest.mark.parametrize("precision", SPLIT_MODES)
+def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu, precision):
     st = orc.make_synthetic_state(n, d, noise=1e-3, seed=n + d, kind=kind, nu=nu, normalize_y=n > 1)
     rng = np.random.RandomState(7)
     Xc = rng.rand(m, d)
     Xc[0] = st.X_train[0]
     y_opt = float(st.meta["y"].min())
     dev = engine.DeviceState(host_state_from_oracle_state(st))
-    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision="split_int8")
+    res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision=precision)
     ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision="fp64")
     mu, sd = orc.predict(st, Xc, return_std=True)
     acq_ref = {a: orc.gaussian_acquisition(Xc, st, y_opt, a, acq_func_kwargs=dict(xi=0.01, kappa=1.96)) for a in ACQS}
     check_against(st, res, mu, sd, acq_ref, var_tol(st), y_opt, k=min(10, m))
     # the two device formulations agree far tighter than the gate
     scale = st.prior_var * st.y_std ** 2
-    print("split vs fp64: max |d var| / prior = %.2e" % (np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / scale))
-    assert np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) <= 2e-10 * scale
+    print("%s (planes %s) vs fp64: max |d var| / prior = %.2e" % (precision, dev.split_info(),
+                                                                   np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / scale))
+    assert np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) <= (2e-10 if precision == "split_int8" else 1e-11) * scale
     for a in ACQS:
         assert res[a]["topk_idx"][0] == ref[a]["topk_idx"][0]
     dev.close()
@@ -150,3 +156,30 @@ def test_split_extreme_scales():
         print("amp=%g noise=%g cond tol %.1e: split-fp64 %.2e, split-oracle %.2e" % (
             amp, noise, vtol, np.max(np.abs(res["std"] ** 2 - ref["std"] ** 2)) / scale,
             np.max(np.abs(res["std"] ** 2 - sd ** 2)) / scale))
+
+
+def test_split_plane_self_check():
+    """precision="split_int8" contracts 6 digit planes only on states whose self-check (256 probe candidates, FP64 against
+    6 planes) agrees to 1e-10 of the prior variance; the choice, the measured difference and the two variants' accuracy."""
+    st = orc.make_synthetic_state(2048, 20, noise=1e-4, seed=0)
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    assert dev.split_info() == (0, -1.0)                            # undecided until the first split-integer call
+    rng = np.random.RandomState(5)
+    Xc = rng.rand(20_000, 20)
+    y_opt = float(st.meta["y"].min())
+    p7 = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8_p7")
+    assert dev.split_info()[0] == 0                                 # the 7-plane mode does not need the check
+    auto = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8")
+    planes, diff = dev.split_info()
+    ref = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="fp64")
+    scale = st.prior_var * st.y_std ** 2
+    e7 = np.max(np.abs(p7["std"] ** 2 - ref["std"] ** 2)) / scale
+    e_auto = np.max(np.abs(auto["std"] ** 2 - ref["std"] ** 2)) / scale
+    print("planes=%d probe diff=%.2e; vs fp64: 7 planes %.2e, auto %.2e" % (planes, diff, e7, e_auto))
+    assert planes == 6 and 0.0 <= diff <= 1e-10                     # this well-conditioned state takes the 6-plane path
+    assert e7 <= 1e-12 and e_auto <= 1e-10 and e7 < e_auto
+    assert np.array_equal(auto["EI"]["topk_idx"], ref["EI"]["topk_idx"])
+    assert np.array_equal(p7["EI"]["topk_idx"], ref["EI"]["topk_idx"])
+    mu, sd = orc.predict(st, Xc[:500], return_std=True)
+    assert np.max(np.abs(auto["std"][:500] ** 2 - sd ** 2)) <= 1e-9 * scale
+    dev.close()

@@ -39,3 +39,36 @@ def test_split_product_matches_extended_precision():
     q = np.sum(U * U, axis=0)
     q_ref = np.einsum("ci,ci->c", K.T @ st.K_inv, K.T)
     assert np.max(np.abs(q - q_ref)) <= 1e-11 * st.prior_var
+
+
+def test_leading_six_digits_are_the_rounded_47_bit_value():
+    """What lets the 6-plane contraction read the first 6 of the 7 packed planes of L_inv: dropping the last balanced
+    digit rounds (|digit| <= 128 = half a unit of the digit before it), so the leading digits are a valid 6-digit
+    expansion of the value to within half a unit of 2^-47 - the same bound as quantising to 47 bits directly."""
+    rng = np.random.RandomState(3)
+    x = (rng.rand(20000) - 0.5)                       # value / scale, |x| <= 0.5
+    x[:3] = [0.5, -0.5, 2.0 ** -50]
+    p7, _ = se.digits(x * 2.0 ** 55, 7)
+    lead = sum(p7[p] * 256 ** (5 - p) for p in range(6))
+    assert np.max(np.abs(lead - x * 2.0 ** 47)) <= 0.5 + 2.0 ** -8
+    assert all(pl.min() >= -128 and pl.max() <= 127 for pl in p7)
+
+
+def test_six_plane_contraction_meets_the_parity_gate_with_margin():
+    """47-bit operands, 21 digit-plane products: the variance term stays within 1e-10 of the prior variance of the exact
+    contraction (the self-check threshold of skb.cu decide_split_planes; the parity gate is 1e-9), 7 planes within 1e-12."""
+    from scipy.linalg import solve_triangular
+    for n, d, noise in ((384, 6, 1e-4), (256, 4, 1e-8), (512, 12, 1e-2)):
+        st = orc.make_synthetic_state(n, d, noise=noise, seed=n)
+        V = solve_triangular(st.L, np.eye(st.n), lower=True)
+        Xc = np.random.RandomState(2).rand(64, d)
+        Xc[::2] = st.X_train[:32]                                    # variance at the noise level: prior - q cancels
+        K = orc.kernel_cross(st, Xc).T
+        exact = V.astype(np.longdouble) @ K.astype(np.longdouble)
+        q_exact = np.sum(exact * exact, axis=0).astype(np.float64)
+        k_scale = se.pow2_scale(abs(st.amplitude) + abs(st.bias))
+        err = {}
+        for planes in (6, 7):
+            U = se.split_matmul(V, K, planes=planes, k_scale=k_scale)
+            err[planes] = np.max(np.abs(np.sum(U * U, axis=0) - q_exact)) / st.prior_var
+        assert err[6] <= 1e-10 and err[7] <= 1e-12 and err[7] < err[6]
