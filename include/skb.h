@@ -55,9 +55,11 @@ typedef enum {
  *                products accumulated exactly in int32 on tcgen05 (kind::i8), recombined in FP64 (csrc/ozaki.cuh);
  *                2e-14 of the prior variance from the exact contraction.
  *   SPLIT_INT8 : the same on the leading 6 planes (47-bit operands, 21 instead of 28 digit-plane products; 4e-12 of the
- *                prior variance) WHEN a self-check run once per state - 256 probe candidates scored with FP64 and with 6
- *                planes - agrees to 1e-10 of the prior variance; otherwise 7 planes.  skb_state_split_info reports the
- *                choice.  The gradient entry points always contract 7 planes. */
+ *                prior variance; the kernel values feeding it are computed to that accuracy only, csrc/kcross.cuh) WHEN a
+ *                self-check run once per state - 256 probe candidates scored with FP64 and with 6 planes - agrees to 1e-10
+ *                on the variance (relative to the prior variance) and on the mean (relative to max(|mean|, y_std));
+ *                otherwise 7 planes.  skb_state_split_info reports the choice and the measured difference.  The gradient
+ *                entry points always contract 7 planes. */
 typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1, SKB_PRECISION_SPLIT_INT8_P7 = 2 } skb_precision;
 
 typedef enum { SKB_ACQ_EI = 0, SKB_ACQ_PI = 1, SKB_ACQ_LCB = 2, SKB_NUM_ACQ = 3 } skb_acq_kind;

@@ -36,7 +36,8 @@ __device__ __forceinline__ double base_kernel(double sq) {
 }
 
 constexpr size_t kcross_smem_bytes(int d_pad) {
-    return sizeof(double) * ((size_t)d_pad * XS_LD + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + BN) + 2 * sizeof(uint64_t);
+    return sizeof(double) * ((size_t)d_pad * XS_LD + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + BN) + 2 * sizeof(uint64_t) +
+           sizeof(double) * 2 * XROWS;                 // + [2][XROWS] squared row norms (6-plane digit kernel only)
 }
 
 template <int KIND>
@@ -147,16 +148,77 @@ struct KDigitParams {
     KCrossParams base;
     int8_t* Kd;               // [tiles64][n_pad/32][2 k halves][P planes][8 cand groups][8 cands][16 B]
     double inv_scale;         // 2^(8P-1) / sK
+    const double* tn;         // [n_pad] squared norms of the scaled training rows (6-plane variant), zero padded
 };
+
+// sqrt(s) for finite s (negative -> 0) as in fastmath.cuh sqrt_nonneg, without its second coupled Newton step: after one
+// step g and h carry a relative error e1 ~ 1.5 e0^2 (e0 <= 2^-20, the seed), and the residual correction leaves
+// e1 * e1' ~ 1e-24, so the second step only matters to the last-bit reproducibility of the FP64 path, which keeps it.
+// The caller clamps s to [1e-290, inf) first (no zero / negative / NaN special cases left in here).
+__device__ __forceinline__ double sqrt_pos_short(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double g = s * y;
+    double h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, s);
+    return fma(d, h, g);
+}
+
+// exp(x) for x <= 0 (or +1e-15-ish), not NaN: fastmath.cuh exp_nonpos with the degree-13 polynomial split into its even
+// and odd halves (two dependency chains of 6 FMAs instead of one of 13) and without the NaN pass-through.
+__device__ __forceinline__ double exp_nonpos_short(double x) {
+    const double fn = fma(x, c_exp[0], c_exp[1]);
+    const double n = fn - c_exp[1];
+    double r = fma(n, c_exp[2], x);
+    r = fma(n, c_exp[3], r);
+    const double r2 = r * r;
+    double po = c_exp[4], pe = c_exp[5];                      // r^13 ... r^1 coefficients / r^12 ... r^0 coefficients
+#pragma unroll
+    for (int i = 6; i <= 16; i += 2) {
+        po = fma(po, r2, c_exp[i]);
+        pe = fma(pe, r2, i + 1 <= 16 ? c_exp[i + 1] : 1.0);
+    }
+    const double p = fma(po, r, pe);
+    const int ni = __double2loint(fn);
+    const double scaled = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return x < c_exp[17] ? 0.0 : scaled;
+}
+
+// kernel value from a squared distance that may be slightly negative (cancellation) but is not NaN
+template <int KIND>
+__device__ __forceinline__ double base_kernel_short(double sq) {
+    if (KIND == 0) return exp_nonpos_short(-0.5 * sq);
+    const double r = sqrt_pos_short(sq > 1e-290 ? sq : 1e-290);
+    if (KIND == 1) return exp_nonpos_short(-r);
+    if (KIND == 2) { const double K = r * 1.7320508075688772; return (1.0 + K) * exp_nonpos_short(-K); }
+    const double K = r * 2.23606797749979;
+    return (1.0 + K + K * K * (1.0 / 3.0)) * exp_nonpos_short(-K);
+}
 
 // Thread (cp, rq): candidates cp and cp + 64 of the 128-candidate tile (one in each 64-candidate MMA tile) x training
 // rows [16 rq, 16 rq + 16) of every 64-row stage, i.e. one k-half of a 32-point chunk.  Two candidates share every
 // broadcast read of a training row, which halves this kernel's shared-memory traffic -- it runs next to the
 // shared-memory-bound contraction kernel (second stream), so that is what decides how much of it is hidden.
 // P = number of digit planes emitted (7: 55-bit values, 6: 47-bit values; ozaki.cuh).
+//
+// The 6-plane variant rounds every kernel value to 2^-47 of the kernel scale (1.4e-14 absolute at scale 4), which buys
+// three savings on the FP64 pipe that bounds this kernel (81 -> 59 FP64 instructions per (candidate, training point)
+// at d = 20), none of them visible above that rounding:
+//   * squared distances as |x|^2 + |t|^2 - 2 x.t (one FMA per feature instead of a subtraction and an FMA; the
+//     cancellation error, ~1e-15 absolute in r^2, only matters for the nu = 1/2 kernel, whose value is not smooth in r^2
+//     at 0 - that kernel keeps the direct differences);
+//   * the square root without its redundant second Newton step (sqrt_nonneg_short);
+//   * digit extraction by one FMA with 1.5 * 2^52 (the low 48 mantissa bits are then the rounded integer in two's
+//     complement) instead of a multiply and a 64-bit float-to-integer conversion.
+// The 7-plane variant is arithmetically the FP64 path's K1 (direct differences, fastmath.cuh).
 template <int KIND, int P>
 __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParams q) {
     constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));     // +128 in each of the P digit bytes
+    constexpr bool FAST = P == 6;
+    constexpr bool DOT = FAST && KIND != 1;
     const KCrossParams& p = q.base;
     extern __shared__ __align__(16) unsigned char smem_k1[];
     const int d_pad = p.d_pad;
@@ -166,6 +228,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     double* xs = al + 2 * XROWS;
     double* mpart = xs + (size_t)d_pad * XS_LD;              // [BN]; reused as [4][BN] staging through xt after the loop
     uint64_t* bars = reinterpret_cast<uint64_t*>(mpart + BN);
+    double* tnb = reinterpret_cast<double*>(bars + 2);        // [2][XROWS] squared norms of the staged training rows (DOT)
 
     const int tid = threadIdx.x, cp = tid & 63, rq = tid >> 6;
     const int64_t tile = blockIdx.x;
@@ -185,9 +248,10 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     __syncthreads();
     auto issue = [&](int st) {
         const int buf = st & 1;
-        mbar_arrive_expect_tx(bars + buf, (uint32_t)(xt_stage + XROWS) * 8u);
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)(xt_stage + XROWS + (DOT ? XROWS : 0)) * 8u);
         bulk_g2s(xt + buf * xt_stage, p.Xp + (size_t)st * xt_stage, (uint32_t)xt_stage * 8u, bars + buf);
         bulk_g2s(al + buf * XROWS, p.alpha_p + (size_t)st * XROWS, XROWS * 8u, bars + buf);
+        if (DOT) bulk_g2s(tnb + buf * XROWS, q.tn + (size_t)st * XROWS, XROWS * 8u, bars + buf);
     };
     if (tid == 0) {
         issue(0);
@@ -195,6 +259,14 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     }
 
     double macc[2] = {0.0, 0.0};
+    double xn[2] = {0.0, 0.0};                                // |x|^2 of this thread's two candidates (6-plane variant)
+    if (FAST) {
+        for (int k = 0; k < d_pad; ++k) {
+            const double a0 = xs[k * XS_LD + cp], a1 = xs[k * XS_LD + cp + 64];
+            xn[0] = fma(a0, a0, xn[0]);
+            xn[1] = fma(a1, a1, xn[1]);
+        }
+    }
     const int nkc_all = p.n_pad / 32;
     // candidate e (0/1) lives in MMA tile 2*tile + e at position cp: [k half][plane][cand group (8)][cand % 8][16 B]
     int8_t* kd_base = q.Kd + ((size_t)(tile * 2) * nkc_all) * (2 * P * 8 * 128) + (cp >> 3) * 128 + (cp & 7) * 16 +
@@ -226,6 +298,17 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                 for (int kk = 0; kk < 4; ++kk) {
                     const double2 t01 = *reinterpret_cast<const double2*>(t + kk * 4);
                     const double2 t23 = *reinterpret_cast<const double2*>(t + kk * 4 + 2);
+                    if (DOT) {
+                        s[0][g * 4 + 0] = fma(x0[kk], t01.x, s[0][g * 4 + 0]);
+                        s[0][g * 4 + 1] = fma(x0[kk], t01.y, s[0][g * 4 + 1]);
+                        s[0][g * 4 + 2] = fma(x0[kk], t23.x, s[0][g * 4 + 2]);
+                        s[0][g * 4 + 3] = fma(x0[kk], t23.y, s[0][g * 4 + 3]);
+                        s[1][g * 4 + 0] = fma(x1[kk], t01.x, s[1][g * 4 + 0]);
+                        s[1][g * 4 + 1] = fma(x1[kk], t01.y, s[1][g * 4 + 1]);
+                        s[1][g * 4 + 2] = fma(x1[kk], t23.x, s[1][g * 4 + 2]);
+                        s[1][g * 4 + 3] = fma(x1[kk], t23.y, s[1][g * 4 + 3]);
+                        continue;
+                    }
                     double a;
                     a = x0[kk] - t01.x; s[0][g * 4 + 0] = fma(a, a, s[0][g * 4 + 0]);
                     a = x0[kk] - t01.y; s[0][g * 4 + 1] = fma(a, a, s[0][g * 4 + 1]);
@@ -245,10 +328,19 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int j = st * XROWS + rq * 16 + r;
-                double val = fma(p.amplitude, base_kernel<KIND>(s[e][r]), p.bias);
-                if (j >= p.n) val = 0.0;
+                double sq = s[e][r];
+                // |x - t|^2 = (|x|^2 + |t|^2) - 2 x.t; a slightly negative result (x == t) becomes r = 0 in the root
+                if (DOT) sq = fma(-2.0, sq, xn[e] + tnb[buf * XROWS + rq * 16 + r]);
+                double val = fma(p.amplitude, FAST ? base_kernel_short<KIND>(sq) : base_kernel<KIND>(sq), p.bias);
+                // padded training rows: L_inv's digit planes are zero there and alpha is zero padded, so the 6-plane variant
+                // (whose values are always finite) needs no masking; the 7-plane variant keeps the FP64 path's exact zeros
+                if (!FAST && j >= p.n) val = 0.0;
                 macc[e] = fma(val, alb[rq * 16 + r], macc[e]);
-                const unsigned long long y = ((unsigned long long)__double2ll_rn(val * q.inv_scale) + DIGIT_BIAS) ^ DIGIT_BIAS;
+                unsigned long long y;
+                if (FAST)       // |val * inv_scale| <= 2^46: the sum's low 48 mantissa bits are the rounded integer
+                    y = ((unsigned long long)__double_as_longlong(fma(val, q.inv_scale, 6755399441055744.0)) + DIGIT_BIAS) ^ DIGIT_BIAS;
+                else
+                    y = ((unsigned long long)__double2ll_rn(val * q.inv_scale) + DIGIT_BIAS) ^ DIGIT_BIAS;
                 lo[r] = (uint32_t)y;
                 hi[r] = (uint32_t)(y >> 32);
             }
@@ -276,6 +368,12 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
     }
     // k . alpha: the four row quarters of a candidate are combined in a fixed order (staged through the xt buffers)
     double* stage = xt;                                       // [4][BN], free after the loop
+    if (FAST) {
+        // the 6-plane transform clamps its argument, which would swallow a NaN / Inf coordinate: hand it to the mean
+        // (0 * NaN = 0 * Inf = NaN), from where it reaches every output like in the other paths
+        macc[0] = fma(0.0, xn[0], macc[0]);
+        macc[1] = fma(0.0, xn[1], macc[1]);
+    }
     stage[rq * BN + cp] = macc[0];
     stage[rq * BN + cp + 64] = macc[1];
     __syncthreads();

@@ -80,7 +80,8 @@ struct skb_state {
     int split_planes = 0;
     double split_probe_diff = -1.0;   // measured |var(6 planes) - var(FP64)| / prior variance on the probe rows
     double* d_probe = nullptr;        // [PROBE_ROWS][d] candidates made from the training rows at state creation
-    double* d_probe_out = nullptr;    // [2][PROBE_ROWS] posterior std: FP64 path | 6-plane split path
+    double* d_probe_out = nullptr;    // [4][PROBE_ROWS] posterior mean, std: FP64 path | mean, std: 6-plane split path
+    double* d_tn = nullptr;           // [n_pad] squared norms of the scaled training rows (6-plane K1: |x|^2 + |t|^2 - 2 x.t)
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
@@ -255,6 +256,16 @@ __global__ void pack_dense_kernel(const double* __restrict__ K, double* __restri
 // Probe candidates for the split-integer self-check (decide_split_planes): PROBE_ROWS rows spread over the training set;
 // even rows are the training points themselves (posterior variance at the noise level: prior - q cancels almost
 // completely), odd rows are moved by up to a quarter of a length scale per coordinate (hash of (row, column)).
+// tn[j] = sum_k Xp[j][k]^2 over the packed, length-scaled training rows (zero for the padding rows)
+__global__ void row_sqnorm_kernel(const double* __restrict__ Xp, double* __restrict__ tn, int n_pad, int d_pad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    const double* row = Xp + (size_t)(j >> 2) * d_pad * 4 + (j & 3);
+    double acc = 0.0;
+    for (int k = 0; k < d_pad; ++k) acc = fma(row[k * 4], row[k * 4], acc);
+    tn[j] = acc;
+}
+
 constexpr int PROBE_ROWS = 256;
 __global__ void make_probe_kernel(const double* __restrict__ X, const double* __restrict__ ls, double* __restrict__ probe,
                                   int n, int d) {
@@ -324,6 +335,7 @@ void launch_kcross_digits_planes(int kernel, const KDigitParams& p, int tiles, s
 int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s) {
     const size_t smem = kcross_smem_bytes(p.base.d_pad);
     p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
+    p.tn = st->d_tn;
     if (planes == 6) launch_kcross_digits_planes<6>(st->kernel, p, tiles, smem, s);
     else launch_kcross_digits_planes<7>(st->kernel, p, tiles, smem, s);
     LAUNCHED();
@@ -408,7 +420,7 @@ void skb_state_destroy(skb_state* st) {
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
     void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
-                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out};
+                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out, st->d_tn};
     for (void* p : ptrs) pool_free(st->device, p);
     for (auto& sp : st->spans) {
         cudaEventDestroy(sp.a);
@@ -495,6 +507,9 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
         CU(cudaMemcpyAsync(st->d_alpha_p, desc->alpha, n * sizeof(double), kind, st->stream));
         pack_xtrain_kernel<<<std::min(1024, (st->n_pad * st->d_pad + 255) / 256), 256, 0, st->stream>>>(
             dX, st->d_ls, st->d_Xp, st->n, st->n_pad, st->d, st->d_pad);
+        LAUNCHED();
+        SKB_PALLOC(st->d_tn, (size_t)st->n_pad * sizeof(double));
+        row_sqnorm_kernel<<<(st->n_pad + 255) / 256, 256, 0, st->stream>>>(st->d_Xp, st->d_tn, st->n_pad, st->d_pad);
         LAUNCHED();
         SKB_PALLOC(st->d_probe, (size_t)PROBE_ROWS * d * sizeof(double));
         make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(dX, st->d_ls, st->d_probe, st->n, st->d);
@@ -863,9 +878,9 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
 }  // extern "C"
 
 // Self-check behind SKB_PRECISION_SPLIT_INT8: score the probe rows of this state with the FP64 DMMA path and with the
-// 6-plane split-integer path; when the posterior variances agree to 1e-10 of the prior variance (a tenth of the 1e-9
-// parity gate; typical: 4e-12) the state contracts 6 planes from now on (21 digit-plane products instead of 28),
-// otherwise all 7.  Runs once per state, on the caller's stream, and waits for it (two 256-candidate passes).
+// 6-plane split-integer path (47-bit operands, dot-product distances in K1); when the posterior variances agree to 1e-10
+// of the prior variance and the means to 1e-10 of max(|mean|, y_std) (a tenth of the 1e-9 parity gates; typical: 4e-12
+// and 1e-13) the state contracts 6 planes from now on (21 digit-plane products instead of 28), otherwise all 7.  Runs once per state, on the caller's stream, and waits for it (two 256-candidate passes).
 // SKB_SPLIT_PLANES=6|7 in the environment skips the check.
 static int decide_split_planes(skb_state* st, cudaStream_t s) {
     static const int forced = [] { const char* e = getenv("SKB_SPLIT_PLANES"); return e ? atoi(e) : 0; }();
@@ -875,7 +890,7 @@ static int decide_split_planes(skb_state* st, cudaStream_t s) {
     }
     int rc;
     if (!st->d_probe_out &&
-        (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), 2 * PROBE_ROWS * sizeof(double))) != SKB_OK)
+        (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), 4 * PROBE_ROWS * sizeof(double))) != SKB_OK)
         return rc;
     skb_acq_params prm;
     std::memset(&prm, 0, sizeof(prm));
@@ -886,28 +901,36 @@ static int decide_split_planes(skb_state* st, cudaStream_t s) {
     const bool timing = st->timing;
     st->timing = false;                                   // the probe is not part of anybody's roofline
     prm.precision = SKB_PRECISION_FP64;
-    o.std = st->d_probe_out;
+    o.mean = st->d_probe_out;
+    o.std = st->d_probe_out + PROBE_ROWS;
     rc = score_dev_impl(st, st->d_probe, PROBE_ROWS, 0, &prm, &o, s, false, nullptr, false, 0);
     if (rc == SKB_OK) {
         prm.precision = SKB_PRECISION_SPLIT_INT8;
-        o.std = st->d_probe_out + PROBE_ROWS;
+        o.mean = st->d_probe_out + 2 * PROBE_ROWS;
+        o.std = st->d_probe_out + 3 * PROBE_ROWS;
         rc = score_dev_impl(st, st->d_probe, PROBE_ROWS, 0, &prm, &o, s, false, nullptr, false, 6);
     }
     st->timing = timing;
     if (rc != SKB_OK) return rc;
-    double h[2 * PROBE_ROWS];
+    double h[4 * PROBE_ROWS];
     CU(cudaMemcpyAsync(h, st->d_probe_out, sizeof(h), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    double worst = 0.0;
+    // variance against the prior variance, mean against max(|mean|, y_std): the scales of the 1e-9 parity gates
+    double worst_var = 0.0, worst_mean = 0.0, mean_scale = std::fabs(st->y_std);
     bool finite = true;
     for (int i = 0; i < PROBE_ROWS; ++i) {
-        const double dv = std::fabs(h[i] * h[i] - h[PROBE_ROWS + i] * h[PROBE_ROWS + i]);
-        if (!(dv == dv)) finite = false;
-        worst = std::max(worst, dv);
+        const double dv = std::fabs(h[PROBE_ROWS + i] * h[PROBE_ROWS + i] - h[3 * PROBE_ROWS + i] * h[3 * PROBE_ROWS + i]);
+        const double dm = std::fabs(h[i] - h[2 * PROBE_ROWS + i]);
+        if (!(dv == dv) || !(dm == dm)) finite = false;
+        worst_var = std::max(worst_var, dv);
+        worst_mean = std::max(worst_mean, dm);
+        mean_scale = std::max(mean_scale, std::fabs(h[i]));
     }
-    const double scale = std::fabs(st->amplitude + st->bias + st->white) * st->y_std * st->y_std;
-    st->split_probe_diff = scale > 0.0 ? worst / scale : worst;
-    st->split_planes = (finite && scale > 0.0 && worst <= 1e-10 * scale) ? 6 : 7;
+    const double var_scale = std::fabs(st->amplitude + st->bias + st->white) * st->y_std * st->y_std;
+    const double rel_var = var_scale > 0.0 ? worst_var / var_scale : INFINITY;
+    const double rel_mean = mean_scale > 0.0 ? worst_mean / mean_scale : INFINITY;
+    st->split_probe_diff = std::max(rel_var, rel_mean);
+    st->split_planes = (finite && st->split_probe_diff <= 1e-10) ? 6 : 7;
     return SKB_OK;
 }
 
