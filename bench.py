@@ -335,7 +335,8 @@ def main():
     ms_total, timing, launches, clocks_summary, argmin_idx = timed_dev(headline)
     e2e_s = timed_host(headline)
     planes, probe_diff = dev.split_info() if headline == "split_int8" else (0, -1.0)
-    ms_p7 = timed_dev("split_int8_p7")[0] if headline == "split_int8" and planes != 7 else None
+    # single-GPU context only (under torchrun every rank would have to take this branch together)
+    ms_p7 = timed_dev("split_int8_p7")[0] if headline == "split_int8" and planes == 6 and world == 1 else None
     ms_fp64, timing_fp64, _, _, argmin_fp64 = timed_dev("fp64") if headline != "fp64" else (ms_total, timing, 0, None, argmin_idx)
     e2e_fp64_s = timed_host("fp64") if headline != "fp64" else e2e_s
 

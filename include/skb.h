@@ -58,8 +58,9 @@ typedef enum {
  *                prior variance; the kernel values feeding it are computed to that accuracy only, csrc/kcross.cuh) WHEN a
  *                self-check run once per state - 256 probe candidates scored with FP64 and with 6 planes - agrees to 1e-10
  *                on the variance (relative to the prior variance) and on the mean (relative to max(|mean|, y_std));
- *                otherwise 7 planes.  skb_state_split_info reports the choice and the measured difference.  The gradient
- *                entry points always contract 7 planes. */
+ *                otherwise 7 planes.  The check runs on the first call with at least 32768 candidates (smaller calls on
+ *                an undecided state contract 7 planes); skb_state_split_info reports the choice and the measured
+ *                difference.  The gradient entry points always contract 7 planes. */
 typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1, SKB_PRECISION_SPLIT_INT8_P7 = 2 } skb_precision;
 
 typedef enum { SKB_ACQ_EI = 0, SKB_ACQ_PI = 1, SKB_ACQ_LCB = 2, SKB_NUM_ACQ = 3 } skb_acq_kind;
@@ -142,6 +143,9 @@ int skb_state_attach_kinv(skb_state* st, const double* K_inv);
 /* Digit planes SKB_PRECISION_SPLIT_INT8 contracts on this state (6 or 7; 0 = not decided yet, the self-check runs on the
  * first split-integer call) and the relative variance difference the self-check measured (-1 before it ran). */
 int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff);
+/* Run the self-check of SKB_PRECISION_SPLIT_INT8 now (on the state's own stream, waits for it) instead of on the first
+ * large call; a no-op once the state has decided. */
+int skb_state_decide_split(skb_state* st);
 /* cudaStream_t owned by the state (so callers can record events on it). */
 void* skb_state_stream(skb_state* st);
 int skb_state_sync(skb_state* st);

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("skb_state_destroy", None, [C.c_void_p]),
     ("skb_state_attach_kinv", C.c_int, [C.c_void_p, C.c_void_p]),
     ("skb_state_split_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    ("skb_state_decide_split", C.c_int, [C.c_void_p]),
     ("skb_state_stream", C.c_void_p, [C.c_void_p]),
     ("skb_state_sync", C.c_int, [C.c_void_p]),
     ("skb_state_set_scratch_limit", C.c_int, [C.c_void_p, C.c_uint64]),

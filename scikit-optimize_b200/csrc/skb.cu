@@ -677,6 +677,7 @@ static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chu
 
 // exact int32 accumulation of the split-integer path: 7 digit-pair sums of at most n products of magnitude <= 2^14
 constexpr int SPLIT_MAX_TRAIN = 16384;
+constexpr int64_t SPLIT_PROBE_MIN_CANDIDATES = 32768;
 
 static int decide_split_planes(skb_state* st, cudaStream_t s);
 
@@ -694,11 +695,13 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (split_mode) {
         if (force_planes) planes = force_planes;
         else if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
-            if (st->split_planes == 0) {
+            // the self-check costs two 256-candidate passes and a stream synchronisation: only worth it for calls that
+            // are large enough to notice the 6-plane saving; smaller calls on an undecided state contract 7 planes
+            if (st->split_planes == 0 && m >= SPLIT_PROBE_MIN_CANDIDATES) {
                 int prc = decide_split_planes(st, s);
                 if (prc != SKB_OK) return prc;
             }
-            planes = st->split_planes;
+            planes = st->split_planes ? st->split_planes : 7;
         }
     }
     const int64_t tiles = (m + BN - 1) / BN;
@@ -935,6 +938,13 @@ static int decide_split_planes(skb_state* st, cudaStream_t s) {
 }
 
 extern "C" {
+
+int skb_state_decide_split(skb_state* st) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    CU(cudaSetDevice(st->device));
+    if (st->n > SPLIT_MAX_TRAIN) return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= %d", SPLIT_MAX_TRAIN);
+    return st->split_planes ? SKB_OK : decide_split_planes(st, st->stream);
+}
 
 int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff) {
     if (!st) return fail(SKB_ERR_INVALID, "state is NULL");

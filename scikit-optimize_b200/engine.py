@@ -240,12 +240,18 @@ class DeviceState:
             self._kinv_attached = True
 
     def split_info(self):
-        """(planes, probe_diff): digit planes precision="split_int8" contracts on this state - 6 when the self-check run on
-        the first split-integer call agreed with the FP64 path to 1e-10 of the prior variance, else 7; 0 before that
-        call - and the relative variance difference the check measured."""
+        """(planes, probe_diff): digit planes precision="split_int8" contracts on this state - 6 when the self-check (run on
+        the first split-integer call with >= 32768 candidates, or by decide_split()) agreed with the FP64 path to 1e-10 on
+        variance and mean, else 7; 0 while undecided (such calls contract 7 planes) - and the difference it measured."""
         planes, diff = C.c_int32(0), C.c_double(-1.0)
         _lib.check(_lib.lib().skb_state_split_info(self._h, C.byref(planes), C.byref(diff)))
         return int(planes.value), float(diff.value)
+
+    def decide_split(self):
+        """Run the 6-or-7-plane self-check now (it otherwise runs on the first split-integer call with >= 32768
+        candidates); returns split_info()."""
+        _lib.check(_lib.lib().skb_state_decide_split(self._h))
+        return self.split_info()
 
     def set_timing(self, enabled):
         _lib.check(_lib.lib().skb_state_set_timing(self._h, 1 if enabled else 0))

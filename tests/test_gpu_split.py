@@ -21,6 +21,8 @@ def test_split_golden_fixture(name, precision):
     rec, meta, est = load(name)
     _, _, ost = load_state(name)
     dev = engine.DeviceState.from_estimator(est)
+    if precision == "split_int8":
+        dev.decide_split()              # small candidate sets would otherwise never reach the 6-plane kernels
     res = dev.score(rec["Xc"], y_opt=float(rec["y_opt"]), acq_funcs=ACQS, xi=float(rec["xi"]), kappa=float(rec["kappa"]),
                     top_k=10, precision=precision)
     vtol = var_tol(ost)
@@ -47,6 +49,8 @@ def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu, precision):
     Xc[0] = st.X_train[0]
     y_opt = float(st.meta["y"].min())
     dev = engine.DeviceState(host_state_from_oracle_state(st))
+    if precision == "split_int8":
+        dev.decide_split()
     res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision=precision)
     ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=min(10, m), precision="fp64")
     mu, sd = orc.predict(st, Xc, return_std=True)
@@ -144,6 +148,7 @@ def test_split_extreme_scales():
         Xc = rng.rand(m, d)
         Xc[:5] = X[:5]
         dev = gpr.device_state()
+        print("self-check:", dev.decide_split())
         y_opt = float(y.min())
         res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="split_int8")
         ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="fp64")
@@ -169,8 +174,14 @@ def test_split_plane_self_check():
     y_opt = float(st.meta["y"].min())
     p7 = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8_p7")
     assert dev.split_info()[0] == 0                                 # the 7-plane mode does not need the check
-    auto = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8")
+    small = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8")
+    assert dev.split_info()[0] == 0                                 # nor does a call below 32768 candidates: 7 planes
+    np.testing.assert_array_equal(small["std"], p7["std"])
+    Xbig = np.concatenate([Xc, rng.rand(20_000, 20)])
+    auto = dev.score(Xbig, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="split_int8")
+    auto = {"std": auto["std"][:20_000], "EI": auto["EI"]}
     planes, diff = dev.split_info()
+    assert dev.decide_split() == (planes, diff)                     # decided: a no-op
     ref = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="fp64")
     scale = st.prior_var * st.y_std ** 2
     e7 = np.max(np.abs(p7["std"] ** 2 - ref["std"] ** 2)) / scale
@@ -178,7 +189,8 @@ def test_split_plane_self_check():
     print("planes=%d probe diff=%.2e; vs fp64: 7 planes %.2e, auto %.2e" % (planes, diff, e7, e_auto))
     assert planes == 6 and 0.0 <= diff <= 1e-10                     # this well-conditioned state takes the 6-plane path
     assert e7 <= 1e-12 and e_auto <= 1e-10 and e7 < e_auto
-    assert np.array_equal(auto["EI"]["topk_idx"], ref["EI"]["topk_idx"])
+    ref_big = dev.score(Xbig, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="fp64")
+    assert np.array_equal(auto["EI"]["topk_idx"], ref_big["EI"]["topk_idx"])
     assert np.array_equal(p7["EI"]["topk_idx"], ref["EI"]["topk_idx"])
     mu, sd = orc.predict(st, Xc[:500], return_std=True)
     assert np.max(np.abs(auto["std"][:500] ** 2 - sd ** 2)) <= 1e-9 * scale
