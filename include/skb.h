@@ -249,7 +249,7 @@ int skb_fit_lml_batch_host(skb_fit* fit, int32_t count, const double* thetas, in
  * skb_state_create_from_fit. */
 int skb_fit_finalize_host(skb_fit* fit, const double* theta, double* lml, double* alpha_out, double* L_out);
 /* Scoring state straight from the finalised fit: replaces skopt gpr.py:223-224 (L_inv, K_inv_ = L_inv^T L_inv on the
- * host) and the upload of skb_state_create - the triangular inverse (cuSOLVER trtri), K^-1 (potri) and their packed
+ * host) and the upload of skb_state_create - the triangular inverse and K^-1 = L^-T L^-1 (cuBLAS trsm + syrk) and their packed
  * FP64 tiles / digit planes are produced on the device from the resident factor, X_train and alpha.  `desc` supplies
  * the scalars and length_scale of the PREDICTION kernel (after skopt silenced the noise term, gpr.py:199-220);
  * its X_train / alpha / L_inv / K_inv pointers are ignored.  Requires a successful skb_fit_finalize_host. */

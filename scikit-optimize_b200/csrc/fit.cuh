@@ -10,7 +10,8 @@
 // The reference materialises dK/dtheta as an n x n x (d + 2) tensor (0.7 GB at n = 2048, d = 20) and contracts it with
 // einsum; here the derivative factors are recomputed from the training rows inside the contraction kernel, so the only
 // n x n objects are K (overwritten by its factor and then by K^-1) - nothing of size n^2 d exists.
-// The factorisation / inverse (potrf, potrs, potri) are plain library calls (cuSOLVER, loaded lazily by skb.cu).
+// The factorisation and solves are plain library calls loaded lazily by skb.cu: cuSOLVER potrf / potrs, and for
+// K^-1 = L^-T L^-1 cuBLAS trsm (on the identity) + syrk.
 #pragma once
 #include "fastmath.cuh"
 #include "kcross.cuh"
@@ -208,6 +209,11 @@ __global__ void fit_grad_reduce_kernel(const double* __restrict__ partial, int n
         __syncthreads();
     }
     if (threadIdx.x == 0) grad[k] = 0.5 * red[0];
+}
+
+__global__ void fit_identity_kernel(double* __restrict__ M, int n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < (size_t)n * n) M[e] = (e / n == e % n) ? 1.0 : 0.0;
 }
 
 // cuSOLVER works on column-major lower triangles; the rest of this library reads row-major matrices.  `src` holds the

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cublas_v2.h>       // declarations only, like cuSOLVER below
 #include <cusolverDn.h>      // declarations only: the library is opened lazily with dlopen (fit objective)
 #include <dlfcn.h>
 
@@ -1523,10 +1524,14 @@ struct SolverApi {
     decltype(&cusolverDnDpotrf_bufferSize) potrf_size = nullptr;
     decltype(&cusolverDnDpotrf) potrf = nullptr;
     decltype(&cusolverDnDpotrs) potrs = nullptr;
-    decltype(&cusolverDnDpotri_bufferSize) potri_size = nullptr;
-    decltype(&cusolverDnDpotri) potri = nullptr;
-    decltype(&cusolverDnXtrtri_bufferSize) trtri_size = nullptr;
-    decltype(&cusolverDnXtrtri) trtri = nullptr;
+    // K^-1 = L^-T L^-1 as two plain library GEMM-class calls (cuBLAS trsm on the identity, then syrk): several times
+    // faster than cuSOLVER's potri at n = 1000..4000, and the reference's own formula (gpr.py:223-224)
+    void* blas_lib = nullptr;
+    decltype(&cublasCreate_v2) blas_create = nullptr;
+    decltype(&cublasDestroy_v2) blas_destroy = nullptr;
+    decltype(&cublasSetStream_v2) blas_set_stream = nullptr;
+    decltype(&cublasDtrsm_v2) trsm = nullptr;
+    decltype(&cublasDsyrk_v2) syrk = nullptr;
     bool ok = false;
 };
 SolverApi g_solver;
@@ -1550,10 +1555,21 @@ int load_solver() {
     SKB_SYM(potrf_size, "cusolverDnDpotrf_bufferSize");
     SKB_SYM(potrf, "cusolverDnDpotrf");
     SKB_SYM(potrs, "cusolverDnDpotrs");
-    SKB_SYM(potri_size, "cusolverDnDpotri_bufferSize");
-    SKB_SYM(potri, "cusolverDnDpotri");
-    SKB_SYM(trtri_size, "cusolverDnXtrtri_bufferSize");
-    SKB_SYM(trtri, "cusolverDnXtrtri");
+#undef SKB_SYM
+    const char* blas_names[] = {"libcublas.so.12", "libcublas.so.13", "libcublas.so"};
+    for (const char* nm : blas_names) {
+        g_solver.blas_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_solver.blas_lib) break;
+    }
+    if (!g_solver.blas_lib) return fail(SKB_ERR_UNSUPPORTED, "cuBLAS (libcublas.so) could not be loaded: %s", dlerror());
+#define SKB_SYM(field, name)                                                                          \
+    g_solver.field = reinterpret_cast<decltype(g_solver.field)>(dlsym(g_solver.blas_lib, name));      \
+    if (!g_solver.field) return fail(SKB_ERR_UNSUPPORTED, "cuBLAS symbol %s not found", name)
+    SKB_SYM(blas_create, "cublasCreate_v2");
+    SKB_SYM(blas_destroy, "cublasDestroy_v2");
+    SKB_SYM(blas_set_stream, "cublasSetStream_v2");
+    SKB_SYM(trsm, "cublasDtrsm_v2");
+    SKB_SYM(syrk, "cublasDsyrk_v2");
 #undef SKB_SYM
     g_solver.ok = true;
     return SKB_OK;
@@ -1564,6 +1580,11 @@ int load_solver() {
         cusolverStatus_t s_ = (call);                                                                     \
         if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ERR_CUDA, "%s -> cusolver status %d", #call, (int)s_); \
     } while (0)
+#define BLAS(call)                                                                                        \
+    do {                                                                                                  \
+        cublasStatus_t s_ = (call);                                                                       \
+        if (s_ != CUBLAS_STATUS_SUCCESS) return fail(SKB_ERR_CUDA, "%s -> cublas status %d", #call, (int)s_); \
+    } while (0)
 }  // namespace
 
 // One evaluation in flight: its own stream, solver handle and n x n workspace, so that several hyper-parameter vectors
@@ -1572,14 +1593,16 @@ int load_solver() {
 struct FitSlot {
     cudaStream_t stream = nullptr;
     cusolverDnHandle_t solver = nullptr;
+    cublasHandle_t blas = nullptr;
     double *d_Xs = nullptr, *d_ls = nullptr, *d_K = nullptr, *d_a = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    double* d_V = nullptr;           // [n][n] L^-1 (column-major lower) on the way to K^-1 = L^-T L^-1
     double* d_work = nullptr;
     int* d_info = nullptr;
     double* h_pinned = nullptr;      // [MAX_DIMS] length scales in | [MAX_DIMS + 4] results out | 4 ints info
     bool want_grad = false;
 };
 constexpr int FIT_MAX_SLOTS = 8;
-struct SolverCtx { cudaStream_t stream; cusolverDnHandle_t solver; double* h_pinned; };
+struct SolverCtx { cudaStream_t stream; cusolverDnHandle_t solver; cublasHandle_t blas; double* h_pinned; };
 static std::vector<SolverCtx> g_ctx_cache[64];
 static std::mutex g_ctx_mu;
 
@@ -1590,11 +1613,8 @@ struct skb_fit {
     double *d_X = nullptr, *d_y = nullptr;
     std::vector<FitSlot> slots;
     // skb_fit_finalize_host / skb_state_create_from_fit: slot 0 keeps the factor of K(theta*); two more n x n buffers
-    // hold row-major copies (L_ for the host, then L^-1 and a second copy of the factor that potri turns into K^-1)
+    // hold the row-major L_ for the host, then the row-major L^-1 (d_T) and the column-major K^-1 (d_T2)
     double *d_T = nullptr, *d_T2 = nullptr;
-    void* d_trtri_work = nullptr;
-    size_t trtri_dev_bytes = 0, trtri_host_bytes = 0;
-    std::vector<char> h_trtri_work;
     bool finalized = false;
 };
 
@@ -1624,6 +1644,7 @@ int fit_add_slot(skb_fit* f) {
         if (!cache.empty()) {
             sl.stream = cache.back().stream;
             sl.solver = cache.back().solver;
+            sl.blas = cache.back().blas;
             sl.h_pinned = cache.back().h_pinned;
             cache.pop_back();
         }
@@ -1632,6 +1653,8 @@ int fit_add_slot(skb_fit* f) {
         CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         SOLVER(g_solver.create(&sl.solver));
         SOLVER(g_solver.set_stream(sl.solver, sl.stream));
+        BLAS(g_solver.blas_create(&sl.blas));
+        BLAS(g_solver.blas_set_stream(sl.blas, sl.stream));
         CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
     }
     int r;
@@ -1639,18 +1662,32 @@ int fit_add_slot(skb_fit* f) {
     if ((r = fit_alloc(f, &sl.d_a, n)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_ls, d)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_K, n * n)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_V, n * n)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_out, d + 4)) != SKB_OK) return r;
     if (f->lwork == 0) {
-        int lw1 = 0, lw2 = 0;
+        int lw1 = 0;
         SOLVER(g_solver.potrf_size(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, sl.d_K, f->n, &lw1));
-        SOLVER(g_solver.potri_size(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, sl.d_K, f->n, &lw2));
-        f->lwork = std::max(std::max(lw1, lw2), 1);
+        f->lwork = std::max(lw1, 1);
     }
     if ((r = fit_alloc(f, &sl.d_work, (size_t)f->lwork)) != SKB_OK) return r;
     double* info_raw = nullptr;
     if ((r = fit_alloc(f, &info_raw, 4)) != SKB_OK) return r;
     sl.d_info = reinterpret_cast<int*>(info_raw);
+    return SKB_OK;
+}
+
+// sl.d_K holds the Cholesky factor L (column-major lower).  Queue  sl.d_V = L^-1  (cuBLAS trsm on the identity: the
+// result is lower triangular with exact zeros above the diagonal) and  out_lower = L^-T L^-1 = K^-1  (syrk, column-major
+// lower triangle; `out_lower` may be sl.d_K itself - the factor is then gone).
+int fit_inverse_from_factor(skb_fit* f, FitSlot& sl, double* out_lower) {
+    const int n = f->n;
+    const double one = 1.0, zero = 0.0;
+    fit_identity_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, sl.stream>>>(sl.d_V, n);
+    LAUNCHED();
+    BLAS(g_solver.trsm(sl.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, n, &one,
+                       sl.d_K, n, sl.d_V, n));
+    BLAS(g_solver.syrk(sl.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, n, n, &one, sl.d_V, n, &zero, out_lower, n));
     return SKB_OK;
 }
 
@@ -1694,7 +1731,8 @@ int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
     fit_lml_kernel<<<1, 256, 0, s>>>(sl.d_K, f->d_y, sl.d_a, n, sl.d_out);
     LAUNCHED();
     if (want_grad) {
-        SOLVER(g_solver.potri(sl.solver, CUBLAS_FILL_MODE_LOWER, n, sl.d_K, n, sl.d_work, f->lwork, sl.d_info + 2));
+        int rc_inv = fit_inverse_from_factor(f, sl, sl.d_K);        // K^-1 (column-major lower) over the factor
+        if (rc_inv != SKB_OK) return rc_inv;
         FitGradParams gp;
         gp.Xs = sl.d_Xs;
         gp.Kinv = sl.d_K;
@@ -1741,11 +1779,12 @@ void skb_fit_destroy(skb_fit* f) {
     cudaSetDevice(f->device);
     for (FitSlot& sl : f->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        if (sl.stream && sl.solver && sl.h_pinned) {
+        if (sl.stream && sl.solver && sl.blas && sl.h_pinned) {
             std::lock_guard<std::mutex> lock(g_ctx_mu);
-            g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.solver, sl.h_pinned});
+            g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.solver, sl.blas, sl.h_pinned});
             continue;
         }
+        if (sl.blas && g_solver.ok) g_solver.blas_destroy(sl.blas);
         if (sl.solver && g_solver.ok) g_solver.destroy(sl.solver);
         if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -1860,35 +1899,17 @@ int skb_state_create_from_fit(skb_fit* f, const skb_state_desc* desc, skb_state*
     int rc;
     if (!f->d_T && (rc = fit_alloc(f, &f->d_T, n * n)) != SKB_OK) return rc;
     if (!f->d_T2 && (rc = fit_alloc(f, &f->d_T2, n * n)) != SKB_OK) return rc;
-    if (!f->d_trtri_work) {
-        size_t dev_bytes = 0, host_bytes = 0;
-        SOLVER(g_solver.trtri_size(sl.solver, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)f->n, CUDA_R_64F, sl.d_K,
-                                   (int64_t)f->n, &dev_bytes, &host_bytes));
-        double* raw = nullptr;
-        if ((rc = fit_alloc(f, &raw, (std::max<size_t>(dev_bytes, 8) + 7) / 8)) != SKB_OK) return rc;
-        f->d_trtri_work = raw;
-        f->trtri_dev_bytes = dev_bytes;
-        f->trtri_host_bytes = host_bytes;
-        f->h_trtri_work.resize(std::max<size_t>(host_bytes, 8));
-    }
     cudaStream_t s = sl.stream;
     const unsigned T = (unsigned)((n + 31) / 32);
-    // d_K holds the factor L (column-major lower).  Keep a copy for potri, invert the factor in place, bring L^-1 into
-    // the row-major form the pack kernels read, then K^-1 = potri(copy) mirrored into a full symmetric matrix.
-    CU(cudaMemcpyAsync(f->d_T2, sl.d_K, n * n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SOLVER(g_solver.trtri(sl.solver, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)f->n, CUDA_R_64F, sl.d_K, (int64_t)f->n,
-                          f->d_trtri_work, f->trtri_dev_bytes, f->h_trtri_work.data(), f->trtri_host_bytes, sl.d_info + 3));
-    fit_unpack_lower_kernel<false><<<dim3(T, T), 256, 0, s>>>(sl.d_K, f->d_T, f->n);
+    // d_K holds the factor L (column-major lower): L^-1 into d_V and K^-1 = L^-T L^-1 into d_T2 (cuBLAS trsm + syrk), then
+    // both into the row-major form the pack kernels read (L^-1 -> d_T, K^-1 mirrored to a full matrix -> d_K)
+    if ((rc = fit_inverse_from_factor(f, sl, f->d_T2)) != SKB_OK) return rc;
+    fit_unpack_lower_kernel<false><<<dim3(T, T), 256, 0, s>>>(sl.d_V, f->d_T, f->n);
     LAUNCHED();
-    SOLVER(g_solver.potri(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, f->d_T2, f->n, sl.d_work, f->lwork, sl.d_info + 2));
     fit_unpack_lower_kernel<true><<<dim3(T, T), 256, 0, s>>>(f->d_T2, sl.d_K, f->n);
     LAUNCHED();
-    int* h_info = slot_h_info(sl);
-    CU(cudaMemcpyAsync(h_info, sl.d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     f->finalized = false;                             // the factor in slot 0 has been consumed
-    if (h_info[2] != 0 || h_info[3] != 0)
-        return fail(SKB_ERR_CUDA, "triangular inverse failed (potri info = %d, trtri info = %d)", h_info[2], h_info[3]);
     skb_state_desc full = *desc;
     full.X_train = f->d_X;
     full.alpha = sl.d_a;
