@@ -73,15 +73,37 @@ def make_problem(n, d, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): NVML polled every
+    2 ms from a thread (the timed region of the default run is ~200 ms, too short for `nvidia-smi -lms`, which is kept
+    as the fallback when the NVML binding is unavailable)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.nvml = index, [], None, None
+        self.sm, self.smax, self.power, self.reasons, self.stop = [], None, [], set(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:                         # noqa: BLE001 - any NVML problem: fall back to nvidia-smi
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        return int(ids[index]) if ids and all(v.strip().isdigit() for v in ids) and index < len(ids) else index
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -92,19 +114,41 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.reasons.update(nm for nm, bit in bits.items() if mask & bit)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+            except Exception:                     # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc):
-        if self.proc is not None:
+        if self.nvml is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None and self.sm:
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "sm_mhz_min": float(np.min(self.sm)),
+                    "power_w_max": float(np.max(self.power)) if self.power else None, "source": "nvml, 2 ms poll"}
         sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -113,13 +157,13 @@ class ClockSampler:
                 sm.append(float(f[1])); smax.append(float(f[2]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
+            for nm, val in zip(self.NAMES, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 _CPU_STATE = {}

@@ -44,7 +44,13 @@ typedef enum {
     SKB_KERNEL_RBF = 0,
     SKB_KERNEL_MATERN12 = 1,    /* nu = 0.5 */
     SKB_KERNEL_MATERN32 = 2,    /* nu = 1.5 */
-    SKB_KERNEL_MATERN52 = 3     /* nu = 2.5 */
+    SKB_KERNEL_MATERN52 = 3,    /* nu = 2.5 */
+    /* HammingKernel.__call__ (skopt/learning/gaussian_process/kernels.py:317-407), the kernel cook_estimator picks for
+     * all-categorical spaces (skopt/utils.py:377-378): k(x, y) = exp(-sum_k length_scale[k] * [x_k != y_k]) on the
+     * UNSCALED coordinates (length_scale[] of the descriptor carries the weights).  Value path only: the reference
+     * has no gradient_x for it (utils.py:320-330 routes such models to acq_optimizer="sampling"), so
+     * skb_score_grad_* and skb_fit_create return SKB_ERR_UNSUPPORTED for this kind. */
+    SKB_KERNEL_HAMMING = 4
 } skb_kernel_kind;
 
 /* Acquisition functions of skopt/acquisition.py: gaussian_ei (:232-321), gaussian_pi (:149-229),

@@ -23,6 +23,7 @@ Third-party arithmetic that the reference reaches (not vendored under
 Reference call sites restated (paths relative to /root/reference):
   * skopt/learning/gaussian_process/gpr.py:299-368     -> predict()
   * skopt/learning/gaussian_process/kernels.py:68-200  -> kernel_gradient_x()
+  * skopt/learning/gaussian_process/kernels.py:317-407 -> kernel_cross() for the HammingKernel
   * skopt/acquisition.py:20-87, 90-146, 149-229, 232-321 -> gaussian_*()
   * skopt/optimizer/optimizer.py:557-570               -> score_candidates()
 """
@@ -37,6 +38,7 @@ from scipy.special import ndtr
 
 KIND_RBF = 0
 KIND_MATERN = 1
+KIND_HAMMING = 2      # skopt HammingKernel: length_scale holds the per-dimension mismatch weights
 
 _SQRT3 = math.sqrt(3)
 _SQRT5 = math.sqrt(5)
@@ -93,6 +95,8 @@ def _reduce_kernel(k):
         return dict(a=1.0, c=0.0, w=0.0, base=(KIND_RBF, math.inf, np.asarray(k.length_scale, dtype=float)))
     if name == "Matern":
         return dict(a=1.0, c=0.0, w=0.0, base=(KIND_MATERN, float(k.nu), np.asarray(k.length_scale, dtype=float)))
+    if name == "HammingKernel":
+        return dict(a=1.0, c=0.0, w=0.0, base=(KIND_HAMMING, math.nan, np.asarray(k.length_scale, dtype=float)))
     if name == "Sum":
         p, q = _reduce_kernel(k.k1), _reduce_kernel(k.k2)
         if p["base"] is not None and q["base"] is not None:
@@ -164,6 +168,11 @@ def base_kernel_from_sqdist(state: GPState, sq):
 def kernel_cross(state: GPState, X):
     """kernel_(X, X_train_): amplitude * base(r) + bias; the White term is 0 off-diagonal."""
     X = np.asarray(X, dtype=np.float64)
+    if state.kind == KIND_HAMMING:
+        # skopt kernels.py:391-392: exp(-sum_j length_scale_j * [x_j != y_j]) on the unscaled coordinates
+        differs = X[:, None, :] != state.X_train[None, :, :]
+        K = np.exp(-np.sum(state.length_scale * differs, axis=2))
+        return state.amplitude * K + state.bias
     sq = _scaled_sqdist(X / state.length_scale, state.X_train / state.length_scale)
     K = base_kernel_from_sqdist(state, sq)
     return state.amplitude * K + state.bias
@@ -172,6 +181,8 @@ def kernel_cross(state: GPState, X):
 def kernel_gradient_x(state: GPState, x):
     """d kernel_(x, X_train_) / dx, shape (n, d)  (skopt kernels.py:68-90, 93-200, 294-308)."""
     x = np.asarray(x, dtype=np.float64)
+    if state.kind == KIND_HAMMING:
+        raise AttributeError("HammingKernel has no gradient_x (skopt kernels.py:317-407; utils.py:320-330)")
     ls = state.length_scale
     diff = (x - state.X_train) / ls            # (n, d)
     sq = np.sum(diff ** 2, axis=1)

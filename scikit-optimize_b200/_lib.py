@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libskb.so")
 
 SKB_OK = 0
 SKB_ERR_NOT_POSDEF = -6
-KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
+KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_HAMMING = 0, 1, 2, 3, 4
 ACQ_EI, ACQ_PI, ACQ_LCB = 0, 1, 2
 ACQ_INDEX = {"EI": ACQ_EI, "PI": ACQ_PI, "LCB": ACQ_LCB}
 PRECISION = {"fp64": 0, "split_int8": 1, "split_int8_p7": 2}

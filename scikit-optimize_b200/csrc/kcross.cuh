@@ -15,7 +15,8 @@ namespace skb {
 
 struct KCrossParams {
     const double* X;          // [m][d] candidates (un-scaled), row-major
-    const double* ls;         // [d] length scales
+    const double* ls;         // [d] length scales (all ones for the Hamming kernel, which compares unscaled values)
+    const double* hw;         // [d_pad] Hamming weights, zero padded (KIND 4 only; set by the launchers)
     const double* Xp;         // packed training set: [n_pad/4][d_pad][4], already divided by ls, zero padded
     const double* alpha_p;    // [n_pad], zero padded
     double* Kt;               // [tiles][n_pad/4][BN][4]  or nullptr (mean-only)
@@ -28,6 +29,7 @@ struct KCrossParams {
 template <int KIND>
 __device__ __forceinline__ double base_kernel(double sq) {
     if (KIND == 0) return exp_nonpos(-0.5 * sq);                  // RBF: exp(-sqeuclidean/2)
+    if (KIND == 4) return exp_nonpos(-sq);                        // Hamming: sq = sum_k w_k [x_k != t_k]
     const double r = sqrt_nonneg(sq);
     if (KIND == 1) return exp_nonpos(-r);                         // Matern 1/2
     if (KIND == 2) { const double K = r * 1.7320508075688772; return (1.0 + K) * exp_nonpos(-K); }
@@ -105,6 +107,14 @@ __global__ void __launch_bounds__(256, 2) kcross_mean_kernel(const KCrossParams 
                 for (int kk = 0; kk < 4; ++kk) {
                     const double2 t01 = *reinterpret_cast<const double2*>(t + kk * 4);
                     const double2 t23 = *reinterpret_cast<const double2*>(t + kk * 4 + 2);
+                    if (KIND == 4) {       // skopt kernels.py:391-392: exp(-sum(length_scale * (x != y)))
+                        const double w = __ldg(p.hw + k0 + kk);
+                        s[gi][0] += x[kk] != t01.x ? w : 0.0;
+                        s[gi][1] += x[kk] != t01.y ? w : 0.0;
+                        s[gi][2] += x[kk] != t23.x ? w : 0.0;
+                        s[gi][3] += x[kk] != t23.y ? w : 0.0;
+                        continue;
+                    }
                     const double d0 = x[kk] - t01.x, d1 = x[kk] - t01.y, d2 = x[kk] - t23.x, d3 = x[kk] - t23.y;
                     s[gi][0] = fma(d0, d0, s[gi][0]);
                     s[gi][1] = fma(d1, d1, s[gi][1]);
@@ -191,6 +201,7 @@ __device__ __forceinline__ double exp_nonpos_short(double x) {
 template <int KIND>
 __device__ __forceinline__ double base_kernel_short(double sq) {
     if (KIND == 0) return exp_nonpos_short(-0.5 * sq);
+    if (KIND == 4) return exp_nonpos_short(-sq);
     const double r = sqrt_pos_short(sq > 1e-290 ? sq : 1e-290);
     if (KIND == 1) return exp_nonpos_short(-r);
     if (KIND == 2) { const double K = r * 1.7320508075688772; return (1.0 + K) * exp_nonpos_short(-K); }
@@ -218,7 +229,7 @@ template <int KIND, int P>
 __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParams q) {
     constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));     // +128 in each of the P digit bytes
     constexpr bool FAST = P == 6;
-    constexpr bool DOT = FAST && KIND != 1;
+    constexpr bool DOT = FAST && KIND != 1 && KIND != 4;
     const KCrossParams& p = q.base;
     extern __shared__ __align__(16) unsigned char smem_k1[];
     const int d_pad = p.d_pad;
@@ -307,6 +318,18 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
                         s[1][g * 4 + 1] = fma(x1[kk], t01.y, s[1][g * 4 + 1]);
                         s[1][g * 4 + 2] = fma(x1[kk], t23.x, s[1][g * 4 + 2]);
                         s[1][g * 4 + 3] = fma(x1[kk], t23.y, s[1][g * 4 + 3]);
+                        continue;
+                    }
+                    if (KIND == 4) {
+                        const double w = __ldg(p.hw + k0 + kk);
+                        s[0][g * 4 + 0] += x0[kk] != t01.x ? w : 0.0;
+                        s[0][g * 4 + 1] += x0[kk] != t01.y ? w : 0.0;
+                        s[0][g * 4 + 2] += x0[kk] != t23.x ? w : 0.0;
+                        s[0][g * 4 + 3] += x0[kk] != t23.y ? w : 0.0;
+                        s[1][g * 4 + 0] += x1[kk] != t01.x ? w : 0.0;
+                        s[1][g * 4 + 1] += x1[kk] != t01.y ? w : 0.0;
+                        s[1][g * 4 + 2] += x1[kk] != t23.x ? w : 0.0;
+                        s[1][g * 4 + 3] += x1[kk] != t23.y ? w : 0.0;
                         continue;
                     }
                     double a;

@@ -67,6 +67,7 @@ struct skb_state {
     int n = 0, n_pad = 0, d = 0, d_pad = 0, kernel = 0;
     double amplitude = 0, bias = 0, white = 0, y_mean = 0, y_std = 1;
     double* d_ls = nullptr;
+    double* d_hw = nullptr;           // [d_pad] Hamming weights, zero padded (SKB_KERNEL_HAMMING only; d_ls is all ones then)
     double* d_Xp = nullptr;
     double* d_alpha_p = nullptr;
     double* d_Vp = nullptr;
@@ -310,9 +311,11 @@ int span_end(skb_state* st, cudaStream_t s) {
     return SKB_OK;
 }
 
-int launch_kcross(skb_state* st, const KCrossParams& p, int tiles, cudaStream_t s) {
+int launch_kcross(skb_state* st, KCrossParams p, int tiles, cudaStream_t s) {
     const size_t smem = kcross_smem_bytes(p.d_pad);
+    p.hw = st->d_hw;
     switch (st->kernel) {
+        case SKB_KERNEL_HAMMING: kcross_mean_kernel<4><<<tiles, 256, smem, s>>>(p); break;
         case SKB_KERNEL_RBF: kcross_mean_kernel<0><<<tiles, 256, smem, s>>>(p); break;
         case SKB_KERNEL_MATERN12: kcross_mean_kernel<1><<<tiles, 256, smem, s>>>(p); break;
         case SKB_KERNEL_MATERN32: kcross_mean_kernel<2><<<tiles, 256, smem, s>>>(p); break;
@@ -328,6 +331,7 @@ void launch_kcross_digits_planes(int kernel, const KDigitParams& p, int tiles, s
         case SKB_KERNEL_RBF: kcross_digits_kernel<0, P><<<tiles, 256, smem, s>>>(p); break;
         case SKB_KERNEL_MATERN12: kcross_digits_kernel<1, P><<<tiles, 256, smem, s>>>(p); break;
         case SKB_KERNEL_MATERN32: kcross_digits_kernel<2, P><<<tiles, 256, smem, s>>>(p); break;
+        case SKB_KERNEL_HAMMING: kcross_digits_kernel<4, P><<<tiles, 256, smem, s>>>(p); break;
         default: kcross_digits_kernel<3, P><<<tiles, 256, smem, s>>>(p); break;
     }
 }
@@ -337,6 +341,7 @@ int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, c
     const size_t smem = kcross_smem_bytes(p.base.d_pad);
     p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
     p.tn = st->d_tn;
+    p.base.hw = st->d_hw;
     if (planes == 6) launch_kcross_digits_planes<6>(st->kernel, p, tiles, smem, s);
     else launch_kcross_digits_planes<7>(st->kernel, p, tiles, smem, s);
     LAUNCHED();
@@ -419,7 +424,7 @@ void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
-    void* ptrs[] = {st->d_ls, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
+    void* ptrs[] = {st->d_ls, st->d_hw, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out, st->d_tn};
     for (void* p : ptrs) pool_free(st->device, p);
@@ -448,9 +453,10 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
     if (desc->n_train <= 0 || desc->n_dims <= 0) return fail(SKB_ERR_INVALID, "n_train and n_dims must be positive");
     if (!desc->length_scale || !desc->X_train || !desc->alpha || !desc->L_inv)
         return fail(SKB_ERR_INVALID, "length_scale / X_train / alpha / L_inv must not be NULL");
-    if (desc->kernel < SKB_KERNEL_RBF || desc->kernel > SKB_KERNEL_MATERN52)
-        return fail(SKB_ERR_UNSUPPORTED, "kernel kind %d is outside the hot-path grammar (RBF, Matern 1/2, 3/2, 5/2)",
+    if (desc->kernel < SKB_KERNEL_RBF || desc->kernel > SKB_KERNEL_HAMMING)
+        return fail(SKB_ERR_UNSUPPORTED, "kernel kind %d is outside the hot-path grammar (RBF, Matern 1/2, 3/2, 5/2, Hamming)",
                     desc->kernel);
+    const bool hamming = desc->kernel == SKB_KERNEL_HAMMING;
     if (desc->n_dims > MAX_DIMS) return fail(SKB_ERR_UNSUPPORTED, "n_dims %d > %d", desc->n_dims, MAX_DIMS);
     for (int k = 0; k < desc->n_dims; ++k)
         if (!(desc->length_scale[k] > 0.0)) return fail(SKB_ERR_INVALID, "length_scale[%d] must be > 0", k);
@@ -501,7 +507,18 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
         SKB_PALLOC(st->d_clamp, sizeof(unsigned long long));
         SKB_PALLOC(dX, n * d * sizeof(double));
         SKB_PALLOC(dV, n * n * sizeof(double));
-        CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        if (hamming) {
+            // the Hamming kernel compares unscaled coordinates: unit scales for the packing / candidate staging, the
+            // descriptor's length_scale[] becomes the per-dimension mismatch weights
+            const std::vector<double> ones(d, 1.0);
+            SKB_PALLOC(st->d_hw, (size_t)st->d_pad * sizeof(double));
+            CU(cudaMemsetAsync(st->d_hw, 0, (size_t)st->d_pad * sizeof(double), st->stream));
+            CU(cudaMemcpyAsync(st->d_hw, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+            CU(cudaMemcpyAsync(st->d_ls, ones.data(), d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+            CU(cudaStreamSynchronize(st->stream));          // `ones` is pageable host memory that dies with this scope
+        } else {
+            CU(cudaMemcpyAsync(st->d_ls, desc->length_scale, d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+        }
         CU(cudaMemcpyAsync(dX, desc->X_train, n * d * sizeof(double), kind, st->stream));
         CU(cudaMemcpyAsync(dV, desc->L_inv, n * n * sizeof(double), kind, st->stream));
         CU(cudaMemsetAsync(st->d_alpha_p, 0, (size_t)st->n_pad * sizeof(double), st->stream));
@@ -1073,6 +1090,9 @@ static int check_grad_args(skb_state* st, const double* X, int64_t m, const skb_
     if (!st || !out) return fail(SKB_ERR_INVALID, "state/out is NULL");
     if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
     if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    if (st->kernel == SKB_KERNEL_HAMMING)
+        return fail(SKB_ERR_UNSUPPORTED, "the Hamming kernel has no input gradient (skopt utils.py:320-330: has_gradients is "
+                                         "False for such models); use the value entry points");
     if (!st->d_Ap) return fail(SKB_ERR_UNSUPPORTED, "state was created without K_inv: gradient entry points are unavailable");
     int rc = check_params(params);
     if (rc == SKB_OK && is_split(params->precision) && st->n > 16384)

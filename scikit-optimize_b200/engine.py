@@ -45,18 +45,20 @@ def _flatten_kernel(kernel):
         else:
             raise NotImplementedError("Matern(nu=%r): only nu in {0.5, 1.5, 2.5, inf} run on the GPU path" % kernel.nu)
         return _Affine(a=1.0, base=(kind, np.asarray(kernel.length_scale, dtype=np.float64)))
+    if cls == "HammingKernel":          # length_scale = per-dimension mismatch weights, coordinates stay unscaled
+        return _Affine(a=1.0, base=(_lib.KERNEL_HAMMING, np.asarray(kernel.length_scale, dtype=np.float64)))
     if cls in ("Sum", "Product"):
         l, r = _flatten_kernel(kernel.k1), _flatten_kernel(kernel.k2)
         if l.base is not None and r.base is not None:
             raise NotImplementedError("%s of two stationary kernels is outside the GPU hot-path grammar "
-                                      "([Constant *] {RBF|Matern} [+ Constant] [+ White])" % cls)
+                                      "([Constant *] {RBF|Matern|Hamming} [+ Constant] [+ White])" % cls)
         base = l.base if l.base is not None else r.base
         if cls == "Sum":
             return _Affine(l.a + r.a, l.c + r.c, l.w + r.w, base)
         off_l, off_r = l.a + l.c, r.a + r.c                 # value at r = 0 without the white term
         return _Affine(l.a * r.c + l.c * r.a, l.c * r.c, (off_l + l.w) * (off_r + r.w) - off_l * off_r, base)
     raise NotImplementedError("kernel %s is outside the GPU hot-path grammar "
-                              "([Constant *] {RBF|Matern} [+ Constant] [+ White])" % cls)
+                              "([Constant *] {RBF|Matern|Hamming} [+ Constant] [+ White])" % cls)
 
 
 class HostState:

@@ -6,7 +6,7 @@ from scipy.optimize import OptimizeResult
 from sklearn.base import is_regressor
 
 from .learning import GaussianProcessRegressor
-from .learning.gaussian_process.kernels import ConstantKernel, Matern
+from .learning.gaussian_process.kernels import ConstantKernel, HammingKernel, Matern
 from .space import Space, normalize_dimensions  # noqa: F401
 
 
@@ -51,14 +51,22 @@ def create_result(Xi, yi, space=None, rng=None, specs=None, models=None):
 
 
 def has_gradients(estimator):
-    """True when predict() can return input gradients: every GP this package builds (the GPU computes them)."""
-    return estimator is not None and hasattr(estimator, "predict")
+    """utils.py:301-330: True when predict() can return input gradients - every GP this package builds (the GPU
+    computes them) except one whose kernel contains a HammingKernel (categorical inputs have no gradient)."""
+    if estimator is None or not hasattr(estimator, "predict"):
+        return False
+    if hasattr(estimator, "kernel"):
+        params = estimator.get_params()
+        if isinstance(estimator.kernel, HammingKernel) or any(isinstance(v, HammingKernel) for v in params.values()):
+            return False
+    return True
 
 
 def cook_estimator(base_estimator, space=None, **kwargs):
     """Default surrogate of gp_minimize: ConstantKernel(1, (0.01, 1000)) * Matern(nu=2.5, ARD length scales in
     (0.01, 100)), normalize_y, noise="gaussian", 2 optimiser restarts (utils.py:366-387).  Only the GP family
-    exists here; tree / GBRT surrogates and the all-categorical HammingKernel GP are outside the GPU hot path."""
+    An all-categorical space gets HammingKernel(ones) in place of the Matern factor (utils.py:377-378).  Only the GP
+    family exists here; tree / GBRT surrogates are outside the GPU hot path."""
     if isinstance(base_estimator, str):
         name = base_estimator.upper()
         if name not in ("GP", "DUMMY"):
@@ -69,12 +77,12 @@ def cook_estimator(base_estimator, space=None, **kwargs):
         if space is None:
             raise ValueError("Expected a Space instance, not None.")
         space = normalize_dimensions(Space(space).dimensions)
-        if space.is_categorical:
-            raise NotImplementedError("all-categorical spaces use the HammingKernel in scikit-optimize, which is "
-                                      "outside the GPU hot-path grammar (RBF / Matern)")
         n_dims = space.transformed_n_dims
-        kernel = ConstantKernel(1.0, (0.01, 1000.0)) * Matern(length_scale=np.ones(n_dims),
-                                                              length_scale_bounds=[(0.01, 100)] * n_dims, nu=2.5)
+        if space.is_categorical:            # only special if *all* dimensions are categorical
+            other = HammingKernel(length_scale=np.ones(n_dims))
+        else:
+            other = Matern(length_scale=np.ones(n_dims), length_scale_bounds=[(0.01, 100)] * n_dims, nu=2.5)
+        kernel = ConstantKernel(1.0, (0.01, 1000.0)) * other
         base_estimator = GaussianProcessRegressor(kernel=kernel, normalize_y=True, noise="gaussian",
                                                   n_restarts_optimizer=2)
     elif not is_regressor(base_estimator):

@@ -27,7 +27,18 @@ def _build_kernel(params, cls, prefix=""):
         return skk.RBF(np.asarray(params[prefix + "length_scale"]), "fixed")
     if cls == "Matern":
         return skk.Matern(np.asarray(params[prefix + "length_scale"]), "fixed", nu=params[prefix + "nu"])
+    if cls == "HammingKernel":
+        from skopt_b200.learning.gaussian_process.kernels import HammingKernel
+        return HammingKernel(np.asarray(params[prefix + "length_scale"]), "fixed")
     raise NotImplementedError(cls)
+
+
+def kernel_code(st):
+    """skb_kernel_kind (include/skb.h) of an oracle state."""
+    if st.kind == orc.KIND_HAMMING:
+        return 4
+    return {(orc.KIND_RBF, np.inf): 0, (orc.KIND_MATERN, 0.5): 1, (orc.KIND_MATERN, 1.5): 2,
+            (orc.KIND_MATERN, 2.5): 3}[(st.kind, st.nu)]
 
 
 class _Est:

@@ -11,7 +11,7 @@ import pytest
 import skopt_b200
 from skopt_b200 import engine
 from oracle import gp_oracle as orc
-from tests._golden import NAMES, load, load_state, var_tol
+from tests._golden import NAMES, kernel_code, load, load_state, var_tol
 
 pytestmark = pytest.mark.gpu
 
@@ -20,8 +20,7 @@ ACQS = ("EI", "PI", "LCB")
 
 def host_state_from_oracle_state(st):
     from scipy.linalg import solve_triangular
-    kind = {(orc.KIND_RBF, np.inf): 0, (orc.KIND_MATERN, 0.5): 1, (orc.KIND_MATERN, 1.5): 2,
-            (orc.KIND_MATERN, 2.5): 3}[(st.kind, st.nu)]
+    kind = kernel_code(st)
     L_inv = solve_triangular(st.L, np.eye(st.n), lower=True)
     return engine.HostState(st.X_train, st.alpha, L_inv, st.length_scale, kind, st.amplitude, st.bias, st.white,
                             st.y_mean, st.y_std, K_inv=st.K_inv)

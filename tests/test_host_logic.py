@@ -14,7 +14,7 @@ from skopt_b200 import _lib, engine
 from skopt_b200.distributed import merge_topk, shard_bounds
 from skopt_b200.optimizer.lbfgs import minimize_batch
 from oracle import gp_oracle as orc
-from tests._golden import NAMES, load
+from tests._golden import NAMES, kernel_code, load
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -50,8 +50,7 @@ def test_kernel_flattening_matches_oracle_walker(name):
     rec, meta, est = load(name)
     hs = engine.host_state_from_estimator(est)
     st = orc.state_from_estimator(est)
-    kind = {(orc.KIND_RBF, np.inf): 0, (orc.KIND_MATERN, 0.5): 1, (orc.KIND_MATERN, 1.5): 2,
-            (orc.KIND_MATERN, 2.5): 3}[(st.kind, st.nu)]
+    kind = kernel_code(st)
     assert hs.kernel == kind
     assert hs.amplitude == pytest.approx(st.amplitude, rel=1e-15) and hs.bias == pytest.approx(st.bias, rel=1e-15)
     assert hs.white == pytest.approx(st.white, rel=1e-15, abs=1e-300)
