@@ -83,7 +83,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc, self.nvml = index, [], None, None
-        self.sm, self.smax, self.power, self.reasons, self.stop = [], None, [], set(), False
+        self.sm, self.smax, self.reasons, self.stop = [], None, set(), False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -125,7 +125,6 @@ class ClockSampler:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
                 self.reasons.update(nm for nm, bit in bits.items() if mask & bit)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
             except Exception:                     # noqa: BLE001
                 pass
             time.sleep(0.002)
@@ -146,8 +145,7 @@ class ClockSampler:
     def summary(self):
         if self.nvml is not None and self.sm:
             return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "sm_mhz_min": float(np.min(self.sm)),
-                    "power_w_max": float(np.max(self.power)) if self.power else None, "source": "nvml, 2 ms poll"}
+                    "samples": len(self.sm), "sm_mhz_min": float(np.min(self.sm)), "source": "nvml, 2 ms poll"}
         sm, smax, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]

@@ -134,7 +134,7 @@ def test_large_categorical_candidate_set_all_precisions_agree():
                                    noise=1e-2, optimizer=None).fit(X, y)
     Xc = np.column_stack([rng.randint(0, k, size=20000) / (k - 1.0) for k in n_cats])
     st = orc.state_from_estimator(est)
-    mu, sd = orc.predict(st, Xc, quad="gemm")
+    mu, sd = orc.predict(st, Xc, return_std=True, quad="gemm")
     ref = -orc.ei_from_posterior(mu, sd, float(y.min()), 0.01)
     dev = engine.DeviceState.from_estimator(est)
     for precision in ("fp64", "split_int8_p7", "split_int8"):
