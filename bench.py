@@ -311,6 +311,8 @@ def main():
     torch.cuda.set_device(local_rank)
     gpr_mod.set_default_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug lines ("NCCL version ...") go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     gpr, y_opt = make_problem(N_TRAIN, N_DIMS)
