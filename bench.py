@@ -275,7 +275,27 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = [None]
+
+
+def reserve_stdout():
+    """Keep the real stdout for the single JSON line and point fd 1 at stderr for everything else (NCCL prints its
+    version banner to stdout from C, torch / cuSOLVER may warn): the driver reads ONE line from stdout."""
+    sys.stdout.flush()
+    _JSON_FD[0] = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD[0] is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD[0], data)
 
 
 def main():
@@ -294,6 +314,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    reserve_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -499,7 +520,7 @@ def main():
                           "contraction (single-threaded as in the reference; BLAS parts on all host threads)"
                           % (args.cpu_sample, dt),
                 "tuned_gemm_variant_evals_s": evals_s_gemm}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
