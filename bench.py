@@ -167,6 +167,12 @@ class ClockSampler:
 _CPU_STATE = {}
 
 
+def library_versions():
+    import scipy
+    import sklearn
+    return {"numpy": np.__version__, "scipy": scipy.__version__, "scikit-learn": sklearn.__version__}
+
+
 def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
     """Oracle (port of the reference's NumPy/SciPy path) timed on this host on `sample_m` candidates."""
     from oracle import gp_oracle as orc
@@ -186,12 +192,40 @@ def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
     return sample_m / best, best
 
 
+def parity_sample(gpr, dev, y_opt, precisions, sample_m=512):
+    """Parity of THIS run's device state against the checker (SURVEY.md 8d gate, in the units of the gate): the oracle
+    is evaluated on the product's own fitted state with the reference's einsum contraction (gpr.py:332) and, for the
+    'reference vs re-ordered reference' jitter the gate asks to be shown next to it, with a GEMM-ordered contraction."""
+    from oracle import gp_oracle as orc
+    st = orc.state_from_estimator(gpr)
+    Xs = np.random.RandomState(7).rand(sample_m, st.d)
+    mu_e, sd_e = orc.predict(st, Xs, return_std=True, quad="einsum")
+    mu_g, sd_g = orc.predict(st, Xs, return_std=True, quad="gemm")
+    ei_e, ei_g = -orc.ei_from_posterior(mu_e, sd_e, y_opt, 0.01), -orc.ei_from_posterior(mu_g, sd_g, y_opt, 0.01)
+    var_scale = st.prior_var * st.y_std ** 2
+
+    def diff(mu, sd, ei):
+        return {"mean": float(np.max(np.abs(mu - mu_e)) / max(np.max(np.abs(mu_e)), st.y_std)),
+                "var": float(np.max(np.abs(sd ** 2 - sd_e ** 2)) / var_scale),
+                "acq": float(np.max(np.abs(ei - ei_e)) / np.max(np.abs(ei_e))),
+                "argmin_equal": bool(int(np.argmin(ei)) == int(np.argmin(ei_e)))}
+
+    out = {"candidates": sample_m, "gate": "1e-9 on each of mean / var / acq (units of SURVEY.md 8d), identical argmin",
+           "reference_vs_reordered_reference": diff(mu_g, sd_g, ei_g)}
+    for prec in precisions:
+        r = dev.score(Xs, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=1, precision=prec)
+        d = diff(r["mean"], r["std"], r["EI"]["values"])
+        d["argmin_equal"] = d["argmin_equal"] and int(r["EI"]["topk_idx"][0]) == int(np.argmin(ei_e))
+        out[prec] = d
+    return out
+
+
 def branin(x):
     a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5.0 / np.pi, 6.0, 10.0, 1.0 / (8 * np.pi)
     return a * (x[1] - b * x[0] ** 2 + c * x[0] - r) ** 2 + s * (1 - t) * np.cos(x[0]) + s
 
 
-def ask_p50_ms(n_tells=30):
+def ask_p50_ms(n_tells=31):
     """Median wall time of the candidate-scoring block (optimizer.py:550-608, fit excluded) over `n_tells` model-based
     tells of BASELINE.json configs[0]: gp_minimize on Branin, acq_optimizer='sampling', n_points=10000, gp_hedge."""
     from skopt_b200 import Optimizer
@@ -214,7 +248,7 @@ def hart6(x):
     return -np.sum(alpha * np.exp(-np.sum(A * (np.array(x) - P) ** 2, axis=1)))
 
 
-def ask_p50_ms_lbfgs(n_tells=20):
+def ask_p50_ms_lbfgs(n_tells=31):
     """Same measurement for BASELINE.json configs[1]: Hartmann-6, gp_hedge, acq_optimizer='lbfgs', 20 restarts
     (candidate scoring + 60 lock-step L-BFGS-B searches with batched GPU gradients)."""
     from skopt_b200 import Optimizer
@@ -271,7 +305,8 @@ def run_reference(args, rank):
                    "n_train": N_TRAIN, "n_dims": N_DIMS, "candidates_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": "%d candidates per step; einsum contraction is single-threaded as in the "
-                                   "reference, BLAS parts may use all %d host threads" % (sample, cores)},
+                                   "reference, BLAS parts may use all %d host threads" % (sample, cores),
+                         "versions": library_versions()},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -519,7 +554,8 @@ def main():
                 "sample": "%d candidates of the same workload, %.1f s; oracle port with the reference's einsum "
                           "contraction (single-threaded as in the reference; BLAS parts on all host threads)"
                           % (args.cpu_sample, dt),
-                "tuned_gemm_variant_evals_s": evals_s_gemm}
+                "tuned_gemm_variant_evals_s": evals_s_gemm, "versions": library_versions()}
+            line["parity_sample"] = parity_sample(gpr, dev, y_opt, sorted({headline, "fp64"}))
         emit(line)
     if world > 1:
         dist.destroy_process_group()
