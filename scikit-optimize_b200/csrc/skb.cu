@@ -115,6 +115,13 @@ struct skb_state {
     double* d_X = nullptr;       size_t x_cap = 0;
     double* d_out = nullptr;     size_t out_cap = 0;
     unsigned long long* d_clamp = nullptr;
+    // pinned staging block for the small results of the host entry points (top-k triplets, counters, the outputs of an
+    // L-BFGS batch): device -> pinned copies are queued without blocking and unpacked after ONE synchronisation, where
+    // copies into pageable caller memory would each be a blocking round trip.  Borrowed from a per-device cache.
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_used = 0;
+    struct Unpack { void* host; size_t offset, bytes; };
+    std::vector<Unpack> unpack;
 };
 
 namespace {
@@ -268,9 +275,80 @@ __global__ void row_sqnorm_kernel(const double* __restrict__ Xp, double* __restr
     tn[j] = acc;
 }
 
+// ---------------- pinned staging of small results ----------------
+constexpr size_t STAGE_BYTES = 1u << 20;          // one block per state
+constexpr size_t STAGE_MAX_COPY = 256u << 10;     // larger outputs are bandwidth-bound: copied straight to the caller
+struct PinnedCache { std::mutex mu; std::vector<unsigned char*> free_blocks; };
+PinnedCache g_pinned[64];
+
+int stage_begin(skb_state* st) {
+    st->h_stage_used = 0;
+    st->unpack.clear();
+    if (st->h_stage) return SKB_OK;
+    PinnedCache& pc = g_pinned[st->device & 63];
+    {
+        std::lock_guard<std::mutex> lock(pc.mu);
+        if (!pc.free_blocks.empty()) {
+            st->h_stage = pc.free_blocks.back();
+            pc.free_blocks.pop_back();
+            return SKB_OK;
+        }
+    }
+    CU(cudaMallocHost(reinterpret_cast<void**>(&st->h_stage), STAGE_BYTES));
+    return SKB_OK;
+}
+
+void stage_release(skb_state* st) {
+    if (!st->h_stage) return;
+    PinnedCache& pc = g_pinned[st->device & 63];
+    std::lock_guard<std::mutex> lock(pc.mu);
+    if (pc.free_blocks.size() < 8) pc.free_blocks.push_back(st->h_stage);
+    else cudaFreeHost(st->h_stage);
+    st->h_stage = nullptr;
+}
+
+// device -> caller copy of `bytes` on stream s: through the pinned block when it is small (unpacked by stage_finish),
+// straight into the caller's memory otherwise
+int d2h(skb_state* st, void* host, const void* dev, size_t bytes, cudaStream_t s) {
+    if (!host || !dev || bytes == 0) return SKB_OK;
+    const size_t off = (st->h_stage_used + 15) & ~(size_t)15;
+    if (st->h_stage && bytes <= STAGE_MAX_COPY && off + bytes <= STAGE_BYTES) {
+        CU(cudaMemcpyAsync(st->h_stage + off, dev, bytes, cudaMemcpyDeviceToHost, s));
+        st->unpack.push_back({host, off, bytes});
+        st->h_stage_used = off + bytes;
+        return SKB_OK;
+    }
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+    return SKB_OK;
+}
+
+// caller -> device copy of a small input through the pinned block (must be called before any d2h of the same call)
+int h2d(skb_state* st, void* dev, const void* host, size_t bytes, cudaStream_t s) {
+    const size_t off = (st->h_stage_used + 15) & ~(size_t)15;
+    if (st->h_stage && bytes <= STAGE_MAX_COPY && off + bytes <= STAGE_BYTES) {
+        std::memcpy(st->h_stage + off, host, bytes);
+        st->h_stage_used = off + bytes;
+        CU(cudaMemcpyAsync(dev, st->h_stage + off, bytes, cudaMemcpyHostToDevice, s));
+        return SKB_OK;
+    }
+    CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s));
+    return SKB_OK;
+}
+
+int stage_finish(skb_state* st, cudaStream_t s) {
+    CU(cudaStreamSynchronize(s));
+    for (const auto& u : st->unpack) std::memcpy(u.host, st->h_stage + u.offset, u.bytes);
+    st->unpack.clear();
+    return SKB_OK;
+}
+
 constexpr int PROBE_ROWS = 256;
+// Probe candidates of the split-plane self-check: even rows are training points themselves (prior - q cancels almost
+// completely there), odd rows are training points moved by up to a quarter length scale per coordinate - or, for
+// categorical inputs (mix_rows: Hamming kernel), rows whose every coordinate comes from a different training row, since
+// only values that occur in the training set can match it.
 __global__ void make_probe_kernel(const double* __restrict__ X, const double* __restrict__ ls, double* __restrict__ probe,
-                                  int n, int d) {
+                                  int n, int d, int mix_rows) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= PROBE_ROWS * d) return;
     const int r = idx / d, k = idx - r * d;
@@ -279,7 +357,8 @@ __global__ void make_probe_kernel(const double* __restrict__ X, const double* __
     if (r & 1) {
         uint32_t h = ((uint32_t)r * 73856093u) ^ ((uint32_t)k * 19349663u) ^ 0x9e3779b9u;
         h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
-        v += ls[k] * 0.5 * ((double)h * (1.0 / 4294967296.0) - 0.5);
+        if (mix_rows) v = X[(size_t)((row + 1 + h % (uint32_t)n) % n) * d + k];
+        else v += ls[k] * 0.5 * ((double)h * (1.0 / 4294967296.0) - 0.5);
     }
     probe[idx] = v;
 }
@@ -436,6 +515,7 @@ void skb_state_destroy(skb_state* st) {
     for (auto& ev : st->ev_k1) cudaEventDestroy(ev);
     for (auto& ev : st->ev_k2) cudaEventDestroy(ev);
     if (st->ev_enter) cudaEventDestroy(st->ev_enter);
+    stage_release(st);
     if (st->aux_stream) cudaStreamDestroy(st->aux_stream);
     if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
     if (st->stream) cudaStreamDestroy(st->stream);
@@ -530,7 +610,8 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
         row_sqnorm_kernel<<<(st->n_pad + 255) / 256, 256, 0, st->stream>>>(st->d_Xp, st->d_tn, st->n_pad, st->d_pad);
         LAUNCHED();
         SKB_PALLOC(st->d_probe, (size_t)PROBE_ROWS * d * sizeof(double));
-        make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(dX, st->d_ls, st->d_probe, st->n, st->d);
+        make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(dX, st->d_ls, st->d_probe, st->n, st->d,
+                                                                                          hamming ? 1 : 0);
         LAUNCHED();
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
@@ -1027,24 +1108,22 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
     if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double),
                                                        is_split(params->precision)))) != SKB_OK) return rc;
     if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) return rc;
-    if (out->n_var_clamped)
-        CU(cudaMemcpyAsync(out->n_var_clamped, st->d_clamp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    if (out->mean) CU(cudaMemcpyAsync(out->mean, dout.mean, m * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->std) CU(cudaMemcpyAsync(out->std, dout.std, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if ((rc = stage_begin(st)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->n_var_clamped, st->d_clamp, sizeof(int64_t), s)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->mean, dout.mean, m * sizeof(double), s)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->std, dout.std, m * sizeof(double), s)) != SKB_OK) return rc;
     for (int a = 0; a < 3; ++a) {
         if (!((params->acq_mask >> a) & 1)) continue;
-        if (out->acq[a]) CU(cudaMemcpyAsync(out->acq[a], dout.acq[a], m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if ((rc = d2h(st, out->acq[a], dout.acq[a], m * sizeof(double), s)) != SKB_OK) return rc;
         if (k > 0) {
             if (!out->topk_val[a] || !out->topk_idx[a])
                 return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
-            CU(cudaMemcpyAsync(out->topk_val[a], dout.topk_val[a], k * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(out->topk_idx[a], dout.topk_idx[a], k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            if (out->first_nan[a])
-                CU(cudaMemcpyAsync(out->first_nan[a], dout.first_nan[a], sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            if ((rc = d2h(st, out->topk_val[a], dout.topk_val[a], k * sizeof(double), s)) != SKB_OK) return rc;
+            if ((rc = d2h(st, out->topk_idx[a], dout.topk_idx[a], k * sizeof(int64_t), s)) != SKB_OK) return rc;
+            if ((rc = d2h(st, out->first_nan[a], dout.first_nan[a], sizeof(int64_t), s)) != SKB_OK) return rc;
         }
     }
-    CU(cudaStreamSynchronize(s));
-    return SKB_OK;
+    return stage_finish(st, s);
 }
 
 int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mean) {
@@ -1056,11 +1135,11 @@ int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mea
     int rc;
     if ((rc = grow(st->device, &st->d_X, &st->x_cap, (size_t)m * st->d)) != SKB_OK) return rc;
     if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)m)) != SKB_OK) return rc;
-    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * st->d * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+    if ((rc = stage_begin(st)) != SKB_OK) return rc;
+    if ((rc = h2d(st, st->d_X, X, (size_t)m * st->d * sizeof(double), st->stream)) != SKB_OK) return rc;
     if ((rc = score_dev_impl(st, st->d_X, m, 0, nullptr, nullptr, st->stream, true, st->d_out)) != SKB_OK) return rc;
-    CU(cudaMemcpyAsync(mean, st->d_out, m * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
-    CU(cudaStreamSynchronize(st->stream));
-    return SKB_OK;
+    if ((rc = d2h(st, mean, st->d_out, m * sizeof(double), st->stream)) != SKB_OK) return rc;
+    return stage_finish(st, st->stream);
 }
 
 }  // extern "C"
@@ -1244,22 +1323,18 @@ int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq
         dout.acq[a] = take(on && out->acq[a], m);
         dout.acq_grad[a] = take(on && out->acq_grad[a], m * d);
     }
-    CU(cudaMemcpyAsync(st->d_X, X, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = stage_begin(st)) != SKB_OK) return rc;
+    if ((rc = h2d(st, st->d_X, X, (size_t)m * d * sizeof(double), s)) != SKB_OK) return rc;
     if ((rc = skb_score_grad_dev(st, st->d_X, m, prm, &dout, s)) != SKB_OK) return rc;
-    auto back = [&](double* host, const double* dev, size_t count) -> int {
-        if (host && dev) CU(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, s));
-        return SKB_OK;
-    };
-    if ((rc = back(out->mean, dout.mean, m)) != SKB_OK) return rc;
-    if ((rc = back(out->std, dout.std, m)) != SKB_OK) return rc;
-    if ((rc = back(out->mean_grad, dout.mean_grad, m * d)) != SKB_OK) return rc;
-    if ((rc = back(out->std_grad, dout.std_grad, m * d)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->mean, dout.mean, m * sizeof(double), s)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->std, dout.std, m * sizeof(double), s)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->mean_grad, dout.mean_grad, m * d * sizeof(double), s)) != SKB_OK) return rc;
+    if ((rc = d2h(st, out->std_grad, dout.std_grad, m * d * sizeof(double), s)) != SKB_OK) return rc;
     for (int a = 0; a < 3; ++a) {
-        if ((rc = back(out->acq[a], dout.acq[a], m)) != SKB_OK) return rc;
-        if ((rc = back(out->acq_grad[a], dout.acq_grad[a], m * d)) != SKB_OK) return rc;
+        if ((rc = d2h(st, out->acq[a], dout.acq[a], m * sizeof(double), s)) != SKB_OK) return rc;
+        if ((rc = d2h(st, out->acq_grad[a], dout.acq_grad[a], m * d * sizeof(double), s)) != SKB_OK) return rc;
     }
-    CU(cudaStreamSynchronize(s));
-    return SKB_OK;
+    return stage_finish(st, s);
 }
 
 int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const double* mu, const double* sd,
