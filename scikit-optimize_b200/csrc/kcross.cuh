@@ -404,4 +404,152 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
         p.kdot[tile * BN + tid] = ((stage[tid] + stage[BN + tid]) + stage[2 * BN + tid]) + stage[3 * BN + tid];
 }
 
+// 6-plane K1 with the x.t part of the squared distances on FP64 tensor-core tiles (DMMA m8n8k4) instead of one DFMA per
+// (candidate, training point, feature): the same FP64 pipe time (DMMA and DFMA share the pipe at the same flop rate), an
+// eighth of the issue slots and a quarter of the shared-memory reads for that part, which is a third of the kernel's FP64
+// work at d = 20.  Warp w = (row quarter rq = w >> 1, MMA tile e = w & 1) owns candidates [64 e, 64 e + 64) x training rows
+// [16 rq, 16 rq + 16) of every 64-row stage as 8 x 2 accumulator tiles of 8 x 8: rows of a tile are candidates
+// (A operand, from the transposed candidate tile xs), columns are training points (B operand).  The training rows of a
+// stage may be taken in any order, so column c of tile ji is row 4 (c / 2) + 2 ji + c % 2 of the 16-row block: lane l then
+// holds, for each of its 8 candidates 8 ci + l / 4, the FOUR CONSECUTIVE training rows 4 (l % 4) .. + 3, i.e. one aligned
+// 32-bit word of the 16-byte K-major digit vector the contraction kernel reads, and a warp stores 128 contiguous bytes
+// per (plane, candidate group).  Transform, digit extraction and the k . alpha reduction are those of
+// kcross_digits_kernel<KIND, 6>; kinds whose distance needs direct differences (Matern 1/2, Hamming) stay there.
+constexpr int XS_LD_MMA = BN + 8;          // = 8 mod 16 doubles: the A-fragment read (4 features x 8 candidates) is conflict-free
+
+constexpr size_t kcross_mma_smem_bytes(int d_pad) {
+    return sizeof(double) * ((size_t)d_pad * XS_LD_MMA + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + 2 * XROWS + BN) +
+           2 * sizeof(uint64_t);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitParams q) {
+    constexpr int P = 6;
+    constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));
+    const KCrossParams& p = q.base;
+    extern __shared__ __align__(16) unsigned char smem_k1[];
+    const int d_pad = p.d_pad;
+    const int xt_stage = XG * d_pad * 4;
+    double* xt = reinterpret_cast<double*>(smem_k1);          // [2][XG][d_pad][4]
+    double* al = xt + 2 * xt_stage;                            // [2][XROWS]
+    double* tnb = al + 2 * XROWS;                              // [2][XROWS] squared norms of the staged training rows
+    double* xs = tnb + 2 * XROWS;                              // [d_pad][XS_LD_MMA]
+    double* xnorm = xs + (size_t)d_pad * XS_LD_MMA;            // [BN] |x|^2 of the candidates
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xnorm + BN);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rq = warp >> 1, e = warp & 1, t4 = lane & 3, c8 = lane >> 2;
+    const int64_t tile = blockIdx.x;
+    const int nst = (p.n + XROWS - 1) / XROWS;
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < BN * d_pad; idx += 256) {
+        const int cc = idx / d_pad, k = idx - cc * d_pad;
+        const int64_t row = tile * BN + cc;
+        double v = 0.0;
+        if (k < p.d && row < p.m) v = p.X[row * p.d + k] / p.ls[k];
+        xs[k * XS_LD_MMA + cc] = v;
+    }
+    __syncthreads();
+    auto issue = [&](int st) {
+        const int buf = st & 1;
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)(xt_stage + 2 * XROWS) * 8u);
+        bulk_g2s(xt + buf * xt_stage, p.Xp + (size_t)st * xt_stage, (uint32_t)xt_stage * 8u, bars + buf);
+        bulk_g2s(al + buf * XROWS, p.alpha_p + (size_t)st * XROWS, XROWS * 8u, bars + buf);
+        bulk_g2s(tnb + buf * XROWS, q.tn + (size_t)st * XROWS, XROWS * 8u, bars + buf);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nst > 1) issue(1);
+    }
+    if (tid < BN) {
+        double a = 0.0;
+        for (int k = 0; k < d_pad; ++k) a = fma(xs[k * XS_LD_MMA + tid], xs[k * XS_LD_MMA + tid], a);
+        xnorm[tid] = a;
+    }
+    __syncthreads();
+
+    double xn[8], macc[8];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+        xn[ci] = xnorm[64 * e + 8 * ci + c8];
+        macc[ci] = 0.0;
+    }
+    const int nkc_all = p.n_pad / 32;
+    // MMA tile 2 * tile + e; [chunk of 32][k half][plane][cand group ci][cand c8][16 B]: this lane's word is bytes 4 t4 .. + 3
+    int8_t* kd_base = q.Kd + ((size_t)(tile * 2 + e) * nkc_all) * (2 * P * 8 * 128) + (rq & 1) * (P * 8 * 128) + c8 * 16 + 4 * t4;
+    const double* xa = xs + t4 * XS_LD_MMA + 64 * e + c8;      // A fragment: feature k0 + t4, candidate 8 ci + c8
+
+    for (int st = 0; st < nst; ++st) {
+        const int buf = st & 1;
+        mbar_wait(bars + buf, (st >> 1) & 1);
+        // B fragment: feature k0 + t4 of the training row behind column c8: group 4 rq + c8 / 2, row-in-group 2 ji + c8 % 2
+        const double* xb = xt + buf * xt_stage + ((size_t)(rq * 4 + (c8 >> 1)) * d_pad + t4) * 4 + (c8 & 1);
+        const double* alb = al + buf * XROWS + rq * 16 + 4 * t4;
+        const double* tn4 = tnb + buf * XROWS + rq * 16 + 4 * t4;
+
+        double acc[8][2][2];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+            for (int ji = 0; ji < 2; ++ji) acc[ci][ji][0] = acc[ci][ji][1] = 0.0;
+        for (int k0 = 0; k0 < d_pad; k0 += 4) {
+            const double b0 = xb[k0 * 4], b1 = xb[k0 * 4 + 2];
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const double a = xa[k0 * XS_LD_MMA + 8 * ci];
+                dmma884(acc[ci][0][0], acc[ci][0][1], a, b0);
+                dmma884(acc[ci][1][0], acc[ci][1][1], a, b1);
+            }
+        }
+        double tnr[4], alr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            tnr[r] = tn4[r];
+            alr[r] = alb[r];
+        }
+        int8_t* dst = kd_base + (size_t)(st * 2 + (rq >> 1)) * (2 * P * 8 * 128);
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {                     // training row 4 t4 + r = tile r >> 1, accumulator r & 1
+                const double sq = fma(-2.0, acc[ci][r >> 1][r & 1], xn[ci] + tnr[r]);
+                const double val = fma(p.amplitude, base_kernel_short<KIND>(sq), p.bias);
+                macc[ci] = fma(val, alr[r], macc[ci]);
+                const unsigned long long y =
+                    ((unsigned long long)__double_as_longlong(fma(val, q.inv_scale, 6755399441055744.0)) + DIGIT_BIAS) ^ DIGIT_BIAS;
+                lo[r] = (uint32_t)y;
+                hi[r] = (uint32_t)(y >> 32);
+            }
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+                const int byte = P - 1 - pl;                   // plane 0 = most significant digit
+                const int b = byte & 3;
+                const uint32_t* src = byte < 4 ? lo : hi;
+                const uint32_t t0 = __byte_perm(src[0], src[1], b | ((4 + b) << 4));
+                const uint32_t t1 = __byte_perm(src[2], src[3], b | ((4 + b) << 4));
+                *reinterpret_cast<uint32_t*>(dst + pl * (8 * 128) + ci * 128) = __byte_perm(t0, t1, 0x5410);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && st + 2 < nst) issue(st + 2);
+    }
+    // k . alpha: the four lanes that share a candidate (fixed xor tree), then the four row quarters in a fixed order
+    double* stage = xt;                                        // [4][BN], free after the loop
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+        double v = fma(0.0, xn[ci], macc[ci]);                 // NaN / Inf coordinates reach the mean (see the DFMA variant)
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (t4 == 0) stage[rq * BN + 64 * e + 8 * ci + c8] = v;
+    }
+    __syncthreads();
+    if (tid < BN)
+        p.kdot[tile * BN + tid] = ((stage[tid] + stage[BN + tid]) + stage[2 * BN + tid]) + stage[3 * BN + tid];
+}
+
 }  // namespace skb

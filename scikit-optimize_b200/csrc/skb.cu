@@ -421,7 +421,18 @@ int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, c
     p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
     p.tn = st->d_tn;
     p.base.hw = st->d_hw;
-    if (planes == 6) launch_kcross_digits_planes<6>(st->kernel, p, tiles, smem, s);
+    // 6 planes, kinds whose distance may be taken as |x|^2 + |t|^2 - 2 x.t: the x.t part on DMMA tiles (SKB_K1_MMA=0 keeps
+    // the DFMA variant, for A/B measurements)
+    static const bool k1_mma = [] { const char* e = std::getenv("SKB_K1_MMA"); return !(e && e[0] == '0'); }();
+    const bool dot_kind = st->kernel == SKB_KERNEL_RBF || st->kernel == SKB_KERNEL_MATERN32 || st->kernel == SKB_KERNEL_MATERN52;
+    if (planes == 6 && k1_mma && dot_kind) {
+        const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad);
+        switch (st->kernel) {
+            case SKB_KERNEL_RBF: kcross_digits_mma_kernel<0><<<tiles, 256, smem_m, s>>>(p); break;
+            case SKB_KERNEL_MATERN32: kcross_digits_mma_kernel<2><<<tiles, 256, smem_m, s>>>(p); break;
+            default: kcross_digits_mma_kernel<3><<<tiles, 256, smem_m, s>>>(p); break;
+        }
+    } else if (planes == 6) launch_kcross_digits_planes<6>(st->kernel, p, tiles, smem, s);
     else launch_kcross_digits_planes<7>(st->kernel, p, tiles, smem, s);
     LAUNCHED();
     return SKB_OK;
@@ -441,14 +452,21 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CU(cudaFuncSetAttribute(kcross_mean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CU(cudaFuncSetAttribute(kcross_mean_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     // the digit kernels are meant to share an SM with the contraction kernel (which needs the maximum shared-memory
     // carve-out): ask for the same carve-out so that the SM does not have to be reconfigured between them
 #define SKB_DIGIT_ATTR(K, P)                                                                                                  \
     CU(cudaFuncSetAttribute(kcross_digits_kernel<K, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));                 \
     CU(cudaFuncSetAttribute(kcross_digits_kernel<K, P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
-    SKB_DIGIT_ATTR(0, 6); SKB_DIGIT_ATTR(1, 6); SKB_DIGIT_ATTR(2, 6); SKB_DIGIT_ATTR(3, 6);
-    SKB_DIGIT_ATTR(0, 7); SKB_DIGIT_ATTR(1, 7); SKB_DIGIT_ATTR(2, 7); SKB_DIGIT_ATTR(3, 7);
+    SKB_DIGIT_ATTR(0, 6); SKB_DIGIT_ATTR(1, 6); SKB_DIGIT_ATTR(2, 6); SKB_DIGIT_ATTR(3, 6); SKB_DIGIT_ATTR(4, 6);
+    SKB_DIGIT_ATTR(0, 7); SKB_DIGIT_ATTR(1, 7); SKB_DIGIT_ATTR(2, 7); SKB_DIGIT_ATTR(3, 7); SKB_DIGIT_ATTR(4, 7);
 #undef SKB_DIGIT_ATTR
+    const int smem1m = (int)kcross_mma_smem_bytes(st->d_pad);
+#define SKB_DIGIT_MMA_ATTR(K)                                                                                                 \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1m));               \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+    SKB_DIGIT_MMA_ATTR(0); SKB_DIGIT_MMA_ATTR(2); SKB_DIGIT_MMA_ATTR(3);
+#undef SKB_DIGIT_MMA_ATTR
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
