@@ -6,10 +6,16 @@ hyper-parameters, 1,000,000 candidates per GPU, FP64.  A step = one pass of the 
 posterior mean/std, -EI, and the top-k (value, index) pairs; with N GPUs every rank owns its own 1M candidates
 (weak scaling, GP state replicated) and the only collective is the all-gather of the per-rank top-k (NCCL).
 
-  value : evals/s, candidates resident in HBM (device entry point, CUDA-event timed, max over ranks)
+  value : evals/s, candidates resident in HBM (device entry point, CUDA-event timed, max over ranks), with the precision
+          the product picks for this workload (engine.resolve_precision("auto"): split-integer contraction on tcgen05)
   e2e   : evals/s through the host entry point (pinned host candidates -> H2D -> kernels -> D2H of the top-k)
-  roofline : dominant kernel (K2, DMMA triangular contraction) algorithmic FP64 flops / its CUDA-event time
+  roofline : dominant kernel of the headline path (K2o, tcgen05 kind::i8 digit-plane contraction) - algorithmic int8
+          ops / its CUDA-event time against 2 x the measured bf16 peak; the pure FP64 DMMA path (K2) is timed in the same
+          run and reported beside it (fp64_dmma_path) against the measured FP64 tensor peak
+  parity_sample : this run's device state against the checker (oracle on the product's fitted state), with the
+          reference's own re-ordering jitter beside it
   cpu_baseline : the CPU oracle (a port of the reference's NumPy/SciPy path) on a bounded sample, this host
+  ask_p50_ms, ask_p50_ms_lbfgs : scoring-block latency of Optimizer.tell at BASELINE.json configs[0] / configs[1]
 
 `--impl reference` times the reference algorithm (oracle port, einsum contraction exactly as gpr.py:332) on the host.
 """
