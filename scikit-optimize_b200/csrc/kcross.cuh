@@ -415,6 +415,33 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_kernel(const KDigitParam
 // 32-bit word of the 16-byte K-major digit vector the contraction kernel reads, and a warp stores 128 contiguous bytes
 // per (plane, candidate group).  Transform, digit extraction and the k . alpha reduction are those of
 // kcross_digits_kernel<KIND, 6>; kinds whose distance needs direct differences (Matern 1/2, Hamming) stay there.
+// sqrt(s) for s >= 1e-290 by ONE third-order step from the hardware seed y ~ 1/sqrt(s) (relative error |d| <= 2^-20):
+// with g = s y and e = 1 - g y (one FMA, = 1 - (1 + d)^2), sqrt(s) = g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8 + O(e^3)); the
+// dropped term is below 2^-58.  Five FP64 instructions instead of the seven of sqrt_pos_short, <= 1.5 ulp.
+__device__ __forceinline__ double sqrt_pos_third(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double g = s * y;
+    const double e = fma(-g, y, 1.0);
+    return fma(g * e, fma(0.375, e, 0.5), g);
+}
+
+// Distance scale folded into the squared distance: the transform receives A * r^2 with A = -1/2 (RBF), 3 (Matern 3/2),
+// 5 (Matern 5/2), so that the square root IS the kernel argument K and no separate multiplication is needed.
+template <int KIND>
+__device__ __forceinline__ constexpr double dist_scale() { return KIND == 0 ? -0.5 : (KIND == 2 ? 3.0 : 5.0); }
+
+// amplitude * base(r) + bias from the scaled squared distance; amp3 = amplitude / 3 (Matern 5/2 only).  The amplitude is
+// folded into the polynomial: amp (1 + K + K^2/3) e^-K + bias = fma(fma(K, fma(K, amp3, amp), amp), e^-K, bias).
+template <int KIND>
+__device__ __forceinline__ double kernel_value_scaled(double sa, double amp, double amp3, double bias) {
+    if (KIND == 0) return fma(amp, exp_nonpos_short(sa), bias);
+    const double K = sqrt_pos_third(sa > 1e-290 ? sa : 1e-290);
+    const double e = exp_nonpos_short(-K);
+    if (KIND == 2) return fma(fma(K, amp, amp), e, bias);
+    return fma(fma(K, fma(K, amp3, amp), amp), e, bias);
+}
+
 constexpr int XS_LD_MMA = BN + 8;          // = 8 mod 16 doubles: the A-fragment read (4 features x 8 candidates) is conflict-free
 
 constexpr size_t kcross_mma_smem_bytes(int d_pad) {
@@ -472,10 +499,12 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
     }
     __syncthreads();
 
-    double xn[8], macc[8];
+    constexpr double A = dist_scale<KIND>();                   // the transform works on A * r^2 (kernel_value_scaled)
+    const double amp3 = p.amplitude * (1.0 / 3.0);
+    double xn[8], macc[8];                                     // xn: A |x|^2
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) {
-        xn[ci] = xnorm[64 * e + 8 * ci + c8];
+        xn[ci] = A * xnorm[64 * e + 8 * ci + c8];
         macc[ci] = 0.0;
     }
     const int nkc_all = p.n_pad / 32;
@@ -508,7 +537,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
         double tnr[4], alr[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            tnr[r] = tn4[r];
+            tnr[r] = A * tn4[r];
             alr[r] = alb[r];
         }
         int8_t* dst = kd_base + (size_t)(st * 2 + (rq >> 1)) * (2 * P * 8 * 128);
@@ -517,8 +546,9 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
             uint32_t lo[4], hi[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {                     // training row 4 t4 + r = tile r >> 1, accumulator r & 1
-                const double sq = fma(-2.0, acc[ci][r >> 1][r & 1], xn[ci] + tnr[r]);
-                const double val = fma(p.amplitude, base_kernel_short<KIND>(sq), p.bias);
+                // A |x - t|^2 = A |x|^2 + A |t|^2 - 2 A x.t; a slightly wrong-signed result (x == t) becomes K = 0
+                const double sa = fma(-2.0 * A, acc[ci][r >> 1][r & 1], xn[ci] + tnr[r]);
+                const double val = kernel_value_scaled<KIND>(sa, p.amplitude, amp3, p.bias);
                 macc[ci] = fma(val, alr[r], macc[ci]);
                 const unsigned long long y =
                     ((unsigned long long)__double_as_longlong(fma(val, q.inv_scale, 6755399441055744.0)) + DIGIT_BIAS) ^ DIGIT_BIAS;
