@@ -206,6 +206,12 @@ int skb_topk_host(int device, const double* values, int64_t m, int64_t index_off
  * skb_candidates_generate_dev draws m * n_dims uniforms from the same stream (dimension by dimension, the reference's
  * draw order) and maps them to the candidate matrix d_X [m][n_dims] with the reference's floating-point operations,
  * bit for bit; key / pos come back advanced.
+ * skb_candidates_generate_jump_dev is the parallel form of the same draw: one CTA per dimension, each started from its own
+ * point of the stream by an MT19937 jump (csrc/rng.cuh).  The caller supplies `window` = the next 624 RAW words of the
+ * generator and, for the columns j = 1 .. n_dims - 1, `polys[j - 1]` = z^(2 m j - 1) mod phi(z) as 624 words (bit b of word
+ * k = coefficient of z^(32 k + b)); `tail` receives the raw words at stream offsets [2 m n_dims - 624, 2 m n_dims + 624)
+ * counted from the first word drawn, from which the caller rebuilds the state NumPy would hold (skopt_b200/mt_jump.py
+ * does both).  Needs 2 m >= 624.  The candidate matrix is bit-identical to skb_candidates_generate_dev's.
  * skb_gather_rows_dev copies the k rows idx[] of d_X to the host (arg-min row / L-BFGS starts). */
 typedef enum { SKB_DIM_REAL_UNIFORM = 0, SKB_DIM_INTEGER_UNIFORM = 1 } skb_dim_kind;
 typedef struct {
@@ -216,6 +222,8 @@ typedef struct {
 int skb_mt19937_uniform_dev(int device, uint32_t* key, int32_t* pos, int64_t count, double* d_out, void* stream);
 int skb_candidates_generate_dev(int device, uint32_t* key, int32_t* pos, int64_t m, int32_t n_dims,
                                 const skb_dim_desc* dims, double* d_X, void* stream);
+int skb_candidates_generate_jump_dev(int device, const uint32_t* window, const uint32_t* polys, int64_t m, int32_t n_dims,
+                                     const skb_dim_desc* dims, double* d_X, uint32_t* tail, void* stream);
 int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
                         void* stream);
 

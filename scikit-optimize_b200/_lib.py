@@ -84,6 +84,8 @@ SYMBOLS = [
     ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
     ("skb_candidates_generate_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32,
                                               C.POINTER(DimDesc), C.c_void_p, C.c_void_p]),
+    ("skb_candidates_generate_jump_dev", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                                   C.POINTER(DimDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_gather_rows_dev", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_fit_create", C.c_int, [C.POINTER(FitDesc), C.c_int, C.POINTER(C.c_void_p)]),
     ("skb_fit_destroy", None, [C.c_void_p]),

@@ -73,6 +73,80 @@ __global__ void __launch_bounds__(256) mt19937_words_kernel(uint32_t* __restrict
     if (tid == 0) *pos_io = pos;
 }
 
+// ---- parallel walk: one CTA per dimension, each started from its own point of the ONE stream --------------------------
+// The stream order of a candidate set is [dimension][candidate] (space.rvs draws dimension by dimension), so column j
+// starts J_j = j * words_per_column words after the generator's current position.  MT19937 is linear over GF(2): with
+// w = the window of the next 624 raw words and A the one-word shift (x_{t+624} = x_{t+397} ^ twist(x_t, x_{t+1})),
+// A^J w = g(A) w for g = z^J mod phi(z) - except for the low 31 bits of the window's first word, which A ignores and
+// drops: so g = z^(J-1) mod phi is applied by Horner's rule (h <- A h ^ g_i w, 19937 steps, one barrier each) and ONE
+// plain step follows.  The polynomials come from the host (skopt_b200/mt_jump.py, cached per (words_per_column, d)).
+//   w: [624] base window; polys: [n_columns - 1][624] (bit b of word k = coefficient of z^(32 k + b));
+//   keys: [n_columns][624], keys[j] = window of column j (usable as a generator key at position 0).
+__global__ void __launch_bounds__(640) mt_jump_kernel(const uint32_t* __restrict__ w, const uint32_t* __restrict__ polys,
+                                                      uint32_t* __restrict__ keys) {
+    __shared__ uint32_t base[MT_N], poly[MT_N], h[2][MT_N];
+    const int t = threadIdx.x, col = blockIdx.x;
+    if (t < MT_N) {
+        base[t] = w[t];
+        h[0][t] = 0u;
+        if (col > 0) poly[t] = polys[(size_t)(col - 1) * MT_N + t];
+    }
+    __syncthreads();
+    if (col == 0) {
+        if (t < MT_N) keys[t] = base[t];
+        return;
+    }
+    int cur = 0;
+    for (int i = MT_N * 32 - 1; i >= 0; --i) {                // leading zero coefficients only shift the zero vector
+        const uint32_t* o = h[cur];
+        if (t < MT_N) {
+            uint32_t v = t < MT_N - 1 ? o[t + 1] : (o[MT_M] ^ mt_twist(o[0], o[1]));
+            if ((poly[i >> 5] >> (i & 31)) & 1u) v ^= base[t];
+            h[cur ^ 1][t] = v;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (t < MT_N) {
+        const uint32_t* o = h[cur];
+        keys[(size_t)col * MT_N + t] = t < MT_N - 1 ? o[t + 1] : (o[MT_M] ^ mt_twist(o[0], o[1]));
+    }
+}
+
+// Column j walks words_per_column raw words from keys[j] into words[j * words_per_column ...]; the last column goes on
+// for 624 more words (`extra`), from which the host rebuilds the (key, position) NumPy itself would hold after the draw.
+__global__ void __launch_bounds__(256) mt19937_columns_kernel(const uint32_t* __restrict__ keys, int64_t words_per_column,
+                                                              uint32_t* __restrict__ words, uint32_t* __restrict__ extra) {
+    __shared__ uint32_t buf[2][MT_N];
+    const int tid = threadIdx.x;
+    const int col = blockIdx.x;
+    const bool last = col == (int)gridDim.x - 1;
+    for (int i = tid; i < MT_N; i += 256) buf[0][i] = keys[(size_t)col * MT_N + i];
+    uint32_t* out = words + (size_t)col * words_per_column;
+    const int64_t total = words_per_column + (last ? MT_N : 0);
+    int cur = 0;
+    __syncthreads();
+    for (int64_t produced = 0; produced < total; produced += MT_N) {
+        if (produced > 0) {
+            const uint32_t* o = buf[cur];
+            uint32_t* n = buf[cur ^ 1];
+            if (tid < 227) n[tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);
+            __syncthreads();
+            if (tid < 227) n[tid + 227] = n[tid] ^ mt_twist(o[tid + 227], o[tid + 228]);
+            __syncthreads();
+            if (tid < 169) n[tid + 454] = n[tid + 227] ^ mt_twist(o[tid + 454], o[tid + 455]);
+            else if (tid == 255) n[623] = n[396] ^ mt_twist(o[623], n[0]);
+            __syncthreads();
+            cur ^= 1;
+        }
+        for (int i = tid; i < MT_N; i += 256) {
+            const int64_t k = produced + i;
+            if (k < words_per_column) out[k] = buf[cur][i];
+            else if (k < total) extra[k - words_per_column] = buf[cur][i];
+        }
+    }
+}
+
 // out[k] = genrand_res53(words[2k], words[2k+1])  ==  RandomState.uniform(0, 1)
 __global__ void mt_words_to_uniform_kernel(const uint32_t* __restrict__ words, int64_t count, double* __restrict__ out) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

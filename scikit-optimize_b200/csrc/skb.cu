@@ -1596,6 +1596,54 @@ int skb_candidates_generate_dev(int device, uint32_t* key, int32_t* pos, int64_t
     return rc;
 }
 
+int skb_candidates_generate_jump_dev(int device, const uint32_t* window, const uint32_t* polys, int64_t m, int32_t n_dims,
+                                     const skb_dim_desc* dims, double* d_X, uint32_t* tail, void* stream) {
+    if (!window || m < 0 || n_dims <= 0 || !dims || !tail || (n_dims > 1 && !polys) || (m > 0 && !d_X))
+        return fail(SKB_ERR_INVALID, "bad argument");
+    if (2 * m < MT_N) return fail(SKB_ERR_INVALID, "the jump generator needs 2 m >= %d words per column, got %lld", MT_N, (long long)(2 * m));
+    for (int j = 0; j < n_dims; ++j) {
+        if (dims[j].kind != SKB_DIM_REAL_UNIFORM && dims[j].kind != SKB_DIM_INTEGER_UNIFORM)
+            return fail(SKB_ERR_UNSUPPORTED, "dimension %d: kind %d has no bit-exact device transform", j, dims[j].kind);
+        if (!(dims[j].high > dims[j].low)) return fail(SKB_ERR_INVALID, "dimension %d: high must exceed low", j);
+    }
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t count = m * n_dims, per_col = 2 * m;
+    void* raw = nullptr;
+    // [words: 2 count][window: 624][polys: (d - 1) 624][keys: d 624][extra: 624][dims]
+    const size_t n_u32 = (size_t)2 * count + (size_t)MT_N * (1 + (n_dims - 1) + n_dims + 1);
+    if ((rc = pool_alloc(device, &raw, n_u32 * sizeof(uint32_t) + 8 + (size_t)n_dims * sizeof(DimDesc))) != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        uint32_t* d_words = static_cast<uint32_t*>(raw);
+        uint32_t* d_window = d_words + 2 * count;
+        uint32_t* d_polys = d_window + MT_N;
+        uint32_t* d_keys = d_polys + (size_t)(n_dims - 1) * MT_N;
+        uint32_t* d_extra = d_keys + (size_t)n_dims * MT_N;
+        DimDesc* d_dims = reinterpret_cast<DimDesc*>((reinterpret_cast<uintptr_t>(d_extra + MT_N) + 7) & ~(uintptr_t)7);
+        std::vector<DimDesc> h(n_dims);
+        for (int j = 0; j < n_dims; ++j) { h[j].kind = dims[j].kind; h[j].pad = 0; h[j].lo = dims[j].low; h[j].hi = dims[j].high; }
+        CU(cudaMemcpyAsync(d_dims, h.data(), (size_t)n_dims * sizeof(DimDesc), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_window, window, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        if (n_dims > 1)
+            CU(cudaMemcpyAsync(d_polys, polys, (size_t)(n_dims - 1) * MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        mt_jump_kernel<<<n_dims, 640, 0, s>>>(d_window, d_polys, d_keys);
+        LAUNCHED();
+        mt19937_columns_kernel<<<n_dims, 256, 0, s>>>(d_keys, per_col, d_words, d_extra);
+        LAUNCHED();
+        candidates_transform_kernel<<<dim3((unsigned)((m + 31) / 32), (unsigned)((n_dims + 31) / 32)), 256, 0, s>>>(
+            d_words, d_dims, m, n_dims, d_X);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(tail, d_words + 2 * count - MT_N, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(tail + MT_N, d_extra, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));                         // `h` is pageable host memory that dies with this scope
+        return SKB_OK;
+    };
+    rc = body();
+    pool_free(device, raw);
+    return rc;
+}
+
 int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32_t k, int32_t n_dims, double* rows,
                         void* stream) {
     if (k < 0 || n_dims <= 0 || (k > 0 && (!d_X || !idx || !rows))) return fail(SKB_ERR_INVALID, "bad argument");

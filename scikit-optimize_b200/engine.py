@@ -7,6 +7,7 @@ Reference interfaces mirrored (paths relative to the reference tree):
 """
 import ctypes as C
 import math
+import os
 import weakref
 
 import numpy as np
@@ -401,21 +402,54 @@ def device_uniform(rng, count, device=0):
     return out
 
 
-def device_candidates(dim_descs, n_samples, rng, device=0):
+# the parallel (jump-ahead) generator pays a one-time polynomial computation per (n_points, n_dims) on the host
+# (~25 ms per dimension, cached) and ~1.5 ms of jump kernel per call: worth it once the serial walk takes several ms
+JUMP_MIN_DOUBLES = 1 << 20
+
+
+def _jump_wanted(jump, n_samples, d):
+    if 2 * int(n_samples) < 624 or d < 2:
+        return False
+    if jump is None:
+        jump = os.environ.get("SKB_MT_JUMP", "auto")
+    if jump in (True, "1", "always"):
+        return True
+    if jump in (False, "0", "never"):
+        return False
+    return int(n_samples) * d >= JUMP_MIN_DOUBLES
+
+
+def device_candidates(dim_descs, n_samples, rng, device=0, jump=None):
     """Candidate matrix (n_samples x n_dims, CUDA float64) for dimensions described as (kind, low, high) triples, with
-    the draw order and arithmetic of `space.transform(space.rvs(n, rng))`; `rng` is advanced as the host call would."""
+    the draw order and arithmetic of `space.transform(space.rvs(n, rng))`; `rng` is advanced as the host call would.
+
+    jump: None = automatic (one CTA per dimension, each started from its own point of the stream by an MT19937 jump, for
+    large candidate sets - mt_jump.py, csrc/rng.cuh; the serial walk otherwise), True / False to force either; the
+    environment variable SKB_MT_JUMP (auto / 1 / 0) sets the default.  Both produce the same bits and leave `rng` in
+    the state NumPy itself would be in."""
     import torch
     name, key, pos, has_gauss, cached = rng.get_state()
     if name != "MT19937":
         raise ValueError("device candidate generation needs a legacy MT19937 RandomState, got %s" % name)
     key = np.ascontiguousarray(key, dtype=np.uint32).copy()
-    pos_c = C.c_int32(int(pos))
     d = len(dim_descs)
     X = torch.empty((int(n_samples), d), dtype=torch.float64, device=torch.device("cuda", device))
     arr = (_lib.DimDesc * d)()
     for j, (kind, lo, hi) in enumerate(dim_descs):
         arr[j].kind, arr[j].low, arr[j].high = int(kind), float(lo), float(hi)
     s = torch.cuda.current_stream(X.device)
+    if _jump_wanted(jump, n_samples, d):
+        from . import mt_jump
+        window = mt_jump.window_from_state(key, pos)
+        polys = mt_jump.column_jump_polynomials(2 * int(n_samples), d)
+        tail = np.empty(2 * mt_jump.N, dtype=np.uint32)
+        _lib.check(_lib.lib().skb_candidates_generate_jump_dev(int(device), window.ctypes.data, polys.ctypes.data,
+                                                               int(n_samples), d, arr, X.data_ptr(), tail.ctypes.data,
+                                                               C.c_void_p(s.cuda_stream)))
+        key, new_pos = mt_jump.canonical_state(pos, 2 * int(n_samples) * d, tail)
+        rng.set_state((name, key, new_pos, has_gauss, cached))
+        return X
+    pos_c = C.c_int32(int(pos))
     _lib.check(_lib.lib().skb_candidates_generate_dev(int(device), key.ctypes.data, C.byref(pos_c), int(n_samples), d, arr,
                                                       X.data_ptr(), C.c_void_p(s.cuda_stream)))
     rng.set_state((name, key, int(pos_c.value), has_gauss, cached))

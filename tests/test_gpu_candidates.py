@@ -47,6 +47,27 @@ def test_device_candidates_equal_host_candidates(name, n):
     assert r_host.randint(0, 2 ** 31 - 1) == r_dev.randint(0, 2 ** 31 - 1)
 
 
+@pytest.mark.parametrize("name", sorted(SPECS))
+@pytest.mark.parametrize("n,burn", [(312, 0), (1000, 5), (10007, 623), (70001, 311)])
+def test_jump_generator_equals_serial_generator_and_host(name, n, burn):
+    """One CTA per dimension, each started by an MT19937 jump (mt_jump.py, csrc/rng.cuh): same matrix, bit for bit, and
+    the host generator ends in NumPy's own state (key AND position)."""
+    space = normalize_dimensions(SPECS[name])
+    descs = device_dim_descs(space)
+    rngs = [np.random.RandomState(77) for _ in range(3)]
+    for r in rngs:
+        r.randint(0, 2 ** 31 - 1, size=burn)
+    X_host = space.rvs_transformed(n, rngs[0])
+    X_serial = engine.device_candidates(descs, n, rngs[1], jump=False).cpu().numpy()
+    X_jump = engine.device_candidates(descs, n, rngs[2], jump=True).cpu().numpy()
+    assert np.array_equal(X_serial, X_host) and np.array_equal(X_jump, X_host)
+    ref = rngs[0].get_state()
+    for r in rngs[1:]:
+        st = r.get_state()
+        assert st[2] == ref[2] and np.array_equal(st[1], ref[1])
+    assert rngs[0].randint(0, 2 ** 31 - 1) == rngs[2].randint(0, 2 ** 31 - 1)
+
+
 def test_unsupported_dimensions_fall_back_to_the_host():
     assert device_dim_descs(normalize_dimensions([(1e-4, 1e2, "log-uniform"), (0.0, 1.0)])) is None
     assert device_dim_descs(Space([(0.0, 1.0)])) is None            # identity transform: not the GP path
