@@ -405,13 +405,14 @@ def device_uniform(rng, count, device=0):
 # the parallel (jump-ahead) generator pays a one-time polynomial computation per (n_points, n_dims) on the host
 # (~25 ms per dimension, cached) and ~1.5 ms of jump kernel per call: worth it once the serial walk takes several ms
 JUMP_MIN_DOUBLES = 1 << 20
+_JUMP_DEFAULT = "0"         # "auto" once the device half has been verified on a B200 (tests/test_gpu_candidates.py)
 
 
 def _jump_wanted(jump, n_samples, d):
     if 2 * int(n_samples) < 624 or d < 2:
         return False
     if jump is None:
-        jump = os.environ.get("SKB_MT_JUMP", "auto")
+        jump = os.environ.get("SKB_MT_JUMP", _JUMP_DEFAULT)
     if jump in (True, "1", "always"):
         return True
     if jump in (False, "0", "never"):
