@@ -402,10 +402,12 @@ def device_uniform(rng, count, device=0):
     return out
 
 
-# the parallel (jump-ahead) generator pays a one-time polynomial computation per (n_points, n_dims) on the host
-# (~25 ms per dimension, cached) and ~1.5 ms of jump kernel per call: worth it once the serial walk takes several ms
+# the parallel (jump-ahead) generator needs one polynomial per dimension from the host (~25 ms each, cached per
+# (n_points, n_dims)) and ~1.5 ms of jump kernel per call: worth it once the serial walk takes several ms.  In the
+# automatic mode the polynomials are computed in a background thread and the serial walk (same bits) serves until
+# they are there.  Measured at 10^6 x 20: 22.5 ms serial, 4.9 ms with the jump (tools/time_candidates.py).
 JUMP_MIN_DOUBLES = 1 << 20
-_JUMP_DEFAULT = "0"         # "auto" once the device half has been verified on a B200 (tests/test_gpu_candidates.py)
+_JUMP_DEFAULT = "auto"
 
 
 def _jump_wanted(jump, n_samples, d):
@@ -439,10 +441,13 @@ def device_candidates(dim_descs, n_samples, rng, device=0, jump=None):
     for j, (kind, lo, hi) in enumerate(dim_descs):
         arr[j].kind, arr[j].low, arr[j].high = int(kind), float(lo), float(hi)
     s = torch.cuda.current_stream(X.device)
+    polys = None
     if _jump_wanted(jump, n_samples, d):
         from . import mt_jump
+        forced = jump in (True, "1", "always") or os.environ.get("SKB_MT_JUMP") in ("1", "always")
+        polys = (mt_jump.column_jump_polynomials if forced else mt_jump.column_jump_polynomials_nowait)(2 * int(n_samples), d)
+    if polys is not None:
         window = mt_jump.window_from_state(key, pos)
-        polys = mt_jump.column_jump_polynomials(2 * int(n_samples), d)
         tail = np.empty(2 * mt_jump.N, dtype=np.uint32)
         _lib.check(_lib.lib().skb_candidates_generate_jump_dev(int(device), window.ctypes.data, polys.ctypes.data,
                                                                int(n_samples), d, arr, X.data_ptr(), tail.ctypes.data,

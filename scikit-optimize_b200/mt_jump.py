@@ -13,6 +13,8 @@ phi by Berlekamp-Massey from the generator's own output (computed once per proce
 multiply, carry-less products by Kronecker substitution on ordinary big-integer multiplication.  Everything here is
 checked on the CPU against numpy.random.RandomState itself (tests/test_mt_jump.py).
 """
+import threading
+
 import numpy as np
 
 N, M = 624, 397
@@ -140,27 +142,59 @@ def z_power(J):
 
 
 _JUMP_CACHE = {}
+_JUMP_PENDING = {}
+_JUMP_LOCK = threading.Lock()
+
+
+def _compute_column_polynomials(words_per_column, n_columns):
+    phi = characteristic_polynomial()
+    L = int(words_per_column)
+    if L < 1:
+        raise ValueError("words_per_column must be positive")
+    stride = z_power(L)
+    g = z_power(L - 1)
+    out = np.zeros((max(n_columns - 1, 0), N), dtype=np.uint32)
+    for j in range(1, n_columns):
+        out[j - 1] = np.frombuffer(g.to_bytes(N * 4, "little"), dtype="<u4")
+        g = poly_mod(poly_mul(g, stride), phi, DEGREE)
+    return out
+
+
+def _store(key, polys):
+    with _JUMP_LOCK:
+        if len(_JUMP_CACHE) > 8:
+            _JUMP_CACHE.clear()
+        _JUMP_CACHE[key] = polys
+        _JUMP_PENDING.pop(key, None)
 
 
 def column_jump_polynomials(words_per_column, n_columns):
     """g_j = z^(j L - 1) mod phi for the columns j = 1 .. n_columns - 1 (L = words_per_column), as an
-    (n_columns - 1, 624) uint32 array: bit b of word k = coefficient of z^(32 k + b)."""
+    (n_columns - 1, 624) uint32 array: bit b of word k = coefficient of z^(32 k + b).  About 25 ms per column, cached
+    per (L, n_columns)."""
     key = (int(words_per_column), int(n_columns))
-    if key not in _JUMP_CACHE:
-        phi = characteristic_polynomial()
-        L = int(words_per_column)
-        if L < 1:
-            raise ValueError("words_per_column must be positive")
-        stride = z_power(L)
-        g = z_power(L - 1)
-        out = np.zeros((max(n_columns - 1, 0), N), dtype=np.uint32)
-        for j in range(1, n_columns):
-            out[j - 1] = np.frombuffer(g.to_bytes(N * 4, "little"), dtype="<u4")
-            g = poly_mod(poly_mul(g, stride), phi, DEGREE)
-        if len(_JUMP_CACHE) > 8:
-            _JUMP_CACHE.clear()
-        _JUMP_CACHE[key] = out
-    return _JUMP_CACHE[key]
+    with _JUMP_LOCK:
+        polys = _JUMP_CACHE.get(key)
+    if polys is None:
+        polys = _compute_column_polynomials(*key)
+        _store(key, polys)
+    return polys
+
+
+def column_jump_polynomials_nowait(words_per_column, n_columns):
+    """The cached polynomials, or None after starting their computation in a background thread: a caller that has a
+    serial generator producing the same bits (engine.device_candidates) uses it until the polynomials are there, so
+    that the first draws of an optimisation never wait for them."""
+    key = (int(words_per_column), int(n_columns))
+    with _JUMP_LOCK:
+        polys = _JUMP_CACHE.get(key)
+        if polys is not None or key in _JUMP_PENDING:
+            return polys
+        worker = threading.Thread(target=lambda: _store(key, _compute_column_polynomials(*key)), daemon=True,
+                                  name="skb-mt-jump-%d-%d" % key)
+        _JUMP_PENDING[key] = worker
+    worker.start()
+    return None
 
 
 def apply_polynomial(words, w):

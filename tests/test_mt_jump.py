@@ -88,3 +88,29 @@ def test_canonical_state_is_numpys_own(burn, total):
     assert new_pos == ref_pos and np.array_equal(new_key, ref_key)
     with pytest.raises(ValueError):
         mj.canonical_state(0, 100, raw[:2 * mj.N])
+
+
+def test_background_computation_hands_over_the_same_polynomials():
+    import time
+    key = (2 * 4321, 3)
+    with mj._JUMP_LOCK:
+        mj._JUMP_CACHE.pop(key, None)
+    assert mj.column_jump_polynomials_nowait(*key) is None               # started in the background: the caller goes serial
+    worker = mj._JUMP_PENDING.get(key)
+    mj.column_jump_polynomials_nowait(*key)                              # a second request never starts a second worker
+    assert mj._JUMP_PENDING.get(key) in (worker, None)
+    deadline = time.time() + 60
+    polys = None
+    while polys is None and time.time() < deadline:
+        time.sleep(0.05)
+        polys = mj.column_jump_polynomials_nowait(*key)
+    assert polys is not None and np.array_equal(polys, mj._compute_column_polynomials(*key))
+    assert mj.column_jump_polynomials(*key) is polys                     # the blocking call sees the cached result
+
+
+def test_automatic_mode_policy():
+    from skopt_b200 import engine
+    assert engine._jump_wanted(None, 10 ** 6, 20) and engine._jump_wanted("auto", 52429, 20)
+    assert not engine._jump_wanted(None, 10000, 20)                       # small sets: the serial walk takes < 1 ms
+    assert not engine._jump_wanted(True, 311, 20) and not engine._jump_wanted(True, 10 ** 6, 1)
+    assert engine._jump_wanted(True, 312, 2) and not engine._jump_wanted(False, 10 ** 7, 20)
