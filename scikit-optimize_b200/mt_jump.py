@@ -152,7 +152,8 @@ def _compute_column_polynomials(words_per_column, n_columns):
     if L < 1:
         raise ValueError("words_per_column must be positive")
     stride = z_power(L)
-    g = z_power(L - 1)
+    # z^-1 mod phi = (phi + 1) / z (phi has constant term 1), so z^(L-1) is one product away from z^L
+    g = poly_mod(poly_mul(stride, (phi ^ 1) >> 1), phi, DEGREE)
     out = np.zeros((max(n_columns - 1, 0), N), dtype=np.uint32)
     for j in range(1, n_columns):
         out[j - 1] = np.frombuffer(g.to_bytes(N * 4, "little"), dtype="<u4")
