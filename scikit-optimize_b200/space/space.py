@@ -14,6 +14,9 @@ import numbers
 import numpy as np
 from sklearn.utils import check_random_state
 
+from .transformers import (CategoricalEncoder, Identity, LabelEncoder, LogN, Normalize, Pipeline,  # noqa: F401
+                           StringEncoder)
+
 _INCLUSIVE_ONE = np.nextafter(1.0, 2.0)       # scipy uniform(0, nextafter(1, 2)): samples include the upper edge
 _EPS = 1e-8
 
@@ -27,11 +30,26 @@ def _affine_inclusive(rng, n, loc, width):
     return rng.uniform(0.0, 1.0, size=n) * np.nextafter(width, width + 1.0) + loc
 
 
+class _Ellipsis(object):
+    def __repr__(self):
+        return "..."
+
+
 class Dimension(object):
     """Base class: a dimension knows how to sample, warp and un-warp 1-D arrays of values."""
     prior = None
-    name = None
     transform_ = "identity"
+    _name = None
+
+    @property
+    def name(self):
+        return self._name
+
+    @name.setter
+    def name(self, value):
+        if not (isinstance(value, str) or value is None):
+            raise ValueError("Dimension's name must be either string or None.")
+        self._name = value
 
     @property
     def size(self):
@@ -43,9 +61,11 @@ class Dimension(object):
 
     def rvs(self, n_samples=1, random_state=None):
         rng = check_random_state(random_state)
-        return self._from_unit(self._draw(rng, n_samples))
+        return self.inverse_transform(self._draw(rng, n_samples))
 
-    # subclasses: _draw (sample in the warped space), _from_unit == inverse_transform, transform
+    # subclasses: _draw (sample in the warped space), _from_unit (warped -> original on whole arrays: the form
+    # Space.rvs_transformed / Space.inverse_transform use), inverse_transform (the same values with the reference's
+    # return types), transform
 
 
 class Real(Dimension):
@@ -95,7 +115,7 @@ class Real(Dimension):
             raise ValueError("All values should be greater than %f" % self._wlow)
         return (w - self._wlow) / (self._whigh - self._wlow)
 
-    def inverse_transform(self, Xt):
+    def _from_unit(self, Xt):
         Xt = np.asarray(Xt, dtype=float)
         if self.transform_ == "normalize":
             if np.any(Xt > 1.0 + _EPS):
@@ -106,7 +126,19 @@ class Real(Dimension):
         out = np.clip(self._unwarp(Xt), self.low, self.high)
         return out if self.dtype in (float, "float") else out.astype(self.dtype)
 
-    _from_unit = inverse_transform
+    def inverse_transform(self, Xt):
+        """Warped -> original; Python floats (a list, or one float for a scalar) for the default dtype, an array of
+        `dtype` otherwise (space.py:337-351)."""
+        out = self._from_unit(Xt)
+        return out.tolist() if self.dtype in (float, "float") else out
+
+    @property
+    def transformer(self):
+        """The reference's transformer object for this dimension (space.py:299-323), built on demand."""
+        warp = Identity() if self.prior == "uniform" else LogN(self.base)
+        if self.transform_ != "normalize":
+            return warp
+        return Pipeline([warp, Normalize(self._wlow, self._whigh)])
 
     @property
     def bounds(self):
@@ -199,7 +231,7 @@ class Integer(Dimension):
             raise ValueError("All values should be greater than %f" % self._wlow)
         return (w - self._wlow) / (self._whigh - self._wlow)
 
-    def inverse_transform(self, Xt):
+    def _from_unit(self, Xt):
         Xt = np.asarray(Xt, dtype=float)
         if self.transform_ == "normalize":
             if np.any(Xt > 1.0 + _EPS):
@@ -214,7 +246,20 @@ class Integer(Dimension):
         out = np.clip(Xt, self.low, self.high)
         return np.round(out).astype(int if self.dtype in (int, "int") else self.dtype)
 
-    _from_unit = inverse_transform
+    def inverse_transform(self, Xt):
+        """Warped -> original; Python ints (a list, or one int for a scalar) when dtype is `int`, an array of `dtype`
+        otherwise (space.py:522-538)."""
+        out = self._from_unit(Xt)
+        return out.tolist() if self.dtype in (int, "int") else out
+
+    @property
+    def transformer(self):
+        """The reference's transformer object for this dimension (space.py:489-511), built on demand."""
+        if self.transform_ != "normalize":
+            return Identity() if self.prior == "uniform" else LogN(self.base)
+        if self.prior == "uniform":
+            return Pipeline([Identity(), Normalize(self.low, self.high, is_int=True)])
+        return Pipeline([LogN(self.base), Normalize(self._wlow, self._whigh)])
 
     @property
     def bounds(self):
@@ -267,6 +312,7 @@ class Categorical(Dimension):
             ordered = [self.categories[int(np.where(cats == u)[0][0])] for u in np.unique(cats)]
         self._order = ordered                                    # label -> category (np.unique order for plain types)
         self._label = {c: i for i, c in enumerate(ordered)}
+        self._onehot_pos = {c: i for i, c in enumerate(self.categories)}
         self.set_transformer(transform or "onehot")
 
     def set_transformer(self, transform="onehot"):
@@ -284,13 +330,14 @@ class Categorical(Dimension):
         return rng.choice(self._n, size=n, p=self.prior_)
 
     def rvs(self, n_samples=None, random_state=None):
+        """Categories drawn from the prior.  Return types follow space.py:688-698: without `n_samples` one category
+        (an array holding one under "normalize"), otherwise a list (an array under "normalize")."""
         rng = check_random_state(random_state)
         scalar = n_samples is None
         draws = self._draw(rng, 1 if scalar else n_samples)
         if self.transform_ == "normalize":
-            out = self.inverse_transform(draws)
-        else:
-            out = [self.categories[int(c)] for c in draws]
+            return self.inverse_transform(draws)
+        out = [self.categories[int(c)] for c in draws]
         return out[0] if scalar else out
 
     def labels(self, X):
@@ -301,18 +348,37 @@ class Categorical(Dimension):
             return X
         if self.transform_ == "string":
             return [str(v) for v in X]
-        lab = self.labels(X)
         if self.transform_ == "label":
-            return lab.astype(int)
+            return self.labels(X).astype(int)
         if self.transform_ == "normalize":
+            lab = self.labels(X)
             if self._n == 1:
                 return lab * 0.0
             return (np.round(lab).astype(int) - 0.0) / (float(self._n - 1) - 0.0)
-        onehot = np.zeros((len(lab), self._n))
-        onehot[np.arange(len(lab)), lab.astype(int)] = 1.0
-        return onehot[:, 1:2].ravel() if self._n == 2 else onehot
+        # one-hot over the categories in the GIVEN order (CategoricalEncoder, transformers.py:113-117); two categories
+        # give one 0/1 column and a single category a column of zeros, like the LabelBinarizer behind the reference
+        pos = np.fromiter((self._onehot_pos[v] for v in X), dtype=np.int64)
+        if self._n <= 2:
+            return (pos if self._n == 2 else pos * 0).reshape(-1, 1)
+        onehot = np.zeros((len(pos), self._n), dtype=np.int64)
+        onehot[np.arange(len(pos)), pos] = 1
+        return onehot
 
     def inverse_transform(self, Xt):
+        """Warped -> categories, as an array like the reference's (space.py:679-687)."""
+        return np.array(self._from_unit(Xt))
+
+    @property
+    def transformer(self):
+        """The reference's transformer object for this dimension (space.py:636-652), built on demand."""
+        if self.transform_ == "normalize":
+            return Pipeline([LabelEncoder(list(self.categories)), Normalize(0, self._n - 1, is_int=True)])
+        enc = {"onehot": CategoricalEncoder, "string": StringEncoder, "label": LabelEncoder,
+               "identity": Identity}[self.transform_]()
+        enc.fit(self.categories)
+        return enc
+
+    def _from_unit(self, Xt):
         if self.transform_ == "identity":
             return list(Xt)
         if self.transform_ == "string":
@@ -329,10 +395,12 @@ class Categorical(Dimension):
             lab = np.round(Xt).astype(int)
         else:
             Xt = Xt.reshape(len(Xt), -1)
-            lab = (Xt[:, 0] > 0.5).astype(int) if self._n == 2 else np.argmax(Xt, axis=1)
+            if self._n <= 2:
+                pos = (Xt[:, 0] > 0.5).astype(int) if self._n == 2 else np.zeros(len(Xt), dtype=int)
+            else:
+                pos = np.argmax(Xt, axis=1)
+            return [self.categories[int(i)] for i in pos]
         return [self._order[int(i)] for i in np.ravel(lab)]
-
-    _from_unit = inverse_transform
 
     @property
     def transformed_size(self):
@@ -369,7 +437,12 @@ class Categorical(Dimension):
     __hash__ = None
 
     def __repr__(self):
-        return "Categorical(categories={}, prior={})".format(self.categories, self.prior)
+        cats, prior = self.categories, self.prior
+        if len(cats) > 7:
+            cats = cats[:3] + (_Ellipsis(),) + cats[-3:]
+        if prior is not None and len(prior) > 7:
+            prior = list(prior[:3]) + [_Ellipsis()] + list(prior[-3:])
+        return "Categorical(categories={}, prior={})".format(cats, prior)
 
 
 def check_dimension(dimension, transform=None):
@@ -425,7 +498,10 @@ class Space(object):
         return iter(self.dimensions)
 
     def __repr__(self):
-        return "Space([{}])".format(",\n       ".join(map(str, self.dimensions)))
+        dims = self.dimensions
+        if len(dims) > 31:
+            dims = dims[:15] + [_Ellipsis()] + dims[-15:]
+        return "Space([{}])".format(",\n       ".join(map(str, dims)))
 
     @property
     def n_dims(self):
@@ -453,7 +529,13 @@ class Space(object):
 
     @property
     def bounds(self):
-        return [dim.bounds for dim in self.dimensions]
+        b = []
+        for dim in self.dimensions:
+            if dim.size == 1:
+                b.append(dim.bounds)
+            else:
+                b.extend(dim.bounds)
+        return b
 
     @property
     def transformed_bounds(self):
@@ -469,8 +551,55 @@ class Space(object):
         for j, dim in enumerate(self.dimensions):
             dim.set_transformer(transform[j] if isinstance(transform, list) else transform)
 
+    def set_transformer_by_type(self, transform, dim_type):
+        for dim in self.dimensions:
+            if isinstance(dim, dim_type):
+                dim.set_transformer(transform)
+
     def get_transformer(self):
         return [dim.transform_ for dim in self.dimensions]
+
+    @property
+    def n_constant_dimensions(self):
+        return sum(1 for dim in self.dimensions if dim.is_constant)
+
+    def __getitem__(self, dimension_names):
+        """`space['foo']` / `space[2]` -> (index, Dimension) or (None, None); a list of names -> a list of such pairs
+        (space.py:1039-1089)."""
+        def find(key):
+            for index, dim in enumerate(self.dimensions):
+                if key == dim.name or key == index:
+                    return index, dim
+            return None, None
+
+        if isinstance(dimension_names, (str, int)):
+            return find(dimension_names)
+        if isinstance(dimension_names, (list, tuple)):
+            return [find(key) for key in dimension_names]
+        raise ValueError("Dimension name should be either string orlist of strings, but got {}.".format(
+            type(dimension_names)))
+
+    @classmethod
+    def from_yaml(cls, yml_path, namespace=None):
+        """Space from a YAML file: a list of one-key mappings {Real | Integer | Categorical: constructor arguments},
+        either at the top level or under a namespace (the first one unless `namespace` names another); keys are
+        case-insensitive and unknown dimension kinds are skipped (space.py:808-872)."""
+        import yaml
+        with open(yml_path, "rb") as f:
+            config = yaml.safe_load(f)
+        if isinstance(config, dict):
+            options = next(iter(config.values())) if namespace is None else config[namespace]
+        elif isinstance(config, list):
+            options = config
+        else:
+            raise TypeError("YaML does not specify a list or dictionary")
+        kinds = {"real": Real, "integer": Integer, "categorical": Categorical}
+        dimensions = []
+        for option in options:
+            kind, arguments = next(iter(option.items()))
+            if kind.lower() in kinds:
+                dimensions.append(kinds[kind.lower()](**{k.lower(): v for k, v in arguments.items()}))
+        return cls(dimensions=dimensions)
 
     def __contains__(self, point):
         return all(component in dim for component, dim in zip(point, self.dimensions))
@@ -523,7 +652,7 @@ class Space(object):
         for dim in self.dimensions:
             width = dim.transformed_size
             block = Xt[:, start] if width == 1 else Xt[:, start:start + width]
-            cols.append(dim.inverse_transform(block))
+            cols.append(dim._from_unit(block))
             start += width
         return _rows(cols)
 
