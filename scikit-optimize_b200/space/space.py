@@ -63,6 +63,10 @@ class Dimension(object):
         rng = check_random_state(random_state)
         return self.inverse_transform(self._draw(rng, n_samples))
 
+    def _sample_column(self, rng, n):
+        """`n` samples in the original space as one column for Space.rvs (an array, or a list of categories)."""
+        return self._from_unit(self._draw(rng, n))
+
     # subclasses: _draw (sample in the warped space), _from_unit (warped -> original on whole arrays: the form
     # Space.rvs_transformed / Space.inverse_transform use), inverse_transform (the same values with the reference's
     # return types), transform
@@ -339,6 +343,12 @@ class Categorical(Dimension):
             return self.inverse_transform(draws)
         out = [self.categories[int(c)] for c in draws]
         return out[0] if scalar else out
+
+    def _sample_column(self, rng, n):
+        draws = self._draw(rng, n)
+        if self.transform_ == "normalize":
+            return self._from_unit(draws)
+        return [self.categories[int(c)] for c in draws]
 
     def labels(self, X):
         return np.array([self._label[v] for v in X], dtype=float)
@@ -634,7 +644,7 @@ class Space(object):
     def rvs(self, n_samples=1, random_state=None):
         """Points in the ORIGINAL space as a list of lists (space.py:874-903): one draw per dimension, in order."""
         rng = check_random_state(random_state)
-        return _rows([dim.rvs(n_samples=n_samples, random_state=rng) for dim in self.dimensions])
+        return _rows([dim._sample_column(rng, n_samples) for dim in self.dimensions])
 
     def transform(self, X):
         """Original space -> warped space, (n, transformed_n_dims) float array (space.py:942-974)."""
