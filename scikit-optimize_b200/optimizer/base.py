@@ -3,6 +3,7 @@ import numbers
 import warnings
 from collections.abc import Iterable
 
+from ..utils import eval_callbacks
 from .optimizer import Optimizer
 
 
@@ -14,15 +15,6 @@ def _as_callbacks(callback):
     if isinstance(callback, list) and all(callable(c) for c in callback):
         return list(callback)
     raise ValueError("callback should be either a callable or a list of callables.")
-
-
-def _run_callbacks(callbacks, result):
-    stop = False
-    for c in callbacks:
-        decision = c(result)
-        if decision is not None:
-            stop = stop or decision
-    return stop
 
 
 def base_minimize(func, dimensions, base_estimator, n_calls=100, n_random_starts=None, n_initial_points=10,
@@ -84,7 +76,7 @@ def base_minimize(func, dimensions, base_estimator, n_calls=100, n_random_starts
             raise ValueError("`x0` and `y0` should have the same length")
         result = optimizer.tell(x0, y0)
         result.specs = specs
-        if _run_callbacks(callbacks, result):
+        if eval_callbacks(callbacks, result):
             return result
 
     for _ in range(n_calls):
@@ -92,6 +84,6 @@ def base_minimize(func, dimensions, base_estimator, n_calls=100, n_random_starts
         next_y = func(next_x)
         result = optimizer.tell(next_x, next_y)
         result.specs = specs
-        if _run_callbacks(callbacks, result):
+        if eval_callbacks(callbacks, result):
             break
     return result

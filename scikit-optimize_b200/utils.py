@@ -1,13 +1,18 @@
 """Host glue used around the hot path; mirrors the relevant pieces of skopt/utils.py: create_result :29-72,
-has_gradients :301-330, cook_estimator :333-405 (GP branch only), normalize_dimensions :569-607, and the list-shape
-helpers used by Optimizer.tell (is_listlike / is_2Dlistlike / check_x_in_space)."""
+eval_callbacks :75-102, has_gradients :301-330, cook_estimator :333-405 (GP branch only), normalize_dimensions
+:569-607, the list-shape helpers used by Optimizer.tell (is_listlike / is_2Dlistlike / check_x_in_space) and the
+helpers callers wrap their objective and search space with (dimensions_aslist :453, point_asdict :489, point_aslist
+:529, check_list_types :610, check_dimension_names :641, use_named_args :663)."""
+from collections import OrderedDict
+from functools import wraps
+
 import numpy as np
 from scipy.optimize import OptimizeResult
 from sklearn.base import is_regressor
 
 from .learning import GaussianProcessRegressor
 from .learning.gaussian_process.kernels import ConstantKernel, HammingKernel, Matern
-from .space import Space, normalize_dimensions  # noqa: F401
+from .space import Dimension, Space, normalize_dimensions  # noqa: F401
 
 
 def is_listlike(x):
@@ -48,6 +53,60 @@ def create_result(Xi, yi, space=None, rng=None, specs=None, models=None):
     res.random_state = rng
     res.specs = specs
     return res
+
+
+def eval_callbacks(callbacks, result):
+    """True when any callback asks to stop; every callback runs, `None` answers do not count (utils.py:75-102)."""
+    stop = False
+    for callback in callbacks or ():
+        decision = callback(result)
+        if decision is not None:
+            stop = stop or decision
+    return stop
+
+
+def dimensions_aslist(search_space):
+    """Dimensions of a {name: Dimension} search space in the order of the sorted names."""
+    return [search_space[name] for name in sorted(search_space)]
+
+
+def point_asdict(search_space, point_as_list):
+    """A point given in sorted-name order -> OrderedDict {name: value}."""
+    return OrderedDict(zip(sorted(search_space), point_as_list))
+
+
+def point_aslist(search_space, point_as_dict):
+    """{name: value} -> the values in sorted-name order."""
+    return [point_as_dict[name] for name in sorted(search_space)]
+
+
+def check_list_types(x, types):
+    wrong = [item for item in x if not isinstance(item, types)]
+    if wrong:
+        raise ValueError("All elements in list must be instances of {}, but found: {}".format(types, wrong))
+
+
+def check_dimension_names(dimensions):
+    unnamed = [dim for dim in dimensions if dim.name is None]
+    if unnamed:
+        raise ValueError("All dimensions must have names, but found: {}".format(unnamed))
+
+
+def use_named_args(dimensions):
+    """Decorator: an objective written with named arguments, `f(lr=..., depth=...)`, becomes the `f(x)` the minimisers
+    call, `x` being the point as a list in the order of `dimensions` (all of which must be named Dimensions)."""
+    def decorator(func):
+        check_list_types(dimensions, Dimension)
+        check_dimension_names(dimensions)
+
+        @wraps(func)
+        def wrapper(x):
+            if len(x) != len(dimensions):
+                raise ValueError("Mismatch in number of search-space dimensions. len(dimensions)=={} and len(x)=={}"
+                                 .format(len(dimensions), len(x)))
+            return func(**{dim.name: value for dim, value in zip(dimensions, x)})
+        return wrapper
+    return decorator
 
 
 def has_gradients(estimator):
