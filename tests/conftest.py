@@ -24,3 +24,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def abi_model(monkeypatch):
+    """Swap the loaded CUDA library for the software model of its host entry points (tests/_abi_model.py) for ONE test,
+    so that the Python host side above the C ABI can be exercised without a GPU.  Candidate generation on the device is
+    switched off (the Optimizer then draws on the host, same bits).  Test infrastructure: the product never does this."""
+    import skopt_b200  # noqa: F401
+    from skopt_b200 import _lib
+    from skopt_b200.optimizer import optimizer as optimizer_module
+    from tests._abi_model import AbiModel
+    model = AbiModel()
+    monkeypatch.setattr(_lib, "_lib", model)
+    monkeypatch.setattr(optimizer_module, "device_dim_descs", lambda space: None)
+    return model
