@@ -53,6 +53,12 @@ def _white_kernel_key(kernel, prefix=""):
     return None
 
 
+def _param_for_white_kernel_in_Sum(kernel, kernel_str=""):
+    """The reference's spelling of the lookup above: (found, key), with "_" as the key of a miss (gpr.py:17-36)."""
+    key = _white_kernel_key(kernel, kernel_str + "__" if kernel_str else "")
+    return (True, key) if key is not None else (False, "_")
+
+
 class GaussianProcessRegressor(_SkGPR):
     def __init__(self, kernel=None, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
                  normalize_y=False, copy_X_train=True, random_state=None, noise=None):

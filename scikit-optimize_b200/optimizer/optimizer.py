@@ -29,7 +29,7 @@ from ..learning import GaussianProcessRegressor
 from ..space import Categorical, Space
 from ..utils import (check_x_in_space, cook_estimator, create_result, has_gradients, is_2Dlistlike, is_listlike,
                      normalize_dimensions)
-from ..acquisition import _gaussian_acquisition, device_topk
+from ..acquisition import _gaussian_acquisition, _is_device_model, device_topk
 from ..distributed import sharded_score, sharded_score_tensor
 from ..engine import device_candidates
 from ..space import device_dim_descs
@@ -287,11 +287,12 @@ class Optimizer(object):
         xi, kappa = kw.get("xi", 0.01), kw.get("kappa", 1.96)
         y_opt = np.min(self.yi)
         acqs = tuple(self.cand_acq_funcs_)
-        if "ps" in self.acq_func:
+        if "ps" in self.acq_func or not hasattr(est, "device_state"):
+            # per-second acquisitions (two models), or a regressor that is not this package's GP: the reference's
+            # duck-typed boundary (optimizer.py:225-227) - posterior from the model's own predict(), acquisition
+            # arithmetic and ranking on the GPU
             X = self.space.rvs_transformed(self.n_points, self.rng)
-            return self._score_and_refine_per_second(est, X, y_opt, transformed_bounds)
-        if not hasattr(est, "device_state"):
-            raise TypeError("the GPU scoring path needs this package's GaussianProcessRegressor, got %s" % type(est))
+            return self._score_and_refine_through_predict(est, X, y_opt, transformed_bounds)
         dev = est.device_state()
         k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), self.n_points))
         # candidate matrix: generated ON the GPU (same MT19937 stream, same arithmetic, same bits as the host path) when
@@ -345,31 +346,42 @@ class Optimizer(object):
             next_xs = [np.clip(x, transformed_bounds[:, 0], transformed_bounds[:, 1]) for x in next_xs]
         return next_xs
 
-    def _score_and_refine_per_second(self, est, X, y_opt, transformed_bounds):
-        """EIps / PIps: two resident GPs (objective, log time); values are composed on the GPU
-        (acquisition._per_second) and ranked on the GPU (acquisition.device_topk)."""
-        acq = self.cand_acq_funcs_[0]
+    def _score_and_refine_through_predict(self, est, X, y_opt, transformed_bounds):
+        """The scoring block for models reached through `predict`: EIps / PIps (`est.estimators_` = objective and
+        log-time model, two resident GPs when they are this package's) and regressors of other families.  Values come
+        from acquisition._gaussian_acquisition (our GPs: fused GPU pass; others: their predict(), then
+        skb_acq_from_posterior_host / skb_ps_combine_host), ranking from acquisition.device_topk (skb_topk_host)."""
+        models = list(est.estimators_) if "ps" in self.acq_func else [est]
+        batched = all(_is_device_model(m) for m in models)      # foreign predict() returns gradients for one row only
         k = 1 if self.acq_optimizer == "sampling" else max(1, min(int(self.n_restarts_optimizer), X.shape[0]))
-        values = _gaussian_acquisition(X, est, y_opt, acq, acq_func_kwargs=self.acq_func_kwargs)
-        tv, ti, first_nan = device_topk(values, k)
-        if self.acq_optimizer == "sampling":
-            next_x = X[first_nan if first_nan >= 0 else int(ti[0])]
-        else:
-            starts = [X[int(i)] for i in ti if i >= 0]
+        next_xs = []
+        for acq in self.cand_acq_funcs_:
+            values = _gaussian_acquisition(X, est, y_opt, acq, acq_func_kwargs=self.acq_func_kwargs)
+            tv, ti, first_nan = device_topk(values, k)
+            if self.acq_optimizer == "sampling":
+                next_x = X[first_nan if first_nan >= 0 else int(ti[0])]
+            else:
+                starts = [X[int(i)] for i in ti if i >= 0]
 
-            def evaluate(tasks, Xq):
-                f, G = _gaussian_acquisition(Xq, est, y_opt, acq, return_grad=True, acq_func_kwargs=self.acq_func_kwargs)
-                return f, np.asarray(G).reshape(len(tasks), -1)
+                def evaluate(tasks, Xq, acq=acq):
+                    if batched:
+                        f, G = _gaussian_acquisition(Xq, est, y_opt, acq, return_grad=True,
+                                                     acq_func_kwargs=self.acq_func_kwargs)
+                        return f, np.asarray(G).reshape(len(tasks), -1)
+                    rows = [_gaussian_acquisition(Xq[i:i + 1], est, y_opt, acq, return_grad=True,
+                                                  acq_func_kwargs=self.acq_func_kwargs) for i in range(len(tasks))]
+                    return np.array([f[0] for f, _ in rows]), np.vstack([np.ravel(g) for _, g in rows])
 
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                results = minimize_batch(starts, evaluate, self.space.transformed_bounds, maxiter=20)
-            cand_xs = np.array([r[0] for r in results])
-            cand_acqs = np.array([r[1] for r in results])
-            next_x = cand_xs[np.argmin(cand_acqs)]
-        if not self.space.is_categorical:
-            next_x = np.clip(next_x, transformed_bounds[:, 0], transformed_bounds[:, 1])
-        return [next_x]
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    results = minimize_batch(starts, evaluate, self.space.transformed_bounds, maxiter=20)
+                cand_xs = np.array([r[0] for r in results])
+                cand_acqs = np.array([r[1] for r in results])
+                next_x = cand_xs[np.argmin(cand_acqs)]
+            if not self.space.is_categorical:
+                next_x = np.clip(next_x, transformed_bounds[:, 0], transformed_bounds[:, 1])
+            next_xs.append(next_x)
+        return next_xs
 
     def _check_y_is_valid(self, x, y):
         if "ps" in self.acq_func:

@@ -109,10 +109,22 @@ def use_named_args(dimensions):
     return decorator
 
 
+def _tree_families():
+    from sklearn.ensemble import BaseEnsemble
+    from sklearn.ensemble._gb import BaseGradientBoosting
+    from sklearn.tree import BaseDecisionTree
+    return (BaseEnsemble, BaseGradientBoosting, BaseDecisionTree)
+
+
+_TREE_FAMILIES = _tree_families()
+
+
 def has_gradients(estimator):
     """utils.py:301-330: True when predict() can return input gradients - every GP this package builds (the GPU
     computes them) except one whose kernel contains a HammingKernel (categorical inputs have no gradient)."""
     if estimator is None or not hasattr(estimator, "predict"):
+        return False
+    if isinstance(estimator, _TREE_FAMILIES) or type(estimator).__name__ == "GradientBoostingQuantileRegressor":
         return False
     if hasattr(estimator, "kernel"):
         params = estimator.get_params()
@@ -128,9 +140,13 @@ def cook_estimator(base_estimator, space=None, **kwargs):
     family exists here; tree / GBRT surrogates are outside the GPU hot path."""
     if isinstance(base_estimator, str):
         name = base_estimator.upper()
-        if name not in ("GP", "DUMMY"):
-            raise ValueError("Valid strings for the base_estimator parameter of the GPU path are 'GP' or 'DUMMY', "
+        if name not in ("GP", "RF", "ET", "GBRT", "DUMMY"):
+            raise ValueError("Valid strings for the base_estimator parameter  are: 'RF', 'ET', 'GP', 'GBRT' or 'DUMMY' "
                              "not %s." % base_estimator)
+        if name in ("RF", "ET", "GBRT"):
+            raise ValueError("base_estimator=%r: tree / GBRT surrogates are not built by this package (the GPU path "
+                             "is the GP family); pass a fitted-able regressor instance instead, it is scored through "
+                             "its own predict()." % base_estimator)
         if name == "DUMMY":
             return None
         if space is None:

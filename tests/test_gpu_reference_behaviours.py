@@ -282,3 +282,36 @@ def test_constant_liar_batches(strategy):
     assert opt2.ask(n_points=5, strategy=strategy) == pts
     with pytest.raises(ValueError):
         opt.ask(n_points=2, strategy="cl_median")
+
+
+def test_a_regressor_of_another_family_is_scored_through_its_own_predict():
+    """optimizer.py:225-227: any sklearn regressor is accepted.  One that is not this package's GP keeps the search space
+    un-normalised and is scored through predict(X, return_std=True), with the acquisition arithmetic and the ranking on the
+    GPU (skb_acq_from_posterior_host, skb_topk_host); the suggestion is the arg-min of the same values on the same
+    candidates."""
+    from sklearn.gaussian_process import GaussianProcessRegressor as SklearnGPR
+    from sklearn.gaussian_process.kernels import RBF as SklearnRBF
+    from skopt_b200.acquisition import _gaussian_acquisition
+    from skopt_b200.utils import has_gradients
+    est = SklearnGPR(SklearnRBF(1.0, "fixed"), alpha=1e-6, optimizer=None)
+    opt = Optimizer([(-2.0, 2.0), (0.0, 3.0)], est, n_initial_points=4, acq_func="gp_hedge", acq_optimizer="sampling",
+                    acq_optimizer_kwargs=dict(n_points=500), random_state=3)
+    assert opt.space.get_transformer() == ["identity", "identity"] and has_gradients(est)
+    for _ in range(6):
+        x = opt.ask()
+        res = opt.tell(x, (x[0] - 0.5) ** 2 + (x[1] - 1.0) ** 2)
+    assert len(res.models) == 3 and isinstance(res.models[-1], SklearnGPR) and len(opt.next_xs_) == 3
+    # replay the last scoring block: same RNG state -> same candidates -> the arg-min of each acquisition
+    twin = Optimizer([(-2.0, 2.0), (0.0, 3.0)], est, n_initial_points=4, acq_func="gp_hedge", acq_optimizer="sampling",
+                     acq_optimizer_kwargs=dict(n_points=500), random_state=3)
+    for x, y in zip(opt.Xi[:-1], opt.yi[:-1]):
+        twin.tell(x, y)
+    state = twin.rng.get_state()
+    twin.tell(opt.Xi[-1], opt.yi[-1])
+    rng = np.random.RandomState(0)
+    rng.set_state(state)
+    X = twin.space.rvs_transformed(500, rng)
+    for acq, got in zip(["EI", "LCB", "PI"], twin.next_xs_):
+        values = _gaussian_acquisition(X, twin.models[-1], np.min(twin.yi), acq)
+        assert np.array_equal(got, X[np.argmin(values)])
+    assert np.array_equal(np.asarray(twin.next_xs_), np.asarray(opt.next_xs_))

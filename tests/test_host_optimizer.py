@@ -72,3 +72,57 @@ globals().update({"test_hamming_" + name[5:]: func for name, func in _mirror(ham
                               "test_gradient_entry_points_refuse_the_hamming_kernel")})
 globals().update({"test_pd_" + name[5:]: func for name, func in _mirror(pd_tests).items()
                   if name == "test_partial_dependence_matches_reference_on_gpu"})
+
+
+def test_foreign_regressor_with_gradients_is_refined_by_lbfgs(abi_model):
+    """A regressor of another family that returns posterior gradients for one row (the reference's convention) runs with
+    acq_optimizer="lbfgs": ranking through skb_topk_host, every L-BFGS evaluation through its own one-row predict() and
+    the chain rule of skb_acq_from_posterior_host.  The model is analytic so the optimum of LCB is known:
+    mu = |x - c|^2, std = 0.5 + 0.1 x_0  ->  argmin(mu - kappa std) = c + 0.05 kappa e_0."""
+    from sklearn.base import BaseEstimator, RegressorMixin
+    from skopt_b200 import Optimizer
+    from skopt_b200.utils import has_gradients
+
+    class Bowl(RegressorMixin, BaseEstimator):
+        def __init__(self, centre=(0.3, -0.4)):
+            self.centre = centre
+
+        def fit(self, X, y):
+            self.n_seen_ = len(y)
+            return self
+
+        def predict(self, X, return_std=False, return_mean_grad=False, return_std_grad=False):
+            X = np.asarray(X, dtype=float)
+            if (return_mean_grad or return_std_grad) and X.shape[0] != 1:
+                raise ValueError("Not implemented for n_samples > 1")
+            c = np.asarray(self.centre)
+            mu, std = np.sum((X - c) ** 2, axis=1), 0.5 + 0.1 * X[:, 0]
+            if return_mean_grad:
+                return mu, std, 2.0 * (X[0] - c), np.array([0.1, 0.0])
+            return (mu, std) if return_std else mu
+
+    model = Bowl()
+    assert has_gradients(model)
+    opt = Optimizer([(-1.0, 1.0), (-1.0, 1.0)], model, n_initial_points=2, acq_func="LCB", acq_optimizer="lbfgs",
+                    acq_optimizer_kwargs=dict(n_points=200, n_restarts_optimizer=3),
+                    acq_func_kwargs=dict(kappa=2.0), random_state=0)
+    for _ in range(3):
+        x = opt.ask()
+        opt.tell(x, float(np.sum(np.square(x))))
+    assert np.allclose(opt.ask(), [0.3 + 0.05 * 2.0, -0.4], atol=1e-6)
+    assert {"skb_acq_from_posterior_host", "skb_topk_host"} <= set(abi_model.calls)
+    assert "skb_state_create" not in abi_model.calls            # no GP state: the model is not ours
+
+
+def test_tree_families_are_routed_to_sampling():
+    from sklearn.ensemble import GradientBoostingRegressor, RandomForestRegressor
+    from skopt_b200 import Optimizer
+    from skopt_b200.utils import cook_estimator, has_gradients
+    assert not has_gradients(RandomForestRegressor()) and not has_gradients(GradientBoostingRegressor())
+    assert Optimizer([(0.0, 1.0)], RandomForestRegressor(), acq_func="EI").acq_optimizer == "sampling"
+    with pytest.raises(ValueError, match="should run with acq_optimizer='sampling'"):
+        Optimizer([(0.0, 1.0)], RandomForestRegressor(), acq_optimizer="lbfgs")
+    with pytest.raises(ValueError, match="'RF', 'ET', 'GP', 'GBRT' or 'DUMMY'"):
+        cook_estimator("rtr")
+    with pytest.raises(ValueError, match="not built by this package"):
+        cook_estimator("ET", space=[(0.0, 1.0)])
