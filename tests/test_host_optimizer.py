@@ -126,3 +126,57 @@ def test_tree_families_are_routed_to_sampling():
         cook_estimator("rtr")
     with pytest.raises(ValueError, match="not built by this package"):
         cook_estimator("ET", space=[(0.0, 1.0)])
+
+
+_SHARDED_WORKER = """
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch.distributed as dist
+import skopt_b200
+from skopt_b200 import Optimizer, _lib
+from skopt_b200.optimizer import optimizer as optimizer_module
+from tests._abi_model import AbiModel
+_lib._lib = AbiModel()                                    # test stand-in for libskb.so (no GPU on the build machine)
+optimizer_module.device_dim_descs = lambda space: None
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+
+def objective(x):
+    return (x[0] - 0.3) ** 2 + (x[1] + 0.2) ** 2 + 0.1 * np.sin(5 * x[2])
+
+def run(shard, search):
+    opt = Optimizer([(-1.0, 1.0)] * 3, "GP", n_initial_points=4, acq_func="gp_hedge", acq_optimizer=search,
+                    acq_optimizer_kwargs=dict(n_points=301, n_restarts_optimizer=3, shard_group=shard), random_state=5)
+    for _ in range(7):
+        x = opt.ask()
+        opt.tell(x, objective(x))
+    batch = opt.ask(n_points=3, strategy="cl_min")
+    return opt.Xi + batch, [r.tolist() for r in opt._last_scoring["EI"]["topk_idx"].reshape(1, -1)]
+
+for search in ("sampling", "lbfgs"):
+    sharded = run(True, search)            # every tell() is a collective: rank r scores its block of the 301 candidates
+    local = run(False, search)             # the same optimiser without the collective
+    assert sharded == local, (search, rank)
+    everyone = [None, None]
+    dist.all_gather_object(everyone, sharded)
+    assert everyone[0] == everyone[1], search
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_optimizer_two_ranks_gloo(tmp_path):
+    """The N > 1 path of the Optimizer on the CPU (gloo, world size 2): with `shard_group=True` every rank drives an
+    identical optimiser, scores its own block of the candidate set and merges the per-rank top-k; asked points (hedge,
+    sampling and L-BFGS, constant-liar batch included) equal the unsharded run's and agree across ranks."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "sharded_worker.py"
+    script.write_text(_SHARDED_WORKER % {"root": root})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
