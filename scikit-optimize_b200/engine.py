@@ -378,6 +378,42 @@ class DeviceState:
         return res
 
 
+def kernel_gradient_x(kernel, x, X_train, device=None):
+    """`kernel.gradient_x(x, X_train)`: d k(x, X_i) / dx for every training row, shape (n_samples, n_features)
+    (skopt/learning/gaussian_process/kernels.py:48-65 and the per-class forms :68-308), on the GPU.
+
+    There is one device implementation of the radial derivatives - the gradient kernel K3g behind skb_score_grad_host -
+    and this reaches it without a second code path: for a stationary kernel d k(x, X_i) / dx = -d k(z, x) / dz at z = X_i,
+    and the right-hand side is the posterior-mean gradient of a one-point GP (training set {x}, alpha = 1, no target
+    scaling) evaluated at the rows of X_train.  The only value that is not antisymmetric is the reference's convention for
+    Matern(nu=0.5) at zero distance (the row -amplitude / length_scale, kernels.py:118-128): those rows keep their sign."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    X_train = np.atleast_2d(np.asarray(X_train, dtype=np.float64))
+    n, d = X_train.shape
+    if x.shape[0] != d:
+        raise ValueError("x has %d features, X_train has %d" % (x.shape[0], d))
+    aff = _flatten_kernel(kernel)
+    if aff.base is None:                           # constants and white noise do not depend on x (kernels.py:260-269)
+        return np.zeros((n, d))
+    (kind, ls), amplitude = aff.base, aff.a
+    if kind == _lib.KERNEL_HAMMING:
+        raise NotImplementedError("HammingKernel has no gradient_x (categorical inputs)")
+    if device is None:
+        from .learning.gaussian_process.gpr import _DEFAULT_DEVICE
+        device = _DEFAULT_DEVICE[0]
+    one = np.ones((1, 1))
+    dev = DeviceState(HostState(x[None, :], np.ones(1), one, ls, kind, amplitude, aff.c, 0.0, 0.0, 1.0, K_inv=one), device)
+    try:
+        mirrored = dev.score_grad(X_train, acq_funcs=())["mean_grad"]
+    finally:
+        dev.close()
+    grad = -mirrored
+    if kind == _lib.KERNEL_MATERN12:
+        same = np.all(X_train == x, axis=1)
+        grad[same] = mirrored[same]
+    return grad
+
+
 def launch_count():
     return int(_lib.lib().skb_launch_count())
 

@@ -2,7 +2,7 @@
 
 On the GPU path the kernel values AND their input gradients are computed by the CUDA kernels from the flattened
 description (engine._flatten_kernel), so these classes only have to build, clone, tune (sklearn's marginal
-likelihood) and describe the kernel; they are sklearn's kernels with operator overloads that keep the result inside
+likelihood) and describe the kernel (`gradient_x`, public in the reference, is answered by the device too); they are sklearn's kernels with operator overloads that keep the result inside
 this module.  Kernels outside the hot-path grammar (RationalQuadratic, ExpSineSquared, DotProduct, Exponentiation;
 SURVEY.md section 2 row 3) are intentionally not provided: asking the GPU path for them raises.
 Mirrors skopt/learning/gaussian_process/kernels.py:20-46 (operators), :68, :93, :260, :266, :285, :294, :317 (classes).
@@ -23,6 +23,13 @@ class Kernel(_sk.Kernel):
 
     def __rmul__(self, b):
         return Product(b if isinstance(b, _sk.Kernel) else ConstantKernel(b), self)
+
+    def gradient_x(self, x, X_train):
+        """Gradient of K(x, X_train) with respect to the single point x, shape (n_samples, n_features)
+        (kernels.py:48-65; RBF :68-90, Matern :93-200, Constant / White :260-269, Sum :285-291, Product :294-308),
+        evaluated on the GPU by the same device code the posterior gradients use (engine.kernel_gradient_x)."""
+        from ... import engine
+        return engine.kernel_gradient_x(self, x, X_train)
 
 
 class RBF(Kernel, _sk.RBF):
