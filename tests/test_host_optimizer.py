@@ -62,6 +62,11 @@ from tests import test_gpu_reference_behaviours as gpu_behaviours  # noqa: E402
 
 globals().update({"test_behaviour_" + name[5:]: func for name, func in _mirror(gpu_behaviours).items()})
 
+# tests/test_z_gpu_api_extensions.py: regressors of other families under the Optimizer, kernel.gradient_x
+from tests import test_z_gpu_api_extensions as gpu_extensions  # noqa: E402
+
+globals().update({"test_extension_" + name[5:]: func for name, func in _mirror(gpu_extensions).items()})
+
 # all-categorical GPs and partial dependence: the `-m gpu` members of the mixed modules that use host entry points only
 # (test_large_categorical_candidate_set_all_precisions_agree compares precisions of the CUDA kernels: GPU only)
 from tests import test_hamming as hamming_tests  # noqa: E402
