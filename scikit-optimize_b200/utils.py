@@ -223,6 +223,16 @@ def expected_minimum(res, n_random_starts=20, random_state=None):
     xs = [res.x]
     if n_random_starts > 0:
         xs.extend(space.rvs(n_random_starts, random_state=random_state))
+    if not hasattr(reg, "device_state"):
+        # a regressor of another family has no resident state and no gradients to batch: minimise its own predict() from
+        # every start, the way the reference does for all models (scipy.optimize.minimize, finite differences)
+        from scipy.optimize import minimize as sp_minimize
+        best_x, best_fun = None, np.inf
+        for x0 in xs:
+            r = sp_minimize(lambda x: reg.predict(space.transform([list(x)]))[0], x0=x0, bounds=space.bounds)
+            if r.fun < best_fun:
+                best_x, best_fun = r.x, r.fun
+        return [v for v in best_x], best_fun
     dev = reg.device_state()
 
     def evaluate(tasks, X):

@@ -185,3 +185,19 @@ def test_sharded_optimizer_two_ranks_gloo(tmp_path):
                          capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_expected_minimum_of_a_foreign_model():
+    """utils.expected_minimum on a result whose model is not this package's GP minimises the model's own predict()."""
+    from sklearn.base import BaseEstimator, RegressorMixin
+    from skopt_b200.space import Space
+    from skopt_b200.utils import create_result, expected_minimum
+
+    class Bowl(RegressorMixin, BaseEstimator):
+        def predict(self, X, return_std=False):
+            return np.sum((np.asarray(X) - np.array([0.25, -0.5])) ** 2, axis=1) + 3.0
+
+    space = Space([(-1.0, 1.0), (-1.0, 1.0)])
+    res = create_result([[0.9, 0.9], [0.0, 0.0]], [5.0, 4.0], space, models=[Bowl()])
+    x, fun = expected_minimum(res, n_random_starts=3, random_state=0)
+    assert np.allclose(x, [0.25, -0.5], atol=1e-5) and abs(fun - 3.0) < 1e-9
