@@ -674,7 +674,7 @@ class Space(object):
         rng = check_random_state(random_state)
         cols = []
         for dim in self.dimensions:
-            original = dim._from_unit(dim._draw(rng, n_samples))
+            original = dim._sample_column(rng, n_samples)
             cols.append(np.asarray(dim.transform(original), dtype=float).reshape((n_samples, -1)))
         return np.ascontiguousarray(np.hstack(cols))
 

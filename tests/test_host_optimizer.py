@@ -201,3 +201,21 @@ def test_expected_minimum_of_a_foreign_model():
     res = create_result([[0.9, 0.9], [0.0, 0.0]], [5.0, 4.0], space, models=[Bowl()])
     x, fun = expected_minimum(res, n_random_starts=3, random_state=0)
     assert np.allclose(x, [0.25, -0.5], atol=1e-5) and abs(fun - 3.0) < 1e-9
+
+
+def test_foreign_regressor_on_a_mixed_unnormalised_space(abi_model):
+    """A regressor of another family keeps the reference's default warpings (one-hot categoricals, identity reals):
+    the candidates, the model's training matrix and the suggested point all live in that space."""
+    from sklearn.gaussian_process import GaussianProcessRegressor as SklearnGPR
+    from skopt_b200 import Optimizer
+    dims = [(-1.0, 1.0), ["red", "green", "blue"], (1, 5)]
+    opt = Optimizer(dims, SklearnGPR(alpha=1e-6), n_initial_points=3, acq_func="EI", acq_optimizer="sampling",
+                    acq_optimizer_kwargs=dict(n_points=200), random_state=2)
+    assert opt.space.get_transformer() == ["identity", "onehot", "identity"] and opt.space.transformed_n_dims == 5
+    for _ in range(5):
+        x = opt.ask()
+        assert x in opt.space and isinstance(x[1], str)
+        opt.tell(x, x[0] ** 2 + {"red": 0.0, "green": 1.0, "blue": 2.0}[x[1]] + 0.1 * x[2])
+    assert opt.models[-1].X_train_.shape == (5, 5)
+    assert set(np.unique(opt.models[-1].X_train_[:, 1:4])) <= {0.0, 1.0}
+    assert opt.next_xs_[0].shape == (5,) and opt.ask() in opt.space
