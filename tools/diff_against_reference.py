@@ -9,6 +9,7 @@ digits only and are reported, not counted.
     python tools/diff_against_reference.py [--device]
 """
 import json
+import os
 import sys
 import warnings
 
@@ -17,7 +18,7 @@ import numpy as np
 if not hasattr(np, "int"):
     np.int = int                      # the reference predates NumPy 1.24
 sys.dont_write_bytecode = True
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(1, "/root/reference")
 warnings.simplefilter("ignore")
 import skopt as R  # noqa: E402
