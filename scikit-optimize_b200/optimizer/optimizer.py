@@ -108,14 +108,14 @@ class Optimizer(object):
         self.precision = acq_optimizer_kwargs.get("precision", "auto")
         # draw the candidate set on the GPU when the space allows a bit-exact device version (engine.device_candidates)
         self.device_candidates = acq_optimizer_kwargs.get("device_candidates", True)
-        # multi-GPU scoring is opt-in: shard_group=True (default process group) or a torch.distributed group makes
-        # every tell() a collective that ALL ranks of the group must enter with identical Optimizer state; the default
-        # keeps tell() local so independent optimisers can live inside an initialised process group
         # where the GP hyper-parameter search evaluates its objective: None = the package setting
         # (learning.gaussian_process.gpr.set_fit_device, default "host"), or "host" / "gpu" for this optimizer
         self.fit_device = acq_optimizer_kwargs.get("fit_device", None)
         if self.fit_device not in (None, "host", "gpu"):
             raise ValueError("fit_device must be None, 'host' or 'gpu', got %r" % (self.fit_device,))
+        # multi-GPU scoring is opt-in: shard_group=True (default process group) or a torch.distributed group makes
+        # every tell() a collective that ALL ranks of the group must enter with identical Optimizer state; the default
+        # keeps tell() local so independent optimisers can live inside an initialised process group
         shard = acq_optimizer_kwargs.get("shard_group", None)
         self._shard_group = False if shard is None or shard is False else (None if shard is True else shard)
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
