@@ -17,7 +17,8 @@ posterior mean/std, -EI, and the top-k (value, index) pairs; with N GPUs every r
   cpu_baseline : the CPU oracle (a port of the reference's NumPy/SciPy path) on a bounded sample, this host
   ask_p50_ms, ask_p50_ms_lbfgs : scoring-block latency of Optimizer.tell at BASELINE.json configs[0] / configs[1]
 
-`--impl reference` times the reference algorithm (oracle port, einsum contraction exactly as gpr.py:332) on the host.
+`--impl reference` times the reference algorithm (oracle port, einsum contraction exactly as gpr.py:332) on the host;
+its cpu_baseline.all_cores adds what one single-threaded copy of that path per core reaches together.
 """
 import argparse
 import json
@@ -199,6 +200,40 @@ def cpu_baseline(n, d, sample_m, quad="einsum", seed=0, reps=1):
     return sample_m / best, best
 
 
+def _all_cores_worker(args):
+    """One worker of cpu_all_cores: the reference path on its own slice of candidates, single-threaded."""
+    n, d, sample_m, passes, seed, barrier = args
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:                     # noqa: BLE001
+        pass
+    cpu_baseline(n, d, sample_m, quad="einsum", seed=0)              # builds the state, warms the caches
+    from oracle import gp_oracle as orc
+    st = _CPU_STATE[(n, d, 0)]
+    Xc = np.random.RandomState(1000 + seed).rand(sample_m, d)
+    y_opt = float(st.meta["y"].min())
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        v = orc.gaussian_acquisition(Xc, st, y_opt, "EI", acq_func_kwargs=dict(xi=0.01, kappa=1.96), quad="einsum")
+        int(np.argmin(v))
+    return time.perf_counter() - t0
+
+
+def cpu_all_cores(n, d, sample_m, passes, workers):
+    """The reference path has no candidate-level parallelism (einsum runs on one thread).  What the box's cores could do
+    with it: `workers` independent processes, one per core, each scoring its own `sample_m` candidates `passes` times
+    after a common barrier; aggregate candidates / slowest worker's time."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        barrier = manager.Barrier(workers)
+        with ctx.Pool(workers) as pool:
+            times = pool.map(_all_cores_worker, [(n, d, sample_m, passes, w, barrier) for w in range(workers)])
+    return workers * passes * sample_m / max(times)
+
+
 def parity_sample(gpr, dev, y_opt, precisions, sample_m=512):
     """Parity of THIS run's device state against the checker (SURVEY.md 8d gate, in the units of the gate): the oracle
     is evaluated on the product's own fitted state with the reference's einsum contraction (gpr.py:332) and, for the
@@ -302,6 +337,12 @@ def run_reference(args, rank):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
+    try:
+        all_cores = {"value": cpu_all_cores(N_TRAIN, N_DIMS, sample, max(1, args.steps), cores), "unit": "evals/s",
+                     "workers": cores, "how": "one single-threaded process per core, each scoring its own candidates "
+                                              "with the same path; aggregate over the slowest worker"}
+    except Exception as exc:              # noqa: BLE001 - an extra, never the reason the arm fails
+        all_cores = {"value": None, "error": repr(exc)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -313,7 +354,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": "%d candidates per step; einsum contraction is single-threaded as in the "
                                    "reference, BLAS parts may use all %d host threads" % (sample, cores),
-                         "versions": library_versions()},
+                         "all_cores": all_cores, "versions": library_versions()},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
