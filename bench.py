@@ -213,7 +213,7 @@ def _all_cores_worker(args):
     st = _CPU_STATE[(n, d, 0)]
     Xc = np.random.RandomState(1000 + seed).rand(sample_m, d)
     y_opt = float(st.meta["y"].min())
-    barrier.wait()
+    barrier.wait(timeout=180)             # a worker that died must not leave the others (and the bench) waiting
     t0 = time.perf_counter()
     for _ in range(passes):
         v = orc.gaussian_acquisition(Xc, st, y_opt, "EI", acq_func_kwargs=dict(xi=0.01, kappa=1.96), quad="einsum")
@@ -230,7 +230,8 @@ def cpu_all_cores(n, d, sample_m, passes, workers):
     with ctx.Manager() as manager:
         barrier = manager.Barrier(workers)
         with ctx.Pool(workers) as pool:
-            times = pool.map(_all_cores_worker, [(n, d, sample_m, passes, w, barrier) for w in range(workers)])
+            job = pool.map_async(_all_cores_worker, [(n, d, sample_m, passes, w, barrier) for w in range(workers)])
+            times = job.get(timeout=600)
     return workers * passes * sample_m / max(times)
 
 
