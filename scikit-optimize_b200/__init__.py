@@ -10,7 +10,7 @@ repository root).
 from . import acquisition, plots, space, utils  # noqa: F401
 from .engine import DeviceState, HostState, host_state_from_estimator, launch_count  # noqa: F401
 from .learning.gaussian_process.gpr import set_default_device, set_fit_device  # noqa: F401
-from .optimizer import Optimizer, base_minimize, gp_minimize  # noqa: F401
+from .optimizer import Optimizer, base_minimize, dummy_minimize, gp_minimize  # noqa: F401
 from .space import Space  # noqa: F401
 from .utils import dump, expected_minimum, expected_minimum_random_sampling, load  # noqa: F401
 

@@ -219,3 +219,29 @@ def test_foreign_regressor_on_a_mixed_unnormalised_space(abi_model):
     assert opt.models[-1].X_train_.shape == (5, 5)
     assert set(np.unique(opt.models[-1].X_train_[:, 1:4])) <= {0.0, 1.0}
     assert opt.next_xs_[0].shape == (5,) and opt.ask() in opt.space
+
+
+def test_dummy_minimize_is_random_search():
+    """skopt/optimizer/dummy.py: no surrogate, every point a draw from the space; nothing reaches the C ABI."""
+    from skopt_b200 import Space, dummy_minimize
+    dims = [(-1.0, 1.0), ["a", "b"], (1, 9)]
+    calls = []
+
+    def objective(x):
+        calls.append(list(x))
+        return (x[0] - 0.3) ** 2 + {"a": 0.0, "b": 1.0}[x[1]] + 0.1 * x[2]
+
+    res = dummy_minimize(objective, dims, n_calls=12, random_state=3)
+    assert res.x_iters == calls and len(calls) == 12 and res.models == [] and res.fun == min(res.func_vals)
+    assert res.x_iters == [p for p in _draws(Space(dims), 12, 3)]
+    calls.clear()
+    res = dummy_minimize(objective, dims, n_calls=5, random_state=1, x0=[[0.1, "a", 2], [0.5, "b", 3]], y0=[1.0, 2.0])
+    assert len(res.x_iters) == 7 and len(calls) == 5 and res.x_iters[:2] == [[0.1, "a", 2], [0.5, "b", 3]]
+    res = dummy_minimize(objective, dims, n_calls=6, random_state=1, x0=[[0.1, "a", 2]])
+    assert len(res.x_iters) == 6 and res.x_iters[0] == [0.1, "a", 2]
+
+
+def _draws(space, n, seed):
+    rng = np.random.RandomState(seed)
+    rng.randint(0, np.iinfo(np.int32).max)          # the Optimizer seeds its (absent) estimator first, like the reference
+    return [space.rvs(random_state=rng)[0] for _ in range(n)]

@@ -10,9 +10,9 @@ under scikit-learn >= 1.2 because of criterion='mse').
                                                    # tests/_abi_model.py (TEST INFRASTRUCTURE; arithmetic by the oracle)
     python tools/run_reference_tests.py --device   # on a box with a B200 and /root/reference: the real libskb.so
 
-Deselected (out of scope): tree / GBRT surrogates, dummy_minimize, the sobol / lhs / halton /
+Deselected (out of scope): tree / GBRT surrogates, the sobol / lhs / halton /
 hammersly / grid initial-point generators, and tests that cannot run on this pytest / scikit-learn at all
-(`pytest.warns(None)`, `is_regressor(None)` inside the reference's dummy_minimize).
+(`pytest.warns(None)`, tree estimators with criterion='mse').
 """
 import argparse
 import os
@@ -26,7 +26,7 @@ REF = "/root/reference/skopt"
 FILES = ["tests/test_space.py", "tests/test_transformers.py", "tests/test_utils.py", "tests/test_acquisition.py",
          "tests/test_optimizer.py", "tests/test_gp_opt.py", "tests/test_common.py", "tests/test_parallel_cl.py",
          "learning/gaussian_process/tests/test_gpr.py"]
-OURS = {"gp_minimize", "Optimizer", "Space", "load", "dump", "expected_minimum", "expected_minimum_random_sampling"}
+OURS = {"gp_minimize", "dummy_minimize", "Optimizer", "Space", "load", "dump", "expected_minimum", "expected_minimum_random_sampling"}
 REDIRECT = [
     (r"^(\s*)from skopt\.optimizer import Optimizer", r"\1from skopt_b200 import Optimizer"),
     (r"^(\s*)from skopt\.acquisition import", r"\1from skopt_b200.acquisition import"),
@@ -37,12 +37,10 @@ REDIRECT = [
     (r"^(\s*)from skopt\.utils import", r"\1from skopt_b200.utils import"),
 ]
 # node ids (regular expressions) of tests about components outside the path
-OUT_OF_SCOPE = [r"forest_minimize", r"gbrt_minimize", r"dummy_minimize", r"RandomForest", r"ExtraTrees", r"GradientBoosting",
+OUT_OF_SCOPE = [r"forest_minimize", r"gbrt_minimize", r"RandomForest", r"ExtraTrees", r"GradientBoosting",
                 r"\[(.*-)?(RF|ET|GBRT|rf|et|gbrt)(-.*)?\]", r"initgen", r"\[(.*-)?(lhs|halton|hammersly|sobol|grid)(-.*)?\]",
                 r"test_common.py::.*\[(optimizer[23]|minimizer[1-9])", r"base_estimator[0-9]"]
-BROKEN_IN_REFERENCE = ["test_common.py::test_repeated_x", "test_common.py::test_init_vals",
-                       "test_common.py::test_categorical_init_vals", "test_common.py::test_mixed_spaces",
-                       "test_common.py::test_init_vals_dummy_minimize", "test_utils.py::test_dump_and_load_optimizer",
+BROKEN_IN_REFERENCE = ["test_common.py::test_repeated_x", "test_utils.py::test_dump_and_load_optimizer",
                        "test_optimizer.py::test_multiple_asks", "test_optimizer.py::test_model_queue_size",
                        "test_optimizer.py::test_returns_result_object", "test_optimizer.py::test_optimizer_copy",
                        "test_optimizer.py::test_acq_optimizer", "test_optimizer.py::test_acq_optimizer_with_time_api",
