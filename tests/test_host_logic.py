@@ -222,3 +222,30 @@ def test_optimizer_host_logic_and_initial_points():
         opt.ask(n_points=0)
     with pytest.raises(ValueError):
         opt.ask(n_points=2, strategy="cl_median")
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/skb.h must compile as C99 (no C++ or torch types) and a C program must link
+    against libskb.so and reach the entry points that need no GPU."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "skb.h"\n'
+                   'int main(void) {\n'
+                   '    skb_state* st = NULL;\n'
+                   '    skb_state_desc desc;\n'
+                   '    memset(&desc, 0, sizeof desc);\n'
+                   '    int rc = skb_state_create(&desc, 0, &st);          /* n_train = 0: refused before any CUDA call */\n'
+                   '    printf("%d %d %d %s\\n", skb_abi_version(), SKB_ABI_VERSION, rc, skb_last_error());\n'
+                   '    return (skb_abi_version() == SKB_ABI_VERSION && rc == SKB_ERR_INVALID && st == NULL) ? 0 : 1;\n'
+                   '}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            str(src), "-o", str(exe), "-L", libdir, "-lskb", "-Wl,-rpath," + libdir],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "n_train and n_dims must be positive" in run.stdout
