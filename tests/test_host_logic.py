@@ -249,3 +249,45 @@ def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "n_train and n_dims must be positive" in run.stdout
+
+
+def test_argument_validation_needs_no_device():
+    """Error behaviour of the C ABI (include/skb.h: negative skb_status + skb_last_error, nothing thrown): arguments are
+    validated before any CUDA call, so these refusals are observable on the build machine through the real library."""
+    import ctypes as C
+    L = _lib.lib()
+    launches_before = L.skb_launch_count()
+
+    def last():
+        return L.skb_last_error().decode()
+
+    handle = C.c_void_p()
+    assert L.skb_state_create(None, 0, C.byref(handle)) == -1 and "NULL" in last()
+    desc = _lib.StateDesc()
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -1 and "must be positive" in last()
+    x = np.ones((2, 3)); a = np.ones(2); li = np.eye(2); ls = np.ones(3)
+    desc.n_train, desc.n_dims, desc.kernel = 2, 3, 3
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -1 and "must not be NULL" in last()
+    desc.length_scale, desc.X_train, desc.alpha, desc.L_inv = ls.ctypes.data, x.ctypes.data, a.ctypes.data, li.ctypes.data
+    desc.kernel = 9
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -2 and "outside the hot-path grammar" in last()
+    desc.kernel, desc.n_dims = 3, 65
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -2 and "n_dims 65 > 64" in last()
+    desc.n_dims = 3
+    ls[1] = 0.0
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -1 and "length_scale[1] must be > 0" in last()
+    assert handle.value is None
+    # entry points that take a state refuse NULL handles; the stateless ones refuse bad sizes
+    prm, out = _lib.AcqParams(), _lib.ScoreOut()
+    assert L.skb_score_host(None, x.ctypes.data, 2, 0, C.byref(prm), C.byref(out)) == -1
+    assert L.skb_predict_mean_host(None, x.ctypes.data, 2, a.ctypes.data) == -1
+    assert L.skb_state_attach_kinv(None, li.ctypes.data) == -1
+    assert L.skb_state_sync(None) == -1 and L.skb_state_set_timing(None, 1) == -1
+    tv, ti = np.empty(4), np.empty(4, dtype=np.int64)
+    assert L.skb_topk_host(0, a.ctypes.data, 2, 0, 0, tv.ctypes.data, ti.ctypes.data, None) == -1 and "top_k" in last()
+    assert L.skb_topk_host(0, a.ctypes.data, -1, 0, 2, tv.ctypes.data, ti.ctypes.data, None) == -1
+    acq = (C.c_void_p * 3)()
+    assert L.skb_acq_from_posterior_host(0, -1, 3, a.ctypes.data, a.ctypes.data, None, None, C.byref(prm), acq, acq) == -1
+    assert L.skb_acq_from_posterior_host(0, 2, 3, None, a.ctypes.data, None, None, C.byref(prm), acq, acq) == -1
+    L.skb_state_destroy(None)                                   # destroying nothing is allowed
+    assert L.skb_launch_count() == launches_before              # nothing was launched by any of this
