@@ -1,11 +1,10 @@
 """API extensions of the reference boundary, on a B200: regressors of other families under the Optimizer (value route
 of the duck-typed boundary) and the public `kernel.gradient_x`.
 
-Added after this round's GPU minutes were spent: both compose entry points the GPU suite already verifies
-(skb_acq_from_posterior_host + skb_topk_host; skb_score_grad_host on an n = 1 state, cf.
-tests/test_gpu_parity.py::test_ragged_and_minimal_shapes), and both pass through the software model of the ABI
-(tests/test_host_optimizer.py), but their first run on a GPU is the next round's.  The file name sorts last so that the
-verified suite runs before them."""
+Added late in the round: both compose entry points the rest of the GPU suite verifies (skb_acq_from_posterior_host +
+skb_topk_host; skb_score_grad_host on an n = 1 state, cf. tests/test_gpu_parity.py::test_ragged_and_minimal_shapes).  First
+run on a B200: 13 passed (profiles/r01_gpu_api_extensions_run.json); the same tests also run through the software model of
+the ABI on the CPU (tests/test_host_optimizer.py)."""
 import numpy as np
 import pytest
 
