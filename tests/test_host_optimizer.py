@@ -184,7 +184,7 @@ def test_sharded_optimizer_two_ranks_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
                          capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok") == 2
+    assert sorted(line for line in out.stdout.splitlines() if line.startswith("rank ")) == ["rank 0 ok", "rank 1 ok"]
 
 
 def test_expected_minimum_of_a_foreign_model():
