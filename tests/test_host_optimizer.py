@@ -246,3 +246,39 @@ def _draws(space, n, seed):
     rng = np.random.RandomState(seed)
     rng.randint(0, np.iinfo(np.int32).max)          # the Optimizer seeds its (absent) estimator first, like the reference
     return [space.rvs(random_state=rng)[0] for _ in range(n)]
+
+
+# ---- less travelled options, against fixtures from the unmodified reference (oracle/make_golden_traj_options.py) --------
+def _options_fixture():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "traj_options.json")) as f:
+        return json.load(f)
+
+
+def _jsonable(value):
+    import json
+    return json.loads(json.dumps(value, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
+
+
+_OPTIONS = _options_fixture()
+
+
+@pytest.mark.parametrize("name", sorted(_OPTIONS["runs"]))
+def test_option_trajectory_identical(abi_model, name):
+    """x0 / y0 hand-over, no random phase, explicit noise, bounded model queue, xi / kappa, integer-only / log-uniform /
+    all-categorical spaces: every asked point, value, minimiser and model count equals the reference's run."""
+    from tests._option_scripts import run_config
+    assert _jsonable(run_config(skopt_b200, _OPTIONS["runs"][name])) == _OPTIONS["results"][name]
+
+
+@pytest.mark.parametrize("index", range(len(_OPTIONS["script_cases"])))
+def test_optimizer_script_identical(abi_model, index):
+    """Batch ask in the random phase, tell(fit=False), constant liar with two strategies and its cache, update_next, run,
+    copy, get_result - one script per acquisition (EI, hedge, LCB, EIps, PIps, eta, model queue), step by step."""
+    from tests._option_scripts import run_script
+    acq, okw = _OPTIONS["script_cases"][index]
+    got, want = _jsonable(run_script(skopt_b200, acq, okw)), _OPTIONS["scripts"][index]
+    assert len(got) == len(want)
+    for step_got, step_want in zip(got, want):
+        assert step_got == step_want, step_want[0]
