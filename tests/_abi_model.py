@@ -106,6 +106,7 @@ def _acquisitions(prm, mu, std, mu_grad=None, std_grad=None):
 
 class AbiModel:
     """Drop-in for the object `_lib.lib()` returns, restricted to the host entry points."""
+    on_device = False
 
     def __init__(self):
         self._states = {}

@@ -15,6 +15,8 @@ from tests import test_gpu_optimizer as gpu_opt
 def test_model_is_what_the_package_talks_to(abi_model):
     from skopt_b200 import _lib, engine
     from oracle import gp_oracle as orc
+    if abi_model.on_device:
+        pytest.skip("the real library is loaded (SKB_TESTS_ON_DEVICE=1)")
     assert _lib.lib() is abi_model
     st = orc.make_synthetic_state(24, 3)
     L_inv = np.linalg.inv(np.linalg.cholesky(np.linalg.inv(st.K_inv)))        # K_inv = L_inv^T L_inv, L_inv lower
@@ -115,8 +117,9 @@ def test_foreign_regressor_with_gradients_is_refined_by_lbfgs(abi_model):
         x = opt.ask()
         opt.tell(x, float(np.sum(np.square(x))))
     assert np.allclose(opt.ask(), [0.3 + 0.05 * 2.0, -0.4], atol=1e-6)
-    assert {"skb_acq_from_posterior_host", "skb_topk_host"} <= set(abi_model.calls)
-    assert "skb_state_create" not in abi_model.calls            # no GP state: the model is not ours
+    if not abi_model.on_device:
+        assert {"skb_acq_from_posterior_host", "skb_topk_host"} <= set(abi_model.calls)
+        assert "skb_state_create" not in abi_model.calls        # no GP state: the model is not ours
 
 
 def test_tree_families_are_routed_to_sampling():
