@@ -1,12 +1,13 @@
 #!/bin/bash
 # One gpurun call that re-establishes the measured state of the repository on a fresh B200 box:
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round_check.sh'
-# 1. the GPU suite (the last-sorted module holds the tests that have not run on a GPU yet), 2. smoke(), 3. the default
+# 1. the GPU suite, 1b. the host-level tests against the real library instead of the ABI model, 2. smoke(), 3. the default
 # bench line, 4. the launch list of the same bench command (ncu, after the plain run has exited 0).  Everything lands in
 # gpurun_out/; copy what should be judged into profiles/.
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/t_all.log 2>&1; echo "pytest -m gpu rc=$?"; tail -3 gpurun_out/t_all.log
+SKB_TESTS_ON_DEVICE=1 timeout 600 python -m pytest tests/test_host_optimizer.py -q > gpurun_out/t_host_on_device.log 2>&1; echo "host-level tests on the device rc=$?"; tail -2 gpurun_out/t_host_on_device.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 600 python bench.py > gpurun_out/bench_head.json 2> gpurun_out/bench_head.err; rc=$?; echo "bench rc=$rc"
 timeout 300 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "reference arm rc=$?"
