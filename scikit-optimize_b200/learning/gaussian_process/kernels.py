@@ -4,7 +4,9 @@ On the GPU path the kernel values AND their input gradients are computed by the 
 description (engine._flatten_kernel), so these classes only have to build, clone, tune (sklearn's marginal
 likelihood) and describe the kernel (`gradient_x`, public in the reference, is answered by the device too); they are sklearn's kernels with operator overloads that keep the result inside
 this module.  Kernels outside the hot-path grammar (RationalQuadratic, ExpSineSquared, DotProduct, Exponentiation;
-SURVEY.md section 2 row 3) are intentionally not provided: asking the GPU path for them raises.
+SURVEY.md section 2 row 3) exist under their names so that code importing them keeps loading and can build and fit
+them on the host, but they have no device form: predict / gradient_x on a model that contains one raises
+NotImplementedError naming the grammar (engine._flatten_kernel) - there is no CPU route to fall back to.
 Mirrors skopt/learning/gaussian_process/kernels.py:20-46 (operators), :68, :93, :260, :266, :285, :294, :317 (classes).
 """
 import numpy as np
@@ -23,6 +25,9 @@ class Kernel(_sk.Kernel):
 
     def __rmul__(self, b):
         return Product(b if isinstance(b, _sk.Kernel) else ConstantKernel(b), self)
+
+    def __pow__(self, b):
+        return Exponentiation(self, b)
 
     def gradient_x(self, x, X_train):
         """Gradient of K(x, X_train) with respect to the single point x, shape (n_samples, n_features)
@@ -53,6 +58,22 @@ class Sum(Kernel, _sk.Sum):
 
 
 class Product(Kernel, _sk.Product):
+    pass
+
+
+class Exponentiation(Kernel, _sk.Exponentiation):
+    pass
+
+
+class RationalQuadratic(Kernel, _sk.RationalQuadratic):
+    pass
+
+
+class ExpSineSquared(Kernel, _sk.ExpSineSquared):
+    pass
+
+
+class DotProduct(Kernel, _sk.DotProduct):
     pass
 
 

@@ -291,3 +291,21 @@ def test_argument_validation_needs_no_device():
     assert L.skb_acq_from_posterior_host(0, 2, 3, None, a.ctypes.data, None, None, C.byref(prm), acq, acq) == -1
     L.skb_state_destroy(None)                                   # destroying nothing is allowed
     assert L.skb_launch_count() == launches_before              # nothing was launched by any of this
+
+
+def test_kernels_outside_the_grammar_load_but_have_no_device_form():
+    """skopt.learning.gaussian_process.kernels exports RationalQuadratic, ExpSineSquared, DotProduct and Exponentiation;
+    here they import, combine, clone and fit on the host, and predict / gradient_x refuse them by name (no CPU route)."""
+    from sklearn.base import clone
+    from skopt_b200.learning import GaussianProcessRegressor
+    from skopt_b200.learning.gaussian_process import kernels as K
+    combo = 2.0 * K.RationalQuadratic(1.0, 0.5) + K.DotProduct(1.0)
+    assert type(combo).__module__ == K.__name__ and isinstance(K.RBF(1.0) ** 2, K.Exponentiation)
+    assert repr(clone(combo)) == repr(combo)
+    rng = np.random.RandomState(0)
+    for kernel in (K.RationalQuadratic(1.0), K.ExpSineSquared(1.0, 2.0), K.DotProduct(1.0), K.RBF(1.0) ** 2, combo):
+        est = GaussianProcessRegressor(kernel, optimizer=None).fit(rng.rand(5, 2), rng.rand(5))
+        with pytest.raises(NotImplementedError, match="outside the GPU hot-path grammar"):
+            est.predict(rng.rand(3, 2), return_std=True)
+        with pytest.raises(NotImplementedError, match="outside the GPU hot-path grammar"):
+            kernel.gradient_x(np.zeros(2), np.zeros((3, 2)))
