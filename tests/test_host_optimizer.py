@@ -285,3 +285,30 @@ def test_optimizer_script_identical(abi_model, index):
     assert len(got) == len(want)
     for step_got, step_want in zip(got, want):
         assert step_got == step_want, step_want[0]
+
+
+def test_optimizer_pickles_without_its_device_handles(abi_model, tmp_path):
+    """test_utils.py::test_dump_and_load_optimizer restated for the GP: an Optimizer with fitted models survives pickle
+    and dump / load (device states are dropped and rebuilt on first use) and continues on the same trajectory."""
+    import pickle
+    from skopt_b200 import Optimizer, dump, load
+
+    def objective(x):
+        return x[0] ** 2 + (x[1] == "b")
+
+    opt = Optimizer([(-1.0, 1.0), ["a", "b"]], "GP", n_initial_points=3, acq_optimizer="sampling",
+                    acq_optimizer_kwargs=dict(n_points=100), random_state=0)
+    for _ in range(5):
+        x = opt.ask()
+        opt.tell(x, objective(x))
+    twin = pickle.loads(pickle.dumps(opt))
+    assert twin.ask() == opt.ask() and len(twin.models) == len(opt.models) == 3
+    assert "_skb_device_state" not in twin.models[-1].__dict__
+    x = opt.ask()
+    a, b = opt.tell(x, objective(x)), twin.tell(x, objective(x))
+    assert a.x_iters == b.x_iters and opt.ask() == twin.ask()
+    dump(opt, str(tmp_path / "opt.pkl"))
+    restored = load(str(tmp_path / "opt.pkl"))
+    assert restored.ask() == opt.ask()
+    mean, std = restored.models[-1].predict(np.array([[0.3, 1.0]]), return_std=True)
+    assert mean.shape == std.shape == (1,)
