@@ -8,9 +8,9 @@ library for this object inside ONE test.  It takes the same arguments the shared
 addresses, sizes), reads and writes the caller's buffers through those addresses, and computes with the CPU oracle
 (oracle/gp_oracle.py).  Nothing under scikit-optimize_b200/ imports it.
 
-Only the `*_host` entry points, state management and the small host-pointer helpers are modelled; the `*_dev` entry points
-(device pointers, streams), candidate generation on the device and the fit objective are not - tests that need them are
-`-m gpu` tests.
+The `*_host` entry points, state management, the small host-pointer helpers and the fit objective (skb_fit_*) are
+modelled; the `*_dev` entry points (device pointers, streams) and candidate generation on the device are not - tests that
+need them are `-m gpu` tests.
 """
 import ctypes as C
 
@@ -260,4 +260,99 @@ class AbiModel:
         _view(topk_idx, (top_k,), np.int64)[:] = ti
         if _addr(first_nan):
             _view(first_nan, (1,), np.int64)[0] = nan
+        return OK
+
+    # ---- fit objective (opt-in GPU fit): log marginal likelihood, finalisation, state from the resident factor ------------
+    def skb_fit_create(self, desc, device, out):
+        desc = _obj(desc)
+        self.calls.append("skb_fit_create")
+        if desc.n_train <= 0 or desc.n_dims <= 0 or not desc.X_train or not desc.y_train:
+            return self._fail(ERR_INVALID, "bad fit descriptor")
+        if desc.kernel == 4:
+            return self._fail(ERR_UNSUPPORTED, "the Hamming kernel has no device fit objective")
+        handle = self._next
+        self._next += 1
+        n, d = desc.n_train, desc.n_dims
+        self._fits = getattr(self, "_fits", {})
+        self._fits[handle] = {"X": _view(desc.X_train, (n, d)).copy(), "y": _view(desc.y_train, (n,)).copy(),
+                              "nu": {0: np.inf, 1: 0.5, 2: 1.5, 3: 2.5}[desc.kernel], "alpha": desc.alpha,
+                              "kernel": desc.kernel, "factor": None}
+        _obj(out).value = handle
+        return OK
+
+    def skb_fit_destroy(self, handle):
+        getattr(self, "_fits", {}).pop(_addr(handle), None)
+
+    def _lml(self, fit, theta, want_grad):
+        with np.errstate(all="ignore"):
+            value, grad = orc.log_marginal_likelihood(fit["X"], fit["y"], fit["nu"], theta, alpha=fit["alpha"])
+        if not np.isfinite(theta[-1]):             # log noise = -inf: no noise term, its gradient entry is 0
+            grad = np.where(np.isfinite(grad), grad, 0.0)
+        return value, (grad if want_grad else np.zeros_like(grad))
+
+    def skb_fit_lml_host(self, handle, theta, want_grad, lml, grad):
+        fit = self._fits[_addr(handle)]
+        self.calls.append("skb_fit_lml_host")
+        d = fit["X"].shape[1]
+        value, g = self._lml(fit, _view(theta, (d + 2,)).copy(), want_grad)
+        _obj(lml).value = value
+        if _addr(grad):
+            _view(grad, (d + 2,))[:] = g
+        return OK
+
+    def skb_fit_lml_batch_host(self, handle, count, thetas, want_grad, lml, grad):
+        fit = self._fits[_addr(handle)]
+        self.calls.append("skb_fit_lml_batch_host")
+        d = fit["X"].shape[1]
+        T = _view(thetas, (count, d + 2))
+        for i in range(count):
+            value, g = self._lml(fit, T[i].copy(), want_grad)
+            _view(lml, (count,))[i] = value
+            if _addr(grad):
+                _view(grad, (count, d + 2))[i] = g
+        return OK
+
+    def skb_fit_finalize_host(self, handle, theta, lml, alpha_out, L_out):
+        """Tail of sklearn's fit (_gpr.py:341-367) at theta: K = kernel(X) + alpha I, L = chol(K), alpha_ = K^-1 y."""
+        from scipy.linalg import cho_solve, cholesky
+        fit = self._fits[_addr(handle)]
+        self.calls.append("skb_fit_finalize_host")
+        X, y = fit["X"], fit["y"]
+        n, d = X.shape
+        theta = _view(theta, (d + 2,)).copy()
+        amplitude, ls, noise = np.exp(theta[0]), np.exp(theta[1:d + 1]), np.exp(theta[d + 1])
+        state = orc.GPState(X_train=X, alpha=np.zeros(n), K_inv=np.eye(n), length_scale=ls,
+                            kind=orc.KIND_RBF if fit["kernel"] == 0 else orc.KIND_MATERN, nu=fit["nu"], amplitude=amplitude)
+        K = orc.kernel_cross(state, X) + (noise + fit["alpha"]) * np.eye(n)
+        try:
+            L = cholesky(K, lower=True, check_finite=False)
+        except np.linalg.LinAlgError:
+            return self._fail(-6, "K(theta) is not positive definite")
+        a = cho_solve((L, True), y, check_finite=False)
+        _obj(lml).value = -0.5 * y.dot(a) - np.log(np.diag(L)).sum() - n / 2.0 * np.log(2.0 * np.pi)
+        _view(alpha_out, (n,))[:] = a
+        if _addr(L_out):
+            _view(L_out, (n, n))[:] = L
+        fit["factor"], fit["alpha_vec"] = L, a
+        return OK
+
+    def skb_state_create_from_fit(self, handle, desc, out):
+        fit = self._fits[_addr(handle)]
+        desc = _obj(desc)
+        self.calls.append("skb_state_create_from_fit")
+        if fit["factor"] is None:
+            return self._fail(ERR_INVALID, "skb_fit_finalize_host has not succeeded on this handle")
+        n, d = fit["X"].shape
+        L_inv = np.linalg.solve(fit["factor"], np.eye(n))
+        st = _State.__new__(_State)
+        st.has_kinv, st.is_hamming = True, False
+        kind = {0: (orc.KIND_RBF, 2.5), 1: (orc.KIND_MATERN, 0.5), 2: (orc.KIND_MATERN, 1.5), 3: (orc.KIND_MATERN, 2.5)}
+        st.gp = orc.GPState(X_train=fit["X"].copy(), alpha=fit["alpha_vec"].copy(), K_inv=L_inv.T @ L_inv,
+                            length_scale=_view(desc.length_scale, (d,)).copy(), kind=kind[desc.kernel][0],
+                            nu=kind[desc.kernel][1], amplitude=desc.amplitude, bias=desc.bias, white=desc.white,
+                            y_mean=desc.y_mean, y_std=desc.y_std)
+        new = self._next
+        self._next += 1
+        self._states[new] = st
+        _obj(out).value = new
         return OK

@@ -312,3 +312,10 @@ def test_optimizer_pickles_without_its_device_handles(abi_model, tmp_path):
     assert restored.ask() == opt.ask()
     mean, std = restored.models[-1].predict(np.array([[0.3, 1.0]]), return_std=True)
     assert mean.shape == std.shape == (1,)
+
+
+# tests/test_gpu_fit.py: the opt-in GPU fit (objective, lock-step restarts, finalisation, state from the resident factor)
+# through the model of skb_fit_* - the host logic of gpr._search_on_device / _finalize_on_device and engine.DeviceFit
+from tests import test_gpu_fit as gpu_fit  # noqa: E402
+
+globals().update({"test_fit_" + name[5:]: func for name, func in _mirror(gpu_fit).items()})
