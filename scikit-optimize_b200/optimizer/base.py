@@ -1,5 +1,6 @@
 """Ask/tell loop shared by the minimisers (mirror of skopt/optimizer/base.py:22-305)."""
 import numbers
+import time
 import warnings
 from collections.abc import Iterable
 
@@ -15,6 +16,41 @@ def _as_callbacks(callback):
     if isinstance(callback, list) and all(callable(c) for c in callback):
         return list(callback)
     raise ValueError("callback should be either a callable or a list of callables.")
+
+
+class _Progress(object):
+    """verbose=True: the lines skopt.callbacks.VerboseCallback prints (callbacks.py:38-113) - an announcement when an
+    iteration starts (provided point / random point / model-based search), and at its end the time taken, the value
+    obtained and the current minimum.  The callback runs after every tell(), so "start" of iteration i + 1 is printed
+    right after the "end" of iteration i."""
+
+    def __init__(self, n_provided, n_random, n_total):
+        self.n_provided, self.n_random, self.n_total = n_provided, n_random, n_total
+        self.iteration = 1
+        self.started = time.time()
+        self._announce(True)
+
+    def _announce(self, start):
+        i = self.iteration
+        status, doing = ("started", "Evaluating function") if start else ("ended", "Evaluation done")
+        if i <= self.n_provided:
+            print("Iteration No: %d %s. %s at provided point." % (i, status, doing))
+        elif i <= self.n_provided + self.n_random:
+            print("Iteration No: %d %s. %s at random point." % (i, status, doing))
+        else:
+            print("Iteration No: %d %s. %s" % (i, status, "Searching for the next optimal point." if start
+                                               else "Search finished for the next optimal point."))
+
+    def __call__(self, res):
+        elapsed = time.time() - self.started
+        self._announce(False)
+        print("Time taken: %0.4f" % elapsed)
+        print("Function value obtained: %0.4f" % res.func_vals[-1])
+        print("Current minimum: %0.4f" % res.fun)
+        self.iteration += 1
+        if self.iteration <= self.n_total:
+            self._announce(True)
+            self.started = time.time()
 
 
 def base_minimize(func, dimensions, base_estimator, n_calls=100, n_random_starts=None, n_initial_points=10,
@@ -57,13 +93,7 @@ def base_minimize(func, dimensions, base_estimator, n_calls=100, n_random_starts
                            % optimizer.space)
     callbacks = _as_callbacks(callback)
     if verbose:
-        state = {"n": 0}
-
-        def _progress(res):
-            state["n"] += 1
-            print("Iteration No: %d ended. Function value obtained: %.4f  Current minimum: %.4f"
-                  % (state["n"], res.func_vals[-1], res.fun))
-        callbacks.append(_progress)
+        callbacks.append(_Progress(n_provided=len(x0) if not y0 else 0, n_random=n_initial_points, n_total=n_calls))
 
     result = None
     if x0 and y0 is None:

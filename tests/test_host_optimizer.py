@@ -319,3 +319,19 @@ def test_optimizer_pickles_without_its_device_handles(abi_model, tmp_path):
 from tests import test_gpu_fit as gpu_fit  # noqa: E402
 
 globals().update({"test_fit_" + name[5:]: func for name, func in _mirror(gpu_fit).items()})
+
+
+def test_verbose_prints_the_reference_progress_lines(abi_model, capsys):
+    """verbose=True (benchmarks/bench_branin.py runs with it): the announcements of skopt.callbacks.VerboseCallback."""
+    import re
+    from skopt_b200 import gp_minimize
+    gp_minimize(lambda x: (x[0] - 0.3) ** 2, [(-1.0, 1.0)], n_calls=4, n_initial_points=1, x0=[[0.1]], verbose=True,
+                acq_optimizer="sampling", n_points=50, random_state=0)
+    lines = [re.sub(r"[-0-9.]+$", "#", line) for line in capsys.readouterr().out.splitlines()]
+    assert lines[:5] == ["Iteration No: 1 started. Evaluating function at provided point.",
+                         "Iteration No: 1 ended. Evaluation done at provided point.",
+                         "Time taken: #", "Function value obtained: #", "Current minimum: #"]
+    assert lines[5] == "Iteration No: 2 started. Evaluating function at random point."
+    assert lines[10] == "Iteration No: 3 started. Searching for the next optimal point."
+    assert lines[11] == "Iteration No: 3 ended. Search finished for the next optimal point."
+    assert len(lines) == 20 and lines[-1] == "Current minimum: #"
