@@ -327,7 +327,7 @@ def test_verbose_prints_the_reference_progress_lines(abi_model, capsys):
     from skopt_b200 import gp_minimize
     gp_minimize(lambda x: (x[0] - 0.3) ** 2, [(-1.0, 1.0)], n_calls=4, n_initial_points=1, x0=[[0.1]], verbose=True,
                 acq_optimizer="sampling", n_points=50, random_state=0)
-    lines = [re.sub(r"[-0-9.]+$", "#", line) for line in capsys.readouterr().out.splitlines()]
+    lines = [re.sub(r": -?[0-9][0-9.e-]*$", ": #", line) for line in capsys.readouterr().out.splitlines()]
     assert lines[:5] == ["Iteration No: 1 started. Evaluating function at provided point.",
                          "Iteration No: 1 ended. Evaluation done at provided point.",
                          "Time taken: #", "Function value obtained: #", "Current minimum: #"]
