@@ -332,6 +332,8 @@ def test_verbose_prints_the_reference_progress_lines(abi_model, capsys):
                          "Iteration No: 1 ended. Evaluation done at provided point.",
                          "Time taken: #", "Function value obtained: #", "Current minimum: #"]
     assert lines[5] == "Iteration No: 2 started. Evaluating function at random point."
-    assert lines[10] == "Iteration No: 3 started. Searching for the next optimal point."
-    assert lines[11] == "Iteration No: 3 ended. Search finished for the next optimal point."
+    # the reference counts the provided point into the random phase as well (base.py:249-274), so iteration 3 is "random"
+    assert lines[10] == "Iteration No: 3 started. Evaluating function at random point."
+    assert lines[15] == "Iteration No: 4 started. Searching for the next optimal point."
+    assert lines[16] == "Iteration No: 4 ended. Search finished for the next optimal point."
     assert len(lines) == 20 and lines[-1] == "Current minimum: #"
