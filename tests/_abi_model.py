@@ -110,6 +110,7 @@ class AbiModel:
 
     def __init__(self):
         self._states = {}
+        self._fits = {}
         self._next = 1
         self._error = b""
         self.calls = []                 # names of the entry points called, in order (tests assert on it)
@@ -273,7 +274,6 @@ class AbiModel:
         handle = self._next
         self._next += 1
         n, d = desc.n_train, desc.n_dims
-        self._fits = getattr(self, "_fits", {})
         self._fits[handle] = {"X": _view(desc.X_train, (n, d)).copy(), "y": _view(desc.y_train, (n,)).copy(),
                               "nu": {0: np.inf, 1: 0.5, 2: 1.5, 3: 2.5}[desc.kernel], "alpha": desc.alpha,
                               "kernel": desc.kernel, "factor": None}
@@ -281,7 +281,7 @@ class AbiModel:
         return OK
 
     def skb_fit_destroy(self, handle):
-        getattr(self, "_fits", {}).pop(_addr(handle), None)
+        self._fits.pop(_addr(handle), None)
 
     def _lml(self, fit, theta, want_grad):
         with np.errstate(all="ignore"):
