@@ -7,7 +7,7 @@
 (the package directory is `scikit-optimize_b200/`; `import skopt_b200` resolves to it through the shim at the
 repository root).
 """
-from . import acquisition, plots, space, utils  # noqa: F401
+from . import acquisition, benchmarks, plots, space, utils  # noqa: F401
 from .engine import DeviceState, HostState, host_state_from_estimator, launch_count  # noqa: F401
 from .learning.gaussian_process.gpr import set_default_device, set_fit_device  # noqa: F401
 from .optimizer import Optimizer, base_minimize, dummy_minimize, gp_minimize  # noqa: F401

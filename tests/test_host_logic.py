@@ -309,3 +309,12 @@ def test_kernels_outside_the_grammar_load_but_have_no_device_form():
             est.predict(rng.rand(3, 2), return_std=True)
         with pytest.raises(NotImplementedError, match="outside the GPU hot-path grammar"):
             kernel.gradient_x(np.zeros(2), np.zeros((3, 2)))
+
+
+def test_benchmark_objectives_have_their_known_minima():
+    from skopt_b200 import benchmarks as B
+    for x in ([-np.pi, 12.275], [np.pi, 2.275], [9.42478, 2.475]):
+        assert abs(B.branin(x) - 0.397887) < 1e-5
+    assert abs(B.hart6([0.20169, 0.15001, 0.476874, 0.275332, 0.311652, 0.6573]) + 3.32237) < 1e-5
+    assert B.bench1([0.0]) == 0.0 and B.bench2([5.0]) == -5.0 and B.bench1_with_time([2.0]) == (4.0, 2.22)
+    assert abs(B.bench3([-0.3]) + 0.9) < 0.1 and B.bench4(["3"]) == 9.0 and B.bench5(["3", 4]) == 25.0

@@ -35,6 +35,7 @@ REDIRECT = [
     (r"^(\s*)from skopt\.learning\.gaussian_process\.(kernels|gpr) import", r"\1from skopt_b200.learning.gaussian_process.\2 import"),
     (r"^(\s*)from skopt\.space(\.space|\.transformers)? import", r"\1from skopt_b200.space import"),
     (r"^(\s*)from skopt\.utils import", r"\1from skopt_b200.utils import"),
+    (r"^(\s*)from skopt\.benchmarks import", r"\1from skopt_b200.benchmarks import"),
 ]
 # node ids (regular expressions) of tests about components outside the path
 OUT_OF_SCOPE = [r"forest_minimize", r"gbrt_minimize", r"RandomForest", r"ExtraTrees", r"GradientBoosting",
