@@ -196,6 +196,18 @@ int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq
 int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
                   int64_t* topk_idx, int64_t* first_nan);
 
+/* Cross-rank half of the same ranking when the candidate set is sharded over GPUs (the reference has no
+ * multi-device path - this is np.argmin / np.argsort[:k] of optimizer.py:564,570 over the CONCATENATED shards).
+ * A top-k record is n_acq * (2 top_k + 1) 8-byte words:
+ *     [n_acq][top_k] values (f64) | [n_acq][top_k] global indices (i64, -1 = padding) | [n_acq] first NaN index (i64, -1)
+ * i.e. the topk_val / topk_idx / first_nan pointers of skb_score_out aimed into ONE buffer, so that a rank's result for
+ * all requested acquisitions travels in one all-gather.  `gathered` = n_records such records back to back (device);
+ * `merged` (device) receives one record: per acquisition the top_k smallest (value, index) pairs of all records (ties to
+ * the lowest index) and the lowest NaN index.  One launch, no host synchronisation; skb_score_dev with m == 0 pads its
+ * outputs (NaN, -1, -1) so that empty shards merge as nothing. */
+int skb_topk_merge_records_dev(int device, const void* gathered, int32_t n_records, int32_t n_acq, int32_t top_k,
+                               void* merged, void* stream);
+
 /* ---- candidate generation on the device (the step that feeds the path: optimizer.py:552-553) ----
  * Replaces: `space.rvs(n_points, random_state=rng)` + `space.transform(...)` (skopt/space/space.py:874-903, 942-974;
  * transformers.py:243-276) for "normalize"-warped Real (uniform prior), Integer and Categorical dimensions.

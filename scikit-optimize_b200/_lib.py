@@ -81,6 +81,8 @@ SYMBOLS = [
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    ("skb_topk_merge_records_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                             C.c_void_p]),
     ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
     ("skb_candidates_generate_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32,
                                               C.POINTER(DimDesc), C.c_void_p, C.c_void_p]),

@@ -807,7 +807,18 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (split_mode && st->n > SPLIT_MAX_TRAIN)
         return fail(SKB_ERR_UNSUPPORTED, "split_int8 precision needs n_train <= %d (int32 accumulators), got %d",
                     SPLIT_MAX_TRAIN, st->n);
-    if (m == 0) return SKB_OK;
+    if (m == 0) {
+        // an empty shard (more ranks than candidates) still owns a top-k record that is gathered and merged: pad it
+        if (!mean_only && prm && out) {
+            if (out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
+            for (int a = 0; a < 3 && prm->top_k > 0; ++a) {
+                if (!((prm->acq_mask >> a) & 1) || (!out->topk_val[a] && !out->topk_idx[a] && !out->first_nan[a])) continue;
+                topk_fill_empty_kernel<<<1, 128, 0, s>>>(out->topk_val[a], out->topk_idx[a], out->first_nan[a], prm->top_k);
+                LAUNCHED();
+            }
+        }
+        return SKB_OK;
+    }
     int planes = 7;
     if (split_mode) {
         if (force_planes) planes = force_planes;
@@ -1504,6 +1515,21 @@ int skb_topk_host(int device, const double* values, int64_t m, int64_t index_off
     cudaDeviceSynchronize();
     pool_free(device, raw);
     return rc;
+}
+
+static int check_device(int device);
+
+int skb_topk_merge_records_dev(int device, const void* gathered, int32_t n_records, int32_t n_acq, int32_t top_k,
+                               void* merged, void* stream) {
+    if (!gathered || !merged) return fail(SKB_ERR_INVALID, "gathered/merged is NULL");
+    if (n_records <= 0 || n_acq <= 0 || n_acq > SKB_NUM_ACQ) return fail(SKB_ERR_INVALID, "n_records / n_acq out of range");
+    if (top_k < 0 || top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [0, 4096]", top_k);
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    topk_merge_records_kernel<<<n_acq, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const int64_t*>(gathered), n_records, n_acq, top_k, static_cast<int64_t*>(merged));
+    LAUNCHED();
+    return SKB_OK;
 }
 
 static int check_device(int device) {

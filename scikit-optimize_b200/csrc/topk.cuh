@@ -36,8 +36,11 @@ __device__ __forceinline__ ValIdx vi_warp_min(ValIdx x) {
 }
 
 // k rounds over `count` entries.  idx_in == nullptr: entry e has global index base + e.
+// seg_len > 0: the entries are `seg_len`-long runs that start `seg_stride` words apart (the per-rank records of
+// topk_merge_records_kernel): entry e lives at (e / seg_len) * seg_stride + e % seg_len.
 __device__ void block_topk_rounds(const double* __restrict__ vals, const int64_t* __restrict__ idx_in, int64_t count,
-                                  int64_t base, int k, double* out_v, int64_t* out_i, int64_t* first_nan) {
+                                  int64_t base, int k, double* out_v, int64_t* out_i, int64_t* first_nan,
+                                  int seg_len = 0, int64_t seg_stride = 0) {
     __shared__ ValIdx s_w[TOPK_THREADS / 32];
     __shared__ ValIdx s_win;
     __shared__ long long s_nan[TOPK_THREADS / 32];
@@ -47,7 +50,8 @@ __device__ void block_topk_rounds(const double* __restrict__ vals, const int64_t
         ValIdx best{0.0, IDX_NONE};
         long long nan_i = INT64_MAX;
         for (int64_t e = tid; e < count; e += TOPK_THREADS) {
-            ValIdx cur{vals[e], idx_in ? idx_in[e] : base + e};
+            const int64_t at = seg_len > 0 ? (e / seg_len) * seg_stride + e % seg_len : e;
+            ValIdx cur{vals[at], idx_in ? idx_in[at] : base + e};
             if (cur.i == IDX_NONE || cur.i < 0) continue;
             if (isnan(cur.v)) {
                 if (cur.i < nan_i) nan_i = cur.i;
@@ -114,6 +118,39 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(const double* 
             if (part_nan[b] >= 0 && part_nan[b] < mn) mn = part_nan[b];
         *out_nan = mn == INT64_MAX ? -1 : mn;
     }
+}
+
+// Cross-rank merge of packed top-k records (one block per acquisition).  A record is `n_acq * (2 k + 1)` 8-byte words:
+//   [n_acq][k] values (f64) | [n_acq][k] global indices (i64, -1 = padding) | [n_acq] lowest NaN index (i64, -1 = none)
+// `gathered` holds `n_records` of them back to back (what one all-gather of the per-rank records delivers); `merged`
+// receives one record of the same layout: per acquisition the k smallest (value, index) pairs over all records, ties to
+// the lowest index, and the lowest NaN index of any record - np.argmin / np.argsort[:k] over the concatenated shards.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_merge_records_kernel(const int64_t* __restrict__ gathered, int n_records,
+                                                                          int n_acq, int k, int64_t* merged) {
+    const int a = blockIdx.x;
+    const int64_t rec_words = (int64_t)n_acq * (2 * k + 1);
+    const double* vals = reinterpret_cast<const double*>(gathered) + (int64_t)a * k;
+    const int64_t* idx = gathered + (int64_t)n_acq * k + (int64_t)a * k;
+    double* out_v = reinterpret_cast<double*>(merged) + (int64_t)a * k;
+    int64_t* out_i = merged + (int64_t)n_acq * k + (int64_t)a * k;
+    if (k > 0) block_topk_rounds(vals, idx, (int64_t)n_records * k, 0, k, out_v, out_i, nullptr, k, rec_words);
+    if (threadIdx.x == 0) {
+        long long mn = INT64_MAX;
+        for (int r = 0; r < n_records; ++r) {
+            const long long v = gathered[r * rec_words + 2 * (int64_t)n_acq * k + a];
+            if (v >= 0 && v < mn) mn = v;
+        }
+        merged[2 * (int64_t)n_acq * k + a] = mn == INT64_MAX ? -1 : mn;
+    }
+}
+
+// Padding of an empty candidate set: NaN values, index -1, no NaN seen (what the host entry points pre-fill).
+__global__ void topk_fill_empty_kernel(double* out_v, int64_t* out_i, int64_t* out_nan, int k) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        if (out_v) out_v[j] = nan("");
+        if (out_i) out_i[j] = -1;
+    }
+    if (threadIdx.x == 0 && out_nan) *out_nan = -1;
 }
 
 }  // namespace skb

@@ -1,9 +1,14 @@
 """Multi-GPU plumbing: candidates are sharded by contiguous row blocks (rank r owns global rows
-[offsets[r], offsets[r+1])), the GP state is replicated, and the only exchange is an all-gather of the per-rank
-top-k (value, global index) pairs followed by a local lexicographic merge -- identical on every rank and identical
-to np.argmin / np.argsort[:k] over the concatenated candidate set (optimizer.py:564,570).  NCCL has no MINLOC, so
-all-gather + local reduce is the idiom.  Works on CUDA tensors (NCCL) and CPU tensors (gloo).
+[offsets[r], offsets[r+1])), the GP state is replicated, and the only exchange is ONE all-gather of a packed per-rank
+record -- the top-k (value, global index) pairs of every requested acquisition plus its first-NaN index,
+`n_acq * (2 k + 1)` 8-byte words (layout: include/skb.h, skb_topk_merge_records_dev) -- followed by one merge launch
+(topk_merge_records_kernel) and one device -> host copy.  The result is identical on every rank and identical to
+np.argmin / np.argsort[:k] over the concatenated candidate set (optimizer.py:564,570).  NCCL has no MINLOC, so
+all-gather + local reduce is the idiom.  CUDA tensors travel over NCCL and merge on the device;
+CPU tensors (gloo, the build machine's world-size-2 tests of this host logic) merge with the torch restatement
+`merge_topk` below, which doubles as the independent checker of the device merge in bench.py's multi_gpu_check.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -28,15 +33,48 @@ def merge_topk(vals, idxs, k):
 
 
 def merge_topk_allgather(vals, idxs, k, group=None):
-    """All-gather each rank's top-k list (k * 16 bytes per rank) and merge; every rank gets the global top-k."""
+    """All-gather one (value, index) top-k list per rank and merge; every rank gets the global top-k.  Kept for callers
+    that rank a single vector; the scoring paths below exchange packed records instead."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_topk(vals, idxs, k)
-    world = dist.get_world_size(group)
-    gv = torch.empty(world * vals.numel(), dtype=vals.dtype, device=vals.device)
-    gi = torch.empty(world * idxs.numel(), dtype=idxs.dtype, device=idxs.device)
-    dist.all_gather_into_tensor(gv, vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(gi, idxs.contiguous(), group=group)
-    return merge_topk(gv, gi, k)
+    rec = torch.cat([vals.contiguous().view(torch.int64), idxs.contiguous(),
+                     torch.full((1,), -1, dtype=torch.int64, device=vals.device)])
+    merged = exchange_records(rec, 1, vals.numel(), group=group, k_out=k)
+    return merged[:k].view(torch.float64), merged[k:2 * k]
+
+
+def merge_records_torch(gathered, n_records, n_acq, k, k_out=None):
+    """torch restatement of topk_merge_records_kernel (CPU tensors of the gloo tests; checker of the device merge)."""
+    k_out = k if k_out is None else k_out
+    words = n_acq * (2 * k + 1)
+    g = gathered.reshape(n_records, words)
+    out = torch.empty(n_acq * (2 * k_out + 1), dtype=torch.int64, device=gathered.device)
+    for a in range(n_acq):
+        v, i = merge_topk(g[:, a * k:(a + 1) * k].contiguous().view(torch.float64),
+                          g[:, n_acq * k + a * k:n_acq * k + (a + 1) * k], k_out)
+        out[a * k_out:(a + 1) * k_out] = v.view(torch.int64)
+        out[n_acq * k_out + a * k_out:n_acq * k_out + (a + 1) * k_out] = i
+        nan = g[:, 2 * n_acq * k + a]
+        nan = torch.where(nan < 0, torch.full_like(nan, _I64_MAX), nan).min()
+        out[2 * n_acq * k_out + a] = -1 if int(nan) == _I64_MAX else nan
+    return out
+
+
+def exchange_records(rec, n_acq, k, group=None, k_out=None):
+    """The one collective of the path: all-gather every rank's packed record and merge.  CUDA records merge in one
+    launch of the library's kernel (no host round trip); CPU records (gloo) through merge_records_torch."""
+    world = _world(group)
+    if world == 1 and (k_out is None or k_out == k):
+        return rec
+    if world > 1:
+        gathered = torch.empty(world * rec.numel(), dtype=torch.int64, device=rec.device)
+        dist.all_gather_into_tensor(gathered, rec.contiguous(), group=group)
+    else:
+        gathered = rec
+    if rec.is_cuda and (k_out is None or k_out == k):
+        from .engine import merge_records_device
+        return merge_records_device(gathered, world, n_acq, k)
+    return merge_records_torch(gathered, world, n_acq, k, k_out)
 
 
 def shard_bounds(m, world):
@@ -56,58 +94,76 @@ def _world(group):
     return dist.get_world_size(group)
 
 
+def _settle_split(dev, precision):
+    """The 6-or-7-plane decision of precision="split_int8" is a property of the (replicated) state, but the library
+    takes it on the first LARGE call - and a rank's shard can be below that size when the whole set is not.  Deciding up
+    front on every rank keeps a candidate's value independent of the rank that scored it."""
+    if precision == "split_int8" and hasattr(dev, "decide_split"):
+        dev.decide_split()
+
+
+def _pack_host_result(res, acq_funcs, k):
+    A = len(acq_funcs)
+    rec = np.empty(A * (2 * k + 1), dtype=np.int64)
+    for j, name in enumerate(acq_funcs):
+        r = res[name]
+        rec[j * k:(j + 1) * k] = np.ascontiguousarray(r["topk_val"], dtype=np.float64).view(np.int64)
+        rec[A * k + j * k:A * k + (j + 1) * k] = r["topk_idx"]
+        rec[2 * A * k + j] = r["first_nan"]
+    return rec
+
+
 def sharded_score(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64"):
     """Score the rows of X that belong to this rank and merge the top-k across ranks.
 
-    `X` is the FULL candidate matrix (identical on every rank); the returned dict has, per acquisition, the GLOBAL
-    'topk_val', 'topk_idx' and 'first_nan' -- the same on every rank and the same as a single-GPU run, because a
+    `X` is the FULL candidate matrix on the host (identical on every rank); the returned dict has, per acquisition, the
+    GLOBAL 'topk_val', 'topk_idx' and 'first_nan' -- the same on every rank and the same as a single-GPU run, because a
     candidate's value does not depend on where it was computed and ties resolve to the lowest global index."""
     world = _world(group)
     if world == 1:
         return dev.score(X, y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
                          want_posterior=False, want_values=False, precision=precision)
+    from .engine import resolve_precision, unpack_record
     rank = dist.get_rank(group)
     b = shard_bounds(X.shape[0], world)
     lo, hi = b[rank], b[rank + 1]
     # the precision is resolved on the FULL problem size so that every rank takes the same path
-    from .engine import resolve_precision
     precision = resolve_precision(precision, dev.host.n_train, X.shape[0]) if hasattr(dev, "host") else precision
+    _settle_split(dev, precision)
     res = dev.score(X[lo:hi], y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k, index_offset=lo,
                     want_posterior=False, want_values=False, precision=precision)
     backend = dist.get_backend(group)
     device = torch.device("cuda", dev.device) if backend == "nccl" else torch.device("cpu")
+    rec = torch.from_numpy(_pack_host_result(res, acq_funcs, top_k)).to(device)
+    merged = unpack_record(exchange_records(rec, len(acq_funcs), top_k, group=group), acq_funcs, top_k)
     for name in acq_funcs:
-        r = res[name]
-        v = torch.from_numpy(r["topk_val"]).to(device)
-        i = torch.from_numpy(r["topk_idx"]).to(device)
-        v, i = merge_topk_allgather(v, i, top_k, group=group)
-        r["topk_val"], r["topk_idx"] = v.cpu().numpy(), i.cpu().numpy()
-        nan = torch.tensor([r["first_nan"] if r["first_nan"] >= 0 else _I64_MAX], dtype=torch.int64, device=device)
-        dist.all_reduce(nan, op=dist.ReduceOp.MIN, group=group)
-        r["first_nan"] = -1 if int(nan) == _I64_MAX else int(nan)
+        res[name].update(merged[name])
     return res
 
 
-def sharded_score_tensor(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64"):
-    """sharded_score for a candidate matrix that already lives on this rank's GPU (a CUDA tensor, identical on every
-    rank): no host copy of the candidates at all; only the k (value, index) pairs per acquisition come back."""
-    from .engine import resolve_precision
+def sharded_score_tensor(dev, X, y_opt, acq_funcs, xi, kappa, top_k, group=None, precision="fp64", row_offset=None,
+                         n_total=None):
+    """sharded_score for candidates that already live on this rank's GPU: no host copy of the candidates at all; one
+    packed record per rank is all-gathered, merged by one kernel, and comes back in one copy.
+
+    Default: `X` is the full matrix (identical on every rank) and this rank scores its row block.  With `row_offset` /
+    `n_total` given, `X` holds ONLY this rank's rows [row_offset, row_offset + len(X)) of an n_total-row set (a rank
+    that generated just its own block)."""
+    from .engine import resolve_precision, unpack_record
     world = _world(group)
     rank = dist.get_rank(group) if world > 1 else 0
-    m = X.shape[0]
+    if row_offset is None:
+        m = X.shape[0]
+        b = shard_bounds(m, world)
+        lo, hi = b[rank], b[rank + 1]
+        part = X[lo:hi] if world > 1 else X
+    else:
+        m, lo, part = int(n_total), int(row_offset), X
     precision = resolve_precision(precision, dev.host.n_train, m)
-    b = shard_bounds(m, world)
-    lo, hi = b[rank], b[rank + 1]
-    part = X[lo:hi] if world > 1 else X
-    res = dev.score_tensors(part.contiguous(), y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
-                            index_offset=lo, precision=precision)
-    out = {"precision": precision}
-    for name in acq_funcs:
-        v, i, nan = res[name]["topk_val"], res[name]["topk_idx"], res[name]["first_nan"]
-        if world > 1:
-            v, i = merge_topk_allgather(v, i, top_k, group=group)
-            nan = torch.where(nan < 0, torch.full_like(nan, _I64_MAX), nan)
-            dist.all_reduce(nan, op=dist.ReduceOp.MIN, group=group)
-            nan = torch.where(nan == _I64_MAX, torch.full_like(nan, -1), nan)
-        out[name] = {"topk_val": v.cpu().numpy(), "topk_idx": i.cpu().numpy(), "first_nan": int(nan.cpu()[0])}
+    if world > 1:
+        _settle_split(dev, precision)
+    rec = dev.score_record(part.contiguous(), y_opt=y_opt, acq_funcs=acq_funcs, xi=xi, kappa=kappa, top_k=top_k,
+                           index_offset=lo, precision=precision)
+    out = unpack_record(exchange_records(rec, len(acq_funcs), top_k, group=group), acq_funcs, top_k)
+    out["precision"] = precision
     return out

@@ -378,6 +378,64 @@ class DeviceState:
         return res
 
 
+    def score_record(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=1, index_offset=0, stream=None,
+                     precision="fp64", values_out=None):
+        """score_tensors() whose top-k outputs for ALL requested acquisitions land in one packed record (an int64 CUDA
+        tensor of len(acq_funcs) * (2 top_k + 1) words, layout of skb_topk_merge_records_dev in include/skb.h): what a
+        rank contributes to the single all-gather of a sharded scoring call.  `X` may have zero rows (the record is
+        then padding).  values_out: optional {acq name: float64 CUDA tensor [m]} to also keep the full value vectors."""
+        import torch
+        if not (X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.is_contiguous()):
+            raise ValueError("X must be a contiguous 2-D float64 CUDA tensor")
+        if X.device.index != self.device or X.shape[1] != self.n_dims:
+            raise ValueError("X is on the wrong device or has the wrong number of features")
+        m, A, k = X.shape[0], len(acq_funcs), int(top_k)
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, k, resolve_precision(precision, self.host.n_train, m))
+        rec = torch.empty(record_words(A, k), dtype=torch.int64, device=X.device)
+        out = _lib.ScoreOut()
+        base = rec.data_ptr()
+        for j, name in enumerate(acq_funcs):               # record slots follow the ORDER of acq_funcs
+            a = _lib.ACQ_INDEX[name]
+            out.topk_val[a] = base + 8 * (j * k)
+            out.topk_idx[a] = base + 8 * (A * k + j * k)
+            out.first_nan[a] = base + 8 * (2 * A * k + j)
+            if values_out is not None and name in values_out:
+                out.acq[a] = values_out[name].data_ptr()
+        s = stream if stream is not None else torch.cuda.current_stream(X.device)
+        _lib.check(_lib.lib().skb_score_dev(self._h, X.data_ptr() if m else None, m, int(index_offset), C.byref(prm),
+                                            C.byref(out), C.c_void_p(s.cuda_stream)))
+        return rec
+
+
+def record_words(n_acq, top_k):
+    """8-byte words of a packed top-k record (include/skb.h, skb_topk_merge_records_dev)."""
+    return int(n_acq) * (2 * int(top_k) + 1)
+
+
+def unpack_record(rec, acq_funcs, top_k):
+    """{acq name: {'topk_val', 'topk_idx', 'first_nan'}} (NumPy) from a packed record (int64 tensor or array, host or
+    device): ONE device -> host copy for everything a sharded scoring call returns."""
+    words = rec.cpu().numpy() if hasattr(rec, "cpu") else np.asarray(rec)
+    A, k = len(acq_funcs), int(top_k)
+    out = {}
+    for j, name in enumerate(acq_funcs):
+        out[name] = {"topk_val": words[j * k:(j + 1) * k].view(np.float64).copy(),
+                     "topk_idx": words[A * k + j * k:A * k + (j + 1) * k].copy(),
+                     "first_nan": int(words[2 * A * k + j])}
+    return out
+
+
+def merge_records_device(gathered, n_records, n_acq, top_k, stream=None):
+    """Merge `n_records` packed records (one int64 CUDA tensor, back to back) into one: a single launch of
+    topk_merge_records_kernel through skb_topk_merge_records_dev."""
+    import torch
+    merged = torch.empty(record_words(n_acq, top_k), dtype=torch.int64, device=gathered.device)
+    s = stream if stream is not None else torch.cuda.current_stream(gathered.device)
+    _lib.check(_lib.lib().skb_topk_merge_records_dev(gathered.device.index, gathered.data_ptr(), int(n_records), int(n_acq),
+                                                     int(top_k), merged.data_ptr(), C.c_void_p(s.cuda_stream)))
+    return merged
+
+
 def kernel_gradient_x(kernel, x, X_train, device=None):
     """`kernel.gradient_x(x, X_train)`: d k(x, X_i) / dx for every training row, shape (n_samples, n_features)
     (skopt/learning/gaussian_process/kernels.py:48-65 and the per-class forms :68-308), on the GPU.

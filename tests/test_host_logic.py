@@ -143,6 +143,23 @@ full = FakeDev().score(X, acq_funcs=("EI", "PI"), top_k=5)
 sh = sharded_score(FakeDev(), X, y_opt=0.0, acq_funcs=("EI", "PI"), xi=0.01, kappa=1.96, top_k=5)
 for a in ("EI", "PI"):
     assert np.array_equal(full[a]["topk_idx"], sh[a]["topk_idx"]) and np.array_equal(full[a]["topk_val"], sh[a]["topk_val"])
+# packed records: every acquisition's top-k + first NaN in ONE all-gather; rank 1's shard is EMPTY (padding record)
+from skopt_b200.distributed import exchange_records, merge_records_torch
+from skopt_b200.engine import unpack_record, record_words
+A, k2 = 3, 4
+assert record_words(A, k2) == 27
+rec = np.empty(27, dtype=np.int64)
+if rank == 0:
+    v = np.array([[0.5, 0.5, 2.0, np.nan], [-1.0, 0.0, 1.0, 2.0], [3.0, 4.0, 5.0, 6.0]])
+    i = np.array([[4, 9, 2, -1], [0, 1, 2, 3], [7, 6, 5, 8]])
+    nan = np.array([11, -1, -1])
+else:
+    v = np.full((A, k2), np.nan); i = np.full((A, k2), -1); nan = np.array([-1, -1, -1])
+rec[:12] = v.reshape(-1).view(np.int64); rec[12:24] = i.reshape(-1); rec[24:] = nan
+got = unpack_record(exchange_records(torch.from_numpy(rec), A, k2), ("EI", "PI", "LCB"), k2)
+assert got["EI"]["topk_idx"].tolist() == [4, 9, 2, -1] and got["EI"]["first_nan"] == 11
+assert got["PI"]["topk_idx"].tolist() == [0, 1, 2, 3] and got["PI"]["first_nan"] == -1
+assert got["LCB"]["topk_idx"].tolist() == [7, 6, 5, 8] and got["LCB"]["topk_val"].tolist() == [3.0, 4.0, 5.0, 6.0]
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
