@@ -63,8 +63,8 @@ typedef enum {
  *   SPLIT_INT8 : the same on the leading 6 planes (47-bit operands, 21 instead of 28 digit-plane products; 4e-12 of the
  *                prior variance; the kernel values feeding it are computed to that accuracy only, csrc/kcross.cuh) WHEN a
  *                self-check run once per state - 256 probe candidates scored with FP64 and with 6 planes - agrees to 1e-10
- *                on the variance (relative to the prior variance) and on the mean (relative to max(|mean|, y_std));
- *                otherwise 7 planes.  The check runs on the first call with at least 32768 candidates (smaller calls on
+ *                on the variance (relative to the prior variance) and on the mean (relative to max(|mean|, y_std)) AND an
+ *                a-priori bound computed from the state (skb_state_split_bounds) is below 2.5e-10; otherwise 7 planes.  The check runs on the first call with at least 32768 candidates (smaller calls on
  *                an undecided state contract 7 planes); skb_state_split_info reports the choice and the measured
  *                difference.  The gradient entry points always contract 7 planes. */
 typedef enum { SKB_PRECISION_FP64 = 0, SKB_PRECISION_SPLIT_INT8 = 1, SKB_PRECISION_SPLIT_INT8_P7 = 2 } skb_precision;
@@ -149,6 +149,11 @@ int skb_state_attach_kinv(skb_state* st, const double* K_inv);
 /* Digit planes SKB_PRECISION_SPLIT_INT8 contracts on this state (6 or 7; 0 = not decided yet, the self-check runs on the
  * first split-integer call) and the relative variance difference the self-check measured (-1 before it ran). */
 int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff);
+/* The a-priori half of that decision (-1 before it ran): bounds, from the row scales of L_inv, the kernel scale, |alpha|
+ * and the size of the scaled training rows, on |var(6 planes) - var(exact)| / prior variance and on
+ * |mean(6 planes) - mean(exact)| / y_std (8 standard deviations of the rounding model in csrc/skb.cu, split_error_bounds).
+ * Six planes are contracted only when both bounds are <= 2.5e-10 AND the measured probe difference is <= 1e-10. */
+int skb_state_split_bounds(skb_state* st, double* bound_var, double* bound_mean);
 /* Run the self-check of SKB_PRECISION_SPLIT_INT8 now (on the state's own stream, waits for it) instead of on the first
  * large call; a no-op once the state has decided. */
 int skb_state_decide_split(skb_state* st);
@@ -195,6 +200,11 @@ int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq
  * host (used after skb_ps_combine_host).  Same ordering rules as skb_score_out.topk_*. */
 int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
                   int64_t* topk_idx, int64_t* first_nan);
+
+/* The same ranking for a value vector that already lives on the state's GPU (e.g. the acq[] output of
+ * skb_score_grad_dev): enqueued on `stream`, no host synchronisation; uses the state's scratch like the scoring calls. */
+int skb_topk_dev(skb_state* st, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
+                 int64_t* topk_idx, int64_t* first_nan, void* stream);
 
 /* Cross-rank half of the same ranking when the candidate set is sharded over GPUs (the reference has no
  * multi-device path - this is np.argmin / np.argsort[:k] of optimizer.py:564,570 over the CONCATENATED shards).
@@ -287,6 +297,12 @@ int skb_state_create_from_fit(skb_fit* fit, const skb_state_desc* desc, skb_stat
  * counts the spans, and resets the accumulation. */
 int skb_state_set_timing(skb_state* st, int enabled);
 int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
+
+/* Roofline denominators of this path measured on `device` now (MEASURED_PEAKS.json has HBM and bf16 only): the issue
+ * rate of tcgen05.mma kind::i8 at M=128, N=256 (MACs per clock per SM from the SM cycle counter, and TOP/s = 2 x MACs / s
+ * over all SMs from CUDA events, operands resident in shared memory) and the FP64 tensor (DMMA m8n8k4) rate in TFLOP/s.
+ * Two ~1 ms kernels, run four times each; synchronises the device. */
+int skb_measure_peaks(int device, double* i8_mac_per_clk_sm, double* i8_tops, double* fp64_dmma_tflops);
 
 /* Number of kernel launches issued through this library by the calling process so far (bench.py reports it). */
 int64_t skb_launch_count(void);

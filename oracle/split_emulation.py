@@ -49,3 +49,26 @@ def split_matmul(V, K, planes=P, k_scale=None):
     for t in range(planes - 2, -1, -1):                 # Horner in 256^-1, as in the kernel epilogue
         acc = acc * 0.00390625 + G[t].astype(np.float64)
     return acc * (sV[:, None] * (sK * 2.0 ** -14))      # the 2^-14 does not depend on the number of planes
+
+
+SPLIT_BOUND_GATE = 2.5e-10
+
+
+def apriori_bounds(L_inv, alpha, Xs, amplitude, bias, white, planes=6):
+    """Restatement of split_error_bounds (csrc/skb.cu): 8 standard deviations of the rounding model of the `planes`-plane
+    contraction, as (bound on |d var| / prior variance, bound on |d mean| / y_std).  L_inv: lower-triangular inverse
+    Cholesky factor; Xs: training rows divided by the length scales."""
+    V = np.tril(np.asarray(L_inv, dtype=np.float64))
+    n = V.shape[0]
+    sV = np.array([pow2_scale(np.max(np.abs(row))) for row in V])
+    sK = pow2_scale(abs(amplitude) + abs(bias))
+    P = planes
+    q2 = 2.0 ** -(16 * P - 2)
+    r2 = 2.0 * float(np.max(np.sum(np.asarray(Xs) ** 2, axis=1)))
+    eps_k2 = sK * sK * q2 / 3.0 + (abs(amplitude) * 2.0 ** -52 * r2) ** 2
+    per_entry = sK * sK * q2 / 48.0 + eps_k2 / 4.0 + (P - 1) * sK * sK * 2.0 ** (-16 * P) * 0.1111
+    s_max = float(np.max(np.sqrt(np.arange(1, n + 1)) * sV)) * np.sqrt(per_entry)
+    prior = abs(amplitude + bias + white)
+    bound_var = 8.0 * 2.0 * np.sqrt(abs(amplitude) + abs(bias)) * s_max / prior
+    bound_mean = 8.0 * float(np.linalg.norm(alpha)) * np.sqrt(eps_k2)
+    return bound_var, bound_mean

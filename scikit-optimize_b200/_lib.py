@@ -60,6 +60,7 @@ SYMBOLS = [
     ("skb_state_destroy", None, [C.c_void_p]),
     ("skb_state_attach_kinv", C.c_int, [C.c_void_p, C.c_void_p]),
     ("skb_state_split_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    ("skb_state_split_bounds", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("skb_state_decide_split", C.c_int, [C.c_void_p]),
     ("skb_state_stream", C.c_void_p, [C.c_void_p]),
     ("skb_state_sync", C.c_int, [C.c_void_p]),
@@ -81,6 +82,8 @@ SYMBOLS = [
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    ("skb_topk_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
     ("skb_topk_merge_records_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p]),
     ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
@@ -95,6 +98,7 @@ SYMBOLS = [
     ("skb_fit_lml_batch_host", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ("skb_fit_finalize_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_state_create_from_fit", C.c_int, [C.c_void_p, C.POINTER(StateDesc), C.POINTER(C.c_void_p)]),
+    ("skb_measure_peaks", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

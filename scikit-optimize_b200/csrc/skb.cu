@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -21,6 +23,7 @@
 #include "grad.cuh"
 #include "kcross.cuh"
 #include "layout.cuh"
+#include "microbench.cuh"
 #include "ozaki.cuh"
 #include "rng.cuh"
 #include "topk.cuh"
@@ -81,6 +84,8 @@ struct skb_state {
     // 0 = not decided yet (decide_split_planes runs on the first split-integer call), else 6 or 7
     int split_planes = 0;
     double split_probe_diff = -1.0;   // measured |var(6 planes) - var(FP64)| / prior variance on the probe rows
+    double split_bound_var = -1.0;    // a-priori bound on |var(6 planes) - var(exact)| / prior variance (split_error_bounds)
+    double split_bound_mean = -1.0;   // a-priori bound on |mean(6 planes) - mean(exact)| / y_std
     double* d_probe = nullptr;        // [PROBE_ROWS][d] candidates made from the training rows at state creation
     double* d_probe_out = nullptr;    // [4][PROBE_ROWS] posterior mean, std: FP64 path | mean, std: 6-plane split path
     double* d_tn = nullptr;           // [n_pad] squared norms of the scaled training rows (6-plane K1: |x|^2 + |t|^2 - 2 x.t)
@@ -105,6 +110,15 @@ struct skb_state {
     // overlaps the kernels of chunk i
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready;
+    // pageable caller memory (what a NumPy user passes) is staged through a ring of pinned pieces by a helper thread, so
+    // that the DMA of piece i overlaps the host copy of piece i+1 and the kernels of the chunks already on the device
+    unsigned char* h_ring = nullptr;
+    cudaEvent_t ring_free[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::thread stager;
+    std::mutex stage_mu;
+    std::condition_variable stage_cv;
+    size_t chunks_recorded = 0;       // chunk_ready[i] has been recorded on the copy stream for all i < chunks_recorded
+    int stage_rc = 0;                 // first CUDA error of the helper thread (cudaError_t), 0 = none
     // split-integer path: K1 of chunk i+1 runs on a second stream while the tensor-core contraction of chunk i runs on
     // the caller's stream (different pipes of the same SMs); the digit-plane scratch is double buffered
     cudaStream_t aux_stream = nullptr;
@@ -280,6 +294,12 @@ constexpr size_t STAGE_BYTES = 1u << 20;          // one block per state
 constexpr size_t STAGE_MAX_COPY = 256u << 10;     // larger outputs are bandwidth-bound: copied straight to the caller
 struct PinnedCache { std::mutex mu; std::vector<unsigned char*> free_blocks; };
 PinnedCache g_pinned[64];
+// ring of pinned pieces for the staged upload of pageable candidates (upload_chunked), recycled across states
+constexpr size_t RING_PIECE = 8u << 20;
+constexpr int RING_PIECES = 4;
+struct RingCache { std::mutex mu; std::vector<unsigned char*> free_rings; };
+RingCache g_rings[64];
+RingCache& g_rings_for(int device) { return g_rings[device & 63]; }
 
 int stage_begin(skb_state* st) {
     st->h_stage_used = 0;
@@ -361,6 +381,31 @@ __global__ void make_probe_kernel(const double* __restrict__ X, const double* __
         else v += ls[k] * 0.5 * ((double)h * (1.0 / 4294967296.0) - 0.5);
     }
     probe[idx] = v;
+}
+
+// Inputs of the a-priori error bound of the 6-plane contraction (split_error_bounds): out[0] = max_i sqrt(i + 1) sV_i (row
+// i of the triangular L_inv has i + 1 entries), out[1] = |alpha|_2, out[2] = max_j |t_j|^2 over the scaled training rows.
+// One block, fixed-order tree reductions.
+__global__ void split_bound_inputs_kernel(const double* __restrict__ sV, const double* __restrict__ alpha_p,
+                                          const double* __restrict__ tn, int n, double* __restrict__ out) {
+    __shared__ double r0[256], r1[256], r2[256];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        a = fmax(a, sqrt((double)(i + 1)) * sV[i]);
+        b = fma(alpha_p[i], alpha_p[i], b);
+        c = fmax(c, tn[i]);
+    }
+    r0[threadIdx.x] = a; r1[threadIdx.x] = b; r2[threadIdx.x] = c;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            r0[threadIdx.x] = fmax(r0[threadIdx.x], r0[threadIdx.x + s]);
+            r1[threadIdx.x] += r1[threadIdx.x + s];
+            r2[threadIdx.x] = fmax(r2[threadIdx.x], r2[threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = r0[0]; out[1] = sqrt(r1[0]); out[2] = r2[0]; }
 }
 
 __global__ void mean_affine_kernel(const double* __restrict__ kdot, double* __restrict__ mean, int64_t m, double y_std,
@@ -520,7 +565,14 @@ int skb_device_count(void) {
 void skb_state_destroy(skb_state* st) {
     if (!st) return;
     cudaSetDevice(st->device);
+    if (st->stager.joinable()) st->stager.join();
     cudaDeviceSynchronize();     // buffers go back to the pool: nothing queued on any stream may still touch them
+    if (st->h_ring) {
+        std::lock_guard<std::mutex> lock(g_rings_for(st->device).mu);
+        g_rings_for(st->device).free_rings.push_back(st->h_ring);
+    }
+    for (cudaEvent_t ev : st->ring_free)
+        if (ev) cudaEventDestroy(ev);
     void* ptrs[] = {st->d_ls, st->d_hw, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
                     st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out, st->d_tn};
@@ -773,6 +825,24 @@ static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_
 }
 
 // Upload X in the same chunks the kernels will consume, on the copy stream, one event per chunk.
+// Pinned (or registered) caller memory is handed to the DMA engine directly.  Pageable memory would make every
+// cudaMemcpyAsync a blocking, driver-staged copy in the calling thread - the kernels of chunk 0 could only be enqueued once
+// the whole matrix had crossed - so a helper thread copies it piece by piece into a ring of pinned buffers and queues the
+// DMA of each piece, while the calling thread enqueues the kernels chunk by chunk as soon as the chunk's event exists.
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static void stager_join(skb_state* st) {
+    if (st->stager.joinable()) st->stager.join();
+}
+
 static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chunk_tiles) {
     const int64_t tiles = (m + BN - 1) / BN;
     const size_t n_chunks = (size_t)((tiles + chunk_tiles - 1) / chunk_tiles);
@@ -781,14 +851,70 @@ static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chu
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         st->chunk_ready.push_back(ev);
     }
-    size_t ci = 0;
-    for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++ci) {
-        const int64_t c0 = t0 * BN;
-        const int64_t mc = std::min<int64_t>(m - c0, chunk_tiles * BN);
-        CU(cudaMemcpyAsync(st->d_X + c0 * st->d, X + c0 * st->d, (size_t)mc * st->d * sizeof(double),
-                           cudaMemcpyHostToDevice, st->copy_stream));
-        CU(cudaEventRecord(st->chunk_ready[ci], st->copy_stream));
+    stager_join(st);
+    st->stage_rc = 0;
+    if (!is_pageable(X)) {
+        size_t ci = 0;
+        for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++ci) {
+            const int64_t c0 = t0 * BN;
+            const int64_t mc = std::min<int64_t>(m - c0, chunk_tiles * BN);
+            CU(cudaMemcpyAsync(st->d_X + c0 * st->d, X + c0 * st->d, (size_t)mc * st->d * sizeof(double),
+                               cudaMemcpyHostToDevice, st->copy_stream));
+            CU(cudaEventRecord(st->chunk_ready[ci], st->copy_stream));
+        }
+        st->chunks_recorded = n_chunks;
+        return SKB_OK;
     }
+    if (!st->h_ring) {
+        RingCache& rc = g_rings_for(st->device);
+        {
+            std::lock_guard<std::mutex> lock(rc.mu);
+            if (!rc.free_rings.empty()) {
+                st->h_ring = rc.free_rings.back();
+                rc.free_rings.pop_back();
+            }
+        }
+        if (!st->h_ring) CU(cudaMallocHost(reinterpret_cast<void**>(&st->h_ring), RING_PIECE * RING_PIECES));
+        for (int b = 0; b < RING_PIECES; ++b)
+            if (!st->ring_free[b]) CU(cudaEventCreateWithFlags(&st->ring_free[b], cudaEventDisableTiming));
+    }
+    st->chunks_recorded = 0;
+    st->stager = std::thread([st, X, m, chunk_tiles, tiles]() {
+        cudaError_t err = cudaSetDevice(st->device);
+        size_t piece = 0, ci = 0;
+        for (int64_t t0 = 0; t0 < tiles && err == cudaSuccess; t0 += chunk_tiles, ++ci) {
+            const int64_t c0 = t0 * BN;
+            const int64_t mc = std::min<int64_t>(m - c0, chunk_tiles * BN);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(X + c0 * st->d);
+            unsigned char* dst = reinterpret_cast<unsigned char*>(st->d_X + c0 * st->d);
+            const size_t bytes = (size_t)mc * st->d * sizeof(double);
+            for (size_t off = 0; off < bytes && err == cudaSuccess; off += RING_PIECE, ++piece) {
+                const int b = (int)(piece % RING_PIECES);
+                const size_t len = std::min(RING_PIECE, bytes - off);
+                if (piece >= (size_t)RING_PIECES) err = cudaEventSynchronize(st->ring_free[b]);   // DMA out of slot b is done
+                if (err != cudaSuccess) break;
+                std::memcpy(st->h_ring + (size_t)b * RING_PIECE, src + off, len);
+                err = cudaMemcpyAsync(dst + off, st->h_ring + (size_t)b * RING_PIECE, len, cudaMemcpyHostToDevice, st->copy_stream);
+                if (err == cudaSuccess) err = cudaEventRecord(st->ring_free[b], st->copy_stream);
+            }
+            if (err == cudaSuccess) err = cudaEventRecord(st->chunk_ready[ci], st->copy_stream);
+            {
+                std::lock_guard<std::mutex> lock(st->stage_mu);
+                if (err != cudaSuccess) st->stage_rc = (int)err;
+                st->chunks_recorded = err == cudaSuccess ? ci + 1 : (size_t)-1;       // on error: release every waiter
+            }
+            st->stage_cv.notify_all();
+        }
+    });
+    return SKB_OK;
+}
+
+// the calling thread may only make the stream wait for chunk_ready[ci] once the helper thread has RECORDED it
+static int wait_chunk_recorded(skb_state* st, size_t ci) {
+    std::unique_lock<std::mutex> lock(st->stage_mu);
+    st->stage_cv.wait(lock, [&] { return st->chunks_recorded > ci; });
+    if (st->stage_rc != 0)
+        return fail(SKB_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString((cudaError_t)st->stage_rc));
     return SKB_OK;
 }
 
@@ -878,7 +1004,10 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (!mean_only && out->n_var_clamped) CU(cudaMemsetAsync(out->n_var_clamped, 0, sizeof(int64_t), s));
     size_t chunk_index = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++chunk_index) {
-        if (wait_chunk_events) CU(cudaStreamWaitEvent(overlap ? st->aux_stream : s, st->chunk_ready[chunk_index], 0));
+        if (wait_chunk_events) {
+            if ((rc = wait_chunk_recorded(st, chunk_index)) != SKB_OK) return rc;
+            CU(cudaStreamWaitEvent(overlap ? st->aux_stream : s, st->chunk_ready[chunk_index], 0));
+        }
         const int64_t nt = std::min(chunk_tiles, tiles - t0);
         const int64_t c0 = t0 * BN;
         const int64_t mc = std::min<int64_t>(m - c0, nt * BN);
@@ -1008,21 +1137,59 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
 
 }  // extern "C"
 
-// Self-check behind SKB_PRECISION_SPLIT_INT8: score the probe rows of this state with the FP64 DMMA path and with the
-// 6-plane split-integer path (47-bit operands, dot-product distances in K1); when the posterior variances agree to 1e-10
-// of the prior variance and the means to 1e-10 of max(|mean|, y_std) (a tenth of the 1e-9 parity gates; typical: 4e-12
-// and 1e-13) the state contracts 6 planes from now on (21 digit-plane products instead of 28), otherwise all 7.  Runs once per state, on the caller's stream, and waits for it (two 256-candidate passes).
-// SKB_SPLIT_PLANES=6|7 in the environment skips the check.
+// ---------------------------------------------------------------------------------------------------------------
+// 6 or 7 digit planes: an a-priori bound AND a measured self-check must both allow 6
+// ---------------------------------------------------------------------------------------------------------------
+// A-priori model of the 6-plane contraction (P = 6; oracle/split_emulation.py restates the arithmetic, tests/
+// test_split_emulation.py pins this bound against it).  u_i = sum_{j <= i} V_ij k_j is evaluated with
+//   (a) V_ij rounded to sV_i 2^-(8P-1)          : error uniform, variance sV_i^2 2^-(16P-2) / 12, times k_j^2 <= (sK/2)^2
+//   (b) k_j rounded to sK 2^-(8P-1), on top of K1's own arithmetic (6-plane K1: trimmed sqrt / exp and |x|^2 + |t|^2 - 2 x.t
+//       distances, rounding error of r^2 ~ 2^-52 (|x|^2 + |t|^2), |dk / dr^2| <= amplitude): variance
+//       eps_k^2 = sK^2 2^-(16P-2) / 3 + (amplitude 2^-52 R2)^2 with R2 = 2 max_j |t_j|^2, times V_ij^2 <= (sV_i/2)^2
+//   (c) the P - 1 dropped digit-plane products with p + q = P (the next order is 2^-16 of it): balanced digits have
+//       variance 256^2 / 12 each, so a dropped pair contributes variance sV_i^2 sK^2 2^-(16P + 3.17)
+// summed over the i + 1 entries of row i:  s_i^2 = (i + 1) sV_i^2 [sK^2 2^-(16P) (1/12 + (P-1) 2^-3.17 ... )], and since
+// q = sum u_i^2, dq = 2 sum u_i du_i has standard deviation <= 2 sqrt(q) max_i s_i with q <= amplitude + bias.  The bound is
+// LAMBDA = 8 of those standard deviations (a candidate set of 10^6..10^8 rows), relative to the prior variance:
+//   bound_var  = 8 * 2 sqrt(amplitude + bias) * max_i s_i / prior_var
+//   bound_mean = 8 * |alpha|_2 * eps_k            (mean = y_std k.alpha + y_mean, relative to y_std)
+// The worst-case (non-probabilistic) version of the same sum is ~sqrt(n) 10^3 times larger and rejects every state, i.e.
+// carries no information; the probabilistic one overestimates the measured difference by 20x..1000x on the fixtures
+// (bench state: bound 1.4e-10, measured 6e-12).  Six planes need bound <= SPLIT_BOUND_GATE = 2.5e-10 (a quarter of the 1e-9
+// parity gate) for both, AND the measured probe difference <= 1e-10.
+constexpr double SPLIT_BOUND_GATE = 2.5e-10;
+constexpr double SPLIT_PROBE_GATE = 1e-10;
+
+static void split_error_bounds(const skb_state* st, double max_sqrt_i_sV, double alpha_norm2, double max_tn,
+                               double* bound_var, double* bound_mean) {
+    constexpr int P = 6;
+    const double sK = st->k_scale;
+    const double q2 = std::ldexp(1.0, -(16 * P - 2));                 // (2^-(8P-1))^2: squared rounding quantum / scale^2
+    const double r2 = 2.0 * max_tn;
+    const double eps_k2 = sK * sK * q2 / 3.0 + std::pow(std::fabs(st->amplitude) * std::ldexp(1.0, -52) * r2, 2.0);
+    const double per_entry = sK * sK * q2 / 48.0                      // (a): q2 / 12 * (sK / 2)^2, in units of sV_i^2
+                             + eps_k2 / 4.0                           // (b): eps_k^2 * (sV_i / 2)^2
+                             + (P - 1) * sK * sK * std::ldexp(1.0, -16 * P) * 0.1111;   // (c): 2^-3.17
+    const double s_max = max_sqrt_i_sV * std::sqrt(per_entry);
+    const double prior = std::fabs(st->amplitude + st->bias + st->white);
+    const double kdiag = std::fabs(st->amplitude) + std::fabs(st->bias);
+    *bound_var = prior > 0.0 ? 8.0 * 2.0 * std::sqrt(kdiag) * s_max / prior : INFINITY;
+    *bound_mean = 8.0 * alpha_norm2 * std::sqrt(eps_k2);
+}
+
+// Self-check: score the probe rows of this state with the FP64 DMMA path and with the 6-plane split-integer path (47-bit
+// operands, dot-product distances in K1); the posterior variances must agree to 1e-10 of the prior variance and the means
+// to 1e-10 of max(|mean|, y_std) (a tenth of the 1e-9 parity gates; typical: 4e-12 and 1e-13).  Together with the a-priori
+// bound above the state then contracts 6 planes from now on (21 digit-plane products instead of 28), otherwise all 7.  Runs
+// once per state, on the caller's stream, and waits for it (two 256-candidate passes).  There is no override: the only way
+// to 6 planes is through both checks (SKB_PRECISION_SPLIT_INT8_P7 always contracts 7).
 static int decide_split_planes(skb_state* st, cudaStream_t s) {
-    static const int forced = [] { const char* e = getenv("SKB_SPLIT_PLANES"); return e ? atoi(e) : 0; }();
-    if (forced == 6 || forced == 7) {
-        st->split_planes = forced;
-        return SKB_OK;
-    }
     int rc;
     if (!st->d_probe_out &&
-        (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), 4 * PROBE_ROWS * sizeof(double))) != SKB_OK)
+        (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), (4 * PROBE_ROWS + 4) * sizeof(double))) != SKB_OK)
         return rc;
+    split_bound_inputs_kernel<<<1, 256, 0, s>>>(st->d_sV, st->d_alpha_p, st->d_tn, st->n, st->d_probe_out + 4 * PROBE_ROWS);
+    LAUNCHED();
     skb_acq_params prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.xi = 0.01;
@@ -1043,9 +1210,11 @@ static int decide_split_planes(skb_state* st, cudaStream_t s) {
     }
     st->timing = timing;
     if (rc != SKB_OK) return rc;
-    double h[4 * PROBE_ROWS];
+    double h[4 * PROBE_ROWS + 4];
     CU(cudaMemcpyAsync(h, st->d_probe_out, sizeof(h), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    split_error_bounds(st, h[4 * PROBE_ROWS], h[4 * PROBE_ROWS + 1], h[4 * PROBE_ROWS + 2], &st->split_bound_var,
+                       &st->split_bound_mean);
     // variance against the prior variance, mean against max(|mean|, y_std): the scales of the 1e-9 parity gates
     double worst_var = 0.0, worst_mean = 0.0, mean_scale = std::fabs(st->y_std);
     bool finite = true;
@@ -1061,7 +1230,9 @@ static int decide_split_planes(skb_state* st, cudaStream_t s) {
     const double rel_var = var_scale > 0.0 ? worst_var / var_scale : INFINITY;
     const double rel_mean = mean_scale > 0.0 ? worst_mean / mean_scale : INFINITY;
     st->split_probe_diff = std::max(rel_var, rel_mean);
-    st->split_planes = (finite && st->split_probe_diff <= 1e-10) ? 6 : 7;
+    const bool bound_ok = st->split_bound_var <= SPLIT_BOUND_GATE && st->split_bound_mean <= SPLIT_BOUND_GATE;
+    const bool probe_ok = finite && st->split_probe_diff <= SPLIT_PROBE_GATE;
+    st->split_planes = (bound_ok && probe_ok) ? 6 : 7;
     return SKB_OK;
 }
 
@@ -1078,6 +1249,13 @@ int skb_state_split_info(skb_state* st, int32_t* planes, double* probe_rel_diff)
     if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
     if (planes) *planes = st->split_planes;
     if (probe_rel_diff) *probe_rel_diff = st->split_probe_diff;
+    return SKB_OK;
+}
+
+int skb_state_split_bounds(skb_state* st, double* bound_var, double* bound_mean) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    if (bound_var) *bound_var = st->split_bound_var;
+    if (bound_mean) *bound_mean = st->split_bound_mean;
     return SKB_OK;
 }
 
@@ -1136,7 +1314,10 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
     if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
     if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double),
                                                        is_split(params->precision)))) != SKB_OK) return rc;
-    if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) return rc;
+    if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) {
+        stager_join(st);
+        return rc;
+    }
     if ((rc = stage_begin(st)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->n_var_clamped, st->d_clamp, sizeof(int64_t), s)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->mean, dout.mean, m * sizeof(double), s)) != SKB_OK) return rc;
@@ -1152,7 +1333,9 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
             if ((rc = d2h(st, out->first_nan[a], dout.first_nan[a], sizeof(int64_t), s)) != SKB_OK) return rc;
         }
     }
-    return stage_finish(st, s);
+    rc = stage_finish(st, s);
+    stager_join(st);
+    return rc;
 }
 
 int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mean) {
@@ -1518,6 +1701,90 @@ int skb_topk_host(int device, const double* values, int64_t m, int64_t index_off
 }
 
 static int check_device(int device);
+
+int skb_measure_peaks(int device, double* i8_mac_per_clk_sm, double* i8_tops, double* fp64_dmma_tflops) {
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    void* raw = nullptr;
+    if ((rc = pool_alloc(device, &raw, sizeof(long long) + (size_t)sms * 2 * 256 * sizeof(double))) != SKB_OK) return rc;
+    auto body = [&]() -> int {
+        long long* d_cycles = static_cast<long long*>(raw);
+        double* d_out = reinterpret_cast<double*>(d_cycles + 1);
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaFuncSetAttribute(umma_i8_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM));
+        const int repeat = 4096;                       // 16384 MMAs of 128 x 256 x 32 per SM: ~1 ms
+        float best_i8 = 1e30f, best_f64 = 1e30f;
+        long long cycles = 0;
+        for (int r = 0; r < 4; ++r) {                  // first pass warms up, best of the rest
+            CU(cudaEventRecord(e0, 0));
+            umma_i8_rate_kernel<<<sms, 128, MB_SMEM, 0>>>(repeat, d_cycles);
+            LAUNCHED();
+            CU(cudaEventRecord(e1, 0));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (r > 0 && ms < best_i8) {
+                best_i8 = ms;
+                CU(cudaMemcpy(&cycles, d_cycles, sizeof(cycles), cudaMemcpyDeviceToHost));
+            }
+        }
+        for (int r = 0; r < 4; ++r) {
+            CU(cudaEventRecord(e0, 0));
+            dmma_rate_kernel<<<sms * 2, 256, 0, 0>>>(d_out, 1.0000001, 1e-9);
+            LAUNCHED();
+            CU(cudaEventRecord(e1, 0));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (r > 0 && ms < best_f64) best_f64 = ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        const double macs_per_sm = (double)repeat * MB_CHUNKS * MB_M * MB_N * MB_KC;
+        if (i8_mac_per_clk_sm) *i8_mac_per_clk_sm = cycles > 0 ? macs_per_sm / (double)cycles : 0.0;
+        if (i8_tops) *i8_tops = 2.0 * macs_per_sm * sms / (best_i8 * 1e-3) / 1e12;
+        if (fp64_dmma_tflops)
+            *fp64_dmma_tflops = (double)sms * 2 * 8 * MB_DMMA_ITERS * 8 * (8 * 8 * 4 * 2.0) / (best_f64 * 1e-3) / 1e12;
+        return SKB_OK;
+    };
+    rc = body();
+    cudaDeviceSynchronize();
+    pool_free(device, raw);
+    return rc;
+}
+
+int skb_topk_dev(skb_state* st, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
+                 int64_t* topk_idx, int64_t* first_nan, void* stream) {
+    if (!st) return fail(SKB_ERR_INVALID, "state is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (top_k <= 0 || top_k > 4096) return fail(SKB_ERR_INVALID, "top_k %d out of range [1, 4096]", top_k);
+    if ((m > 0 && !values) || !topk_val || !topk_idx) return fail(SKB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(st->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m == 0) {
+        topk_fill_empty_kernel<<<1, 128, 0, s>>>(topk_val, topk_idx, first_nan, top_k);
+        LAUNCHED();
+        return SKB_OK;
+    }
+    const int nblk = (int)std::min<int64_t>((int64_t)st->sm_count * TOPK_BLOCKS_PER_SM, (m + 1023) / 1024);
+    const int64_t slice = (m + nblk - 1) / nblk;
+    int rc;
+    if ((rc = grow(st->device, &st->d_part_v, &st->part_v_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_part_i, &st->part_i_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_part_nan, &st->part_nan_cap, (size_t)nblk)) != SKB_OK) return rc;
+    if ((rc = span_begin(st, 2, s)) != SKB_OK) return rc;
+    topk_partial_kernel<<<nblk, TOPK_THREADS, 0, s>>>(values, m, slice, index_offset, top_k, st->d_part_v, st->d_part_i,
+                                                      st->d_part_nan);
+    LAUNCHED();
+    topk_merge_kernel<<<1, TOPK_THREADS, 0, s>>>(st->d_part_v, st->d_part_i, st->d_part_nan, nblk, top_k, topk_val, topk_idx,
+                                                 first_nan);
+    LAUNCHED();
+    return span_end(st, s);
+}
 
 int skb_topk_merge_records_dev(int device, const void* gathered, int32_t n_records, int32_t n_acq, int32_t top_k,
                                void* merged, void* stream) {

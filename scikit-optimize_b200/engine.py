@@ -250,6 +250,13 @@ class DeviceState:
         _lib.check(_lib.lib().skb_state_split_info(self._h, C.byref(planes), C.byref(diff)))
         return int(planes.value), float(diff.value)
 
+    def split_bounds(self):
+        """(bound_var, bound_mean): the a-priori error bounds of the 6-plane contraction for this state (-1 before the
+        decision ran); 6 planes need both <= 2.5e-10 and the measured probe difference <= 1e-10."""
+        bv, bm = C.c_double(-1.0), C.c_double(-1.0)
+        _lib.check(_lib.lib().skb_state_split_bounds(self._h, C.byref(bv), C.byref(bm)))
+        return float(bv.value), float(bm.value)
+
     def decide_split(self):
         """Run the 6-or-7-plane self-check now (it otherwise runs on the first split-integer call with >= 32768
         candidates); returns split_info()."""
@@ -407,6 +414,46 @@ class DeviceState:
         return rec
 
 
+    def score_grad_tensors(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, precision="fp64", top_k=0,
+                           index_offset=0, stream=None, out=None):
+        """score_grad() for a CUDA float64 tensor resident on this state's GPU; asynchronous on `stream`.  Returns CUDA
+        tensors ('mean', 'std', 'mean_grad', 'std_grad', per acquisition 'values' / 'grad') and, with top_k > 0, 'record':
+        the packed top-k record of the acquisition VALUES (slots in the order of acq_funcs) for the cross-rank arg-min.
+        `out`: a dict returned by an earlier call of the same shape, whose tensors are then overwritten (no allocation)."""
+        import torch
+        if not (X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.is_contiguous()):
+            raise ValueError("X must be a contiguous 2-D float64 CUDA tensor")
+        if X.device.index != self.device or X.shape[1] != self.n_dims:
+            raise ValueError("X is on the wrong device or has the wrong number of features")
+        m, d = X.shape
+        A, k = len(acq_funcs), int(top_k)
+        self._attach_kinv()
+        prm = _acq_params(y_opt, xi, kappa, acq_funcs, 0, resolve_precision(precision, self.host.n_train, m))
+        g = _lib.GradOut()
+        if out is None:
+            new = lambda *shape: torch.empty(*shape, dtype=torch.float64, device=X.device)   # noqa: E731
+            out = {"mean": new(m), "std": new(m), "mean_grad": new(m, d), "std_grad": new(m, d)}
+            for name in acq_funcs:
+                out[name] = {"values": new(m), "grad": new(m, d)}
+            if k > 0:
+                out["record"] = torch.empty(record_words(A, k), dtype=torch.int64, device=X.device)
+        g.mean, g.std = out["mean"].data_ptr(), out["std"].data_ptr()
+        g.mean_grad, g.std_grad = out["mean_grad"].data_ptr(), out["std_grad"].data_ptr()
+        for name in acq_funcs:
+            a = _lib.ACQ_INDEX[name]
+            g.acq[a], g.acq_grad[a] = out[name]["values"].data_ptr(), out[name]["grad"].data_ptr()
+        s = stream if stream is not None else torch.cuda.current_stream(X.device)
+        sp = C.c_void_p(s.cuda_stream)
+        L = _lib.lib()
+        _lib.check(L.skb_score_grad_dev(self._h, X.data_ptr() if m else None, m, C.byref(prm), C.byref(g), sp))
+        if k > 0:
+            base = out["record"].data_ptr()
+            for j, name in enumerate(acq_funcs):
+                _lib.check(L.skb_topk_dev(self._h, out[name]["values"].data_ptr() if m else None, m, int(index_offset), k,
+                                          base + 8 * (j * k), base + 8 * (A * k + j * k), base + 8 * (2 * A * k + j), sp))
+        return out
+
+
 def record_words(n_acq, top_k):
     """8-byte words of a packed top-k record (include/skb.h, skb_topk_merge_records_dev)."""
     return int(n_acq) * (2 * int(top_k) + 1)
@@ -470,6 +517,13 @@ def kernel_gradient_x(kernel, x, X_train, device=None):
         same = np.all(X_train == x, axis=1)
         grad[same] = mirrored[same]
     return grad
+
+
+def measure_peaks(device=0):
+    """{'i8_mac_per_clk_sm', 'i8_tops', 'fp64_dmma_tflops'} measured on the device now (skb_measure_peaks)."""
+    a, b, c = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+    _lib.check(_lib.lib().skb_measure_peaks(int(device), C.byref(a), C.byref(b), C.byref(c)))
+    return {"i8_mac_per_clk_sm": float(a.value), "i8_tops": float(b.value), "fp64_dmma_tflops": float(c.value)}
 
 
 def launch_count():

@@ -160,6 +160,10 @@ class AbiModel:
         _obj(planes).value, _obj(diff).value = 0, -1.0
         return OK
 
+    def skb_state_split_bounds(self, handle, bound_var, bound_mean):
+        _obj(bound_var).value, _obj(bound_mean).value = -1.0, -1.0
+        return OK
+
     def skb_state_decide_split(self, handle):
         return OK
 

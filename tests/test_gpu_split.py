@@ -67,7 +67,7 @@ def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu, precision):
 
 
 def test_split_full_size_c3():
-    n, d, m = 2048, 20, 200_000
+    n, d, m = 2048, 20, 1_000_000            # the headline configuration at its full candidate count
     st = orc.make_synthetic_state(n, d, noise=1e-4, seed=0)
     rng = np.random.RandomState(123)
     Xc = rng.rand(m, d)
@@ -76,6 +76,7 @@ def test_split_full_size_c3():
     dev = engine.DeviceState(host_state_from_oracle_state(st))
     res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=20, precision="split_int8")
     ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=20, precision="fp64")
+    assert dev.split_info()[0] == 6 and max(dev.split_bounds()) <= 2.5e-10       # bound AND probe let this state take 6 planes
     sample = rng.choice(m, 1000, replace=False)
     mu, sd = orc.predict(st, Xc[sample], return_std=True)
     assert np.max(np.abs(res["mean"][sample] - mu)) <= 1e-9 * max(np.max(np.abs(mu)), st.y_std)
@@ -148,7 +149,10 @@ def test_split_extreme_scales():
         Xc = rng.rand(m, d)
         Xc[:5] = X[:5]
         dev = gpr.device_state()
-        print("self-check:", dev.decide_split())
+        planes, probe = dev.decide_split()
+        bv, bm = dev.split_bounds()
+        print("self-check: planes %d, probe %.2e, a-priori bounds var %.2e mean %.2e" % (planes, probe, bv, bm))
+        assert planes == (6 if (max(bv, bm) <= 2.5e-10 and probe <= 1e-10) else 7)
         y_opt = float(y.min())
         res = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="split_int8")
         ref = dev.score(Xc, y_opt=y_opt, acq_funcs=ACQS, top_k=5, precision="fp64")
@@ -188,6 +192,8 @@ def test_split_plane_self_check():
     e_auto = np.max(np.abs(auto["std"] ** 2 - ref["std"] ** 2)) / scale
     print("planes=%d probe diff=%.2e; vs fp64: 7 planes %.2e, auto %.2e" % (planes, diff, e7, e_auto))
     assert planes == 6 and 0.0 <= diff <= 1e-10                     # this well-conditioned state takes the 6-plane path
+    bv, bm = dev.split_bounds()
+    assert e_auto <= bv <= 2.5e-10 and 0.0 <= bm <= 2.5e-10         # ... and the a-priori bound covers what was measured
     assert e7 <= 1e-12 and e_auto <= 1e-10 and e7 < e_auto
     ref_big = dev.score(Xbig, y_opt=y_opt, acq_funcs=("EI",), top_k=8, precision="fp64")
     assert np.array_equal(auto["EI"]["topk_idx"], ref_big["EI"]["topk_idx"])
@@ -195,3 +201,37 @@ def test_split_plane_self_check():
     mu, sd = orc.predict(st, Xc[:500], return_std=True)
     assert np.max(np.abs(auto["std"][:500] ** 2 - sd ** 2)) <= 1e-9 * scale
     dev.close()
+
+
+@pytest.mark.parametrize("case", ["cooked_branin_gaussian", "clustered_noise1e-10"])
+def test_split_falls_back_to_seven_planes(case):
+    """States whose a-priori bound does not allow 47-bit operands MUST contract 7 planes, whatever the probe measured:
+    the cooked Branin fixture (cond(K) = 7.5e8 after a real fit) and clustered points with noise 1e-10 (rows of L_inv scaled
+    like 1e5).  There is no environment override (SKB_SPLIT_PLANES is gone), so split_info() is the decision."""
+    import os
+    os.environ["SKB_SPLIT_PLANES"] = "6"                # the round-1 override: must be ignored now
+    try:
+        if case == "cooked_branin_gaussian":
+            rec, meta, est = load(case)
+            _, _, st = load_state(case)
+            dev = engine.DeviceState.from_estimator(est)
+            Xc = rec["Xc"]
+            y_opt = float(rec["y_opt"])
+        else:
+            rng = np.random.RandomState(4)
+            st = orc.make_synthetic_state(320, 4, noise=1e-10, seed=0)        # 320 points in [0, 1]^4: near-duplicates
+            dev = engine.DeviceState(host_state_from_oracle_state(st))
+            Xc = rng.rand(2000, 4)
+            y_opt = float(st.meta["y"].min())
+        planes, probe = dev.decide_split()
+        bv, bm = dev.split_bounds()
+        print("%s: planes %d, probe %.2e, bounds var %.2e mean %.2e" % (case, planes, probe, bv, bm))
+        assert max(bv, bm) > 2.5e-10
+        assert planes == 7
+        res = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=4, precision="split_int8")
+        p7 = dev.score(Xc, y_opt=y_opt, acq_funcs=("EI",), top_k=4, precision="split_int8_p7")
+        np.testing.assert_array_equal(res["std"], p7["std"])              # what ran IS the 7-plane contraction
+        np.testing.assert_array_equal(res["EI"]["values"], p7["EI"]["values"])
+        dev.close()
+    finally:
+        os.environ.pop("SKB_SPLIT_PLANES", None)

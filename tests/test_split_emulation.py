@@ -72,3 +72,40 @@ def test_six_plane_contraction_meets_the_parity_gate_with_margin():
             U = se.split_matmul(V, K, planes=planes, k_scale=k_scale)
             err[planes] = np.max(np.abs(np.sum(U * U, axis=0) - q_exact)) / st.prior_var
         assert err[6] <= 1e-10 and err[7] <= 1e-12 and err[7] < err[6]
+
+
+def _bound_case(st, m=160, seed=5):
+    from scipy.linalg import solve_triangular
+    V = solve_triangular(st.L, np.eye(st.n), lower=True)
+    rng = np.random.RandomState(seed)
+    lo, hi = st.X_train.min(0), st.X_train.max(0)
+    Xc = lo + (hi - lo) * rng.rand(m, st.d)
+    Xc[:m // 2] = st.X_train[rng.randint(0, st.n, m // 2)]        # at training points: prior - q cancels almost completely
+    K = orc.kernel_cross(st, Xc).T
+    q = np.sum((V @ K) ** 2, axis=0)
+    sK = se.pow2_scale(abs(st.amplitude) + abs(st.bias))
+    U6 = se.split_matmul(V, K, planes=6, k_scale=sK)
+    measured = float(np.max(np.abs(np.sum(U6 * U6, axis=0) - q)) / st.prior_var)
+    bound_var, bound_mean = se.apriori_bounds(V, st.alpha, st.X_train / st.length_scale, st.amplitude, st.bias, st.white)
+    return measured, bound_var, bound_mean
+
+
+def test_apriori_bound_covers_the_emulated_six_plane_error():
+    """The a-priori bound behind the 6-plane decision (csrc/skb.cu split_error_bounds, restated in
+    oracle/split_emulation.apriori_bounds) is an upper bound of what the exact-integer emulation of the 6-plane contraction
+    measures, on well- and ill-conditioned states; it lets the bench-like states through (<= 2.5e-10) and sends the
+    ill-conditioned ones (cooked Branin after a real fit, noise 1e-10 on clustered points) to 7 planes."""
+    from tests import _golden
+    allowed, refused = [], []
+    for name in ("matern25_n256_d10", "rbf_aniso", "matern25_const_noise", "cooked_branin_gaussian"):
+        _, _, st = _golden.load_state(name)
+        measured, bv, bm = _bound_case(st)
+        assert measured <= bv, (name, measured, bv)
+        (allowed if max(bv, bm) <= se.SPLIT_BOUND_GATE else refused).append(name)
+    for n, d, noise in ((384, 8, 1e-4), (320, 4, 1e-10)):
+        st = orc.make_synthetic_state(n, d, noise=noise, seed=0)
+        measured, bv, bm = _bound_case(st)
+        assert measured <= bv, (n, d, noise, measured, bv)
+        (allowed if max(bv, bm) <= se.SPLIT_BOUND_GATE else refused).append((n, d, noise))
+    assert "matern25_n256_d10" in allowed and (384, 8, 1e-4) in allowed
+    assert "cooked_branin_gaussian" in refused and (320, 4, 1e-10) in refused
