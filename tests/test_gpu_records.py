@@ -12,7 +12,8 @@ def _records(rng, world, A, k, m_per_rank, ties=True):
     if ties:
         for a in range(A):
             vals[0][a, 3] = vals[-1][a, 5] = -7.0            # the same minimum on two ranks: lowest global index wins
-        vals[1][0, 2] = np.nan
+        r_nan = next(r for r in range(1, len(vals)) if vals[r].shape[1] > 2)   # a non-empty rank other than 0
+        vals[r_nan][0, 2] = np.nan
     recs, offs = [], np.concatenate([[0], np.cumsum(m_per_rank)])
     for r, v in enumerate(vals):
         rec = np.empty(A * (2 * k + 1), dtype=np.int64)
