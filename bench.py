@@ -4,14 +4,24 @@
 Workload (BASELINE.json configs[2]): synthetic GP, n_train=2048, d=20, Matern-5/2 with fixed
 hyper-parameters, 1,000,000 candidates per GPU, FP64.  A step = one pass of the hot path over the candidate set:
 posterior mean/std, -EI, and the top-k (value, index) pairs; with N GPUs every rank owns its own 1M candidates
-(weak scaling, GP state replicated) and the only collective is the all-gather of the per-rank top-k (NCCL).
+(weak scaling, GP state replicated) and the only collective is ONE all-gather of a packed per-rank top-k record (NCCL).
 
   value : evals/s, candidates resident in HBM (device entry point, CUDA-event timed, max over ranks), with the precision
-          the product picks for this workload (engine.resolve_precision("auto"): split-integer contraction on tcgen05)
-  e2e   : evals/s through the host entry point (pinned host candidates -> H2D -> kernels -> D2H of the top-k)
+          the product picks for this workload (engine.resolve_precision("auto"): split-integer contraction on tcgen05);
+          value_fp64 / value_p7: the strict FP64 DMMA path and the 7-plane split, timed in the same run
+  e2e   : evals/s through the host entry point (pinned host candidates -> H2D -> kernels -> D2H of the top-k);
+          e2e_pageable: the same call on a plain NumPy array (pageable memory, staged by skb_score_host)
+  measured_peaks : tcgen05 kind::i8 issue rate and FP64 DMMA rate measured on this GPU in this run (skb_measure_peaks):
+          the denominators of every roofline entry
   roofline : dominant kernel of the headline path (K2o, tcgen05 kind::i8 digit-plane contraction) - algorithmic int8
-          ops / its CUDA-event time against 2 x the measured bf16 peak; the pure FP64 DMMA path (K2) is timed in the same
-          run and reported beside it (fp64_dmma_path) against the measured FP64 tensor peak
+          ops / its CUDA-event time against the measured int8 peak (burst clock) and against the peak at the clock sampled
+          during the timed region, plus frac_fp64_algorithmic; fp64_dmma_path.roofline: K2 on DMMA
+  c4_grad : BASELINE.json configs[3] (n_train=4096, d=50, EI + LCB with gradients, 10^6 candidates per rank), K2d / K3g
+          rooflines, parity_sample with gradients against the oracle's loop of single-point calls
+  strong : the 10^6 candidates of configs[2] split over the N ranks (one tell()-equivalent), time per tell
+  c5_cl : BASELINE.json configs[4]: ask(n_points=8, 'cl_min') at n_train=1024, d=10, 10^6 candidates per liar step
+  multi_gpu_check : at N > 1, true iff every merged top-k record of this run equals, bit for bit, the top-k of the
+          concatenated per-rank value vectors (computed with torch's stable sort, not with the product's kernels)
   parity_sample : this run's device state against the checker (oracle on the product's fitted state), with the
           reference's own re-ordering jitter beside it
   cpu_baseline : the CPU oracle (a port of the reference's NumPy/SciPy path) on a bounded sample, this host
@@ -34,7 +44,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TRAIN, N_DIMS, M_PER_GPU, TOP_K = 2048, 20, 1_000_000, 16
-FP64_PEAK_TFLOPS = 37.0   # measured DMMA issue peak on this pool's B200 (profiles/r01_fp64_peaks.txt); cuBLAS DGEMM: 35.5
 
 def split_products(planes):
     """Digit-plane products the split-integer contraction keeps (p + q <= planes - 1): 28 for 7 planes, 21 for 6."""
@@ -56,14 +65,6 @@ def int8_ops_k2(n, planes):
     """int8 operations (2 per MAC) the split-integer scheme needs per candidate: 28 (7 planes) or 21 (6 planes) plane
     products over the lower-triangular n(n+1)/2 entries of L_inv."""
     return split_products(planes) * n * (n + 1)
-
-
-def measured_bf16_peak():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst)"
-    except Exception:
-        return 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
 def make_problem(n, d, seed=0):
@@ -383,6 +384,264 @@ def emit(line):
         os.write(_JSON_FD[0], data)
 
 
+class Ctx:
+    """What every leg needs: ranks, the CUDA stream the product launches on, barrier + max-over-ranks helpers."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.torch, self.dist = torch, dist
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def rank_max(self, *xs):
+        t = self.torch.tensor([float(x) for x in xs], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        out = [float(v) for v in t.cpu()]
+        return out[0] if len(out) == 1 else out
+
+    def rank_all(self, flag):
+        """True on every rank iff `flag` holds on every rank."""
+        return self.rank_max(0.0 if flag else 1.0) == 0.0
+
+    def timed(self, fn, steps, warmup):
+        """CUDA-event time (ms) of `steps` calls of fn on the launching stream, barrier + synchronize on both sides."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        last = None
+        for _ in range(steps):
+            last = fn()
+        b.record(self.stream)
+        self.barrier()
+        return a.elapsed_time(b), last
+
+
+def expected_record(values_by_acq, k):
+    """The top-k of the CONCATENATED candidate set, computed independently of the product's kernels: torch's stable
+    sort (ties -> lowest global index, NaNs last and excluded), packed in the record layout of include/skb.h."""
+    import torch
+    A = len(values_by_acq)
+    rec = torch.empty(A * (2 * k + 1), dtype=torch.int64, device=values_by_acq[0].device)
+    for j, v in enumerate(values_by_acq):
+        sv, si = torch.sort(v, stable=True)
+        nan = torch.isnan(v)
+        good = int((~nan).sum().item())
+        kk = min(k, good)
+        tv = torch.full((k,), float("nan"), dtype=torch.float64, device=v.device)
+        ti = torch.full((k,), -1, dtype=torch.int64, device=v.device)
+        tv[:kk], ti[:kk] = sv[:kk], si[:kk]
+        rec[j * k:(j + 1) * k] = tv.view(torch.int64)
+        rec[A * k + j * k:A * k + (j + 1) * k] = ti
+        rec[2 * A * k + j] = int(torch.nonzero(nan)[0].item()) if bool(nan.any()) else -1
+    return rec
+
+
+def gather_values(ctx, v):
+    """All ranks' value vectors back to back (equal shard sizes)."""
+    if ctx.world == 1:
+        return v
+    out = ctx.torch.empty(ctx.world * v.numel(), dtype=v.dtype, device=v.device)
+    ctx.dist.all_gather_into_tensor(out, v.contiguous())
+    return out
+
+
+def leg_c4_grad(ctx, peaks):
+    """BASELINE.json configs[3]: posterior + EI/LCB WITH input gradients at n_train=4096, d=50, `--m-grad` candidates per
+    rank (10^6 -> 8 M at N=8), sharded with one packed top-k record exchanged per step (gpr.py:345-362,
+    acquisition.py:305-319 evaluated for every candidate at once)."""
+    import torch
+    from skopt_b200 import engine
+    from skopt_b200.distributed import exchange_records
+    args, rank, world = ctx.args, ctx.rank, ctx.world
+    n, d, m, acqs = 4096, 50, args.m_grad, ("EI", "LCB")
+    t0 = time.perf_counter()
+    gpr, y_opt = make_problem(n, d, seed=1)
+    dev = gpr.device_state(ctx.local_rank)
+    X = torch.from_numpy(np.random.RandomState(2000 + rank).rand(m, d)).cuda()
+    setup_s = time.perf_counter() - t0
+    res = {"config": "BASELINE.json configs[3]: n_train=%d, d=%d, EI + LCB with gradients, %d candidates per GPU, "
+                     "NCCL arg-min (one packed top-%d record per rank)" % (n, d, m, TOP_K),
+           "n_train": n, "n_dims": d, "candidates_per_gpu": m, "setup_s": setup_s}
+    steps, warm = max(2, min(args.steps, 3)), 1
+    buf = {"out": None}
+    ok_all, merged_by_prec = True, {}
+    for prec in (engine.resolve_precision("auto", n, m), "fp64"):
+        if prec in merged_by_prec:
+            continue
+
+        def step():
+            buf["out"] = dev.score_grad_tensors(X, y_opt=y_opt, acq_funcs=acqs, xi=0.01, kappa=1.96, precision=prec,
+                                                top_k=TOP_K, index_offset=rank * m, out=buf["out"])
+            return exchange_records(buf["out"]["record"], len(acqs), TOP_K)
+
+        for _ in range(warm + 1):
+            step()
+        dev.set_timing(True)
+        dev.get_timing()
+        ms, merged = ctx.timed(step, steps, 0)
+        tm = dev.get_timing()
+        dev.set_timing(False)
+        ms = ctx.rank_max(ms)
+        merged_by_prec[prec] = merged
+        # multi-GPU self-check on this leg's records: merged top-k == top-k of the concatenated value vectors, bit for bit
+        exp = expected_record([gather_values(ctx, buf["out"][a]["values"]) for a in acqs], TOP_K)
+        ok = ctx.rank_all(bool(torch.equal(exp, merged)))
+        ok_all = ok_all and ok
+        per = ms / steps
+        k2_ms, k2_n = tm["k2"]
+        g_ms, g_n = tm["grad"]
+        k1_ms, _ = tm["k1"]
+        entry = {"value": world * m / (per / 1e3), "unit": "evals/s", "ms_per_step": per, "steps": steps,
+                 "topk_equals_concatenated_topk": ok,
+                 "k1_share": k1_ms / ms, "k2d_share": k2_ms / ms, "k3g_share": g_ms / ms}
+        cand_per = m * steps / max(k2_n, 1)
+        if prec == "fp64":
+            ach = 2.0 * n * n * cand_per / (k2_ms / max(k2_n, 1) / 1e3) / 1e12
+            entry["roofline_k2d"] = {"bound": "tensor", "kernel": "trmm_kernel<1> (dense W = K_inv . K_trans^T on DMMA)",
+                                     "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                                     "frac": ach / peaks["fp64_dmma_tflops"], "algorithmic_flops_per_candidate": 2 * n * n,
+                                     "candidates_per_launch": cand_per, "avg_launch_ms": k2_ms / max(k2_n, 1)}
+        else:
+            ops = 2.0 * split_products(7) * n * n
+            ach = ops * cand_per / (k2_ms / max(k2_n, 1) / 1e3) / 1e12
+            entry["roofline_k2d"] = {"bound": "tensor", "kernel": "ozaki_trmm_kernel<1, 7> (dense W = K_inv . K_trans^T: "
+                                     "tcgen05.mma kind::i8 over 7 digit planes, FP64 recombination)",
+                                     "achieved": ach, "peak": peaks["i8_tops"], "unit": "TOP/s", "frac": ach / peaks["i8_tops"],
+                                     "algorithmic_ops_per_candidate": ops, "candidates_per_launch": cand_per,
+                                     "avg_launch_ms": k2_ms / max(k2_n, 1),
+                                     "fp64_equivalent_tflops": 2.0 * n * n * cand_per / (k2_ms / max(k2_n, 1) / 1e3) / 1e12}
+            entry["roofline_k2d"]["frac_fp64_algorithmic"] = entry["roofline_k2d"]["fp64_equivalent_tflops"] / peaks["fp64_dmma_tflops"]
+        fl_g = n * (3 * d + 12) + 6 * n * d + 2 * n + 60 * d
+        ach_g = fl_g * (m * steps / max(g_n, 1)) / (g_ms / max(g_n, 1) / 1e3) / 1e12
+        entry["roofline_k3g"] = {"bound": "tensor", "kernel": "grad_contract_kernel (K3g: FP64 pipe, DFMA + DMMA)",
+                                 "achieved": ach_g, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                                 "frac": ach_g / peaks["fp64_dmma_tflops"], "algorithmic_flops_per_candidate": fl_g,
+                                 "avg_launch_ms": g_ms / max(g_n, 1)}
+        res[prec] = entry
+    headline = engine.resolve_precision("auto", n, m)
+    res["value"], res["unit"], res["precision"] = res[headline]["value"], "evals/s", headline
+    res["multi_gpu_check"] = ok_all
+    rec = engine.unpack_record(merged_by_prec[headline], acqs, TOP_K)
+    res["argmin_index"] = {a: int(rec[a]["topk_idx"][0]) for a in acqs}
+    if "fp64" in merged_by_prec and headline != "fp64":
+        rec64 = engine.unpack_record(merged_by_prec["fp64"], acqs, TOP_K)
+        res["argmin_equals_fp64_path"] = all(int(rec[a]["topk_idx"][0]) == int(rec64[a]["topk_idx"][0]) for a in acqs)
+    if world == 1 and not args.no_cpu_baseline:
+        # gradients against the loop of single-point reference calls (oracle), 48 candidates of this run's matrix
+        from oracle import gp_oracle as orc
+        st = orc.state_from_estimator(gpr)
+        Xs = X[:48].cpu().numpy()
+        mu, sd, gm, gs = orc.predict_with_grads_batched(st, Xs)
+        par = {"candidates": 48, "gate": "1e-9 mean / var / mean_grad, 1e-8 std_grad (tests/test_gpu_parity.py)"}
+        for prec in merged_by_prec:
+            r = dev.score_grad(Xs, y_opt=y_opt, acq_funcs=acqs, xi=0.01, kappa=1.96, precision=prec)
+            ei, gei = zip(*[orc.gaussian_acquisition(Xs[i:i + 1], st, y_opt, "EI", return_grad=True,
+                                                     acq_func_kwargs=dict(xi=0.01, kappa=1.96)) for i in range(8)])
+            par[prec] = {"mean": float(np.max(np.abs(r["mean"] - mu)) / max(np.max(np.abs(mu)), st.y_std)),
+                         "var": float(np.max(np.abs(r["std"] ** 2 - sd ** 2)) / (st.prior_var * st.y_std ** 2)),
+                         "mean_grad": float(np.max(np.abs(r["mean_grad"] - gm)) / np.max(np.abs(gm))),
+                         "std_grad": float(np.max(np.abs(r["std_grad"] - gs)) / np.max(np.abs(gs))),
+                         "ei_grad": float(np.max(np.abs(r["EI"]["grad"][:8] - np.asarray(gei).reshape(8, -1))) /
+                                          max(np.max(np.abs(np.asarray(gei))), 1e-300))}
+        res["parity_sample"] = par
+    dev.close()
+    del buf["out"], X
+    torch.cuda.empty_cache()
+    return res
+
+
+def leg_strong(ctx, gpr, dev, y_opt, ms_one_gpu_step):
+    """Strong scaling of ONE tell()-equivalent: the 10^6 candidates of configs[2] split over the N ranks
+    (optimizer.py:552-564), one packed record exchanged; plus the multi-GPU self-check on that very set."""
+    import torch
+    from skopt_b200 import engine
+    from skopt_b200.distributed import exchange_records, shard_bounds
+    args, rank, world = ctx.args, ctx.rank, ctx.world
+    m_total = args.m
+    b = shard_bounds(m_total, world)
+    lo, hi = b[rank], b[rank + 1]
+    Xfull = np.random.RandomState(4242).rand(m_total, N_DIMS)            # the same set on every rank; rank r owns [lo, hi)
+    X = torch.from_numpy(Xfull[lo:hi]).cuda()
+    del Xfull
+    prec = engine.resolve_precision("auto", N_TRAIN, m_total)             # resolved on the GLOBAL size
+    if prec == "split_int8":
+        dev.decide_split()
+    vals = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+
+    def step():
+        rec = dev.score_record(X, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K, index_offset=lo,
+                               precision=prec, values_out={"EI": vals})
+        return exchange_records(rec, 1, TOP_K)
+
+    ms, merged = ctx.timed(step, max(args.steps, 5), 3)
+    ms = ctx.rank_max(ms) / max(args.steps, 5)
+    check = None
+    if m_total % world == 0:
+        exp = expected_record([gather_values(ctx, vals)], TOP_K)
+        check = ctx.rank_all(bool(torch.equal(exp, merged)))
+    rec = engine.unpack_record(merged, ("EI",), TOP_K)
+    return {"config": "configs[2] as one tell(): %d candidates in total, split over %d rank(s); n_train=%d, d=%d, EI, top-%d"
+                      % (m_total, world, N_TRAIN, N_DIMS, TOP_K),
+            "ms_per_tell": ms, "value": m_total / (ms / 1e3), "unit": "evals/s", "scaling": "strong",
+            "candidates_per_rank": hi - lo, "precision": prec,
+            "speedup_vs_one_gpu_step": (ms_one_gpu_step / ms) if ms_one_gpu_step else None,
+            "one_gpu_ms": ms_one_gpu_step,
+            "topk_equals_concatenated_topk": check, "argmin_index": int(rec["EI"]["topk_idx"][0])}
+
+
+def leg_c5_cl(ctx):
+    """BASELINE.json configs[4]: Optimizer.ask(n_points=8, strategy='cl_min') at n_train=1024, d=10, 10^6 candidates per
+    liar step (optimizer.py:388-417: 8 sequential {lie -> refit -> score}); every liar step's candidates are sharded
+    over the N ranks (one posterior replica per GPU, liar-updated together), fit objective on the GPU."""
+    import warnings
+    from skopt_b200 import Optimizer
+    args, world = ctx.args, ctx.world
+    n, d = 1024, 10
+    rng = np.random.RandomState(0)
+    X = rng.rand(n, d)
+    y = np.sin(X.dot(rng.randn(d))) + 0.1 * rng.randn(n)
+    out = {"config": "BASELINE.json configs[4]: ask(n_points=8, 'cl_min'), n_train=%d, d=%d, %d candidates per liar step "
+                     "sharded over %d GPU(s), Matern-5/2 ARD + White refitted on every lie" % (n, d, args.m_cl, world),
+           "n_gpus": world}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for mode in getattr(Optimizer, "LIAR_UPDATES", ("refit",)):
+            kw = dict(n_points=args.m_cl, fit_device="gpu", shard_group=world > 1)
+            if mode != "refit":
+                kw["liar_update"] = mode
+            opt = Optimizer([(0.0, 1.0)] * d, "GP", n_initial_points=n, acq_func="EI", acq_optimizer="sampling",
+                            acq_optimizer_kwargs=kw, random_state=1)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            opt.tell(X.tolist(), y.tolist())
+            ctx.barrier()
+            t_tell = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            batch = opt.ask(n_points=8, strategy="cl_min")
+            ctx.barrier()
+            t_ask = time.perf_counter() - t0
+            t_tell, t_ask = ctx.rank_max(t_tell, t_ask)
+            same = True
+            if world > 1:
+                pts = [None] * world
+                ctx.dist.all_gather_object(pts, batch)
+                same = all(p == pts[0] for p in pts)
+            out[mode] = {"ask8_s": t_ask, "first_tell_s": t_tell, "ranks_agree_on_batch": same,
+                         "scoring_s_per_liar_step": float(np.median(opt.scoring_times_[1:] or opt.scoring_times_)),
+                         "batch_first_point": [float(v) for v in batch[0][:3]]}
+    out["value"], out["unit"] = out["refit"]["ask8_s"], "s per ask(n_points=8)"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,11 +649,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--m", type=int, default=M_PER_GPU, help="candidates per GPU per step")
+    ap.add_argument("--m-grad", type=int, default=1_000_000, help="candidates per GPU of the configs[3] gradient leg")
+    ap.add_argument("--m-cl", type=int, default=1_000_000, help="candidates per liar step of the configs[4] leg")
     ap.add_argument("--ref-sample", type=int, default=256, help="candidates per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="candidates of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ask", action="store_true", help="skip the ask() p50 latency leg")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs: c4,strong,c5,pageable (default: all)")
     args = ap.parse_args()
+    legs = {"c4", "strong", "c5", "pageable"} if args.legs == "all" else {x for x in args.legs.split(",") if x}
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -409,7 +672,7 @@ def main():
     import torch.distributed as dist
     import skopt_b200
     from skopt_b200 import engine
-    from skopt_b200.distributed import merge_topk_allgather
+    from skopt_b200.distributed import exchange_records
     from skopt_b200.learning.gaussian_process import gpr as gpr_mod
 
     if not torch.cuda.is_available():
@@ -420,35 +683,35 @@ def main():
         # stdout carries exactly one JSON line: NCCL's banner / debug lines ("NCCL version ...") go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Ctx(args, rank, world, local_rank)
+
+    # roofline denominators measured on THIS device now (tcgen05 kind::i8 issue rate, DMMA rate): skb_measure_peaks
+    peaks = engine.measure_peaks(local_rank)
 
     gpr, y_opt = make_problem(N_TRAIN, N_DIMS)
     dev = gpr.device_state(local_rank)
     m = args.m
     offset = rank * m
-    Xc_host = torch.from_numpy(np.random.RandomState(1000 + rank).rand(m, N_DIMS)).pin_memory()
+    Xc_np = np.random.RandomState(1000 + rank).rand(m, N_DIMS)           # pageable, what a NumPy user passes
+    Xc_host = torch.from_numpy(Xc_np).pin_memory()
     Xc_dev = Xc_host.cuda(non_blocking=True)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    stream = ctx.stream
+    barrier = ctx.barrier
+    vals_dev = torch.empty(m, dtype=torch.float64, device="cuda")
 
-    def barrier():
+    def step_dev(precision="auto", keep_values=False):
+        rec = dev.score_record(Xc_dev, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
+                               index_offset=offset, precision=precision, values_out={"EI": vals_dev} if keep_values else None)
+        return exchange_records(rec, 1, TOP_K)
+
+    def step_host(precision="auto", X=None):
+        res = dev.score(Xc_host.numpy() if X is None else X, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96,
+                        top_k=TOP_K, index_offset=offset, want_posterior=False, want_values=False, precision=precision)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_dev(precision="auto"):
-        res = dev.score_tensors(Xc_dev, y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
-                                index_offset=offset, precision=precision)
-        return merge_topk_allgather(res["EI"]["topk_val"], res["EI"]["topk_idx"], TOP_K) if world > 1 else \
-            (res["EI"]["topk_val"], res["EI"]["topk_idx"])
-
-    def step_host(precision="auto"):
-        res = dev.score(Xc_host.numpy(), y_opt=y_opt, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=TOP_K,
-                        index_offset=offset, want_posterior=False, want_values=False, precision=precision)
-        if world > 1:
-            v = torch.from_numpy(res["EI"]["topk_val"]).cuda()
-            i = torch.from_numpy(res["EI"]["topk_idx"]).cuda()
-            v, i = merge_topk_allgather(v, i, TOP_K)
-            return v.cpu(), i.cpu()
+            rec = np.concatenate([res["EI"]["topk_val"].view(np.int64), res["EI"]["topk_idx"],
+                                  np.asarray([res["EI"]["first_nan"]], dtype=np.int64)])
+            return exchange_records(torch.from_numpy(rec).cuda(), 1, TOP_K).cpu()
         return res["EI"]["topk_val"], res["EI"]["topk_idx"]
 
     # ---------------------------------------------------------------- device-resident throughput
@@ -469,34 +732,56 @@ def main():
         n_launch = engine.launch_count() - l0
         tm = dev.get_timing()
         dev.set_timing(False)
-        return a.elapsed_time(b), tm, n_launch, clk.summary(), int(best_[1][0].item())
+        return a.elapsed_time(b), tm, n_launch, clk.summary(), int(best_[TOP_K].item())
 
-    def timed_host(precision):
+    def timed_host(precision, X=None):
         for _ in range(2):
-            step_host(precision)
+            step_host(precision, X)
         barrier()
         t0_ = time.perf_counter()
         for _ in range(args.steps):
-            step_host(precision)
+            step_host(precision, X)
         barrier()
         return time.perf_counter() - t0_
 
     headline = engine.resolve_precision("auto", N_TRAIN, m)          # what the product picks for this workload
     ms_total, timing, launches, clocks_summary, argmin_idx = timed_dev(headline)
     e2e_s = timed_host(headline)
+    e2e_pageable_s = timed_host(headline, Xc_np) if "pageable" in legs else None
     planes, probe_diff = dev.split_info() if headline == "split_int8" else (0, -1.0)
-    # single-GPU context only (under torchrun every rank would have to take this branch together)
-    ms_p7 = timed_dev("split_int8_p7")[0] if headline == "split_int8" and planes == 6 and world == 1 else None
+    bound_var, bound_mean = dev.split_bounds() if headline == "split_int8" else (-1.0, -1.0)
+    # every rank takes these branches together (the merge is a collective)
+    planes_all = int(ctx.rank_max(planes))
+    ms_p7 = timed_dev("split_int8_p7")[0] if headline == "split_int8" and planes_all == 6 else None
     ms_fp64, timing_fp64, _, _, argmin_fp64 = timed_dev("fp64") if headline != "fp64" else (ms_total, timing, 0, None, argmin_idx)
     e2e_fp64_s = timed_host("fp64") if headline != "fp64" else e2e_s
 
-    t = torch.tensor([ms_total, e2e_s * 1e3, ms_fp64, e2e_fp64_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, ms_fp64, e2e_fp64_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_total, e2e_ms, ms_fp64, e2e_fp64_ms = ctx.rank_max(ms_total, e2e_s * 1e3, ms_fp64, e2e_fp64_s * 1e3)
+    ms_p7 = ctx.rank_max(ms_p7) if ms_p7 is not None else None
+    e2e_pageable_ms = ctx.rank_max(e2e_pageable_s * 1e3) if e2e_pageable_s is not None else None
     ms_per_step = ms_total / args.steps
     value = world * m / (ms_per_step / 1e3)
     e2e_value = world * m * args.steps / (e2e_ms / 1e3)
+
+    # multi-GPU self-check (every N > 1): the merged top-k must equal the top-k of the CONCATENATED per-rank value vectors
+    multi_gpu_check = None
+    if world > 1:
+        merged = step_dev(headline, keep_values=True)
+        exp = expected_record([gather_values(ctx, vals_dev)], TOP_K)
+        multi_gpu_check = ctx.rank_all(bool(torch.equal(exp, merged)))
+
+    extra = {}
+    if "strong" in legs:
+        # one GPU scoring the whole 10^6 set = this run's headline step when --m is the total
+        extra["strong"] = leg_strong(ctx, gpr, dev, y_opt, ms_per_step)
+        if extra["strong"]["topk_equals_concatenated_topk"] is not None and world > 1:
+            multi_gpu_check = bool(multi_gpu_check) and extra["strong"]["topk_equals_concatenated_topk"]
+    if "c4" in legs:
+        extra["c4_grad"] = leg_c4_grad(ctx, peaks)
+        if world > 1:
+            multi_gpu_check = bool(multi_gpu_check) and extra["c4_grad"]["multi_gpu_check"]
+    if "c5" in legs:
+        extra["c5_cl"] = leg_c5_cl(ctx)
 
     if rank == 0:
         def k2_stats(tm, total_ms):
@@ -505,55 +790,60 @@ def main():
             avg = k2_ms_ / max(k2_n, 1)
             return cand, avg, k2_ms_ / total_ms, tm["k1"][0] / total_ms
 
+        def traffic_from(profile, cand):
+            path = os.path.join(ROOT, "profiles", profile)
+            if not os.path.exists(path):
+                return None, None
+            rec = json.load(open(path))
+            return rec.get("dram_bytes_per_candidate", 0.0) * cand, rec.get("source")
+
+        run_clock = clocks_summary.get("sm_mhz_mean") or clocks_summary.get("sm_mhz") or 1965.0
         cand_per_k2, k2_avg_ms, k2_share, k1_share = k2_stats(timing, ms_total)
         fp64_equiv = flops_k2(N_TRAIN) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
         if headline == "split_int8":
-            bf16_peak, bf16_src = measured_bf16_peak()
-            peak = 2.0 * bf16_peak
+            peak = peaks["i8_tops"]
             achieved = int8_ops_k2(N_TRAIN, planes) * cand_per_k2 / (k2_avg_ms / 1e3) / 1e12
-            traffic_o = None
-            prof_o = os.path.join(ROOT, "profiles", "k2o_dram_bytes_per_launch.json")
-            if os.path.exists(prof_o):
-                traffic_o = json.load(open(prof_o)).get("dram_bytes_per_candidate", 0.0) * cand_per_k2
+            traffic_o, traffic_src = traffic_from("r02_k2o_dram_bytes_per_launch.json", cand_per_k2)
+            issue_peak_run = 2 * peaks["i8_mac_per_clk_sm"] * 148 * run_clock / 1e6
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
-                        "traffic": traffic_o,
+                        "traffic": traffic_o, "traffic_source": traffic_src,
                         "kernel": "ozaki_trmm_kernel<0, %d> (K2o: tcgen05.mma kind::i8 over %d s8 digit planes, exact s32 "
                                   "accumulation in TMEM, FP64 recombination)" % (planes, planes),
                         "digit_planes": planes,
-                        "digit_planes_self_check": "6 planes when 256 probe candidates scored with FP64 and with 6 planes "
-                                                   "agree to 1e-10 of the prior variance, else 7 (csrc/skb.cu "
-                                                   "decide_split_planes); measured difference: %.2e" % probe_diff,
-                        "seven_plane_evals_s": (world * m / (ms_p7 / args.steps / 1e3)) if ms_p7 else None,
-                        "peak_source": "int8 dense = 2 x " + bf16_src + "; MEASURED_PEAKS.json has no int8 entry, the 2:1 "
-                                       "int8:bf16 issue ratio is measured in profiles/r01_umma_i8_rates.txt",
+                        "digit_planes_decision": "6 planes need BOTH the a-priori bound <= 2.5e-10 (this state: var %.2e, "
+                                                 "mean %.2e) and the 256-probe difference to FP64 <= 1e-10 (measured %.2e); "
+                                                 "else 7 (csrc/skb.cu decide_split_planes; no override)"
+                                                 % (bound_var, bound_mean, probe_diff),
+                        "peak_source": "skb_measure_peaks on this GPU in this run: tcgen05.mma kind::i8 M=128 N=256 issue "
+                                       "rate, operands resident in shared memory, %.0f MAC/clk/SM, %.0f TOP/s at burst clock "
+                                       "(MEASURED_PEAKS.json has no int8 entry)" % (peaks["i8_mac_per_clk_sm"], peaks["i8_tops"]),
                         "algorithmic_ops_per_candidate": int8_ops_k2(N_TRAIN, planes),
                         "algorithmic_ops_definition": "2 x %d digit-plane products x n(n+1)/2 (the scheme's own minimum at "
                                                       "%d planes)" % (split_products(planes), planes),
-                        "issue_peak": 2 * 8175 * 148 * (clocks_summary.get("sm_mhz_mean") or clocks_summary.get("sm_mhz")
-                                                         or 1965.0) / 1e6,
-                        "issue_peak_definition": "2 x 8175 MAC/clk/SM (measured kind::i8 issue rate at N=256, "
-                                                 "profiles/r01_umma_i8_rates.txt) x 148 SMs x mean SM clock during the timed region",
+                        "peak_at_run_clock": issue_peak_run,
+                        "frac_at_run_clock": achieved / issue_peak_run,
+                        "peak_at_run_clock_definition": "2 x measured MAC/clk/SM x 148 SMs x mean SM clock sampled during "
+                                                        "the timed region (%.0f MHz; the board sits at its power cap)" % run_clock,
                         "fp64_equivalent_tflops": fp64_equiv,
-                        "fp64_equivalent_vs_dmma_peak": fp64_equiv / FP64_PEAK_TFLOPS,
+                        "frac_fp64_algorithmic": fp64_equiv / peaks["fp64_dmma_tflops"],
+                        "frac_fp64_algorithmic_definition": "SURVEY.md 8(d): (n^2 + 2n + 40) FP64 flop per candidate / K2o "
+                                                            "time, over the measured FP64 DMMA peak - above 1 because the "
+                                                            "contraction does not run on the FP64 pipe; the FP64-pipe "
+                                                            "figure is fp64_dmma_path.roofline",
                         "candidates_per_launch": cand_per_k2, "avg_launch_ms": k2_avg_ms,
                         "k2_share_of_step": k2_share, "k1_share_of_step": k1_share,
                         "whole_path_fp64_equivalent_tflops": flops_value_path(N_TRAIN, N_DIMS) * world * m /
                                                               (ms_total / args.steps / 1e3) / world / 1e12}
-            roofline["frac_of_issue_peak"] = roofline["achieved"] / roofline["issue_peak"]
         else:
             roofline = None
         c2, a2, s2, s1 = k2_stats(timing_fp64, ms_fp64)
         achieved64 = flops_k2(N_TRAIN) * c2 / (a2 / 1e3) / 1e12
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "k2_dram_bytes_per_launch.json")
-        if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("dram_bytes_per_candidate", 0.0) * c2
-        roofline_fp64 = {"bound": "tensor", "achieved": achieved64, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved64 / FP64_PEAK_TFLOPS, "traffic": traffic,
+        traffic, traffic_src64 = traffic_from("k2_dram_bytes_per_launch.json", c2)
+        roofline_fp64 = {"bound": "tensor", "achieved": achieved64, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved64 / peaks["fp64_dmma_tflops"], "traffic": traffic,
                          "kernel": "trmm_kernel<0> (K2: DMMA triangular contraction + acquisition epilogue)",
-                         "peak_source": "measured FP64 DMMA issue peak on this pool (tools/microbench/fp64_peaks.cu -> "
-                                        "profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM "
-                                        "8192^3 measured 35.5",
+                         "peak_source": "skb_measure_peaks on this GPU in this run: mma.sync m8n8k4 f64 issue rate "
+                                        "(MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 measured 35.5 in round 1)",
                          "algorithmic_flops_per_candidate": flops_k2(N_TRAIN), "candidates_per_launch": c2,
                          "avg_launch_ms": a2, "k2_share_of_step": s2, "k1_share_of_step": s1}
         if roofline is None:
@@ -571,20 +861,31 @@ def main():
                        "n_train": N_TRAIN, "n_dims": N_DIMS, "candidates_per_gpu": m, "top_k": TOP_K,
                        "precision": headline + " (engine.resolve_precision('auto'); 1e-9 parity gate: tests/test_gpu_split.py)",
                        "kernel": "1.3 * Matern(nu=2.5, length_scale=1.5) + noise 1e-4, normalize_y",
-                       "sharding": "candidates sharded across ranks, GP state replicated, NCCL all-gather of top-k",
+                       "sharding": "candidates sharded across ranks, GP state replicated, ONE NCCL all-gather of a packed "
+                                   "top-k record per step, merged by one kernel",
                        "l2_policy": "inputs larger than L2 (candidates %.0f MB + ~1 GiB cross-covariance scratch per "
                                     "chunk vs 126 MB L2)" % (m * N_DIMS * 8 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": m * N_DIMS * 8,
-                    "d2h_bytes_per_step": TOP_K * 16 + 16},
+                    "d2h_bytes_per_step": TOP_K * 16 + 16, "host_memory": "pinned"},
+            "e2e_pageable": ({"value": world * m * args.steps / (e2e_pageable_ms / 1e3), "unit": "evals/s",
+                              "host_memory": "pageable NumPy array (np.random.rand), staged through a pinned ring by "
+                                             "skb_score_host"} if e2e_pageable_ms else None),
+            "value_fp64": fp64_value,
+            "value_p7": (world * m / (ms_p7 / args.steps / 1e3)) if ms_p7 else None,
+            "value_definitions": "value: precision the product picks ('auto' -> %s, %d planes); value_fp64: strict FP64 DMMA "
+                                 "path; value_p7: 7-plane split (55-bit operands)" % (headline, planes),
             "gpu_launches": launches,
             "clocks": clocks_summary,
+            "measured_peaks": peaks,
             "roofline": roofline,
             "fp64_dmma_path": {"value": fp64_value, "unit": "evals/s", "ms_per_step": ms_fp64 / args.steps,
                                "e2e": world * m * args.steps / (e2e_fp64_ms / 1e3), "roofline": roofline_fp64,
                                "whole_path_tflops": flops_value_path(N_TRAIN, N_DIMS) * fp64_value / world / 1e12,
                                "argmin_index": argmin_fp64},
             "argmin_index": argmin_idx,
+            "multi_gpu_check": multi_gpu_check,
         }
+        line.update(extra)
         # the ask-latency and CPU legs are single-GPU context for the headline: rank 0 at N=1 only
         if not args.no_ask and world == 1:
             p50, cnt = ask_p50_ms()
@@ -609,6 +910,7 @@ def main():
             line["parity_sample"] = parity_sample(gpr, dev, y_opt, sorted({headline, "fp64"}))
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
