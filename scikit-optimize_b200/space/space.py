@@ -651,8 +651,7 @@ class Space(object):
         n = len(X)
         cols = []
         for j, dim in enumerate(self.dimensions):
-            col = dim.transform([X[i][j] for i in range(n)])
-            cols.append(np.asarray(col, dtype=float).reshape((n, -1)))
+            cols.append(_as_column(dim.transform([X[i][j] for i in range(n)]), n))
         return np.hstack(cols) if cols else np.empty((n, 0))
 
     def inverse_transform(self, Xt):
@@ -675,8 +674,18 @@ class Space(object):
         cols = []
         for dim in self.dimensions:
             original = dim._sample_column(rng, n_samples)
-            cols.append(np.asarray(dim.transform(original), dtype=float).reshape((n_samples, -1)))
+            cols.append(_as_column(dim.transform(original), n_samples))
         return np.ascontiguousarray(np.hstack(cols))
+
+
+def _as_column(col, n):
+    """One dimension's transformed values as an (n, width) block: float for every numeric transform; a Categorical with
+    transform "identity" / "string" keeps its labels (NumPy then makes the stacked matrix a string / object array, as
+    the reference's np.hstack does, space.py:967-974)."""
+    arr = np.asarray(col)
+    if arr.dtype.kind in "biuf":
+        arr = arr.astype(float, copy=False)
+    return arr.reshape((n, -1))
 
 
 def device_dim_descs(space):
