@@ -8,7 +8,8 @@
 repository root).
 """
 from . import acquisition, benchmarks, plots, space, utils  # noqa: F401
-from .engine import DeviceState, HostState, host_state_from_estimator, launch_count  # noqa: F401
+from .engine import (DeviceState, HostState, host_state_from_estimator, launch_count,  # noqa: F401
+                     set_default_precision)
 from .learning.gaussian_process.gpr import set_default_device, set_fit_device  # noqa: F401
 from .optimizer import Optimizer, base_minimize, dummy_minimize, gp_minimize  # noqa: F401
 from .space import Space  # noqa: F401

@@ -16,7 +16,7 @@ import warnings
 
 import numpy as np
 
-from . import _lib
+from . import _lib, engine
 from .engine import _acq_params
 
 
@@ -84,7 +84,8 @@ def _evaluate(X, model, acq, y_opt, xi, kappa, return_grad):
         g = dev.score_grad(X, y_opt=y_opt, acq_funcs=(acq,), xi=xi, kappa=kappa)
         grad = g[acq]["grad"]
         return g[acq]["values"], (grad[0] if X.shape[0] == 1 else grad)
-    res = dev.score(X, y_opt=y_opt, acq_funcs=(acq,), xi=xi, kappa=kappa, want_posterior=False, precision="auto")
+    res = dev.score(X, y_opt=y_opt, acq_funcs=(acq,), xi=xi, kappa=kappa, want_posterior=False,
+                    precision=engine.default_precision(model))
     return res[acq]["values"]
 
 
@@ -130,7 +131,7 @@ def _time_posterior(X, time_model, return_grad):
         if return_grad:
             g = dev.score_grad(X, acq_funcs=())
             return g["mean"], g["std"], g["mean_grad"], g["std_grad"]
-        r = dev.score(X, acq_funcs=(), want_posterior=True, precision="auto")
+        r = dev.score(X, acq_funcs=(), want_posterior=True, precision=engine.default_precision(time_model))
         return r["mean"], r["std"], None, None
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

@@ -132,7 +132,29 @@ AUTO_SPLIT_MAX_TRAIN = 16384          # exact int32 accumulation bound of the sp
 AUTO_SPLIT_MIN_CANDIDATES = 8192
 
 
+_DEFAULT_PRECISION = ["auto"]
+
+
+def set_default_precision(precision):
+    """Precision of the calls that have no argument for it - predict(return_std=True), gaussian_ei / pi / lcb,
+    _gaussian_acquisition and an Optimizer built without acq_optimizer_kwargs["precision"]: "auto" (default; the
+    split-integer contraction once n_train >= 512 and the call has >= 8192 candidates, FP64 DMMA below), "fp64" (every
+    call on the FP64 path, bit-pinned against the reference fixtures at every size), "split_int8", "split_int8_p7".
+    An estimator attribute `precision` overrides it for that estimator.  Returns the previous setting."""
+    if precision != "auto" and precision not in _lib.PRECISION:
+        raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISION))
+    old, _DEFAULT_PRECISION[0] = _DEFAULT_PRECISION[0], precision
+    return old
+
+
+def default_precision(estimator=None):
+    own = getattr(estimator, "precision", None) if estimator is not None else None
+    return own if own is not None else _DEFAULT_PRECISION[0]
+
+
 def resolve_precision(precision, n_train, m):
+    if precision is None:
+        precision = _DEFAULT_PRECISION[0]
     if precision == "auto":
         return "split_int8" if (AUTO_SPLIT_MIN_TRAIN <= n_train <= AUTO_SPLIT_MAX_TRAIN and
                                 m >= AUTO_SPLIT_MIN_CANDIDATES) else "fp64"

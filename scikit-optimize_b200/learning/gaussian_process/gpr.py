@@ -323,7 +323,7 @@ class GaussianProcessRegressor(_SkGPR):
                 return g["mean"], g["std"], mean_grad
             return g["mean"], mean_grad
         if return_std:
-            res = dev.score(X, acq_funcs=(), want_posterior=True, precision="auto")
+            res = dev.score(X, acq_funcs=(), want_posterior=True, precision=engine.default_precision(self))
             if np.any(res["clamped"]):
                 warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
             return res["mean"], res["std"]

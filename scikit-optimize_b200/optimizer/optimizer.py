@@ -105,7 +105,7 @@ class Optimizer(object):
         self.n_restarts_optimizer = acq_optimizer_kwargs.get("n_restarts_optimizer", 5)
         self.n_jobs = acq_optimizer_kwargs.get("n_jobs", 1)      # accepted for compatibility; restarts are batched
         # arithmetic of the variance contraction: "auto" (default), "fp64" or "split_int8" (see engine.resolve_precision)
-        self.precision = acq_optimizer_kwargs.get("precision", "auto")
+        self.precision = acq_optimizer_kwargs.get("precision", None)      # None: engine.default_precision() at call time
         # draw the candidate set on the GPU when the space allows a bit-exact device version (engine.device_candidates)
         self.device_candidates = acq_optimizer_kwargs.get("device_candidates", True)
         # where the GP hyper-parameter search evaluates its objective: None = the package setting
@@ -258,8 +258,11 @@ class Optimizer(object):
                 self.models.append(est)
 
             # only the newest model needs to stay resident on the GPU; older ones re-upload lazily if predict()ed
+            # (per-second models keep theirs on the two regressors inside MultiOutputRegressor)
             for old in self.models[:-1]:
                 old.__dict__.pop("_skb_device_state", None)
+                for sub in getattr(old, "estimators_", []):
+                    sub.__dict__.pop("_skb_device_state", None)
 
             t_score = time.perf_counter()
             self.next_xs_ = self._score_and_refine(est, transformed_bounds)

@@ -335,3 +335,27 @@ def test_benchmark_objectives_have_their_known_minima():
     assert abs(B.hart6([0.20169, 0.15001, 0.476874, 0.275332, 0.311652, 0.6573]) + 3.32237) < 1e-5
     assert B.bench1([0.0]) == 0.0 and B.bench2([5.0]) == -5.0 and B.bench1_with_time([2.0]) == (4.0, 2.22)
     assert abs(B.bench3([-0.3]) + 0.9) < 0.1 and B.bench4(["3"]) == 9.0 and B.bench5(["3", 4]) == 25.0
+
+
+def test_default_precision_setter_and_estimator_override():
+    """engine.set_default_precision: the precision of the calls without an argument for it (predict(return_std=True),
+    gaussian_ei, an Optimizer without acq_optimizer_kwargs['precision']); an estimator attribute overrides it."""
+    from skopt_b200 import engine
+
+    class Est:
+        precision = None
+
+    old = engine.set_default_precision("fp64")
+    try:
+        assert old == "auto"
+        assert engine.resolve_precision(None, 2048, 10 ** 6) == "fp64"
+        assert engine.default_precision(Est()) == "fp64"
+        e = Est()
+        e.precision = "split_int8_p7"
+        assert engine.default_precision(e) == "split_int8_p7"
+        with pytest.raises(ValueError):
+            engine.set_default_precision("fp16")
+    finally:
+        engine.set_default_precision(old)
+    assert engine.resolve_precision(None, 2048, 10 ** 6) == "split_int8"
+    assert engine.resolve_precision(None, 100, 10 ** 6) == "fp64" and engine.resolve_precision("auto", 2048, 100) == "fp64"
