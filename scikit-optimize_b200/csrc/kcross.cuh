@@ -442,16 +442,20 @@ __device__ __forceinline__ double kernel_value_scaled(double sa, double amp, dou
     return fma(fma(K, fma(K, amp3, amp), amp), e, bias);
 }
 
-constexpr int XS_LD_MMA = BN + 8;          // = 8 mod 16 doubles: the A-fragment read (4 features x 8 candidates) is conflict-free
-
-constexpr size_t kcross_mma_smem_bytes(int d_pad) {
-    return sizeof(double) * ((size_t)d_pad * XS_LD_MMA + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + 2 * XROWS + BN) +
+// CB = candidates per CTA: 128 (8 warps, two CTAs per SM: the stand-alone configuration) or 64 (4 warps, 16 K registers
+// and ~40 KB of shared memory: small enough to share an SM with one CTA of the contraction kernel, skb.cu split_overlaps).
+// The row stride CB + 8 of the transposed candidate tile is 8 mod 16 doubles: the A-fragment read (4 features x 8
+// candidates) is conflict-free.
+constexpr size_t kcross_mma_smem_bytes(int d_pad, int cb = BN) {
+    return sizeof(double) * ((size_t)d_pad * (cb + 8) + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + 2 * XROWS + cb) +
            2 * sizeof(uint64_t);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitParams q) {
+template <int KIND, int CB = BN>
+__global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(const KDigitParams q) {
     constexpr int P = 6;
+    constexpr int XS_LD_MMA = CB + 8;
+    constexpr int NT = 2 * CB;
     constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));
     const KCrossParams& p = q.base;
     extern __shared__ __align__(16) unsigned char smem_k1[];
@@ -461,11 +465,11 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
     double* al = xt + 2 * xt_stage;                            // [2][XROWS]
     double* tnb = al + 2 * XROWS;                              // [2][XROWS] squared norms of the staged training rows
     double* xs = tnb + 2 * XROWS;                              // [d_pad][XS_LD_MMA]
-    double* xnorm = xs + (size_t)d_pad * XS_LD_MMA;            // [BN] |x|^2 of the candidates
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xnorm + BN);
+    double* xnorm = xs + (size_t)d_pad * XS_LD_MMA;            // [CB] |x|^2 of the candidates
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xnorm + CB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rq = warp >> 1, e = warp & 1, t4 = lane & 3, c8 = lane >> 2;
+    const int rq = CB == 128 ? warp >> 1 : warp, e = CB == 128 ? warp & 1 : 0, t4 = lane & 3, c8 = lane >> 2;
     const int64_t tile = blockIdx.x;
     const int nst = (p.n + XROWS - 1) / XROWS;
     if (tid == 0) {
@@ -473,9 +477,9 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
         mbar_init(bars + 1, 1);
         mbar_fence_init();
     }
-    for (int idx = tid; idx < BN * d_pad; idx += 256) {
+    for (int idx = tid; idx < CB * d_pad; idx += NT) {
         const int cc = idx / d_pad, k = idx - cc * d_pad;
-        const int64_t row = tile * BN + cc;
+        const int64_t row = tile * CB + cc;
         double v = 0.0;
         if (k < p.d && row < p.m) v = p.X[row * p.d + k] / p.ls[k];
         xs[k * XS_LD_MMA + cc] = v;
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
         issue(0);
         if (nst > 1) issue(1);
     }
-    if (tid < BN) {
+    if (tid < CB) {
         double a = 0.0;
         for (int k = 0; k < d_pad; ++k) a = fma(xs[k * XS_LD_MMA + tid], xs[k * XS_LD_MMA + tid], a);
         xnorm[tid] = a;
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
     }
     const int nkc_all = p.n_pad / 32;
     // MMA tile 2 * tile + e; [chunk of 32][k half][plane][cand group ci][cand c8][16 B]: this lane's word is bytes 4 t4 .. + 3
-    int8_t* kd_base = q.Kd + ((size_t)(tile * 2 + e) * nkc_all) * (2 * P * 8 * 128) + (rq & 1) * (P * 8 * 128) + c8 * 16 + 4 * t4;
+    int8_t* kd_base = q.Kd + ((size_t)(tile * (CB / 64) + e) * nkc_all) * (2 * P * 8 * 128) + (rq & 1) * (P * 8 * 128) + c8 * 16 + 4 * t4;
     const double* xa = xs + t4 * XS_LD_MMA + 64 * e + c8;      // A fragment: feature k0 + t4, candidate 8 ci + c8
 
     for (int st = 0; st < nst; ++st) {
@@ -569,17 +573,17 @@ __global__ void __launch_bounds__(256, 2) kcross_digits_mma_kernel(const KDigitP
         if (tid == 0 && st + 2 < nst) issue(st + 2);
     }
     // k . alpha: the four lanes that share a candidate (fixed xor tree), then the four row quarters in a fixed order
-    double* stage = xt;                                        // [4][BN], free after the loop
+    double* stage = xt;                                        // [4][CB], free after the loop
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) {
         double v = fma(0.0, xn[ci], macc[ci]);                 // NaN / Inf coordinates reach the mean (see the DFMA variant)
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (t4 == 0) stage[rq * BN + 64 * e + 8 * ci + c8] = v;
+        if (t4 == 0) stage[rq * CB + 64 * e + 8 * ci + c8] = v;
     }
     __syncthreads();
-    if (tid < BN)
-        p.kdot[tile * BN + tid] = ((stage[tid] + stage[BN + tid]) + stage[2 * BN + tid]) + stage[3 * BN + tid];
+    if (tid < CB)
+        p.kdot[tile * CB + tid] = ((stage[tid] + stage[CB + tid]) + stage[2 * CB + tid]) + stage[3 * CB + tid];
 }
 
 }  // namespace skb

@@ -47,7 +47,15 @@ __host__ __device__ constexpr int oz_a_bytes(int P) { return P * BM * OZ_KC; }  
 __host__ __device__ constexpr int oz_b_half(int P) { return P * (OZ_NC / 8) * 128; }                // [plane][cand group 8][8 cands][16 B] per k half
 __host__ __device__ constexpr int oz_b_chunk(int P) { return 2 * oz_b_half(P); }                    // 14,336 B (P = 7), 12,288 B (P = 6)
 __host__ __device__ constexpr int oz_stage_bytes(int P) { return oz_a_bytes(P) + oz_b_chunk(P); }   // 43,008 B / 36,864 B
-__host__ __device__ constexpr int oz_stages(int P) { return P >= 7 ? 4 : 5; }
+// Build-time knobs for the co-residency experiment (profiles/r02_k2o_diagnosis.md): -DOZ_STAGES6=4 -DOZ_MAXNREG=152 leave
+// room on the SM for one 64-candidate K1 CTA (SKB_SPLIT_OVERLAP=1); measured equal in speed to the defaults.
+#ifndef OZ_STAGES6
+#define OZ_STAGES6 5
+#endif
+#ifndef OZ_MAXNREG
+#define OZ_MAXNREG 168
+#endif
+__host__ __device__ constexpr int oz_stages(int P) { return P >= 7 ? 4 : OZ_STAGES6; }
 
 // byte offset of (row, k) inside one canonical K-major, no-swizzle (rows x 32) int8 block: 8-row x 16-byte core matrices
 __host__ __device__ inline int oz_canon(int rows, int row, int k) {
@@ -122,6 +130,7 @@ struct OzakiParams {
     double* acq[3];
     unsigned long long* clamp_count;
     double* Wt;               // MODE 1: [tiles128][n_pad][BN] = K_inv . K_trans^T in FP64 for the gradient kernel
+    long long* dbg_cycles;    // diagnostics (skb_debug_k2o): SM cycles each CTA spent between its setup and its teardown
 };
 
 constexpr size_t oz_smem_bytes(int P) { return (size_t)oz_stages(P) * oz_stage_bytes(P) + 4 * OZ_NC * sizeof(double) + 256; }
@@ -175,8 +184,12 @@ __device__ __forceinline__ double oz_colsum32(double (&v)[32], int lane) {
 
 // MODE 0: triangular L_inv, U squared and reduced, posterior + acquisition epilogue; grid.x = 64-candidate tile.
 // MODE 1: dense K_inv, W = K_inv . K_trans^T stored in FP64; grid = (row block, 64-candidate tile).
-template <int MODE, int P>
-__global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
+// DBG (diagnostics only, skb_debug_k2o / tools/k2o_diag.py; 0 in every product launch): bit 0 = the epilogue warps skip
+// the TMEM reads and the FP64 recombination, bit 1 = the producer signals the stages full without copying anything,
+// bit 2 = no accumulator hand-over between row blocks (one at the very end), bit 4 = no stage barriers at all (the MMAs
+// read whatever the stages hold); any bit: the CTA's SM cycle count goes to p.dbg_cycles.
+template <int MODE, int P, int DBG = 0>
+__global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     constexpr int OZ_STAGES = oz_stages(P);
     constexpr int OZ_STAGE_BYTES = oz_stage_bytes(P);
     constexpr int OZ_B_HALF = oz_b_half(P);
@@ -209,6 +222,7 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
+    const long long dbg_t0 = DBG ? clock64() : 0;
 
     const int tile_id = MODE == 0 ? blockIdx.x : blockIdx.y;
     const int I_begin = MODE == 0 ? 0 : blockIdx.x;
@@ -219,7 +233,7 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
 
     if (warp == 0) {
         // ---------------- producer ----------------
-        if (lane == 0) {
+        if (lane == 0 && !(DBG & 16)) {
             uint32_t it = 0;
             for (int I = I_begin; I < I_end; ++I) {
                 const int nkc = MODE == 0 ? min((I + 1) * (BM / OZ_KC), nkc_used) : nkc_used;
@@ -228,6 +242,10 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
                     const int s = it % OZ_STAGES;
                     const uint32_t ph = (it / OZ_STAGES) & 1;
                     mbar_wait(empty + s, ph ^ 1);
+                    if (DBG & 2) {
+                        mbar_arrive(full + s);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(full + s, OZ_STAGE_BYTES);
                     unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
                     bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, A_BYTES, full + s);        // leading P of the 7 packed planes
@@ -241,14 +259,14 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
             uint32_t it = 0;
             for (int I = I_begin; I < I_end; ++I) {
                 const int nkc = MODE == 0 ? min((I + 1) * (BM / OZ_KC), nkc_used) : nkc_used;
-                if (I > I_begin) {
+                if (I > I_begin && !(DBG & 4)) {
                     mbar_wait(tmem_empty, (uint32_t)((I - I_begin - 1) & 1));   // epilogue of the previous row block drained TMEM
                     asm volatile("tcgen05.fence::after_thread_sync;");
                 }
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int s = it % OZ_STAGES;
                     const uint32_t ph = (it / OZ_STAGES) & 1;
-                    mbar_wait(full + s, ph);
+                    if (!(DBG & 16)) mbar_wait(full + s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t a_base = smem_u32(stages + (size_t)s * OZ_STAGE_BYTES);
                     const uint32_t b_base = a_base + A_BYTES;
@@ -270,9 +288,9 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
                             oz_mma(tmem + OZ_NC * pl + r0, da, db, oz_idesc(N), (acc | (pl > 0 ? 1u : 0u)));
                         }
                     }
-                    oz_commit(empty + s);                   // smem slot is free once these MMAs have read it
+                    if (!(DBG & 16)) oz_commit(empty + s);  // smem slot is free once these MMAs have read it
                 }
-                oz_commit(tmem_full);                       // all MMAs of row block I retired -> epilogue may read
+                if (!(DBG & 4) || I == I_end - 1) oz_commit(tmem_full);   // all MMAs of row block I retired -> epilogue may read
             }
         }
     } else {
@@ -284,12 +302,12 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
         double qacc[OZ_NC / 2];
 #pragma unroll
         for (int c = 0; c < OZ_NC / 2; ++c) qacc[c] = 0.0;
-        for (int I = I_begin; I < I_end; ++I) {
-            mbar_wait(tmem_full, (uint32_t)((I - I_begin) & 1));
+        for (int I = (DBG & 4) ? I_end - 1 : I_begin; I < I_end; ++I) {
+            mbar_wait(tmem_full, (DBG & 4) ? 0u : (uint32_t)((I - I_begin) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
 #pragma unroll
-            for (int jj = 0; jj < OZ_NC / 16; ++jj) {
+            for (int jj = 0; jj < ((DBG & 1) ? 0 : OZ_NC / 16); ++jj) {
                 const int j = half * (OZ_NC / 16) + jj;
                 // all P regions of these 8 candidates are requested before the single wait: one TMEM round trip
                 uint32_t g[P][8];
@@ -337,6 +355,7 @@ __global__ void __maxnreg__(168) ozaki_trmm_kernel(const OzakiParams p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (DBG && threadIdx.x == 0 && p.dbg_cycles) p.dbg_cycles[blockIdx.x] = clock64() - dbg_t0;
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 

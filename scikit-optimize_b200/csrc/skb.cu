@@ -461,7 +461,7 @@ void launch_kcross_digits_planes(int kernel, const KDigitParams& p, int tiles, s
 }
 
 // `planes` digit planes per kernel value (6 or 7); p.inv_scale is set here to 2^(8 planes - 1) / sK
-int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s) {
+int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s, bool small_cta = false) {
     const size_t smem = kcross_smem_bytes(p.base.d_pad);
     p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
     p.tn = st->d_tn;
@@ -470,7 +470,15 @@ int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, c
     // the DFMA variant, for A/B measurements)
     static const bool k1_mma = [] { const char* e = std::getenv("SKB_K1_MMA"); return !(e && e[0] == '0'); }();
     const bool dot_kind = st->kernel == SKB_KERNEL_RBF || st->kernel == SKB_KERNEL_MATERN32 || st->kernel == SKB_KERNEL_MATERN52;
-    if (planes == 6 && k1_mma && dot_kind) {
+    if (planes == 6 && k1_mma && dot_kind && small_cta) {
+        // 64 candidates per CTA (4 warps): the configuration that shares an SM with the contraction kernel
+        const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad, 64);
+        switch (st->kernel) {
+            case SKB_KERNEL_RBF: kcross_digits_mma_kernel<0, 64><<<2 * tiles, 128, smem_m, s>>>(p); break;
+            case SKB_KERNEL_MATERN32: kcross_digits_mma_kernel<2, 64><<<2 * tiles, 128, smem_m, s>>>(p); break;
+            default: kcross_digits_mma_kernel<3, 64><<<2 * tiles, 128, smem_m, s>>>(p); break;
+        }
+    } else if (planes == 6 && k1_mma && dot_kind) {
         const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad);
         switch (st->kernel) {
             case SKB_KERNEL_RBF: kcross_digits_mma_kernel<0><<<tiles, 256, smem_m, s>>>(p); break;
@@ -510,6 +518,12 @@ int set_kernel_attributes(skb_state* st) {
 #define SKB_DIGIT_MMA_ATTR(K)                                                                                                 \
     CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1m));               \
     CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+    SKB_DIGIT_MMA_ATTR(0); SKB_DIGIT_MMA_ATTR(2); SKB_DIGIT_MMA_ATTR(3);
+#undef SKB_DIGIT_MMA_ATTR
+    const int smem1s = (int)kcross_mma_smem_bytes(st->d_pad, 64);
+#define SKB_DIGIT_MMA_ATTR(K)                                                                                                 \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1s));           \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K, 64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
     SKB_DIGIT_MMA_ATTR(0); SKB_DIGIT_MMA_ATTR(2); SKB_DIGIT_MMA_ATTR(3);
 #undef SKB_DIGIT_MMA_ATTR
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -804,14 +818,16 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
 }
 
 // candidate tiles processed per K1/K2 launch pair: as many as the scratch limit allows, in whole waves of SMs
-// Split-integer path: K1 of chunk i+1 CAN run on a second stream under the contraction of chunk i when a K1 CTA fits on
-// an SM next to a contraction CTA (shared memory decides: small n_dims only).  Measured at (2048, 20), 10^6 candidates:
-// the overlapped schedule is 1 % SLOWER than running the two kernels back to back (18.6 vs 18.8 M evals/s) - the board
-// is at its power cap under the contraction, so co-running FP64 work only lowers the clock - and it needs twice the
-// scratch and three times the launches.  It therefore stays off unless SKB_SPLIT_OVERLAP=1 is exported.
+// Split-integer path: K1 of chunk i+1 CAN run on a second stream under the contraction of chunk i.  Round 2 made the two
+// kernels truly co-resident (a 64-candidate, 4-warp K1 CTA - kcross_digits_mma_kernel<KIND, 64> - next to one contraction
+// CTA built with -DOZ_STAGES6=4 -DOZ_MAXNREG=152) and measured it at (2048, 20), 10^6 candidates: both kernels do run
+// concurrently (K1 spans 61 % and K2o spans 86 % of the step) and the step takes 39.3 ms against 38.7 ms back to back, at
+// the same 1.71 GHz mean SM clock - the board sits at its 1 kW power cap under the contraction, so the step time is set
+// by the ENERGY of the work, not by pipe occupancy, and overlapping pipes buys nothing (profiles/r02_k2o_diagnosis.md).
+// It therefore stays off unless SKB_SPLIT_OVERLAP=1 is exported (and only pays off in a build with those two knobs).
 static bool split_overlaps(const skb_state* st) {
     static const bool enabled = [] { const char* e = getenv("SKB_SPLIT_OVERLAP"); return e && e[0] == '1'; }();
-    return enabled && kcross_smem_bytes(st->d_pad) + oz_smem_bytes(7) + 4096 <= 232448;
+    return enabled && kcross_mma_smem_bytes(st->d_pad, 64) + oz_smem_bytes(7) + 4096 <= 232448;
 }
 
 static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
@@ -1037,7 +1053,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             dp.base.kdot = buf ? st->d_kdot2 : st->d_kdot;
             dp.Kd = reinterpret_cast<int8_t*>(buf ? st->d_Kt2 : st->d_Kt);   // `planes` (<= 7) bytes per (training point, candidate)
             if ((rc = span_begin(st, 0, s1)) != SKB_OK) return rc;
-            if ((rc = launch_kcross_digits(st, dp, planes, (int)nt, s1)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, planes, (int)nt, s1, overlap)) != SKB_OK) return rc;
             if ((rc = span_end(st, s1)) != SKB_OK) return rc;
             if (overlap) {
                 CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
@@ -1755,6 +1771,83 @@ int skb_measure_peaks(int device, double* i8_mac_per_clk_sm, double* i8_tops, do
     cudaDeviceSynchronize();
     pool_free(device, raw);
     return rc;
+}
+
+// Diagnostics: time `reps` launches of the 6-plane contraction kernel alone over `tiles64` 64-candidate tiles of whatever
+// the scratch holds (results are discarded), with parts of the kernel switched off (dbg bit 0: no epilogue work, bit 1: no
+// operand copies).  Tells which of {tensor pipe, epilogue drain, operand delivery} bounds K2o; not used by any product path.
+int skb_debug_k2o(skb_state* st, int dbg, int64_t tiles64, int reps, double* ms_per_launch, double* cycles_per_cta) {
+    if (!st || !ms_per_launch || tiles64 <= 0 || reps <= 0) return fail(SKB_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(st->device));
+    int rc;
+    const int64_t tiles = (tiles64 + 1) / 2;
+    if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)tiles * BN)) != SKB_OK) return rc;
+    OzakiParams op;
+    std::memset(&op, 0, sizeof(op));
+    op.Vd = st->d_Vd;
+    op.sV = st->d_sV;
+    op.Kd = reinterpret_cast<int8_t*>(st->d_Kt);
+    op.kdot = st->d_kdot;
+    op.k_scale = st->k_scale;
+    op.n = st->n;
+    op.n_pad = st->n_pad;
+    op.m = tiles64 * OZ_NC;
+    op.a.prior_var = st->amplitude + st->bias + st->white;
+    op.a.y_std = 1.0;
+    op.a.acq_mask = 1;
+    void* d_cyc = nullptr;
+    if ((rc = pool_alloc(st->device, &d_cyc, (size_t)tiles64 * sizeof(long long))) != SKB_OK) return rc;
+    op.dbg_cycles = dbg ? static_cast<long long*>(d_cyc) : nullptr;
+    cudaStream_t s = st->stream;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    auto launch = [&]() {
+        const unsigned g = (unsigned)tiles64;
+        switch (dbg) {
+            case 1: ozaki_trmm_kernel<0, 6, 1><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 2: ozaki_trmm_kernel<0, 6, 2><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 3: ozaki_trmm_kernel<0, 6, 3><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 7: ozaki_trmm_kernel<0, 6, 7><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 5: ozaki_trmm_kernel<0, 6, 5><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 8: ozaki_trmm_kernel<0, 6, 8><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 23: ozaki_trmm_kernel<0, 6, 23><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            default: ozaki_trmm_kernel<0, 6><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+        }
+    };
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    launch();
+    CU(cudaEventRecord(e0, s));
+    for (int r = 0; r < reps; ++r) {
+        launch();
+        LAUNCHED();
+    }
+    CU(cudaEventRecord(e1, s));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / reps;
+    if (cycles_per_cta) {
+        *cycles_per_cta = 0.0;
+        if (dbg) {
+            std::vector<long long> h((size_t)tiles64);
+            CU(cudaMemcpy(h.data(), d_cyc, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double sum = 0.0;
+            for (long long v : h) sum += (double)v;
+            *cycles_per_cta = sum / (double)tiles64;
+        }
+    }
+    pool_free(st->device, d_cyc);
+    return SKB_OK;
 }
 
 int skb_topk_dev(skb_state* st, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
