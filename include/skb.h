@@ -258,8 +258,9 @@ int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32
  *   grad  = d lml / d theta, [n_dims + 2] in the order of theta (the caller drops fixed hyper-parameters and sums the
  *           length-scale entries of an isotropic kernel).
  * A K that is not positive definite gives lml = -inf and a zero gradient, like the reference.  The dK/dtheta tensor
- * of the reference (n x n x (n_dims + 2)) is never formed.  Cholesky / solve / inverse are cuSOLVER calls (loaded on
- * first use); the kernel matrix and the gradient contraction are this library's kernels. */
+ * of the reference (n x n x (n_dims + 2)) is never formed.  Every step is this library's own kernel: the kernel matrix,
+ * a blocked right-looking Cholesky, the triangular inverse by recursive doubling, alpha = L^-T (L^-1 y),
+ * K^-1 = L^-T L^-1 and the gradient contraction (csrc/fit.cuh, csrc/chol.cuh); no cuSOLVER / cuBLAS is loaded. */
 typedef struct skb_fit skb_fit;
 typedef struct {
     int32_t n_train, n_dims;

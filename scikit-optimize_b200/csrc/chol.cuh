@@ -1,0 +1,396 @@
+// Dense FP64 factorisation kernels of the fit objective: what scikit-learn's
+// log_marginal_likelihood does with LAPACK (sklearn/gaussian_process/_gpr.py:541-657: cholesky, cho_solve, and for the
+// gradient K^-1) and what skopt's fit adds (gpr.py:223-224: L^-1, K^-1 = L^-T L^-1), written for one B200:
+//
+//   chol_panel_kernel  : block column k of a right-looking Cholesky.  Every CTA refactorises the 64 x 64 diagonal block
+//                        in shared memory (7 us; cheaper than a launch + a trip through L2 for a broadcast), inverts it in
+//                        the same sweep, and turns its own 64-row slab of the panel into L by ONE small matrix product with
+//                        that inverse (no triangular solve anywhere).  The diagonal CTA keeps the inverse: tri_inverse needs it.
+//   chol_update_kernel : trailing update A_ij -= L_ik L_jk^T of the lower tiles, 64 x 64 x 64 per CTA.
+//   tri_inverse        : X = L^-1 by recursive doubling, X21 = -X22 (L21 X11): 2 log2(n / 64) launches of tile products
+//                        instead of n / 64 dependent steps.
+//   tri_gram_kernel    : K^-1 = X^T X (lower triangle), the formula of gpr.py:224.
+//   tri_matvec_*       : alpha = X^T (X y) (cho_solve with the explicit inverse; X is needed anyway).
+//
+// All matrices are n x n column-major with the lower triangle significant (element (i, j), i >= j, at A[j n + i]) - the
+// layout the kernel-matrix builder writes and the gradient kernel reads.  n is arbitrary; partial blocks are padded with
+// the identity inside shared memory.  Reductions run in a fixed order: results are reproducible run to run.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace skb {
+
+constexpr int CH_NB = 64;                 // block size
+constexpr int CH_LD = CH_NB + 1;          // shared-memory row stride (conflict-free rows and columns)
+constexpr int CH_THREADS = 256;
+constexpr size_t ch_smem_bytes() { return 3 * (size_t)CH_NB * CH_LD * sizeof(double); }
+
+// dst[r][c] = src(row0 + r, col0 + c) (TRANS = false) or src(row0 + c, col0 + r) (TRANS = true); zero outside the matrix.
+// Global reads run along a column (contiguous), shared writes are conflict-free in both modes.
+template <bool TRANS>
+__device__ __forceinline__ void ch_load_tile(double* dst, const double* __restrict__ src, int n, int row0, int col0) {
+    const int fast = threadIdx.x & 63, slow = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int p = 0; p < CH_NB; p += 4) {
+        const int gi = row0 + fast, gj = col0 + slow + p;
+        const double v = (gi < n && gj < n) ? src[(size_t)gj * n + gi] : 0.0;
+        if (TRANS) dst[(slow + p) * CH_LD + fast] = v;
+        else dst[fast * CH_LD + slow + p] = v;
+    }
+}
+
+// Thread (ty, tx) of a 16 x 16 grid owns rows tx + 16 i and columns ty + 16 j of the 64 x 64 tile: the 16 row reads of a
+// half-warp hit 16 different bank pairs (row stride 65 doubles), the column reads are broadcasts, and a half-warp stores
+// 16 consecutive doubles of a column.   acc[i][j] += sum_kk As[tx + 16 i][kk] * Bs[kk][ty + 16 j]
+__device__ __forceinline__ void ch_tile_fma(const double* As, const double* Bs, double (&acc)[4][4]) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll 8
+    for (int kk = 0; kk < CH_NB; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[(tx + 16 * i) * CH_LD + kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[kk * CH_LD + ty + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+}
+
+// rl ~ 1 / sqrt(x), l ~ sqrt(x) for x > 0 (NaN for x <= 0 or NaN, which is what a failed factorisation should spread).
+__device__ __forceinline__ void ch_rsqrt(double x, double& rl, double& l) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;                           // g ~ sqrt(x), h ~ 1 / (2 sqrt(x))
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double dd = fma(-g, g, x);                         // residual correction of the root
+    g = fma(dd, h, g);
+    const bool ok = x > 0.0;
+    l = ok ? g : sqrt(x);
+    rl = ok ? 2.0 * h : 1.0 / sqrt(x);
+}
+
+// Columns 16 Q .. 16 Q + 15 of the sweep in chol_panel_kernel (see there).
+template <int Q>
+__device__ __forceinline__ void ch_sweep16(double (&d)[4][4], double (&e)[4][4], double* colv, double* rowE, double* pivs,
+                                           int* info, int k0, bool report) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+        const int c = 16 * Q + o;                            // element (c, c) lives in thread (ty = o, tx = o) at [Q][Q]
+        __syncthreads();                                     // pivot of column c published; column c - 1 fully consumed
+        const double piv = *pivs;
+        if (!(piv > 0.0) && threadIdx.x == 0 && report) atomicCAS(info, 0, k0 + c + 1);
+        // 1 / sqrt(piv) and sqrt(piv) from the hardware seed and two coupled Newton steps (<= 1 ulp): FP64 sqrt and
+        // division are ~40 dependent instructions each and this is the critical path of every column
+        double rl, l;
+        ch_rsqrt(piv, rl, l);
+        if (ty == o) {                                       // owners of column c: scale it and publish it
+#pragma unroll
+            for (int i = Q; i < 4; ++i) {
+                const int r = tx + 16 * i;
+                if (r > c) d[i][Q] *= rl;
+                else if (r == c) d[i][Q] = l;
+                colv[r] = d[i][Q];
+            }
+        }
+        if (tx == o) {                                       // owners of row c of the inverse: it becomes final
+#pragma unroll
+            for (int j = 0; j <= Q; ++j) {
+                const int col = ty + 16 * j;
+                if (col <= c) e[Q][j] *= rl;
+                rowE[col] = e[Q][j];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = Q; i < 4; ++i) {                        // row groups above Q are finished
+            const int r = tx + 16 * i;
+            const double lr = r > c ? colv[r] : 0.0;
+#pragma unroll
+            for (int j = Q; j < 4; ++j) {                    // block columns that can still be right of c
+                const int cc = ty + 16 * j;
+                if (cc > c && r >= cc) d[i][j] = fma(-lr, colv[cc], d[i][j]);
+            }
+#pragma unroll
+            for (int j = 0; j <= Q; ++j) {                   // columns of the inverse that can be <= c
+                const int cc = ty + 16 * j;
+                if (cc <= c && r > c) e[i][j] = fma(-lr, rowE[cc], e[i][j]);
+            }
+        }
+        // publish the next pivot
+        if (o < 15) {
+            if (tx == o + 1 && ty == o + 1) *pivs = d[Q][Q];
+        } else if (Q < 3) {
+            if (tx == 0 && ty == 0) *pivs = d[Q < 3 ? Q + 1 : Q][Q < 3 ? Q + 1 : Q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cholesky
+// ---------------------------------------------------------------------------------------------------------------
+// grid.x = number of 64-row blocks from the diagonal block down.  Dinv: [n_blocks][64][64] row-major inverses of the
+// diagonal blocks of L.  info: 0, or 1 + the index of the first non-positive pivot (LAPACK's convention).
+__global__ void __launch_bounds__(CH_THREADS) chol_panel_kernel(double* __restrict__ A, int n, int k0, double* __restrict__ Dinv,
+                                                                 int* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned char ch_smem[];
+    double* D = reinterpret_cast<double*>(ch_smem);          // [64][65] diagonal block -> its factor (lower)
+    double* E = D + CH_NB * CH_LD;                           // [64][65] identity -> inverse of the factor (lower)
+    double* S = E + CH_NB * CH_LD;                           // [64][65] this CTA's slab of the panel
+    const int tid = threadIdx.x;
+    ch_load_tile<false>(D, A, n, k0, k0);
+    if (blockIdx.x > 0) ch_load_tile<false>(S, A, n, k0 + CH_NB * blockIdx.x, k0);
+    __syncthreads();
+    // rows past the end of the matrix: identity, so that the factor and its inverse stay defined
+    if (tid < CH_NB && k0 + tid >= n) {
+        for (int c = 0; c < CH_NB; ++c) D[tid * CH_LD + c] = c == tid ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // Right-looking sweep over the 64 columns of the block with the inverse carried along (forward substitution on the
+    // identity, also right-looking, so that no update is a dependent chain).  Thread (ty, tx) of a 16 x 16 grid keeps
+    // its 4 x 4 share of the block and of the inverse in REGISTERS for the whole sweep - element (tx + 16 i, ty + 16 j) -
+    // and only the current column / row travel through shared memory: two barriers and ~100 instructions per column
+    // (ch_sweep16, one instantiation per 16 columns so that register indices stay compile-time constants without
+    // unrolling all 64 columns, which would make the kernel instruction-fetch bound).
+    const int tx = tid & 15, ty = tid >> 4;
+    __shared__ double colv[CH_NB], rowE[CH_NB], pivs;
+    double d[4][4], e[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            d[i][j] = D[(tx + 16 * i) * CH_LD + ty + 16 * j];
+            e[i][j] = (tx + 16 * i == ty + 16 * j) ? 1.0 : 0.0;
+        }
+    if (tid == 0) pivs = d[0][0];
+    const bool report = blockIdx.x == 0;
+    ch_sweep16<0>(d, e, colv, rowE, &pivs, info, k0, report);
+    ch_sweep16<1>(d, e, colv, rowE, &pivs, info, k0, report);
+    ch_sweep16<2>(d, e, colv, rowE, &pivs, info, k0, report);
+    ch_sweep16<3>(d, e, colv, rowE, &pivs, info, k0, report);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            D[(tx + 16 * i) * CH_LD + ty + 16 * j] = d[i][j];
+            E[(tx + 16 * i) * CH_LD + ty + 16 * j] = e[i][j];
+        }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        // the diagonal CTA publishes the factor (lower triangle of the block) and the inverse
+        double* dinv = Dinv + (size_t)(k0 / CH_NB) * CH_NB * CH_NB;
+        for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
+            const int c = idx >> 6, r = idx & 63;                              // r fastest: contiguous in a column
+            if (r >= c && k0 + r < n) A[(size_t)(k0 + c) * n + k0 + r] = D[r * CH_LD + c];
+            dinv[(idx >> 6) * CH_NB + (idx & 63)] = E[(idx >> 6) * CH_LD + (idx & 63)];
+        }
+        return;
+    }
+    // slab: L_slab = A_slab . inv(L_kk)^T, i.e. out(r, c) = sum_j S[r][j] E[c][j]  (E lower: j <= c)
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+    for (int kk = 0; kk < CH_NB; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = S[(tx + 16 * i) * CH_LD + kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = E[(ty + 16 * j) * CH_LD + kk];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    const int row0 = k0 + CH_NB * blockIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gi = row0 + tx + 16 * i, gj = k0 + ty + 16 * j;
+            if (gi < n && gj < n) A[(size_t)gj * n + gi] = acc[i][j];
+        }
+}
+
+// Trailing update after block column k0: tile (bi, bj), bi >= bj, of the blocks below / right of the panel.
+// grid.x enumerates the lower-triangular tile pairs.
+__global__ void __launch_bounds__(CH_THREADS) chol_update_kernel(double* __restrict__ A, int n, int k0) {
+    extern __shared__ __align__(16) unsigned char ch_smem[];
+    double* As = reinterpret_cast<double*>(ch_smem);
+    double* Bs = As + CH_NB * CH_LD;
+    // blockIdx.x -> (bi, bj), bi >= bj >= 0 (triangular enumeration)
+    int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+    while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+    const int bj = blockIdx.x - bi * (bi + 1) / 2;
+    const int i0 = k0 + CH_NB * (bi + 1), j0 = k0 + CH_NB * (bj + 1);
+    ch_load_tile<false>(As, A, n, i0, k0);                    // As[r][kk] = L(i0 + r, k0 + kk)
+    ch_load_tile<true>(Bs, A, n, j0, k0);                     // Bs[kk][c] = L(j0 + c, k0 + kk)
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    ch_tile_fma(As, Bs, acc);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
+            if (gi < n && gj < n && gi >= gj) A[(size_t)gj * n + gi] -= acc[i][j];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Triangular inverse by recursive doubling
+// ---------------------------------------------------------------------------------------------------------------
+// X := 0 with the inverted diagonal blocks on the diagonal.
+__global__ void tri_inverse_seed_kernel(const double* __restrict__ Dinv, double* __restrict__ X, int n) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int j = (int)(idx / n), i = (int)(idx % n);
+    double v = 0.0;
+    if (i >= j && i / CH_NB == j / CH_NB) v = Dinv[(size_t)(i / CH_NB) * CH_NB * CH_NB + (i % CH_NB) * CH_NB + (j % CH_NB)];
+    X[idx] = v;
+}
+
+// One level: the matrix is cut into diagonal blocks of 2h rows; in each, X11 (h x h) and X22 are already inverted and
+//   PHASE 0:  W21 = L21 . X11          (k runs over the first half from the column block down: X11 is lower triangular)
+//   PHASE 1:  X21 = -X22 . W21         (k runs over the second half up to the row block: X22 is lower triangular)
+// grid = (tiles per h x h block = (h / 64)^2, number of 2h blocks).
+template <int PHASE>
+__global__ void __launch_bounds__(CH_THREADS) tri_inverse_level_kernel(const double* __restrict__ L, double* __restrict__ X,
+                                                                        double* __restrict__ W, int n, int h) {
+    extern __shared__ __align__(16) unsigned char ch_smem[];
+    double* As = reinterpret_cast<double*>(ch_smem);
+    double* Bs = As + CH_NB * CH_LD;
+    const int hb = h / CH_NB;
+    const int ti = blockIdx.x / hb, tj = blockIdx.x % hb;
+    const int base = 2 * h * blockIdx.y;                      // first row / column of this 2h block
+    const int i0 = base + h + CH_NB * ti, j0 = base + CH_NB * tj;
+    if (i0 >= n) return;                                      // the second half does not exist (uniform per CTA)
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int kb_lo = PHASE == 0 ? tj : 0, kb_hi = PHASE == 0 ? hb - 1 : ti;
+    for (int kb = kb_lo; kb <= kb_hi; ++kb) {
+        const int k0 = (PHASE == 0 ? base : base + h) + CH_NB * kb;
+        __syncthreads();
+        if (PHASE == 0) {
+            ch_load_tile<false>(As, L, n, i0, k0);            // L21(i, k)
+            ch_load_tile<false>(Bs, X, n, k0, j0);            // X11(k, j)
+        } else {
+            ch_load_tile<false>(As, X, n, i0, k0);            // X22(i, k)
+            ch_load_tile<false>(Bs, W, n, k0, j0);            // W21(k, j)
+        }
+        __syncthreads();
+        ch_tile_fma(As, Bs, acc);
+    }
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double* out = PHASE == 0 ? W : X;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
+            if (gi < n && gj < n) out[(size_t)gj * n + gi] = PHASE == 0 ? acc[i][j] : -acc[i][j];
+        }
+}
+
+// out(i, j) = sum_{k >= i} X(k, i) X(k, j) for i >= j (lower triangle of X^T X); grid.x enumerates the lower tile pairs.
+__global__ void __launch_bounds__(CH_THREADS) tri_gram_kernel(const double* __restrict__ X, double* __restrict__ out, int n) {
+    extern __shared__ __align__(16) unsigned char ch_smem[];
+    double* As = reinterpret_cast<double*>(ch_smem);
+    double* Bs = As + CH_NB * CH_LD;
+    int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+    while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+    const int bj = blockIdx.x - bi * (bi + 1) / 2;
+    const int i0 = CH_NB * bi, j0 = CH_NB * bj;
+    const int nb = (n + CH_NB - 1) / CH_NB;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int kb = bi; kb < nb; ++kb) {
+        __syncthreads();
+        ch_load_tile<true>(As, X, n, CH_NB * kb, i0);         // As[r][kk] = X(k0 + kk, i0 + r)
+        ch_load_tile<false>(Bs, X, n, CH_NB * kb, j0);        // Bs[kk][c] = X(k0 + kk, j0 + c)
+        __syncthreads();
+        ch_tile_fma(As, Bs, acc);
+    }
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
+            if (gi < n && gj < n && gi >= gj) out[(size_t)gj * n + gi] = acc[i][j];
+        }
+}
+
+// z = X y for lower-triangular X: z_i = sum_{j <= i} X(i, j) y_j.  grid = (64-row blocks, chunks of CH_MV_COLS columns);
+// CTA (b, ch) writes the partial sum of its columns to part[ch][i]; tri_matvec_reduce_kernel adds the chunks in order.
+constexpr int CH_MV_COLS = 256;
+__global__ void __launch_bounds__(CH_THREADS) tri_matvec_n_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                                   double* __restrict__ part, int n) {
+    __shared__ double red[4][CH_NB];
+    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int i = blockIdx.x * CH_NB + r;
+    const int j0 = blockIdx.y * CH_MV_COLS;
+    if (j0 > blockIdx.x * CH_NB + CH_NB - 1) return;         // this chunk lies right of the diagonal for all 64 rows
+    double s = 0.0;
+    if (i < n) {
+        const int jend = min(i, j0 + CH_MV_COLS - 1);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};                // 4 loads in flight per thread; fixed combination order
+        int j = j0 + g;
+        for (; j + 12 <= jend; j += 16)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fma(X[(size_t)(j + 4 * u) * n + i], y[j + 4 * u], acc[u]);
+        for (int u = 0; j <= jend; j += 4, ++u) acc[u & 3] = fma(X[(size_t)j * n + i], y[j], acc[u & 3]);
+        s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+    red[g][r] = s;
+    __syncthreads();
+    if (g == 0 && i < n) part[(size_t)blockIdx.y * n + i] = ((red[0][r] + red[1][r]) + red[2][r]) + red[3][r];
+}
+
+__global__ void tri_matvec_reduce_kernel(const double* __restrict__ part, double* __restrict__ z, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int chunks = i / CH_MV_COLS + 1;                   // chunks left of (or on) the diagonal of row i
+    double s = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) s += part[(size_t)ch * n + i];
+    z[i] = s;
+}
+
+// a = X^T z: a_j = sum_{i >= j} X(i, j) z_i.  One warp per column (contiguous), fixed xor tree.
+__global__ void __launch_bounds__(CH_THREADS) tri_matvec_t_kernel(const double* __restrict__ X, const double* __restrict__ z,
+                                                                   double* __restrict__ a, int n) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (CH_THREADS / 32) + (threadIdx.x >> 5);
+    if (j >= n) return;
+    double s = 0.0;
+    for (int i = j + lane; i < n; i += 32) s = fma(X[(size_t)j * n + i], z[i], s);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) a[j] = s;
+}
+
+}  // namespace skb

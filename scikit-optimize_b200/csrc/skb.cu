@@ -14,11 +14,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <cublas_v2.h>       // declarations only, like cuSOLVER below
-#include <cusolverDn.h>      // declarations only: the library is opened lazily with dlopen (fit objective)
-#include <dlfcn.h>
 
 #include "../../include/skb.h"
+#include "chol.cuh"
 #include "fit.cuh"
 #include "grad.cuh"
 #include "kcross.cuh"
@@ -2061,100 +2059,91 @@ int skb_gather_rows_dev(int device, const double* d_X, const int64_t* idx, int32
 // GP fit objective (log marginal likelihood + gradient), fit.cuh
 // ------------------------------------------------------------------------------------------------
 namespace {
-// cuSOLVER is only needed by the fit objective; it is opened on first use so that the scoring path neither links nor
-// loads it.
-struct SolverApi {
-    void* lib = nullptr;
-    decltype(&cusolverDnCreate) create = nullptr;
-    decltype(&cusolverDnDestroy) destroy = nullptr;
-    decltype(&cusolverDnSetStream) set_stream = nullptr;
-    decltype(&cusolverDnDpotrf_bufferSize) potrf_size = nullptr;
-    decltype(&cusolverDnDpotrf) potrf = nullptr;
-    decltype(&cusolverDnDpotrs) potrs = nullptr;
-    // K^-1 = L^-T L^-1 as two plain library GEMM-class calls (cuBLAS trsm on the identity, then syrk): several times
-    // faster than cuSOLVER's potri at n = 1000..4000, and the reference's own formula (gpr.py:223-224)
-    void* blas_lib = nullptr;
-    decltype(&cublasCreate_v2) blas_create = nullptr;
-    decltype(&cublasDestroy_v2) blas_destroy = nullptr;
-    decltype(&cublasSetStream_v2) blas_set_stream = nullptr;
-    decltype(&cublasDtrsm_v2) trsm = nullptr;
-    decltype(&cublasDsyrk_v2) syrk = nullptr;
-    bool ok = false;
-};
-SolverApi g_solver;
-std::mutex g_solver_mu;
-
-int load_solver() {
-    std::lock_guard<std::mutex> lock(g_solver_mu);
-    if (g_solver.ok) return SKB_OK;
-    const char* names[] = {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"};
-    for (const char* nm : names) {
-        g_solver.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (g_solver.lib) break;
-    }
-    if (!g_solver.lib) return fail(SKB_ERR_UNSUPPORTED, "cuSOLVER (libcusolver.so) could not be loaded: %s", dlerror());
-#define SKB_SYM(field, name)                                                                          \
-    g_solver.field = reinterpret_cast<decltype(g_solver.field)>(dlsym(g_solver.lib, name));           \
-    if (!g_solver.field) return fail(SKB_ERR_UNSUPPORTED, "cuSOLVER symbol %s not found", name)
-    SKB_SYM(create, "cusolverDnCreate");
-    SKB_SYM(destroy, "cusolverDnDestroy");
-    SKB_SYM(set_stream, "cusolverDnSetStream");
-    SKB_SYM(potrf_size, "cusolverDnDpotrf_bufferSize");
-    SKB_SYM(potrf, "cusolverDnDpotrf");
-    SKB_SYM(potrs, "cusolverDnDpotrs");
-#undef SKB_SYM
-    const char* blas_names[] = {"libcublas.so.12", "libcublas.so.13", "libcublas.so"};
-    for (const char* nm : blas_names) {
-        g_solver.blas_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (g_solver.blas_lib) break;
-    }
-    if (!g_solver.blas_lib) return fail(SKB_ERR_UNSUPPORTED, "cuBLAS (libcublas.so) could not be loaded: %s", dlerror());
-#define SKB_SYM(field, name)                                                                          \
-    g_solver.field = reinterpret_cast<decltype(g_solver.field)>(dlsym(g_solver.blas_lib, name));      \
-    if (!g_solver.field) return fail(SKB_ERR_UNSUPPORTED, "cuBLAS symbol %s not found", name)
-    SKB_SYM(blas_create, "cublasCreate_v2");
-    SKB_SYM(blas_destroy, "cublasDestroy_v2");
-    SKB_SYM(blas_set_stream, "cublasSetStream_v2");
-    SKB_SYM(trsm, "cublasDtrsm_v2");
-    SKB_SYM(syrk, "cublasDsyrk_v2");
-#undef SKB_SYM
-    g_solver.ok = true;
+// Factorisation / inversion chain of the fit objective: this library's own kernels (csrc/chol.cuh), no cuSOLVER / cuBLAS.
+// Everything is queued on `s`; nothing waits.
+int chol_set_attributes() {            // per device; called by skb_fit_create with the device current (cheap, idempotent)
+    const int big = (int)ch_smem_bytes(), two = (int)(2 * CH_NB * CH_LD * sizeof(double));
+    CU(cudaFuncSetAttribute((const void*)chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute((const void*)chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU(cudaFuncSetAttribute((const void*)tri_inverse_level_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU(cudaFuncSetAttribute((const void*)tri_inverse_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU(cudaFuncSetAttribute((const void*)tri_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     return SKB_OK;
 }
 
-#define SOLVER(call)                                                                                      \
-    do {                                                                                                  \
-        cusolverStatus_t s_ = (call);                                                                     \
-        if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ERR_CUDA, "%s -> cusolver status %d", #call, (int)s_); \
-    } while (0)
-#define BLAS(call)                                                                                        \
-    do {                                                                                                  \
-        cublasStatus_t s_ = (call);                                                                       \
-        if (s_ != CUBLAS_STATUS_SUCCESS) return fail(SKB_ERR_CUDA, "%s -> cublas status %d", #call, (int)s_); \
-    } while (0)
+constexpr size_t CH_TWO_TILES = 2 * (size_t)CH_NB * CH_LD * sizeof(double);
+
+// A (column-major, lower triangle significant) -> its Cholesky factor in place; Dinv gets the inverted diagonal blocks;
+// *info = 0 or 1 + index of the first non-positive pivot.  2 launches per 64 columns.
+int chol_factor(double* A, int n, double* Dinv, int* info, cudaStream_t s) {
+    const int T = (n + CH_NB - 1) / CH_NB;
+    for (int kb = 0; kb < T; ++kb) {
+        chol_panel_kernel<<<T - kb, CH_THREADS, ch_smem_bytes(), s>>>(A, n, kb * CH_NB, Dinv, info);
+        LAUNCHED();
+        const int below = T - kb - 1;
+        if (below > 0) {
+            chol_update_kernel<<<below * (below + 1) / 2, CH_THREADS, CH_TWO_TILES, s>>>(A, n, kb * CH_NB);
+            LAUNCHED();
+        }
+    }
+    return SKB_OK;
+}
+
+// X = L^-1 (lower triangular, exact zeros above the diagonal) from the factor L and its inverted diagonal blocks; W is an
+// n x n scratch.  1 + 2 ceil(log2(n / 64)) launches.
+int tri_inverse(const double* L, const double* Dinv, double* X, double* W, int n, cudaStream_t s) {
+    tri_inverse_seed_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(Dinv, X, n);
+    LAUNCHED();
+    const int T = (n + CH_NB - 1) / CH_NB;
+    for (int h = CH_NB; h < T * CH_NB; h *= 2) {
+        const dim3 grid((unsigned)((h / CH_NB) * (h / CH_NB)), (unsigned)((n + 2 * h - 1) / (2 * h)));
+        tri_inverse_level_kernel<0><<<grid, CH_THREADS, CH_TWO_TILES, s>>>(L, X, W, n, h);
+        LAUNCHED();
+        tri_inverse_level_kernel<1><<<grid, CH_THREADS, CH_TWO_TILES, s>>>(L, X, W, n, h);
+        LAUNCHED();
+    }
+    return SKB_OK;
+}
+
+// out (column-major, lower triangle) = X^T X = K^-1 (gpr.py:224)
+int tri_gram(const double* X, double* out, int n, cudaStream_t s) {
+    const int T = (n + CH_NB - 1) / CH_NB;
+    tri_gram_kernel<<<T * (T + 1) / 2, CH_THREADS, CH_TWO_TILES, s>>>(X, out, n);
+    LAUNCHED();
+    return SKB_OK;
+}
+
+// a = K^-1 y = X^T (X y); z is an n-vector of scratch, part holds ceil(n / CH_MV_COLS) n-vectors
+int tri_solve(const double* X, const double* y, double* z, double* part, double* a, int n, cudaStream_t s) {
+    const dim3 grid((unsigned)((n + CH_NB - 1) / CH_NB), (unsigned)((n + CH_MV_COLS - 1) / CH_MV_COLS));
+    tri_matvec_n_kernel<<<grid, CH_THREADS, 0, s>>>(X, y, part, n);
+    LAUNCHED();
+    tri_matvec_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(part, z, n);
+    LAUNCHED();
+    tri_matvec_t_kernel<<<(n + CH_THREADS / 32 - 1) / (CH_THREADS / 32), CH_THREADS, 0, s>>>(X, z, a, n);
+    LAUNCHED();
+    return SKB_OK;
+}
 }  // namespace
 
-// One evaluation in flight: its own stream, solver handle and n x n workspace, so that several hyper-parameter vectors
-// (the L-BFGS-B restarts of a fit advance in lock step) are evaluated concurrently - a single evaluation at n ~ 1000 is
-// a chain of ~100 small launches that leaves most SMs idle.
 struct FitSlot {
     cudaStream_t stream = nullptr;
-    cusolverDnHandle_t solver = nullptr;
-    cublasHandle_t blas = nullptr;
     double *d_Xs = nullptr, *d_ls = nullptr, *d_K = nullptr, *d_a = nullptr, *d_partial = nullptr, *d_out = nullptr;
-    double* d_V = nullptr;           // [n][n] L^-1 (column-major lower) on the way to K^-1 = L^-T L^-1
-    double* d_work = nullptr;
+    double* d_V = nullptr;           // [n][n] L^-1 (column-major lower, zeros above the diagonal)
+    double* d_W = nullptr;           // [n][n] scratch of the triangular inversion
+    double* d_Dinv = nullptr;        // [ceil(n / 64)][64][64] inverted diagonal blocks of the factor
+    double* d_z = nullptr;           // [n] L^-1 y
     int* d_info = nullptr;
     double* h_pinned = nullptr;      // [MAX_DIMS] length scales in | [MAX_DIMS + 4] results out | 4 ints info
     bool want_grad = false;
 };
 constexpr int FIT_MAX_SLOTS = 8;
-struct SolverCtx { cudaStream_t stream; cusolverDnHandle_t solver; cublasHandle_t blas; double* h_pinned; };
+struct SolverCtx { cudaStream_t stream; double* h_pinned; };
 static std::vector<SolverCtx> g_ctx_cache[64];
 static std::mutex g_ctx_mu;
 
 struct skb_fit {
-    int device = 0, n = 0, d = 0, kernel = 0, n_blocks = 0, lwork = 0;
+    int device = 0, n = 0, d = 0, kernel = 0, n_blocks = 0;
     double alpha = 0;
     std::vector<void*> ptrs;
     double *d_X = nullptr, *d_y = nullptr;
@@ -2184,24 +2173,17 @@ int fit_add_slot(skb_fit* f) {
     FitSlot& sl = f->slots.back();
     const size_t n = (size_t)f->n, d = (size_t)f->d;
     {
-        // stream + solver handle + pinned staging are recycled across fits: creating / destroying a cuSOLVER handle
-        // costs tens of milliseconds, a BO loop builds one skb_fit per tell()
+        // stream + pinned staging are recycled across fits: a BO loop builds one skb_fit per tell()
         std::lock_guard<std::mutex> lock(g_ctx_mu);
         std::vector<SolverCtx>& cache = g_ctx_cache[f->device & 63];
         if (!cache.empty()) {
             sl.stream = cache.back().stream;
-            sl.solver = cache.back().solver;
-            sl.blas = cache.back().blas;
             sl.h_pinned = cache.back().h_pinned;
             cache.pop_back();
         }
     }
     if (!sl.stream) {
         CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        SOLVER(g_solver.create(&sl.solver));
-        SOLVER(g_solver.set_stream(sl.solver, sl.stream));
-        BLAS(g_solver.blas_create(&sl.blas));
-        BLAS(g_solver.blas_set_stream(sl.blas, sl.stream));
         CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
     }
     int r;
@@ -2212,30 +2194,19 @@ int fit_add_slot(skb_fit* f) {
     if ((r = fit_alloc(f, &sl.d_V, n * n)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_out, d + 4)) != SKB_OK) return r;
-    if (f->lwork == 0) {
-        int lw1 = 0;
-        SOLVER(g_solver.potrf_size(sl.solver, CUBLAS_FILL_MODE_LOWER, f->n, sl.d_K, f->n, &lw1));
-        f->lwork = std::max(lw1, 1);
-    }
-    if ((r = fit_alloc(f, &sl.d_work, (size_t)f->lwork)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_W, n * n)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_Dinv, (size_t)((f->n + CH_NB - 1) / CH_NB) * CH_NB * CH_NB)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_z, n)) != SKB_OK) return r;
     double* info_raw = nullptr;
     if ((r = fit_alloc(f, &info_raw, 4)) != SKB_OK) return r;
     sl.d_info = reinterpret_cast<int*>(info_raw);
     return SKB_OK;
 }
 
-// sl.d_K holds the Cholesky factor L (column-major lower).  Queue  sl.d_V = L^-1  (cuBLAS trsm on the identity: the
-// result is lower triangular with exact zeros above the diagonal) and  out_lower = L^-T L^-1 = K^-1  (syrk, column-major
-// lower triangle; `out_lower` may be sl.d_K itself - the factor is then gone).
+// sl.d_K holds the Cholesky factor L and sl.d_V its inverse (fit_issue leaves both).  Queue  out_lower = L^-T L^-1 = K^-1
+// (column-major lower triangle; `out_lower` may be sl.d_K itself - the factor is then gone).
 int fit_inverse_from_factor(skb_fit* f, FitSlot& sl, double* out_lower) {
-    const int n = f->n;
-    const double one = 1.0, zero = 0.0;
-    fit_identity_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, sl.stream>>>(sl.d_V, n);
-    LAUNCHED();
-    BLAS(g_solver.trsm(sl.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, n, &one,
-                       sl.d_K, n, sl.d_V, n));
-    BLAS(g_solver.syrk(sl.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, n, n, &one, sl.d_V, n, &zero, out_lower, n));
-    return SKB_OK;
+    return tri_gram(sl.d_V, out_lower, f->n, sl.stream);
 }
 
 // queue one evaluation on the slot's stream; nothing here waits for the GPU
@@ -2272,9 +2243,11 @@ int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
     CU(cudaMemsetAsync(sl.d_info, 0, 4 * sizeof(int), s));
     // a failed factorisation (info > 0) is only looked at after the whole chain: the later steps then work on garbage
     // but stay inside the workspace, and the result is replaced by (-inf, 0)
-    SOLVER(g_solver.potrf(sl.solver, CUBLAS_FILL_MODE_LOWER, n, sl.d_K, n, sl.d_work, f->lwork, sl.d_info));
-    CU(cudaMemcpyAsync(sl.d_a, f->d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SOLVER(g_solver.potrs(sl.solver, CUBLAS_FILL_MODE_LOWER, n, 1, sl.d_K, n, sl.d_a, n, sl.d_info + 1));
+    // L = chol(K) in place, X = L^-1, alpha = X^T (X y): chol.cuh (sklearn: cholesky + cho_solve, _gpr.py:583-597)
+    int rc_ch;
+    if ((rc_ch = chol_factor(sl.d_K, n, sl.d_Dinv, sl.d_info, s)) != SKB_OK) return rc_ch;
+    if ((rc_ch = tri_inverse(sl.d_K, sl.d_Dinv, sl.d_V, sl.d_W, n, s)) != SKB_OK) return rc_ch;
+    if ((rc_ch = tri_solve(sl.d_V, f->d_y, sl.d_z, sl.d_W, sl.d_a, n, s)) != SKB_OK) return rc_ch;   // d_W: free again after tri_inverse
     fit_lml_kernel<<<1, 256, 0, s>>>(sl.d_K, f->d_y, sl.d_a, n, sl.d_out);
     LAUNCHED();
     if (want_grad) {
@@ -2326,13 +2299,11 @@ void skb_fit_destroy(skb_fit* f) {
     cudaSetDevice(f->device);
     for (FitSlot& sl : f->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        if (sl.stream && sl.solver && sl.blas && sl.h_pinned) {
+        if (sl.stream && sl.h_pinned) {
             std::lock_guard<std::mutex> lock(g_ctx_mu);
-            g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.solver, sl.blas, sl.h_pinned});
+            g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.h_pinned});
             continue;
         }
-        if (sl.blas && g_solver.ok) g_solver.blas_destroy(sl.blas);
-        if (sl.solver && g_solver.ok) g_solver.destroy(sl.solver);
         if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
@@ -2350,7 +2321,8 @@ int skb_fit_create(const skb_fit_desc* desc, int device, skb_fit** out) {
     if (!(desc->alpha >= 0.0)) return fail(SKB_ERR_INVALID, "alpha must be >= 0");
     int rc = check_device(device);
     if (rc != SKB_OK) return rc;
-    if ((rc = load_solver()) != SKB_OK) return rc;
+    CU(cudaSetDevice(device));
+    if ((rc = chol_set_attributes()) != SKB_OK) return rc;
     skb_fit* f = new (std::nothrow) skb_fit();
     if (!f) return fail(SKB_ERR_NOMEM, "host allocation failed");
     f->device = device;
@@ -2419,7 +2391,7 @@ int skb_fit_finalize_host(skb_fit* f, const double* theta, double* lml, double* 
     if (rc != SKB_OK) return rc;
     if ((rc = fit_collect(f, sl, lml, nullptr)) != SKB_OK) return rc;
     if (*slot_h_info(sl) != 0)
-        return fail(SKB_ERR_NOT_POSDEF, "kernel matrix is not positive definite (potrf info = %d)", *slot_h_info(sl));
+        return fail(SKB_ERR_NOT_POSDEF, "kernel matrix is not positive definite (first non-positive pivot: %d)", *slot_h_info(sl));
     CU(cudaMemcpyAsync(alpha_out, sl.d_a, n * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
     if (L_out) {
         if (!f->d_T && (rc = fit_alloc(f, &f->d_T, n * n)) != SKB_OK) return rc;
@@ -2448,7 +2420,7 @@ int skb_state_create_from_fit(skb_fit* f, const skb_state_desc* desc, skb_state*
     if (!f->d_T2 && (rc = fit_alloc(f, &f->d_T2, n * n)) != SKB_OK) return rc;
     cudaStream_t s = sl.stream;
     const unsigned T = (unsigned)((n + 31) / 32);
-    // d_K holds the factor L (column-major lower): L^-1 into d_V and K^-1 = L^-T L^-1 into d_T2 (cuBLAS trsm + syrk), then
+    // d_K holds the factor L (column-major lower) and d_V its inverse: K^-1 = L^-T L^-1 into d_T2 (tri_gram_kernel), then
     // both into the row-major form the pack kernels read (L^-1 -> d_T, K^-1 mirrored to a full matrix -> d_K)
     if ((rc = fit_inverse_from_factor(f, sl, f->d_T2)) != SKB_OK) return rc;
     fit_unpack_lower_kernel<false><<<dim3(T, T), 256, 0, s>>>(sl.d_V, f->d_T, f->n);
