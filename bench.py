@@ -612,6 +612,10 @@ def leg_c5_cl(ctx):
     out = {"config": "BASELINE.json configs[4]: ask(n_points=8, 'cl_min'), n_train=%d, d=%d, %d candidates per liar step "
                      "sharded over %d GPU(s), Matern-5/2 ARD + White refitted on every lie" % (n, d, args.m_cl, world),
            "n_gpus": world}
+    # one-time, per (n_points, n_dims): the MT19937 jump polynomials of the device candidate generator (pure-Python big-integer
+    # work that otherwise runs in a background thread and takes the GIL away from the first fits)
+    from skopt_b200 import mt_jump
+    mt_jump.column_jump_polynomials(2 * args.m_cl, d)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for mode in getattr(Optimizer, "LIAR_UPDATES", ("refit",)):

@@ -6,6 +6,7 @@ shapes and exceptions.  fit() stays on the host (scikit-learn's marginal-likelih
 produces the state; predict() ships that state to the GPU once and runs the CUDA kernels.  There is no CPU fallback
 for the posterior: without the CUDA library or a B200, predict() on a fitted model raises.
 """
+import copy
 import warnings
 
 import numpy as np
@@ -275,6 +276,58 @@ class GaussianProcessRegressor(_SkGPR):
             self.y_train_std_ = self._y_train_std
             self.y_train_mean_ = self._y_train_mean
         return self
+
+    def append_observation(self, x, y):
+        """A fitted copy of this model with ONE more observation (x, y) and the SAME hyper-parameters: the Cholesky factor
+        grows by one row, L' = [[L, 0], [l^T, lam]] with l = L^-1 k(X, x), lam^2 = k(x, x) + noise + alpha - l.l, its
+        inverse by the row [-l^T L^-1 / lam, 1 / lam], and alpha_ = L'^-T L'^-1 y' for the re-normalised targets -
+        O(n^2) instead of the O(n^3) per evaluation of a new hyper-parameter search.  This is what
+        GaussianProcessRegressor(kernel=self.kernel_ [+ the fitted noise], optimizer=None).fit(X', y') computes (tests/
+        test_rank1_append.py); the reference's constant liar (optimizer.py:388-417) instead refits the hyper-parameters on
+        every lie, so the Optimizer only uses this with acq_optimizer_kwargs={"liar_update": "rank1"}.
+        x: one point in the model's (transformed) input space; y: its raw target value."""
+        if not hasattr(self, "X_train_") or "L_" not in self.__dict__:
+            raise ValueError("append_observation needs a fitted model")
+        if np.ndim(self.alpha) != 0 or np.ndim(self.y_train_) != 1:
+            raise NotImplementedError("append_observation supports a scalar alpha and a single target")
+        x = np.asarray(x, dtype=np.float64).reshape(1, -1)
+        if x.shape[1] != self.X_train_.shape[1]:
+            raise ValueError("x has %d features, the model was fitted with %d" % (x.shape[1], self.X_train_.shape[1]))
+        n = self.X_train_.shape[0]
+        L_inv = self._L_inv_lower                           # materialised from L_ on first use (__getattr__)
+        k_vec = self.kernel_(self.X_train_, x)[:, 0]        # kernel_ carries no observation noise any more (fit)
+        kappa = float(self.kernel_(x)[0, 0]) + (self.noise_ or 0.0) + float(self.alpha)
+        l = L_inv.dot(k_vec)
+        lam2 = kappa - float(l.dot(l))
+        if not lam2 > 0.0:
+            raise np.linalg.LinAlgError("the kernel matrix with the appended point is not positive definite")
+        lam = np.sqrt(lam2)
+        new = copy.copy(self)                               # shares kernel_ and the constructor parameters
+        new.__dict__ = dict(self.__dict__)
+        for stale in ("_skb_device_state", "K_inv_", "_skb_device_fit", "log_marginal_likelihood_value_"):
+            new.__dict__.pop(stale, None)
+        L_new = np.zeros((n + 1, n + 1))
+        L_new[:n, :n] = self.L_
+        L_new[n, :n] = l
+        L_new[n, n] = lam
+        Li_new = np.zeros((n + 1, n + 1))
+        Li_new[:n, :n] = L_inv
+        Li_new[n, :n] = -(l.dot(L_inv)) / lam
+        Li_new[n, n] = 1.0 / lam
+        y_raw = np.append(self.y_train_ * self._y_train_std + self._y_train_mean, float(y))
+        if self.normalize_y:
+            new._y_train_mean = np.mean(y_raw, axis=0)
+            new._y_train_std = _handle_zeros_in_scale(np.std(y_raw, axis=0), copy=False)
+        y_new = (y_raw - new._y_train_mean) / new._y_train_std
+        new.y_train_mean_, new.y_train_std_ = new._y_train_mean, new._y_train_std
+        new.X_train_ = np.vstack([self.X_train_, x])
+        new.y_train_ = y_new
+        new.L_ = L_new
+        new._L_inv_lower = Li_new
+        new.alpha_ = Li_new.T.dot(Li_new.dot(y_new))
+        new.log_marginal_likelihood_value_ = float(-0.5 * y_new.dot(new.alpha_) - np.log(np.diag(L_new)).sum()
+                                                   - 0.5 * (n + 1) * np.log(2.0 * np.pi))
+        return new
 
     def device_state(self, device=None):
         """The fitted state resident on the GPU (created on first use, rebuilt after every fit)."""

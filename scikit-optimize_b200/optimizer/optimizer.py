@@ -14,6 +14,7 @@ the reference so that trajectories stay comparable; the scoring block (:550-608)
       n_restarts x fmin_l_bfgs_b(gaussian_acquisition_1D)      lock-step batched restarts, one launch per L-BFGS step
   gains_ -= est.predict(next_xs_)                              device mean-only predict
 """
+import copy
 import sys
 import time
 import warnings
@@ -116,6 +117,12 @@ class Optimizer(object):
         # multi-GPU scoring is opt-in: shard_group=True (default process group) or a torch.distributed group makes
         # every tell() a collective that ALL ranks of the group must enter with identical Optimizer state; the default
         # keeps tell() local so independent optimisers can live inside an initialised process group
+        # constant-liar batches: "refit" (the reference, optimizer.py:388-417: hyper-parameters re-optimised on every lie)
+        # or "rank1" (hyper-parameters of the current model frozen, every lie appended to its Cholesky factor in O(n^2):
+        # GaussianProcessRegressor.append_observation)
+        self.liar_update = acq_optimizer_kwargs.get("liar_update", "refit")
+        if self.liar_update not in self.LIAR_UPDATES:
+            raise ValueError("liar_update must be one of %s, got %r" % (self.LIAR_UPDATES, self.liar_update))
         shard = acq_optimizer_kwargs.get("shard_group", None)
         self._shard_group = False if shard is None or shard is False else (None if shard is True else shard)
         self.acq_optimizer_kwargs = acq_optimizer_kwargs
@@ -156,6 +163,36 @@ class Optimizer(object):
             optimizer._tell(self.Xi, self.yi)
         return optimizer
 
+    LIAR_UPDATES = ("refit", "rank1")
+
+    def _ask_batch_rank1(self, n_points, strategy):
+        """ask(n_points, strategy) with liar_update="rank1": the lies are appended to the CURRENT model (no refit, not
+        even of the throw-away copy): n_points x {score the candidate set, append (x, lie) to the factor}."""
+        sandbox = copy.copy(self)                           # shares the space and the estimator; own lists / rng
+        sandbox.Xi, sandbox.yi = list(self.Xi), list(self.yi)
+        sandbox.models = list(self.models)
+        sandbox.rng = np.random.RandomState(self.rng.randint(0, _INT32_MAX))
+        sandbox.cache_ = {}
+        sandbox.scoring_times_ = self.scoring_times_       # one history: the caller reads the per-step scoring times
+        est = sandbox.models[-1]
+        transformed_bounds = np.array(self.space.transformed_bounds)
+        X = [self._next_x]
+        pick = {"cl_min": np.min, "cl_mean": np.mean, "cl_max": np.max}[strategy]
+        for step in range(n_points):
+            x = X[-1]
+            y_lie = float(pick(sandbox.yi))
+            sandbox.Xi.append(x)
+            sandbox.yi.append(y_lie)
+            if step + 1 == n_points:
+                break
+            est = est.append_observation(self.space.transform([x])[0], y_lie)
+            t_score = time.perf_counter()
+            next_xs = sandbox._score_and_refine(est, transformed_bounds)
+            sandbox.scoring_times_.append(time.perf_counter() - t_score)
+            est.__dict__.pop("_skb_device_state", None)     # one resident state at a time
+            X.append(self.space.inverse_transform(np.asarray(next_xs[0]).reshape((1, -1)))[0])
+        return X
+
     def ask(self, n_points=None, strategy="cl_min"):
         """One point, or `n_points` points by the constant-liar strategy (cl_min / cl_mean / cl_max)."""
         if n_points is None:
@@ -167,6 +204,11 @@ class Optimizer(object):
             raise ValueError("Expected parallel_strategy to be one of " + str(supported) + ", " + "got %s" % strategy)
         if (n_points, strategy) in self.cache_:
             return self.cache_[(n_points, strategy)]
+        if (self.liar_update == "rank1" and self.models and self._n_initial_points <= 0 and hasattr(self, "_next_x")
+                and self.acq_func in ("EI", "PI", "LCB") and hasattr(self.models[-1], "append_observation")):
+            X = self._ask_batch_rank1(n_points, strategy)
+            self.cache_ = {(n_points, strategy): X}
+            return X
 
         # the lies are told to a throw-away copy (one rng draw seeds it, as in the reference)
         opt = self.copy(random_state=self.rng.randint(0, _INT32_MAX))

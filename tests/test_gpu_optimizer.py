@@ -232,3 +232,41 @@ def test_expected_minimum_and_persistence(tmp_path):
     assert back.x == res.x and back.fun == res.fun
     Xq = np.random.RandomState(0).rand(50, 2)
     np.testing.assert_array_equal(back.models[-1].predict(Xq), model.predict(Xq))
+
+
+def test_constant_liar_rank1_batch_equals_manual_frozen_kernel_loop():
+    """Optimizer(liar_update="rank1").ask(n_points, 'cl_min'): every lie is appended to the current model's factor
+    (hyper-parameters frozen); the batch equals a hand-written loop that refits a fixed-kernel GP from scratch on the
+    lied data and scores the same candidate stream on the GPU."""
+    import numpy as np
+    from skopt_b200 import Optimizer
+    from skopt_b200.learning import GaussianProcessRegressor
+    rng = np.random.RandomState(3)
+    d, n0 = 3, 30
+    X0 = rng.rand(n0, d)
+    y0 = np.sin(X0.dot(rng.randn(d))) + 0.05 * rng.randn(n0)
+    kw = dict(n_points=5000, liar_update="rank1")
+    opt = Optimizer([(0.0, 1.0)] * d, "GP", n_initial_points=n0, acq_func="EI", acq_optimizer="sampling",
+                    acq_optimizer_kwargs=kw, random_state=7)
+    opt.tell(X0.tolist(), y0.tolist())
+    state = opt.rng.get_state()
+    batch = opt.ask(n_points=4, strategy="cl_min")
+    assert len(batch) == 4 and batch[0] == opt._next_x and len({tuple(b) for b in batch}) == 4
+    assert opt.ask(n_points=4, strategy="cl_min") is batch                     # cached, like the reference
+    # manual loop: same sandbox seed, same candidate streams, from-scratch fits with the fitted kernel frozen
+    model = opt.models[-1]
+    sandbox_rng = np.random.RandomState()
+    sandbox_rng.set_state(state)
+    sandbox_rng = np.random.RandomState(sandbox_rng.randint(0, np.iinfo(np.int32).max))
+    Xi, yi = [list(x) for x in X0.tolist()], list(y0)
+    expect = [batch[0]]
+    for step in range(3):
+        Xi.append(expect[-1])
+        yi.append(float(np.min(yi)))
+        frozen = GaussianProcessRegressor(kernel=model.kernel_, noise=model.noise_, normalize_y=model.normalize_y,
+                                          alpha=model.alpha, optimizer=None).fit(opt.space.transform(Xi), yi)
+        cand = opt.space.rvs_transformed(5000, sandbox_rng)
+        res = frozen.device_state().score(cand, y_opt=float(np.min(yi)), acq_funcs=("EI",), top_k=1)
+        x = np.clip(cand[int(res["EI"]["topk_idx"][0])], 0.0, 1.0)
+        expect.append(opt.space.inverse_transform(x.reshape(1, -1))[0])
+    assert batch == expect
