@@ -62,7 +62,35 @@ def _reverse_communication_driver():
 _SETULB = _reverse_communication_driver()
 
 
-def _minimize_batch_stepper(x0s, evaluate, bounds, maxiter, m=10, factr=1e7, pgtol=1e-5, maxls=20):
+def _stepper_agrees_with_public_api():
+    """The stepper drives a PRIVATE SciPy routine with a hand-written argument list; a SciPy whose workspace layout or task
+    codes changed could pass the one-call probe above and still produce other iterates.  So, once per process: a small
+    bounded problem (Rosenbrock in 3 variables, active bounds) through the stepper and through fmin_l_bfgs_b must give
+    identical x, f, iteration and evaluation counts - otherwise the threaded public-API driver is used."""
+    def fg(x):
+        f = float(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1.0 - x[:-1]) ** 2))
+        g = np.zeros_like(x)
+        g[:-1] = -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1.0 - x[:-1])
+        g[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+        return f, g
+
+    bounds = [(-1.5, 0.8), (-0.5, 2.0), (0.1, 3.0)]
+    starts = [np.array([-1.2, 1.0, 0.5]), np.array([0.5, 0.5, 2.5])]
+    try:
+        def evaluate(tasks, X):
+            vals = [fg(x) for x in X]
+            return np.array([v[0] for v in vals]), np.vstack([v[1] for v in vals])
+        got = _minimize_batch_stepper(starts, evaluate, bounds, maxiter=25)
+        for x0, (x, f, info) in zip(starts, got):
+            xr, fr, ir = fmin_l_bfgs_b(fg, x0, bounds=bounds, approx_grad=False, maxiter=25)
+            if not (np.array_equal(x, xr) and f == fr and info["nit"] == ir["nit"] and info["funcalls"] == ir["funcalls"]):
+                return False
+        return True
+    except Exception:    # noqa: BLE001
+        return False
+
+
+def _minimize_batch_stepper(x0s, evaluate, bounds, maxiter, m=10, factr=1e7, pgtol=1e-5, maxls=20, maxfun=15000):
     """Same searches as fmin_l_bfgs_b (identical arguments to the same compiled stepper, same bookkeeping as
     scipy/optimize/_lbfgsb_py.py:_minimize_lbfgsb), but all of them are stepped from ONE Python loop: every search
     runs until it asks for f and g, the requests are evaluated in one batch, and so on.  No threads, and SciPy's
@@ -107,6 +135,9 @@ def _minimize_batch_stepper(x0s, evaluate, bounds, maxiter, m=10, factr=1e7, pgt
                 _SETULB(m, s.x, low_bnd, upper_bnd, nbd, s.f, s.g, factr, pgtol, s.wa, s.iwa, s.task, s.lsave, s.isave,
                         s.dsave, maxls, s.ln_task)
                 if s.task[0] == 3:                  # wants f and g at the current x
+                    if s.nfev >= maxfun:            # SciPy's evaluation budget (_lbfgsb_py.py: task 5 / 502, warnflag 1)
+                        s.task[0], s.task[1] = 5, 502
+                        continue
                     pending.append(t)
                     break
                 if s.task[0] == 1:                  # a new iterate has been accepted
@@ -126,7 +157,8 @@ def _minimize_batch_stepper(x0s, evaluate, bounds, maxiter, m=10, factr=1e7, pgt
             s.g = np.array(G[i], dtype=np.float64, copy=True)
             s.nfev += 1
     return [(s.x, s.f, {"grad": s.g, "funcalls": s.nfev, "nit": s.nit,
-                        "warnflag": 0 if s.task[0] == 4 else (1 if s.nit >= maxiter else 2)}) for s in searches]
+                        "warnflag": 0 if s.task[0] == 4 else (1 if (s.nit >= maxiter or s.nfev >= maxfun) else 2)})
+            for s in searches]
 
 
 def minimize_batch(x0s, evaluate, bounds, maxiter=20, driver="auto"):
@@ -194,3 +226,7 @@ def minimize_batch(x0s, evaluate, bounds, maxiter=20, driver="auto"):
         if e is not None:
             raise e
     return results
+
+
+if _SETULB is not None and not _stepper_agrees_with_public_api():
+    _SETULB = None                                     # fall back to fmin_l_bfgs_b in threads (same iterates, slower)
