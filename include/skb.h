@@ -305,6 +305,12 @@ int skb_state_get_timing(skb_state* st, double* ms_by_kind, int64_t* launches_by
  * Two ~1 ms kernels, run four times each; synchronises the device. */
 int skb_measure_peaks(int device, double* i8_mac_per_clk_sm, double* i8_tops, double* fp64_dmma_tflops);
 
+/* Diagnostics of the 6-plane contraction kernel (tools/k2o_diag.py, profiles/r02_k2o_diagnosis.md): `reps` launches of the kernel
+ * alone over `tiles64` 64-candidate tiles of whatever the scratch holds, with parts switched off (dbg bit 0: no epilogue work,
+ * bit 1: no operand copies, bit 2: no accumulator hand-over, bit 4: no stage barriers; 8: complete kernel, only timed).
+ * Returns milliseconds per launch and the mean SM cycles a CTA spent.  Not used by any product path. */
+int skb_debug_k2o(skb_state* st, int dbg, int64_t tiles64, int reps, double* ms_per_launch, double* cycles_per_cta);
+
 /* Number of kernel launches issued through this library by the calling process so far (bench.py reports it). */
 int64_t skb_launch_count(void);
 

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("skb_fit_finalize_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_state_create_from_fit", C.c_int, [C.c_void_p, C.POINTER(StateDesc), C.POINTER(C.c_void_p)]),
     ("skb_measure_peaks", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("skb_debug_k2o", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("skb_launch_count", C.c_int64, []),
 ]
 

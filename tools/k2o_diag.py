@@ -13,8 +13,6 @@ if os.environ.get('SKB_LIB'):
 gpr, y_opt = bench.make_problem(2048, 20)
 dev = gpr.device_state(0)
 L = _lib.lib()
-L.skb_debug_k2o.restype = C.c_int
-L.skb_debug_k2o.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
 tiles = 148 * 8
 out = {}
 for name, dbg in (("full", 0), ("full_timed", 8), ("no_epilogue", 1), ("no_copies", 2), ("mma_only", 3), ("mma_only_no_handover", 7), ("mma_only_no_barriers", 23), ("copies_no_handover_no_epilogue", 5), ("full_again", 0)):
