@@ -90,3 +90,47 @@ def test_score_record_matches_score_tensors_and_pads_empty_shards():
     for name in acqs:
         assert np.array_equal(merged[name]["topk_idx"], rec[name]["topk_idx"])
         assert np.array_equal(merged[name]["topk_val"].view(np.int64), rec[name]["topk_val"].view(np.int64))
+
+
+def test_topk_dev_and_gradient_records_match_numpy():
+    """skb_topk_dev ranks a value vector that already lives on the GPU; score_grad_tensors(top_k=...) uses it to pack the
+    record of the acquisition values next to the gradients (bench.py c4_grad).  Against np.lexsort on the same values."""
+    import torch
+    from skopt_b200 import engine
+    from oracle import gp_oracle as orc
+    from tests.test_gpu_parity import host_state_from_oracle_state
+    st = orc.make_synthetic_state(96, 5, noise=1e-4, seed=2)
+    dev = engine.DeviceState(host_state_from_oracle_state(st))
+    rng = np.random.RandomState(5)
+    X = rng.rand(3000, 5)
+    X[7] = X[1500]                                          # an exact tie: the lower index must win
+    acqs, k, off = ("EI", "LCB"), 12, 10_000
+    out = dev.score_grad_tensors(torch.from_numpy(X).cuda(), y_opt=float(st.meta["y"].min()), acq_funcs=acqs, top_k=k,
+                                 index_offset=off)
+    torch.cuda.synchronize()
+    rec = engine.unpack_record(out["record"], acqs, k)
+    host = dev.score_grad(X, y_opt=float(st.meta["y"].min()), acq_funcs=acqs)
+    for name in acqs:
+        v = out[name]["values"].cpu().numpy()
+        assert np.array_equal(v, host[name]["values"])                         # tensor and host entry points agree bit for bit
+        assert np.array_equal(out[name]["grad"].cpu().numpy(), host[name]["grad"])
+        order = np.lexsort((np.arange(v.size), v))[:k]
+        assert rec[name]["topk_idx"].tolist() == (order + off).tolist()
+        assert np.array_equal(rec[name]["topk_val"].view(np.int64), v[order].view(np.int64))
+        assert rec[name]["first_nan"] == -1
+    # a second call into the same output buffers (no allocation) gives the same record
+    again = dev.score_grad_tensors(torch.from_numpy(X).cuda(), y_opt=float(st.meta["y"].min()), acq_funcs=acqs, top_k=k,
+                                   index_offset=off, out=out)
+    torch.cuda.synchronize()
+    assert again is out and torch.equal(again["record"], out["record"])
+    dev.close()
+
+
+def test_measure_peaks_is_plausible():
+    """skb_measure_peaks: the roofline denominators bench.py uses, measured on the device (tcgen05 kind::i8 issue rate at
+    M=128, N=256 and the DMMA rate)."""
+    from skopt_b200 import engine
+    p = engine.measure_peaks(0)
+    assert 7000.0 < p["i8_mac_per_clk_sm"] <= 8192.5                # 8192 MAC per clock per SM is the issue limit
+    assert 2000.0 < p["i8_tops"] < 6000.0
+    assert 20.0 < p["fp64_dmma_tflops"] < 45.0
