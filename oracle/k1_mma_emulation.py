@@ -90,3 +90,30 @@ def matern52_scaled(s5, amp, bias, seed_rel_error=0.0):
     """kernel_value_scaled<3>: s5 = 5 r^2; amplitude folded into the polynomial."""
     K = sqrt_third_order(np.maximum(s5, 1e-290), seed_rel_error)
     return fma(fma(K, fma(K, amp * (1.0 / 3.0), amp), amp), np.exp(-K), bias)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exp_nonpos_table (csrc/kcross.cuh): 32-entry table + degree-6 polynomial, restated with NumPy (no fused multiply-add on
+# the host: each fma is rounded twice here, so this restatement is a few 1e-17 LESS accurate than the kernel)
+# ---------------------------------------------------------------------------------------------------------------
+EXP32_TABLE = np.array([
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
+    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467,
+    1.4768261459394993, 1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
+    1.9152065613971474, 1.9571441241754002])
+
+
+def exp_table(x):
+    x = np.asarray(x, dtype=np.float64)
+    magic = 6755399441055744.0
+    fn = x * 46.16624130844683 + magic
+    n = fn - magic
+    r = (x + n * -0.02166084938653512) + n * -5.9631716539705866e-12
+    p = r * (1.0 / 720.0) + 1.0 / 120.0
+    for c in (1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0):
+        p = p * r + c
+    ni = n.astype(np.int64)
+    out = np.ldexp(p * EXP32_TABLE[ni & 31], (ni >> 5).astype(np.int32))
+    return np.where(x < -708.0, 0.0, out)

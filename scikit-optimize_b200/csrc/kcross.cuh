@@ -426,6 +426,42 @@ __device__ __forceinline__ double sqrt_pos_third(double s) {
     return fma(g * e, fma(0.375, e, 0.5), g);
 }
 
+// exp(x) for x <= 0 (or +1e-15-ish), not NaN, by a 32-entry table: x = (32 m + j) ln2 / 32 + r with |r| <= ln2 / 64, so
+// exp(x) = 2^m * 2^(j/32) * exp(r) and exp(r) needs a degree-6 polynomial (remainder r^7 / 5040 < 4e-18) instead of the
+// degree-13 one of exp_nonpos_short: 11 instead of 18 FP64 instructions per kernel value (K1 spends 53 per value at d = 20).
+// The table (correctly rounded 2^(j/32)) is staged in shared memory by the kernel: lanes index it independently.
+__constant__ double c_exp32[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
+    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467,
+    1.4768261459394993, 1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
+    1.9152065613971474, 1.9571441241754002};
+__constant__ double c_exp32k[10] = {
+    46.16624130844683,                  // [0] 32 / ln2
+    6755399441055744.0,                 // [1] 1.5 * 2^52
+    -0.02166084938653512,               // [2] -ln2 / 32, high part (21 trailing zero bits: n * hi is exact for |n| < 2^16)
+    -5.9631716539705866e-12,            // [3] -ln2 / 32, low part
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,      // [4..8]
+    -708.0                              // [9]
+};
+__device__ __forceinline__ double exp_nonpos_table(double x, const double* __restrict__ tab) {
+    const double fn = fma(x, c_exp32k[0], c_exp32k[1]);
+    const double n = fn - c_exp32k[1];
+    double r = fma(n, c_exp32k[2], x);
+    r = fma(n, c_exp32k[3], r);
+    double p = fma(r, c_exp32k[4], c_exp32k[5]);
+    p = fma(p, r, c_exp32k[6]);
+    p = fma(p, r, c_exp32k[7]);
+    p = fma(p, r, c_exp32k[8]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(fn);                        // low word of (1.5 * 2^52 + n): n in two's complement
+    p *= tab[ni & 31];
+    const double scaled = __hiloint2double(__double2hiint(p) + ((ni >> 5) << 20), __double2loint(p));
+    return x < c_exp32k[9] ? 0.0 : scaled;
+}
+
 // Distance scale folded into the squared distance: the transform receives A * r^2 with A = -1/2 (RBF), 3 (Matern 3/2),
 // 5 (Matern 5/2), so that the square root IS the kernel argument K and no separate multiplication is needed.
 template <int KIND>
@@ -434,10 +470,10 @@ __device__ __forceinline__ constexpr double dist_scale() { return KIND == 0 ? -0
 // amplitude * base(r) + bias from the scaled squared distance; amp3 = amplitude / 3 (Matern 5/2 only).  The amplitude is
 // folded into the polynomial: amp (1 + K + K^2/3) e^-K + bias = fma(fma(K, fma(K, amp3, amp), amp), e^-K, bias).
 template <int KIND>
-__device__ __forceinline__ double kernel_value_scaled(double sa, double amp, double amp3, double bias) {
-    if (KIND == 0) return fma(amp, exp_nonpos_short(sa), bias);
+__device__ __forceinline__ double kernel_value_scaled(double sa, double amp, double amp3, double bias, const double* __restrict__ etab) {
+    if (KIND == 0) return fma(amp, exp_nonpos_table(sa, etab), bias);
     const double K = sqrt_pos_third(sa > 1e-290 ? sa : 1e-290);
-    const double e = exp_nonpos_short(-K);
+    const double e = exp_nonpos_table(-K, etab);
     if (KIND == 2) return fma(fma(K, amp, amp), e, bias);
     return fma(fma(K, fma(K, amp3, amp), amp), e, bias);
 }
@@ -447,7 +483,7 @@ __device__ __forceinline__ double kernel_value_scaled(double sa, double amp, dou
 // The row stride CB + 8 of the transposed candidate tile is 8 mod 16 doubles: the A-fragment read (4 features x 8
 // candidates) is conflict-free.
 constexpr size_t kcross_mma_smem_bytes(int d_pad, int cb = BN) {
-    return sizeof(double) * ((size_t)d_pad * (cb + 8) + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + 2 * XROWS + cb) +
+    return sizeof(double) * ((size_t)d_pad * (cb + 8) + 2 * (size_t)XG * d_pad * 4 + 2 * XROWS + 2 * XROWS + cb + 32) +
            2 * sizeof(uint64_t);
 }
 
@@ -466,7 +502,8 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
     double* tnb = al + 2 * XROWS;                              // [2][XROWS] squared norms of the staged training rows
     double* xs = tnb + 2 * XROWS;                              // [d_pad][XS_LD_MMA]
     double* xnorm = xs + (size_t)d_pad * XS_LD_MMA;            // [CB] |x|^2 of the candidates
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xnorm + CB);
+    double* etab = xnorm + CB;                                 // [32] 2^(j/32) for exp_nonpos_table
+    uint64_t* bars = reinterpret_cast<uint64_t*>(etab + 32);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rq = CB == 128 ? warp >> 1 : warp, e = CB == 128 ? warp & 1 : 0, t4 = lane & 3, c8 = lane >> 2;
@@ -477,6 +514,7 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
         mbar_init(bars + 1, 1);
         mbar_fence_init();
     }
+    if (tid < 32) etab[tid] = c_exp32[tid];
     for (int idx = tid; idx < CB * d_pad; idx += NT) {
         const int cc = idx / d_pad, k = idx - cc * d_pad;
         const int64_t row = tile * CB + cc;
@@ -552,7 +590,7 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
             for (int r = 0; r < 4; ++r) {                     // training row 4 t4 + r = tile r >> 1, accumulator r & 1
                 // A |x - t|^2 = A |x|^2 + A |t|^2 - 2 A x.t; a slightly wrong-signed result (x == t) becomes K = 0
                 const double sa = fma(-2.0 * A, acc[ci][r >> 1][r & 1], xn[ci] + tnr[r]);
-                const double val = kernel_value_scaled<KIND>(sa, p.amplitude, amp3, p.bias);
+                const double val = kernel_value_scaled<KIND>(sa, p.amplitude, amp3, p.bias, etab);
                 macc[ci] = fma(val, alr[r], macc[ci]);
                 const unsigned long long y =
                     ((unsigned long long)__double_as_longlong(fma(val, q.inv_scale, 6755399441055744.0)) + DIGIT_BIAS) ^ DIGIT_BIAS;

@@ -61,3 +61,25 @@ def test_third_order_square_root_and_folded_polynomial():
     # the 6-plane path rounds kernel values to 2^-47 of the kernel scale: the transform must be far inside that
     assert np.max(np.abs(got - reference)) <= 2.0 ** -50 * (amp + bias)
     assert em.matern52_scaled(np.array([0.0, -1e-17]), amp, bias)[0] == amp + bias  # x == t (also when cancellation leaves -0)
+
+
+def test_table_exponential_accuracy():
+    """exp_nonpos_table (the 6-plane K1's exponential since round 2): 32-entry table + degree-6 polynomial.  The NumPy
+    restatement (double rounding instead of FMA, so slightly worse than the kernel) stays within 4e-16 relative of a
+    high-precision exponential over the whole argument range of the kernels; the 6-plane path needs 3.5e-15 of the
+    kernel SCALE; entries of the table are the correctly rounded 2^(j/32)."""
+    from decimal import Decimal, getcontext
+    from oracle import k1_mma_emulation as em
+    getcontext().prec = 50
+    ln2 = Decimal(2).ln()
+    for j in range(32):
+        assert em.EXP32_TABLE[j] == float((ln2 * j / 32).exp())
+    rng = np.random.RandomState(0)
+    x = -np.concatenate([rng.rand(20000) * 40.0, rng.rand(2000) * 1e-6, rng.rand(2000) * 700.0, [0.0, 1e-300, 708.0]])
+    got = em.exp_table(x)
+    ref = np.array([float(Decimal(float(v)).exp()) for v in x[::37]])
+    rel = np.abs(got[::37] - ref) / ref
+    assert rel.max() <= 4e-16, rel.max()
+    assert np.max(np.abs(got - np.exp(x)) / np.exp(x)) <= 6e-16          # and against libm on all points
+    assert em.exp_table(np.array([-709.0, -1e4]))[0] == 0.0 and em.exp_table(np.array([-1e4]))[0] == 0.0
+    assert em.exp_table(np.array([0.0]))[0] == 1.0
