@@ -149,6 +149,10 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void oz_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -187,8 +191,15 @@ __device__ __forceinline__ double oz_colsum32(double (&v)[32], int lane) {
 // DBG (diagnostics only, skb_debug_k2o / tools/k2o_diag.py; 0 in every product launch): bit 0 = the epilogue warps skip
 // the TMEM reads and the FP64 recombination, bit 1 = the producer signals the stages full without copying anything,
 // bit 2 = no accumulator hand-over between row blocks (one at the very end), bit 4 = no stage barriers at all (the MMAs
-// read whatever the stages hold); any bit: the CTA's SM cycle count goes to p.dbg_cycles.
-template <int MODE, int P, int DBG = 0>
+// read whatever the stages hold), bit 5 = operands are copied once per stage and re-used (real data, no L2 -> SM traffic);
+// any bit: the CTA's SM cycle count goes to p.dbg_cycles.
+// CL > 1 (MODE 0 only): the kernel is launched in clusters of CL CTAs along x.  All CTAs of a cluster walk the same
+// (row block, chunk) sequence for different candidate tiles, so every L_inv chunk is fetched from L2 ONCE per cluster: CTA r
+// copies slice r of it and multicasts the slice into the same stage of all CL CTAs; a stage is free again when the MMAs of
+// ALL CL CTAs have read it (tcgen05.commit multicast onto every CTA's `empty` barrier, which counts CL arrivals).  The
+// L2 -> SM operand traffic is what holds this kernel's clock down under the board's power cap (tools/k2o_power.py: the
+// same MMAs on operands that stay in shared memory run 18 % faster); the L_inv planes are two thirds of it.
+template <int MODE, int P, int DBG = 0, int CL = 1>
 __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     constexpr int OZ_STAGES = oz_stages(P);
     constexpr int OZ_STAGE_BYTES = oz_stage_bytes(P);
@@ -208,7 +219,7 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, CL);
         }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, OZ_EPI_WARPS);
@@ -220,11 +231,16 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();             // every CTA's barriers exist before a peer's copy or commit can reach them
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
     const long long dbg_t0 = DBG ? clock64() : 0;
+    const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
 
-    const int tile_id = MODE == 0 ? blockIdx.x : blockIdx.y;
+    // a cluster launch rounds the grid up: surplus CTAs re-read the last tile's planes and store nothing (cand >= m)
+    const int last_tile = MODE == 0 ? (int)((p.m + OZ_NC - 1) / OZ_NC) - 1 : 0;
+    const int tile_id = MODE == 0 ? (CL > 1 ? min((int)blockIdx.x, last_tile) : (int)blockIdx.x) : blockIdx.y;
     const int I_begin = MODE == 0 ? 0 : blockIdx.x;
     const int I_end = MODE == 0 ? p.n_pad / BM : blockIdx.x + 1;
     const int nkc_used = (p.n + OZ_KC - 1) / OZ_KC;
@@ -242,13 +258,19 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
                     const int s = it % OZ_STAGES;
                     const uint32_t ph = (it / OZ_STAGES) & 1;
                     mbar_wait(empty + s, ph ^ 1);
-                    if (DBG & 2) {
+                    if ((DBG & 2) || ((DBG & 32) && it >= (uint32_t)OZ_STAGES)) {   // 32: real operands once per stage, then stale
                         mbar_arrive(full + s);
                         continue;
                     }
                     mbar_arrive_expect_tx(full + s, OZ_STAGE_BYTES);
                     unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
-                    bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, A_BYTES, full + s);        // leading P of the 7 packed planes
+                    if (CL == 1) {
+                        bulk_g2s(dst, vrow + (size_t)kc * OZ_A_CHUNK, A_BYTES, full + s);    // leading P of the 7 packed planes
+                    } else {
+                        constexpr int SLICE = A_BYTES / CL;                                   // my share of the chunk, to everybody
+                        bulk_g2s_multicast(dst + cl_rank * SLICE, vrow + (size_t)kc * OZ_A_CHUNK + cl_rank * SLICE, SLICE, full + s,
+                                           CL_MASK);
+                    }
                     bulk_g2s(dst + A_BYTES, kd_tile + (size_t)kc * OZ_B_CHUNK, OZ_B_CHUNK, full + s);
                 }
             }
@@ -288,7 +310,10 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
                             oz_mma(tmem + OZ_NC * pl + r0, da, db, oz_idesc(N), (acc | (pl > 0 ? 1u : 0u)));
                         }
                     }
-                    if (!(DBG & 16)) oz_commit(empty + s);  // smem slot is free once these MMAs have read it
+                    if (!(DBG & 16)) {                      // smem slot is free once these MMAs (of every CTA of the cluster) have read it
+                        if (CL == 1) oz_commit(empty + s);
+                        else oz_commit_multicast(empty + s, CL_MASK);
+                    }
                 }
                 if (!(DBG & 4) || I == I_end - 1) oz_commit(tmem_full);   // all MMAs of row block I retired -> epilogue may read
             }
@@ -355,6 +380,7 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();             // nobody leaves while a peer's commit may still be on its way to this CTA
     if (DBG && threadIdx.x == 0 && p.dbg_cycles) p.dbg_cycles[blockIdx.x] = clock64() - dbg_t0;
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }

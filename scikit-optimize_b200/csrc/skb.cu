@@ -770,6 +770,57 @@ static int attach_kinv_impl(skb_state* st, const double* K_inv, cudaMemcpyKind k
     return rc;
 }
 
+constexpr int K2O_CLUSTER_DEFAULT = 1;
+
+// K2o launch, optionally in clusters of `cl` CTAs that share every L_inv chunk by multicast (ozaki.cuh).  cl = 1: plain launch.
+template <int P, int DBG, int CL>
+static int launch_k2o_cluster(const OzakiParams& op, unsigned tiles64, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, P, DBG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(P)));
+        CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, P, DBG, CL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dev & 63] = true;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((tiles64 + CL - 1) / CL * CL, 1, 1);
+    cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = oz_smem_bytes(P);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, ozaki_trmm_kernel<0, P, DBG, CL>, op));
+    return SKB_OK;
+}
+
+// CTAs per cluster of the value-path contraction: SKB_K2O_CLUSTER = 1 | 2 | 4 (default below)
+static int k2o_cluster_size() {
+    static const int cl = [] {
+        const char* e = getenv("SKB_K2O_CLUSTER");
+        const int v = e ? atoi(e) : K2O_CLUSTER_DEFAULT;
+        return (v == 2 || v == 4) ? v : 1;
+    }();
+    return cl;
+}
+
+template <int P>
+static int launch_k2o(const OzakiParams& op, unsigned tiles64, cudaStream_t s) {
+    switch (k2o_cluster_size()) {
+        case 2: return launch_k2o_cluster<P, 0, 2>(op, tiles64, s);
+        case 4: return launch_k2o_cluster<P, 0, 4>(op, tiles64, s);
+        default:
+            ozaki_trmm_kernel<0, P><<<tiles64, OZ_THREADS, oz_smem_bytes(P), s>>>(op);
+            return SKB_OK;
+    }
+}
+
 extern "C" {
 
 void* skb_state_stream(skb_state* st) { return st ? (void*)st->stream : nullptr; }
@@ -1080,10 +1131,8 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             op.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
             if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
             op.Wt = nullptr;
-            if (planes == 6)
-                ozaki_trmm_kernel<0, 6><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(6), s>>>(op);
-            else
-                ozaki_trmm_kernel<0, 7><<<(unsigned)((mc + OZ_NC - 1) / OZ_NC), OZ_THREADS, oz_smem_bytes(7), s>>>(op);
+            if ((rc = planes == 6 ? launch_k2o<6>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)
+                                  : launch_k2o<7>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)) != SKB_OK) return rc;
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
             if (overlap) CU(cudaEventRecord(st->ev_k2[chunk_index], s));
@@ -1811,6 +1860,9 @@ int skb_debug_k2o(skb_state* st, int dbg, int64_t tiles64, int reps, double* ms_
             case 5: ozaki_trmm_kernel<0, 6, 5><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
             case 8: ozaki_trmm_kernel<0, 6, 8><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
             case 23: ozaki_trmm_kernel<0, 6, 23><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 32: ozaki_trmm_kernel<0, 6, 32><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
+            case 102: launch_k2o_cluster<6, 8, 2>(op, g, s); break;      // complete kernel in clusters of 2 / 4, timed
+            case 104: launch_k2o_cluster<6, 8, 4>(op, g, s); break;
             default: ozaki_trmm_kernel<0, 6><<<g, OZ_THREADS, oz_smem_bytes(6), s>>>(op); break;
         }
     };
@@ -1821,6 +1873,7 @@ int skb_debug_k2o(skb_state* st, int dbg, int64_t tiles64, int reps, double* ms_
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
     launch();
     CU(cudaEventRecord(e0, s));
     for (int r = 0; r < reps; ++r) {
