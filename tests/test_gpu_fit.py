@@ -129,14 +129,17 @@ def _fixed_kernel_problem(n, d, nu, seed):
     return X, y, kernel, rng
 
 
-@pytest.mark.parametrize("n,d", [(33, 2), (300, 5), (1100, 12)])
+# sizes around the 64-column blocks of the library's own Cholesky / recursive-doubling inverse (csrc/chol.cuh): one block,
+# partial blocks, 2 / 3 / 5 blocks (odd block counts leave a pair without its second half at some level)
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 1), (33, 2), (63, 2), (64, 2), (65, 2), (127, 3), (128, 3), (129, 3), (200, 3),
+                                 (300, 5), (321, 4), (1100, 12)])
 def test_finalize_matches_host_factorisation(n, d):
     """skb_fit_finalize_host: L_, alpha_ and the lml at theta* against SciPy's Cholesky of the same K."""
     from scipy.linalg import cho_solve, cholesky
     from skopt_b200.engine import DeviceFit, FitLayout
     from skopt_b200.learning.gaussian_process.kernels import WhiteKernel
     X, y, kernel, _ = _fixed_kernel_problem(n, d, 2.5, n)
-    y = (y - y.mean()) / y.std()
+    y = (y - y.mean()) / (y.std() if y.std() > 0 else 1.0)
     full_kernel = kernel + WhiteKernel(1e-3, "fixed")
     lay = FitLayout(full_kernel, d)
     fit = DeviceFit(X, y, lay.kind, 1e-10)
@@ -171,7 +174,7 @@ def test_finalize_not_positive_definite_raises():
     fit.close()
 
 
-@pytest.mark.parametrize("n,d,nu", [(33, 2, 2.5), (300, 5, 1.5), (1100, 12, 2.5)])
+@pytest.mark.parametrize("n,d,nu", [(33, 2, 2.5), (65, 2, 2.5), (129, 3, 1.5), (300, 5, 1.5), (1100, 12, 2.5)])
 def test_state_built_on_device_scores_like_the_host_built_state(n, d, nu):
     """fit(optimizer=None) finalised on the GPU (skb_state_create_from_fit: trtri, potri, packing on the device) against
     the same model finalised on the host (SciPy factor, solve_triangular, upload): posterior, acquisition, arg-min and
