@@ -201,6 +201,11 @@ int skb_ps_combine_host(int device, int64_t m, int32_t n_dims, const double* acq
 int skb_topk_host(int device, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,
                   int64_t* topk_idx, int64_t* first_nan);
 
+/* predict(X, return_cov=True) (gpr.py:315-325): mean [m] (may be NULL) and quad [m * m] = K_trans . K_inv . K_trans^T (row-major,
+ * kernel units; the caller forms (kernel(X) - quad) * y_std^2).  Needs K_inv (skb_state_attach_kinv); all m points form one
+ * batch, limited by the state's scratch (SKB_ERR_UNSUPPORTED beyond it: a joint covariance is asked for a handful of points). */
+int skb_predict_cov_host(skb_state* st, const double* X, int64_t m, double* mean, double* quad);
+
 /* The same ranking for a value vector that already lives on the state's GPU (e.g. the acq[] output of
  * skb_score_grad_dev): enqueued on `stream`, no host synchronisation; uses the state's scratch like the scoring calls. */
 int skb_topk_dev(skb_state* st, const double* values, int64_t m, int64_t index_offset, int32_t top_k, double* topk_val,

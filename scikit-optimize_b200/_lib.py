@@ -82,6 +82,7 @@ SYMBOLS = [
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("skb_topk_host", C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    ("skb_predict_cov_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("skb_topk_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     ("skb_topk_merge_records_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

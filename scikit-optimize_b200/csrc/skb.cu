@@ -1612,6 +1612,69 @@ int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq
     return stage_finish(st, s);
 }
 
+// predict(X, return_cov=True) (gpr.py:315-325): mean [m] (may be NULL) and quad [m * m] = K_trans . K_inv . K_trans^T in
+// kernel units; the caller forms (kernel(X) - quad) * y_std^2.  All of X is one batch: the two n_pad x 128 x tiles scratch
+// panels must fit the state's scratch limit (a joint covariance is asked for a handful of points).
+int skb_predict_cov_host(skb_state* st, const double* X, int64_t m, double* mean, double* quad) {
+    if (!st || !quad) return fail(SKB_ERR_INVALID, "state/quad is NULL");
+    if (m < 0) return fail(SKB_ERR_INVALID, "m must be >= 0");
+    if (m > 0 && !X) return fail(SKB_ERR_INVALID, "X is NULL");
+    if (!st->d_Ap) return fail(SKB_ERR_UNSUPPORTED, "state was created without K_inv: the covariance entry point is unavailable");
+    CU(cudaSetDevice(st->device));
+    if (m == 0) return SKB_OK;
+    cudaStream_t s = st->stream;
+    const int64_t tiles = (m + BN - 1) / BN;
+    const size_t tile_bytes = 2 * (size_t)st->n_pad * BN * sizeof(double);
+    if ((size_t)tiles * tile_bytes > st->scratch_limit)
+        return fail(SKB_ERR_UNSUPPORTED, "return_cov on the device takes at most %lld points for this state (scratch limit), got %lld",
+                    (long long)(st->scratch_limit / tile_bytes * BN), (long long)m);
+    int rc;
+    const size_t d = st->d;
+    if ((rc = grow(st->device, &st->d_X, &st->x_cap, (size_t)m * d)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)m * m + (size_t)m)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_Wt, &st->wt_cap, (size_t)tiles * st->n_pad * BN)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)tiles * BN)) != SKB_OK) return rc;
+    if ((rc = stage_begin(st)) != SKB_OK) return rc;
+    if ((rc = h2d(st, st->d_X, X, (size_t)m * d * sizeof(double), s)) != SKB_OK) return rc;
+    KCrossParams kp;
+    kp.X = st->d_X;
+    kp.ls = st->d_ls;
+    kp.Xp = st->d_Xp;
+    kp.alpha_p = st->d_alpha_p;
+    kp.Kt = st->d_Kt;
+    kp.kdot = st->d_kdot;
+    kp.m = m;
+    kp.n = st->n;
+    kp.n_pad = st->n_pad;
+    kp.d = st->d;
+    kp.d_pad = st->d_pad;
+    kp.amplitude = st->amplitude;
+    kp.bias = st->bias;
+    if ((rc = launch_kcross(st, kp, (int)tiles, s)) != SKB_OK) return rc;
+    TrmmParams tp;
+    std::memset(&tp, 0, sizeof(tp));
+    tp.Kt = st->d_Kt;
+    tp.n_pad = st->n_pad;
+    tp.n = st->n;
+    tp.m = m;
+    tp.Ap = st->d_Ap;
+    tp.Wt = st->d_Wt;
+    trmm_kernel<1><<<dim3(st->n_pad / BM, (unsigned)tiles), TRMM_THREADS, trmm_smem_bytes(), s>>>(tp);
+    LAUNCHED();
+    double* d_quad = st->d_out;
+    double* d_mean = st->d_out + (size_t)m * m;
+    cov_quad_kernel<<<dim3((unsigned)tiles, (unsigned)tiles), 256, 0, s>>>(st->d_Kt, st->d_Wt, d_quad, st->n, st->n_pad, m);
+    LAUNCHED();
+    if (mean) {
+        mean_affine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(st->d_kdot, d_mean, m, st->y_std, st->y_mean);
+        LAUNCHED();
+        if ((rc = d2h(st, mean, d_mean, m * sizeof(double), s)) != SKB_OK) return rc;
+    }
+    if ((rc = d2h(st, quad, d_quad, (size_t)m * m * sizeof(double), s)) != SKB_OK) return rc;
+    return stage_finish(st, s);
+}
+
 int skb_acq_from_posterior_host(int device, int64_t m, int32_t n_dims, const double* mu, const double* sd,
                                 const double* mu_grad, const double* sd_grad, const skb_acq_params* prm,
                                 double* const acq[3], double* const acq_grad[3]) {

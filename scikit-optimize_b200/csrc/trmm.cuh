@@ -240,4 +240,52 @@ __global__ void __launch_bounds__(TRMM_THREADS, 1) trmm_kernel(const TrmmParams 
     }
 }
 
+
+// Joint posterior covariance of a handful of points (gpr.py:320-325, `predict(return_cov=True)`): after the dense product
+// W = K_inv . K_trans^T (trmm_kernel<1>) the quadratic form Q = K_trans . W is one more tile product,
+//   Q[a][b] = sum_j Kt(tile ta, j, ca) * Wt(tile tb, j, cb),
+// grid = (tb, ta), thread (ty, tx) owns rows ty + 16 i, columns tx + 16 j of the 128 x 128 block; 16 training points per round.
+constexpr int COV_JB = 16;
+__global__ void __launch_bounds__(256) cov_quad_kernel(const double* __restrict__ Kt, const double* __restrict__ Wt,
+                                                        double* __restrict__ Q, int n, int n_pad, int64_t m) {
+    __shared__ double sK[COV_JB][BN + 1];
+    __shared__ double sW[COV_JB][BN];
+    const int tb = blockIdx.x, ta = blockIdx.y, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double* kt = Kt + (size_t)ta * n_pad * BN;          // [n_pad / 4][BN][4]
+    const double* wt = Wt + (size_t)tb * n_pad * BN;          // [n_pad][BN]
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int j0 = 0; j0 < n; j0 += COV_JB) {
+        __syncthreads();
+        for (int e = tid; e < COV_JB * BN; e += 256) {
+            const int g4 = e / (BN * 4), c = (e % (BN * 4)) >> 2, q = e & 3;
+            sK[g4 * 4 + q][c] = kt[(size_t)(j0 / 4) * BN * 4 + e];
+            sW[e / BN][e % BN] = wt[(size_t)j0 * BN + e];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int jj = 0; jj < COV_JB; ++jj) {
+            double a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = sK[jj][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = sW[jj][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t ra = (int64_t)ta * BN + ty + 16 * i, cb = (int64_t)tb * BN + tx + 16 * j;
+            if (ra < m && cb < m) Q[ra * m + cb] = acc[i][j];
+        }
+}
+
 }  // namespace skb

@@ -310,6 +310,16 @@ class DeviceState:
         _lib.check(_lib.lib().skb_predict_mean_host(self._h, X.ctypes.data, X.shape[0], mean.ctypes.data))
         return mean
 
+    def predict_cov(self, X):
+        """(mean [m], quad [m, m]) with quad = K_trans K_inv K_trans^T in kernel units: the device half of
+        predict(return_cov=True) (gpr.py:315-325).  Raises SkbError (unsupported) when m exceeds the state's scratch."""
+        X = self._check_X(X)
+        m = X.shape[0]
+        self._attach_kinv()
+        mean, quad = np.empty(m), np.empty((m, m))
+        _lib.check(_lib.lib().skb_predict_cov_host(self._h, X.ctypes.data, m, mean.ctypes.data, quad.ctypes.data))
+        return mean, quad
+
     def score(self, X, y_opt=None, acq_funcs=("EI",), xi=0.01, kappa=1.96, top_k=0, index_offset=0,
               want_posterior=True, want_values=True, precision="fp64"):
         """One pass over the candidates: posterior, every requested acquisition, and their top-k.

@@ -17,7 +17,7 @@ from sklearn.preprocessing._data import _handle_zeros_in_scale
 from sklearn.utils import check_array, check_random_state
 from sklearn.utils.validation import validate_data
 
-from ... import engine
+from ... import _lib, engine
 from .kernels import RBF, ConstantKernel, Sum, WhiteKernel
 
 _DEFAULT_DEVICE = [0]
@@ -358,7 +358,15 @@ class GaussianProcessRegressor(_SkGPR):
             return y_mean
 
         if return_cov:
-            # off the hot path: joint covariance of a handful of points, kept on the host
+            # gpr.py:320-325.  The O(n^2 m) product K_inv K_trans^T and the O(n m^2) quadratic form run on the GPU; kernel_(X)
+            # (m^2 d) stays on the host.  Point sets beyond the state's scratch (thousands of points) fall back to the host.
+            if X.shape[0] <= 2048 and hasattr(self, "K_inv_"):
+                try:
+                    y_mean, quad = self.device_state().predict_cov(X)
+                    return y_mean, (self.kernel_(X) - quad) * self.y_train_std_ ** 2
+                except _lib.SkbError as exc:
+                    if exc.code != -2:                 # SKB_ERR_UNSUPPORTED: more points than the scratch holds
+                        raise
             K_trans = self.kernel_(X, self.X_train_)
             y_mean = self.y_train_std_ * K_trans.dot(self.alpha_) + self.y_train_mean_
             y_cov = self.kernel_(X) - K_trans.dot(cho_solve((self.L_, True), K_trans.T))

@@ -186,6 +186,16 @@ class AbiModel:
         _view(mean, (m,))[:] = orc.predict(st.gp, _view(X, (m, st.gp.d)))
         return OK
 
+    def skb_predict_cov_host(self, handle, X, m, mean, quad):
+        st = self._states[_addr(handle)]
+        self.calls.append("skb_predict_cov_host")
+        Xv = _view(X, (m, st.gp.d))
+        K_trans = orc.kernel_cross(st.gp, Xv)
+        if mean:
+            _view(mean, (m,))[:] = orc.predict(st.gp, Xv)
+        _view(quad, (m, m))[:] = K_trans.dot(st.gp.K_inv).dot(K_trans.T)
+        return OK
+
     def skb_score_host(self, handle, X, m, index_offset, prm, out):
         st = self._states[_addr(handle)]
         prm, out = _obj(prm), _obj(out)

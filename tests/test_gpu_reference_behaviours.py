@@ -282,3 +282,32 @@ def test_constant_liar_batches(strategy):
     assert opt2.ask(n_points=5, strategy=strategy) == pts
     with pytest.raises(ValueError):
         opt.ask(n_points=2, strategy="cl_median")
+
+
+@pytest.mark.parametrize("m", [1, 5, 130, 300])
+def test_return_cov_on_device_matches_the_reference_formula(m):
+    """predict(return_cov=True) (gpr.py:315-325): the quadratic form K_trans K_inv K_trans^T is computed on the GPU
+    (skb_predict_cov_host: K1, dense K_inv product, one more tile product); against cho_solve on the host at 1e-9 of the
+    prior variance, symmetric to rounding, and the diagonal equal to return_std squared."""
+    from scipy.linalg import cho_solve
+    from skopt_b200.learning import GaussianProcessRegressor
+    from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
+    rng = np.random.RandomState(m)
+    n, d = 200, 4
+    X = rng.rand(n, d)
+    y = np.sin(X.dot(rng.randn(d))) + 0.05 * rng.randn(n)
+    gpr = GaussianProcessRegressor(ConstantKernel(1.7, "fixed") * Matern(np.full(d, 0.7), "fixed", nu=1.5), normalize_y=True,
+                                   noise=1e-3, optimizer=None).fit(X, y)
+    Xq = rng.rand(m, d)
+    Xq[0] = X[3]                                             # a training point: covariance row close to the noise level
+    mean, cov = gpr.predict(Xq, return_cov=True)
+    K_trans = gpr.kernel_(Xq, gpr.X_train_)
+    ref_mean = gpr.y_train_std_ * K_trans.dot(gpr.alpha_) + gpr.y_train_mean_
+    ref = (gpr.kernel_(Xq) - K_trans.dot(cho_solve((gpr.L_, True), K_trans.T))) * gpr.y_train_std_ ** 2
+    scale = 1.7 * gpr.y_train_std_ ** 2
+    assert cov.shape == (m, m)
+    assert np.max(np.abs(mean - ref_mean)) <= 1e-9 * max(np.max(np.abs(ref_mean)), gpr.y_train_std_)
+    assert np.max(np.abs(cov - ref)) <= 1e-9 * scale
+    assert np.max(np.abs(cov - cov.T)) <= 1e-12 * scale
+    _, std = gpr.predict(Xq, return_std=True)
+    assert np.max(np.abs(np.diag(cov) - std ** 2)) <= 1e-9 * scale
