@@ -487,9 +487,10 @@ constexpr size_t kcross_mma_smem_bytes(int d_pad, int cb = BN) {
            2 * sizeof(uint64_t);
 }
 
-template <int KIND, int CB = BN>
+template <int KIND, int CB = BN, int NCT = 64>
 __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(const KDigitParams q) {
     constexpr int P = 6;
+    static_assert(NCT == 64 || (NCT == 80 && CB == 128), "contraction tiles of 64 candidates, or 80 with the 128-candidate CTA");
     constexpr int XS_LD_MMA = CB + 8;
     constexpr int NT = 2 * CB;
     constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull >> (8 * (8 - P));
@@ -550,8 +551,21 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
         macc[ci] = 0.0;
     }
     const int nkc_all = p.n_pad / 32;
-    // MMA tile 2 * tile + e; [chunk of 32][k half][plane][cand group ci][cand c8][16 B]: this lane's word is bytes 4 t4 .. + 3
-    int8_t* kd_base = q.Kd + ((size_t)(tile * (CB / 64) + e) * nkc_all) * (2 * P * 8 * 128) + (rq & 1) * (P * 8 * 128) + c8 * 16 + 4 * t4;
+    // Digit bytes go where the contraction kernel reads them: per contraction tile of NC = 8 G candidates and per chunk of 32
+    // training rows, [k half][plane][candidate group of 8][candidate][16 B]; this lane's word is bytes 4 t4 .. + 3 of a
+    // candidate's 16-byte vector.  The CTA's 8-candidate groups are numbered through the whole candidate stream
+    // (group index / G = contraction tile, % G = group inside it), so the same kernel serves 64- and 80-candidate tiles
+    // (NCT): with G = 8 a warp's eight groups fill exactly one tile, with G = 10 they straddle at most one tile boundary;
+    // groups past it (ci >= ci_wrap) land `wrap` bytes further on, in the next tile (at most 8 MB: n_pad <= 16384).
+    constexpr int G = NCT / 8;
+    constexpr uint32_t chunk_bytes = 2 * P * G * 128;
+    const int64_t grp0 = tile * (CB / 8) + 8 * e;             // first of this warp's eight groups
+    const int g0 = (int)(grp0 % G);
+    const int ci_wrap = G - g0;                                // >= 8 when G == 8: never
+    const uint32_t wrap = (uint32_t)nkc_all * chunk_bytes - (uint32_t)G * 128;
+    int8_t* kd_base = q.Kd + (size_t)(grp0 / G) * nkc_all * chunk_bytes + (size_t)(rq & 1) * (P * G * 128) + (size_t)g0 * 128 +
+                      c8 * 16 + 4 * t4;
+    constexpr int plane_stride = G * 128;
     const double* xa = xs + t4 * XS_LD_MMA + 64 * e + c8;      // A fragment: feature k0 + t4, candidate 8 ci + c8
 
     for (int st = 0; st < nst; ++st) {
@@ -582,7 +596,7 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
             tnr[r] = A * tn4[r];
             alr[r] = alb[r];
         }
-        int8_t* dst = kd_base + (size_t)(st * 2 + (rq >> 1)) * (2 * P * 8 * 128);
+        int8_t* dst = kd_base + (size_t)(st * 2 + (rq >> 1)) * chunk_bytes;
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
             uint32_t lo[4], hi[4];
@@ -604,7 +618,7 @@ __global__ void __launch_bounds__(2 * CB, 256 / CB) kcross_digits_mma_kernel(con
                 const uint32_t* src = byte < 4 ? lo : hi;
                 const uint32_t t0 = __byte_perm(src[0], src[1], b | ((4 + b) << 4));
                 const uint32_t t1 = __byte_perm(src[2], src[3], b | ((4 + b) << 4));
-                *reinterpret_cast<uint32_t*>(dst + pl * (8 * 128) + ci * 128) = __byte_perm(t0, t1, 0x5410);
+                *reinterpret_cast<uint32_t*>(dst + pl * plane_stride + ci * 128 + (G != 8 && ci >= ci_wrap ? wrap : 0u)) = __byte_perm(t0, t1, 0x5410);
             }
         }
         __syncthreads();

@@ -44,18 +44,20 @@ constexpr unsigned long long OZ_BIAS = 0x0080808080808080ull;      // +128 in ea
 // 28): difference to the exact contraction 4e-12 of the prior variance at (2048, 20) - the 1e-9 gate with a factor
 // of 200 to spare - against 2e-14 for P = 7 (oracle/split_emulation.py, tests/test_split_emulation.py).
 __host__ __device__ constexpr int oz_a_bytes(int P) { return P * BM * OZ_KC; }                      // leading planes of one A chunk
-__host__ __device__ constexpr int oz_b_half(int P) { return P * (OZ_NC / 8) * 128; }                // [plane][cand group 8][8 cands][16 B] per k half
-__host__ __device__ constexpr int oz_b_chunk(int P) { return 2 * oz_b_half(P); }                    // 14,336 B (P = 7), 12,288 B (P = 6)
-__host__ __device__ constexpr int oz_stage_bytes(int P) { return oz_a_bytes(P) + oz_b_chunk(P); }   // 43,008 B / 36,864 B
+__host__ __device__ constexpr int oz_b_half(int P, int nc = OZ_NC) { return P * (nc / 8) * 128; }                // [plane][cand group 8][8 cands][16 B] per k half
+__host__ __device__ constexpr int oz_b_chunk(int P, int nc = OZ_NC) { return 2 * oz_b_half(P, nc); }                    // 14,336 B (P = 7), 12,288 B (P = 6)
+__host__ __device__ constexpr int oz_stage_bytes(int P, int nc = OZ_NC) { return oz_a_bytes(P) + oz_b_chunk(P, nc); }   // 43,008 B / 36,864 B
 // Build-time knobs for the co-residency experiment (profiles/r02_k2o_diagnosis.md): -DOZ_STAGES6=4 -DOZ_MAXNREG=152 leave
 // room on the SM for one 64-candidate K1 CTA (SKB_SPLIT_OVERLAP=1); measured equal in speed to the defaults.
 #ifndef OZ_STAGES6
 #define OZ_STAGES6 5
 #endif
+// 168 is the ceiling for this CTA shape: its 10 warps land 3 + 3 + 2 + 2 on the SM's four sub-partitions of 16,384 registers
+// each, and 3 warps x 32 lanes x 176 registers no longer fit one of them ("too many resources requested for launch").
 #ifndef OZ_MAXNREG
 #define OZ_MAXNREG 168
 #endif
-__host__ __device__ constexpr int oz_stages(int P) { return P >= 7 ? 4 : OZ_STAGES6; }
+__host__ __device__ constexpr int oz_stages(int P, int nc = OZ_NC) { return P >= 7 ? 4 : OZ_STAGES6; }
 
 // byte offset of (row, k) inside one canonical K-major, no-swizzle (rows x 32) int8 block: 8-row x 16-byte core matrices
 __host__ __device__ inline int oz_canon(int rows, int row, int k) {
@@ -133,7 +135,9 @@ struct OzakiParams {
     long long* dbg_cycles;    // diagnostics (skb_debug_k2o): SM cycles each CTA spent between its setup and its teardown
 };
 
-constexpr size_t oz_smem_bytes(int P) { return (size_t)oz_stages(P) * oz_stage_bytes(P) + 4 * OZ_NC * sizeof(double) + 256; }
+constexpr size_t oz_smem_bytes(int P, int nc = OZ_NC) {
+    return (size_t)oz_stages(P, nc) * oz_stage_bytes(P, nc) + 4 * nc * sizeof(double) + 256;
+}
 
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -199,17 +203,22 @@ __device__ __forceinline__ double oz_colsum32(double (&v)[32], int lane) {
 // ALL CL CTAs have read it (tcgen05.commit multicast onto every CTA's `empty` barrier, which counts CL arrivals).  The
 // L2 -> SM operand traffic is what holds this kernel's clock down under the board's power cap (tools/k2o_power.py: the
 // same MMAs on operands that stay in shared memory run 18 % faster); the L_inv planes are two thirds of it.
-template <int MODE, int P, int DBG = 0, int CL = 1>
+// NC = candidates per CTA: 64, or 80 (P = 6 only: 6 x 80 = 480 of the 512 TMEM columns).  The wider tile delivers 13 % fewer
+// operand bytes per MAC into shared memory (what the power cap charges for, tools/k2o_power.py) and its instruction widths
+// (240+240 | 208+192 | 160+160 | 240 | 160 | 80) run at 0.995 of the issue rate instead of 0.982 (umma_i8_shapes.cu).
+template <int MODE, int P, int DBG = 0, int CL = 1, int NC = OZ_NC>
 __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
-    constexpr int OZ_STAGES = oz_stages(P);
-    constexpr int OZ_STAGE_BYTES = oz_stage_bytes(P);
-    constexpr int OZ_B_HALF = oz_b_half(P);
-    constexpr int OZ_B_CHUNK = oz_b_chunk(P);
+    static_assert(NC % 16 == 0 && NC * P <= OZ_TMEM_COLS, "accumulator regions must fit TMEM");
+    static_assert(MODE == 0 || NC == OZ_NC, "the dense mode keeps 64-candidate tiles");
+    constexpr int OZ_STAGES = oz_stages(P, NC);
+    constexpr int OZ_STAGE_BYTES = oz_stage_bytes(P, NC);
+    constexpr int OZ_B_HALF = oz_b_half(P, NC);
+    constexpr int OZ_B_CHUNK = oz_b_chunk(P, NC);
     constexpr int A_BYTES = oz_a_bytes(P);
     extern __shared__ __align__(1024) unsigned char smem_oz[];
     unsigned char* stages = smem_oz;                                          // [OZ_STAGES][A chunk | B chunk]
-    double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][OZ_NC]
-    uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 4 * OZ_NC);
+    double* sRed = reinterpret_cast<double*>(stages + (size_t)OZ_STAGES * OZ_STAGE_BYTES);   // [4 row quarters][NC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 4 * NC);
     uint64_t* empty = full + OZ_STAGES;
     uint64_t* tmem_full = empty + OZ_STAGES;
     uint64_t* tmem_empty = tmem_full + 1;
@@ -239,7 +248,7 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
 
     // a cluster launch rounds the grid up: surplus CTAs re-read the last tile's planes and store nothing (cand >= m)
-    const int last_tile = MODE == 0 ? (int)((p.m + OZ_NC - 1) / OZ_NC) - 1 : 0;
+    const int last_tile = MODE == 0 ? (int)((p.m + NC - 1) / NC) - 1 : 0;
     const int tile_id = MODE == 0 ? (CL > 1 ? min((int)blockIdx.x, last_tile) : (int)blockIdx.x) : blockIdx.y;
     const int I_begin = MODE == 0 ? 0 : blockIdx.x;
     const int I_end = MODE == 0 ? p.n_pad / BM : blockIdx.x + 1;
@@ -298,8 +307,8 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
                         const uint64_t da = oz_smem_desc(a_base + pl * (BM * OZ_KC), (BM / 8) * 128, 128);
                         // B rows [0, 64 (P - pl)) = planes 0 .. P-1-pl of all 64 candidates -> accumulator columns
                         // [64 pl, 64 P); split so that every instruction has N <= 256 (and N a multiple of 16).
-                        const int rows = OZ_NC * (P - pl);
-                        const int n0 = rows <= 256 ? rows : (pl == 0 ? 256 : rows / 2);
+                        const int rows = NC * (P - pl);
+                        const int n0 = rows <= 256 ? rows : (NC == OZ_NC ? (pl == 0 ? 256 : rows / 2) : (rows / 2 + 15) / 16 * 16);
 #pragma unroll
                         for (int piece = 0; piece < 2; ++piece) {
                             const int r0 = piece == 0 ? 0 : n0;
@@ -307,7 +316,7 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
                             if (N <= 0) continue;
                             const uint64_t db = oz_smem_desc(b_base + (r0 >> 3) * 128, OZ_B_HALF, 128);
                             // plane 0 touches every column first: it clears the accumulators on the first chunk
-                            oz_mma(tmem + OZ_NC * pl + r0, da, db, oz_idesc(N), (acc | (pl > 0 ? 1u : 0u)));
+                            oz_mma(tmem + NC * pl + r0, da, db, oz_idesc(N), (acc | (pl > 0 ? 1u : 0u)));
                         }
                     }
                     if (!(DBG & 16)) {                      // smem slot is free once these MMAs (of every CTA of the cluster) have read it
@@ -324,20 +333,20 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
         // (no cross-lane traffic per row block); lanes and quarters are combined once at the end. ----------------
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const double cK = p.k_scale * 6.103515625e-05;       // sK * 2^-14
-        double qacc[OZ_NC / 2];
+        double qacc[NC / 2];
 #pragma unroll
-        for (int c = 0; c < OZ_NC / 2; ++c) qacc[c] = 0.0;
+        for (int c = 0; c < NC / 2; ++c) qacc[c] = 0.0;
         for (int I = (DBG & 4) ? I_end - 1 : I_begin; I < I_end; ++I) {
             mbar_wait(tmem_full, (DBG & 4) ? 0u : (uint32_t)((I - I_begin) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const double rs = p.sV[I * BM + quarter * 32 + lane] * cK;
 #pragma unroll
-            for (int jj = 0; jj < ((DBG & 1) ? 0 : OZ_NC / 16); ++jj) {
-                const int j = half * (OZ_NC / 16) + jj;
+            for (int jj = 0; jj < ((DBG & 1) ? 0 : NC / 16); ++jj) {
+                const int j = half * (NC / 16) + jj;
                 // all P regions of these 8 candidates are requested before the single wait: one TMEM round trip
                 uint32_t g[P][8];
 #pragma unroll
-                for (int t = 0; t < P; ++t) oz_ld8_issue(tmem + ((uint32_t)(quarter * 32) << 16) + OZ_NC * t + 8 * j, g[t]);
+                for (int t = 0; t < P; ++t) oz_ld8_issue(tmem + ((uint32_t)(quarter * 32) << 16) + NC * t + 8 * j, g[t]);
                 oz_ld_wait();
                 double u[8];
 #pragma unroll
@@ -351,7 +360,7 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
                 if (MODE == 1) {
                     // row of W owned by this lane, 8 consecutive candidates: one 64-byte store
                     double* w = p.Wt + ((size_t)(tile_id >> 1) * p.n_pad + I * BM + quarter * 32 + lane) * BN +
-                                (tile_id & 1) * OZ_NC + 8 * j;
+                                (tile_id & 1) * NC + 8 * j;
                     *reinterpret_cast<double4*>(w) = make_double4(u[0], u[1], u[2], u[3]);
                     *reinterpret_cast<double4*>(w + 4) = make_double4(u[4], u[5], u[6], u[7]);
                 }
@@ -360,13 +369,27 @@ __global__ void __maxnreg__(OZ_MAXNREG) ozaki_trmm_kernel(const OzakiParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
         }
-        if (MODE == 0) sRed[quarter * OZ_NC + half * (OZ_NC / 2) + lane] = oz_colsum32(qacc, lane);
+        if (MODE == 0) {
+            if (NC / 2 > 32) {
+                // columns 32 .. NC/2 - 1 first (xor tree over the lanes, the same fixed order for every column) ...
+#pragma unroll
+                for (int c = 32; c < NC / 2; ++c) {
+                    double v = qacc[c];
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == c - 32) sRed[quarter * NC + half * (NC / 2) + c] = v;
+                }
+            }
+            // ... then the transposing butterfly over the first 32 (it overwrites its argument)
+            double (&q32)[32] = *reinterpret_cast<double (*)[32]>(&qacc[0]);
+            sRed[quarter * NC + half * (NC / 2) + lane] = oz_colsum32(q32, lane);
+        }
         named_bar_sync(1, 32 * OZ_EPI_WARPS);
         const int t = threadIdx.x - 64;                       // 0 .. 255 over the epilogue warps
-        if (MODE == 0 && t < OZ_NC) {
-            const int64_t cand = (int64_t)blockIdx.x * OZ_NC + t;
+        if (MODE == 0 && t < NC) {
+            const int64_t cand = (int64_t)blockIdx.x * NC + t;
             if (cand < p.m) {
-                const double q = ((sRed[t] + sRed[OZ_NC + t]) + sRed[2 * OZ_NC + t]) + sRed[3 * OZ_NC + t];
+                const double q = ((sRed[t] + sRed[NC + t]) + sRed[2 * NC + t]) + sRed[3 * NC + t];
                 double mu, sd, acq[3];
                 if (posterior_from_q(p.a, p.kdot[cand], q, mu, sd) && p.clamp_count) atomicAdd(p.clamp_count, 1ull);
                 acquisition_values(p.a, mu, sd, acq);

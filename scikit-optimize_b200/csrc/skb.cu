@@ -458,17 +458,35 @@ void launch_kcross_digits_planes(int kernel, const KDigitParams& p, int tiles, s
     }
 }
 
-// `planes` digit planes per kernel value (6 or 7); p.inv_scale is set here to 2^(8 planes - 1) / sK
-int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s, bool small_cta = false) {
+// 6 planes, kinds whose distance may be taken as |x|^2 + |t|^2 - 2 x.t: the x.t part on DMMA tiles (SKB_K1_MMA=0 keeps
+// the DFMA variant, for A/B measurements)
+static bool k1_uses_mma(const skb_state* st, int planes) {
+    static const bool k1_mma = [] { const char* e = std::getenv("SKB_K1_MMA"); return !(e && e[0] == '0'); }();
+    const bool dot_kind = st->kernel == SKB_KERNEL_RBF || st->kernel == SKB_KERNEL_MATERN32 || st->kernel == SKB_KERNEL_MATERN52;
+    return planes == 6 && k1_mma && dot_kind;
+}
+
+// Candidates per contraction tile of the value path: 64.  SKB_K2O_NC=80 selects the 80-candidate tile (6 x 80 = 480 of the 512
+// TMEM columns) where the 6-plane digits come from kcross_digits_mma_kernel, the kernel that can address either tile width.
+// Measured at (2048, 20), 10^6 candidates, chunks of whole waves for both widths (gpurun A/B, 2 x 2 bench runs): the
+// contraction gains 0.6 % per candidate (13 % fewer operand bytes per MAC, instruction widths at 0.995 of the issue rate), K1
+// loses 5 % (the wrap of a warp's eight groups over a tile boundary costs registers: 52 bytes of spills), the step loses 1 % -
+// so the wide tile is an experiment, not the default (profiles/r02_k2o_nc80.md).
+static int k2o_tile_candidates(const skb_state* st, int planes, bool small_cta) {
+    static const bool wide = [] { const char* e = std::getenv("SKB_K2O_NC"); return e && std::atoi(e) == 80; }();
+    return wide && !small_cta && k1_uses_mma(st, planes) ? 80 : OZ_NC;
+}
+
+// `planes` digit planes per kernel value (6 or 7); p.inv_scale is set here to 2^(8 planes - 1) / sK; nc = candidates per
+// contraction tile the digit bytes are laid out for (k2o_tile_candidates)
+int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, cudaStream_t s, bool small_cta = false, int nc = OZ_NC) {
     const size_t smem = kcross_smem_bytes(p.base.d_pad);
     p.inv_scale = std::ldexp(1.0, 8 * planes - 1) / st->k_scale;
     p.tn = st->d_tn;
     p.base.hw = st->d_hw;
-    // 6 planes, kinds whose distance may be taken as |x|^2 + |t|^2 - 2 x.t: the x.t part on DMMA tiles (SKB_K1_MMA=0 keeps
-    // the DFMA variant, for A/B measurements)
-    static const bool k1_mma = [] { const char* e = std::getenv("SKB_K1_MMA"); return !(e && e[0] == '0'); }();
-    const bool dot_kind = st->kernel == SKB_KERNEL_RBF || st->kernel == SKB_KERNEL_MATERN32 || st->kernel == SKB_KERNEL_MATERN52;
-    if (planes == 6 && k1_mma && dot_kind && small_cta) {
+    const bool mma = k1_uses_mma(st, planes);
+    if (nc != OZ_NC && !mma) return fail(SKB_ERR_INVALID, "internal: %d-candidate tiles need the DMMA digit kernel", nc);
+    if (mma && small_cta) {
         // 64 candidates per CTA (4 warps): the configuration that shares an SM with the contraction kernel
         const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad, 64);
         switch (st->kernel) {
@@ -476,7 +494,14 @@ int launch_kcross_digits(skb_state* st, KDigitParams p, int planes, int tiles, c
             case SKB_KERNEL_MATERN32: kcross_digits_mma_kernel<2, 64><<<2 * tiles, 128, smem_m, s>>>(p); break;
             default: kcross_digits_mma_kernel<3, 64><<<2 * tiles, 128, smem_m, s>>>(p); break;
         }
-    } else if (planes == 6 && k1_mma && dot_kind) {
+    } else if (mma && nc == 80) {
+        const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad);
+        switch (st->kernel) {
+            case SKB_KERNEL_RBF: kcross_digits_mma_kernel<0, BN, 80><<<tiles, 256, smem_m, s>>>(p); break;
+            case SKB_KERNEL_MATERN32: kcross_digits_mma_kernel<2, BN, 80><<<tiles, 256, smem_m, s>>>(p); break;
+            default: kcross_digits_mma_kernel<3, BN, 80><<<tiles, 256, smem_m, s>>>(p); break;
+        }
+    } else if (mma) {
         const size_t smem_m = kcross_mma_smem_bytes(p.base.d_pad);
         switch (st->kernel) {
             case SKB_KERNEL_RBF: kcross_digits_mma_kernel<0><<<tiles, 256, smem_m, s>>>(p); break;
@@ -518,6 +543,11 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
     SKB_DIGIT_MMA_ATTR(0); SKB_DIGIT_MMA_ATTR(2); SKB_DIGIT_MMA_ATTR(3);
 #undef SKB_DIGIT_MMA_ATTR
+#define SKB_DIGIT_MMA_ATTR(K)                                                                                                 \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K, BN, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1m));       \
+    CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K, BN, 80>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+    SKB_DIGIT_MMA_ATTR(0); SKB_DIGIT_MMA_ATTR(2); SKB_DIGIT_MMA_ATTR(3);
+#undef SKB_DIGIT_MMA_ATTR
     const int smem1s = (int)kcross_mma_smem_bytes(st->d_pad, 64);
 #define SKB_DIGIT_MMA_ATTR(K)                                                                                                 \
     CU(cudaFuncSetAttribute(kcross_digits_mma_kernel<K, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1s));           \
@@ -529,6 +559,8 @@ int set_kernel_attributes(skb_state* st) {
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6)));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(7)));
     CU(cudaFuncSetAttribute(ozaki_trmm_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(7)));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 0, 1, 80>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ozaki_trmm_kernel<0, 6, 0, 1, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(6, 80)));
     CU(cudaFuncSetAttribute(trmm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     CU(cudaFuncSetAttribute(trmm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trmm_smem_bytes()));
     const int smem3 = (int)grad_smem_bytes(st->d_pad);
@@ -879,12 +911,35 @@ static bool split_overlaps(const skb_state* st) {
     return enabled && kcross_mma_smem_bytes(st->d_pad, 64) + oz_smem_bytes(7) + 4096 <= 232448;
 }
 
-static int64_t chunk_tiles_for(const skb_state* st, int64_t m, size_t bytes_per_tile, bool split = false) {
+// bytes of K1 -> K2 scratch budgeted per 128-candidate tile: one FP64 kernel value per (training row, candidate); the digit
+// planes of the split-integer path (6 or 7 bytes per value) are budgeted alike, so both paths cut a call into the same chunks
+static size_t value_tile_bytes(const skb_state* st, int /*planes*/) { return (size_t)st->n_pad * BN * sizeof(double); }
+
+// planes = 0: FP64 path; 6 / 7: split-integer path contracting that many digit planes, in tiles of `nc` candidates
+static int64_t chunk_tiles_for(const skb_state* st, int64_t m, int planes = 0, int nc = OZ_NC) {
+    const bool split = planes != 0;
     const int64_t tiles = (m + BN - 1) / BN;
-    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / bytes_per_tile));
+    int64_t cap = std::max<int64_t>(1, (int64_t)(st->scratch_limit / value_tile_bytes(st, planes)));
     // split-integer path with overlap: two scratch buffers (half the budget each) and chunks of two K1 waves, so that
     // K1 of the next chunk runs under the contraction of the current one even for moderate candidate counts
     if (split && split_overlaps(st)) cap = std::min<int64_t>(std::max<int64_t>(1, cap / 2), 2 * (int64_t)st->sm_count);
+    if (nc != OZ_NC && tiles > cap) {
+        // 80-candidate contraction tiles: 128 t candidates are 1.6 t contraction CTAs (one per SM) and t K1 CTAs (two per
+        // SM); take the chunk in (cap / 2, cap] whose last waves are fullest, weighted by the kernels' shares of the step.
+        // 1480 tiles = 16 contraction waves = 5 K1 waves is exact.
+        const double sm = (double)st->sm_count;
+        int64_t best = cap;
+        double best_eff = 0.0;
+        for (int64_t t = cap; t > cap / 2; --t) {
+            const double w2 = (double)((t * BN + nc - 1) / nc) / sm, w1 = (double)t / (2.0 * sm);
+            const double eff = 0.75 * w2 / std::ceil(w2) + 0.25 * w1 / std::ceil(w1);
+            if (eff > best_eff + 1e-12) {
+                best_eff = eff;
+                best = t;
+            }
+        }
+        return best;
+    }
     if (cap > st->sm_count) cap = cap / st->sm_count * st->sm_count;
     return std::min(tiles, cap);
 }
@@ -989,6 +1044,23 @@ constexpr int64_t SPLIT_PROBE_MIN_CANDIDATES = 32768;
 
 static int decide_split_planes(skb_state* st, cudaStream_t s);
 
+// Digit planes a split-integer call of m candidates contracts.  force_planes: 0 = follow the precision mode
+// (SPLIT_INT8_P7: 7; SPLIT_INT8: the state's self-checked choice), 6 / 7 = use that.
+static int split_planes_for_call(skb_state* st, const skb_acq_params* prm, int64_t m, int force_planes, cudaStream_t s, int* planes) {
+    *planes = 7;
+    if (force_planes) *planes = force_planes;
+    else if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
+        // the self-check costs two 256-candidate passes and a stream synchronisation: only worth it for calls that
+        // are large enough to notice the 6-plane saving; smaller calls on an undecided state contract 7 planes
+        if (st->split_planes == 0 && m >= SPLIT_PROBE_MIN_CANDIDATES) {
+            int prc = decide_split_planes(st, s);
+            if (prc != SKB_OK) return prc;
+        }
+        *planes = st->split_planes ? st->split_planes : 7;
+    }
+    return SKB_OK;
+}
+
 // force_planes: 0 = follow the precision mode (SPLIT_INT8_P7: 7; SPLIT_INT8: the state's self-checked choice), 6 / 7 = use that
 static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t index_offset, const skb_acq_params* prm,
                           const skb_score_out* out, cudaStream_t s, bool mean_only, double* mean_only_out,
@@ -1010,27 +1082,17 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         }
         return SKB_OK;
     }
-    int planes = 7;
-    if (split_mode) {
-        if (force_planes) planes = force_planes;
-        else if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
-            // the self-check costs two 256-candidate passes and a stream synchronisation: only worth it for calls that
-            // are large enough to notice the 6-plane saving; smaller calls on an undecided state contract 7 planes
-            if (st->split_planes == 0 && m >= SPLIT_PROBE_MIN_CANDIDATES) {
-                int prc = decide_split_planes(st, s);
-                if (prc != SKB_OK) return prc;
-            }
-            planes = st->split_planes ? st->split_planes : 7;
-        }
-    }
+    int planes = 0, rc;
+    if (split_mode && (rc = split_planes_for_call(st, prm, m, force_planes, s, &planes)) != SKB_OK) return rc;
     const int64_t tiles = (m + BN - 1) / BN;
-    const size_t tile_bytes = (size_t)st->n_pad * BN * sizeof(double);
-    const int64_t chunk_tiles = chunk_tiles_for(st, m, tile_bytes, split_mode);
-
     const bool overlap = split_mode && split_overlaps(st);
-    int rc;
+    const int nc = split_mode ? k2o_tile_candidates(st, planes, overlap) : OZ_NC;
+    const int64_t chunk_tiles = chunk_tiles_for(st, m, planes, nc);
+    // doubles of scratch per chunk; the digit planes of a chunk end with a whole contraction tile (up to nc - 1 candidates more)
+    const size_t kt_elems = split_mode ? (((size_t)chunk_tiles * BN + nc) * st->n_pad * planes + 7) / 8 : (size_t)chunk_tiles * st->n_pad * BN;
+
     if (overlap) {
-        if ((rc = grow(st->device, &st->d_Kt2, &st->kt2_cap, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_Kt2, &st->kt2_cap, kt_elems)) != SKB_OK) return rc;
         if ((rc = grow(st->device, &st->d_kdot2, &st->kdot2_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
         const size_t n_chunks = (size_t)((tiles + chunk_tiles - 1) / chunk_tiles);
         while (st->ev_k1.size() < n_chunks) {
@@ -1044,7 +1106,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
         CU(cudaStreamWaitEvent(st->aux_stream, st->ev_enter, 0));
     }
     if (!mean_only) {
-        if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)chunk_tiles * st->n_pad * BN)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, kt_elems)) != SKB_OK) return rc;
     }
     if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)chunk_tiles * BN)) != SKB_OK) return rc;
 
@@ -1102,7 +1164,7 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             dp.base.kdot = buf ? st->d_kdot2 : st->d_kdot;
             dp.Kd = reinterpret_cast<int8_t*>(buf ? st->d_Kt2 : st->d_Kt);   // `planes` (<= 7) bytes per (training point, candidate)
             if ((rc = span_begin(st, 0, s1)) != SKB_OK) return rc;
-            if ((rc = launch_kcross_digits(st, dp, planes, (int)nt, s1, overlap)) != SKB_OK) return rc;
+            if ((rc = launch_kcross_digits(st, dp, planes, (int)nt, s1, overlap, nc)) != SKB_OK) return rc;
             if ((rc = span_end(st, s1)) != SKB_OK) return rc;
             if (overlap) {
                 CU(cudaEventRecord(st->ev_k1[chunk_index], s1));
@@ -1131,8 +1193,10 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
             op.clamp_count = reinterpret_cast<unsigned long long*>(out->n_var_clamped);
             if ((rc = span_begin(st, 1, s)) != SKB_OK) return rc;
             op.Wt = nullptr;
-            if ((rc = planes == 6 ? launch_k2o<6>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)
-                                  : launch_k2o<7>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)) != SKB_OK) return rc;
+            if (nc == 80) {
+                ozaki_trmm_kernel<0, 6, 0, 1, 80><<<(unsigned)((mc + 79) / 80), OZ_THREADS, oz_smem_bytes(6, 80), s>>>(op);
+            } else if ((rc = planes == 6 ? launch_k2o<6>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)
+                                         : launch_k2o<7>(op, (unsigned)((mc + OZ_NC - 1) / OZ_NC), s)) != SKB_OK) return rc;
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
             if (overlap) CU(cudaEventRecord(st->ev_k2[chunk_index], s));
@@ -1375,8 +1439,12 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         }
     }
     if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
-    if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, (size_t)st->n_pad * BN * sizeof(double),
-                                                       is_split(params->precision)))) != SKB_OK) return rc;
+    // the same chunks score_dev_impl will consume (the 6-or-7-plane decision is settled here if it is due)
+    int up_planes = 0;
+    const bool up_split = is_split(params->precision) && st->n <= SPLIT_MAX_TRAIN;
+    if (up_split && (rc = split_planes_for_call(st, params, m, 0, s, &up_planes)) != SKB_OK) return rc;
+    const int up_nc = up_split ? k2o_tile_candidates(st, up_planes, split_overlaps(st)) : OZ_NC;
+    if ((rc = upload_chunked(st, X, m, chunk_tiles_for(st, m, up_planes, up_nc))) != SKB_OK) return rc;
     if ((rc = score_dev_impl(st, st->d_X, m, index_offset, params, &dout, s, false, nullptr, true)) != SKB_OK) {
         stager_join(st);
         return rc;

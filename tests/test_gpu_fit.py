@@ -203,7 +203,9 @@ def test_state_built_on_device_scores_like_the_host_built_state(n, d, nu):
         assert np.max(np.abs(rg["mean"] - rh["mean"])) <= 1e-9 * max(np.max(np.abs(rh["mean"])), float(h.y_train_std_))
         assert np.max(np.abs(rg["std"] ** 2 - rh["std"] ** 2)) <= max(1e-9, 1e-15 * cond) * prior
         for a in ("EI", "LCB"):
-            assert np.max(np.abs(rg[a]["values"] - rh[a]["values"])) <= 1e-9 * np.max(np.abs(rh[a]["values"]))
+            # relative to the largest value, with a floor at 1e-12 of the target scale (EI can be ~1e-8 everywhere)
+            assert np.max(np.abs(rg[a]["values"] - rh[a]["values"])) <= (1e-9 * np.max(np.abs(rh[a]["values"])) +
+                                                                          1e-12 * float(h.y_train_std_))
             assert rg[a]["topk_idx"][0] == rh[a]["topk_idx"][0]
     gh = h.device_state().score_grad(Xq[:200], y_opt=y_opt, acq_funcs=("EI",))
     gg = g.device_state().score_grad(Xq[:200], y_opt=y_opt, acq_funcs=("EI",))
