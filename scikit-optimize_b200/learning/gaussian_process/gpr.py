@@ -10,14 +10,14 @@ import copy
 import warnings
 
 import numpy as np
-from scipy.linalg import cho_solve, solve_triangular
+from scipy.linalg import solve_triangular
 from sklearn.base import clone
 from sklearn.gaussian_process import GaussianProcessRegressor as _SkGPR
 from sklearn.preprocessing._data import _handle_zeros_in_scale
 from sklearn.utils import check_array, check_random_state
 from sklearn.utils.validation import validate_data
 
-from ... import _lib, engine
+from ... import engine
 from .kernels import RBF, ConstantKernel, Sum, WhiteKernel
 
 _DEFAULT_DEVICE = [0]
@@ -329,6 +329,30 @@ class GaussianProcessRegressor(_SkGPR):
                                                    - 0.5 * (n + 1) * np.log(2.0 * np.pi))
         return new
 
+    _COV_BLOCK = 1024          # points per block of a blocked joint covariance: one device call holds two blocks
+
+    def _cov_quadratic_on_device(self, X):
+        """(mean [m], K_trans K_inv K_trans^T [m, m] in kernel units) from DeviceState.predict_cov.  One call takes what the
+        state's scratch holds (2048 points up to n_train = 65536); larger point sets are assembled from calls on pairs
+        of 1024-point blocks, so every entry still comes from the device kernels."""
+        dev = self.device_state()
+        m = X.shape[0]
+        B = self._COV_BLOCK
+        if m <= 2 * B:
+            return dev.predict_cov(X)
+        mean, quad = np.empty(m), np.empty((m, m))
+        starts = list(range(0, m, B))
+        for bi, i0 in enumerate(starts):
+            i1 = min(i0 + B, m)
+            for j0 in starts[bi + 1:]:
+                j1 = min(j0 + B, m)
+                mu, q = dev.predict_cov(np.vstack([X[i0:i1], X[j0:j1]]))
+                ni = i1 - i0
+                mean[i0:i1], mean[j0:j1] = mu[:ni], mu[ni:]
+                quad[i0:i1, i0:i1], quad[i0:i1, j0:j1] = q[:ni, :ni], q[:ni, ni:]
+                quad[j0:j1, i0:i1], quad[j0:j1, j0:j1] = q[ni:, :ni], q[ni:, ni:]
+        return mean, quad
+
     def device_state(self, device=None):
         """The fitted state resident on the GPU (created on first use, rebuilt after every fit)."""
         dev = self.__dict__.get("_skb_device_state")
@@ -359,18 +383,9 @@ class GaussianProcessRegressor(_SkGPR):
 
         if return_cov:
             # gpr.py:320-325.  The O(n^2 m) product K_inv K_trans^T and the O(n m^2) quadratic form run on the GPU; kernel_(X)
-            # (m^2 d) stays on the host.  Point sets beyond the state's scratch (thousands of points) fall back to the host.
-            if X.shape[0] <= 2048 and hasattr(self, "K_inv_"):
-                try:
-                    y_mean, quad = self.device_state().predict_cov(X)
-                    return y_mean, (self.kernel_(X) - quad) * self.y_train_std_ ** 2
-                except _lib.SkbError as exc:
-                    if exc.code != -2:                 # SKB_ERR_UNSUPPORTED: more points than the scratch holds
-                        raise
-            K_trans = self.kernel_(X, self.X_train_)
-            y_mean = self.y_train_std_ * K_trans.dot(self.alpha_) + self.y_train_mean_
-            y_cov = self.kernel_(X) - K_trans.dot(cho_solve((self.L_, True), K_trans.T))
-            return y_mean, y_cov * self.y_train_std_ ** 2
+            # (m^2 d) is formed on the host like the reference's.  There is no host route for the quadratic form.
+            y_mean, quad = self._cov_quadratic_on_device(X)
+            return y_mean, (self.kernel_(X) - quad) * self.y_train_std_ ** 2
 
         dev = self.device_state()
         if return_mean_grad or return_std_grad:

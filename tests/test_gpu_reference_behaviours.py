@@ -284,13 +284,16 @@ def test_constant_liar_batches(strategy):
         opt.ask(n_points=2, strategy="cl_median")
 
 
-@pytest.mark.parametrize("m", [1, 5, 130, 300])
-def test_return_cov_on_device_matches_the_reference_formula(m):
+@pytest.mark.parametrize("m, block", [(1, None), (5, None), (130, None), (300, None), (300, 64), (2500, None)])
+def test_return_cov_on_device_matches_the_reference_formula(m, block, monkeypatch):
     """predict(return_cov=True) (gpr.py:315-325): the quadratic form K_trans K_inv K_trans^T is computed on the GPU
     (skb_predict_cov_host: K1, dense K_inv product, one more tile product); against cho_solve on the host at 1e-9 of the
-    prior variance, symmetric to rounding, and the diagonal equal to return_std squared."""
+    prior variance, symmetric to rounding, and the diagonal equal to return_std squared.  Point sets larger than two
+    blocks (2 x 1024 points; `block` shrinks that for the test) are assembled from device calls on pairs of blocks."""
     from scipy.linalg import cho_solve
     from skopt_b200.learning import GaussianProcessRegressor
+    if block:
+        monkeypatch.setattr(GaussianProcessRegressor, "_COV_BLOCK", block)
     from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern
     rng = np.random.RandomState(m)
     n, d = 200, 4
