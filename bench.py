@@ -775,17 +775,26 @@ def main():
         multi_gpu_check = ctx.rank_all(bool(torch.equal(exp, merged)))
 
     extra = {}
+
+    def guarded(fn, *a):
+        # an extra leg must never cost the headline line: a leg that raises (on every rank alike - the legs are
+        # deterministic) is reported as {"error": ...} and the run goes on
+        try:
+            return fn(*a)
+        except Exception as exc:          # noqa: BLE001
+            return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+
     if "strong" in legs:
         # one GPU scoring the whole 10^6 set = this run's headline step when --m is the total
-        extra["strong"] = leg_strong(ctx, gpr, dev, y_opt, ms_per_step)
-        if extra["strong"]["topk_equals_concatenated_topk"] is not None and world > 1:
+        extra["strong"] = guarded(leg_strong, ctx, gpr, dev, y_opt, ms_per_step)
+        if world > 1 and extra["strong"].get("topk_equals_concatenated_topk") is not None:
             multi_gpu_check = bool(multi_gpu_check) and extra["strong"]["topk_equals_concatenated_topk"]
     if "c4" in legs:
-        extra["c4_grad"] = leg_c4_grad(ctx, peaks)
+        extra["c4_grad"] = guarded(leg_c4_grad, ctx, peaks)
         if world > 1:
-            multi_gpu_check = bool(multi_gpu_check) and extra["c4_grad"]["multi_gpu_check"]
+            multi_gpu_check = bool(multi_gpu_check) and bool(extra["c4_grad"].get("multi_gpu_check"))
     if "c5" in legs:
-        extra["c5_cl"] = leg_c5_cl(ctx)
+        extra["c5_cl"] = guarded(leg_c5_cl, ctx)
 
     if rank == 0:
         def k2_stats(tm, total_ms):
@@ -891,27 +900,36 @@ def main():
         }
         line.update(extra)
         # the ask-latency and CPU legs are single-GPU context for the headline: rank 0 at N=1 only
-        if not args.no_ask and world == 1:
+        def ask_legs():
             p50, cnt = ask_p50_ms()
             p50_l, cnt_l = ask_p50_ms_lbfgs()
-            line["ask_p50_ms_lbfgs"] = {"value": p50_l, "tells": cnt_l, "config": "BASELINE.json configs[1]: Hartmann-6, "
-                                        "gp_hedge, lbfgs, 20 restarts, n_points=10000: scoring block incl. the 60 "
-                                        "lock-step L-BFGS-B searches (reference, measured in SURVEY.md section 6: "
-                                        "35.0 s / 40 tells = 875 ms)"}
-            line["ask_p50_ms"] = {"value": p50, "tells": cnt, "config": "BASELINE.json configs[0]: Branin, gp_hedge, "
-                                  "sampling, n_points=10000, n_train 10..39: scoring block of Optimizer._tell, fit "
-                                  "excluded (candidate generation + one fused GPU pass + top-k + inverse transform)",
-                                  "cpu_port_ms": ask_p50_ms_cpu() if not args.no_cpu_baseline else None}
-        if not args.no_cpu_baseline and world == 1:
+            return {"ask_p50_ms_lbfgs": {"value": p50_l, "tells": cnt_l, "config": "BASELINE.json configs[1]: Hartmann-6, "
+                                         "gp_hedge, lbfgs, 20 restarts, n_points=10000: scoring block incl. the 60 "
+                                         "lock-step L-BFGS-B searches (reference, measured in SURVEY.md section 6: "
+                                         "35.0 s / 40 tells = 875 ms)"},
+                    "ask_p50_ms": {"value": p50, "tells": cnt, "config": "BASELINE.json configs[0]: Branin, gp_hedge, "
+                                   "sampling, n_points=10000, n_train 10..39: scoring block of Optimizer._tell, fit "
+                                   "excluded (candidate generation + one fused GPU pass + top-k + inverse transform)",
+                                   "cpu_port_ms": ask_p50_ms_cpu() if not args.no_cpu_baseline else None}}
+
+        def cpu_legs():
             evals_s, dt = cpu_baseline(N_TRAIN, N_DIMS, args.cpu_sample, quad="einsum")
             evals_s_gemm, _ = cpu_baseline(N_TRAIN, N_DIMS, 4 * args.cpu_sample, quad="gemm")
-            line["cpu_baseline"] = {
-                "value": evals_s, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
-                "sample": "%d candidates of the same workload, %.1f s; oracle port with the reference's einsum "
-                          "contraction (single-threaded as in the reference; BLAS parts on all host threads)"
-                          % (args.cpu_sample, dt),
-                "tuned_gemm_variant_evals_s": evals_s_gemm, "versions": library_versions()}
-            line["parity_sample"] = parity_sample(gpr, dev, y_opt, sorted({headline, "fp64"}))
+            return {"cpu_baseline": {
+                        "value": evals_s, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": "%d candidates of the same workload, %.1f s; oracle port with the reference's einsum "
+                                  "contraction (single-threaded as in the reference; BLAS parts on all host threads)"
+                                  % (args.cpu_sample, dt),
+                        "tuned_gemm_variant_evals_s": evals_s_gemm, "versions": library_versions()},
+                    "parity_sample": parity_sample(gpr, dev, y_opt, sorted({headline, "fp64"}))}
+
+        # the ask-latency and CPU legs are single-GPU context for the headline: rank 0 at N=1 only
+        if not args.no_ask and world == 1:
+            res = guarded(ask_legs)
+            line.update(res if "error" not in res else {"ask_p50_ms": res})
+        if not args.no_cpu_baseline and world == 1:
+            res = guarded(cpu_legs)
+            line.update(res if "error" not in res else {"cpu_baseline": res})
         emit(line)
     if world > 1:
         dist.barrier()
