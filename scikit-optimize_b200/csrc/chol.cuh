@@ -19,45 +19,57 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "ptx.cuh"
+
 namespace skb {
 
 constexpr int CH_NB = 64;                 // block size
-constexpr int CH_LD = CH_NB + 1;          // shared-memory row stride (conflict-free rows and columns)
+constexpr int CH_LD = CH_NB + 4;          // shared-memory row stride: 4 mod 16 doubles, so that the DMMA fragment reads (4 k x 8 rows)
+                                          // and the 4 x 4 patches of the tile loader both touch 16 different 8-byte banks per half-warp
 constexpr int CH_THREADS = 256;
 constexpr size_t ch_smem_bytes() { return 3 * (size_t)CH_NB * CH_LD * sizeof(double); }
 
 // dst[r][c] = src(row0 + r, col0 + c) (TRANS = false) or src(row0 + c, col0 + r) (TRANS = true); zero outside the matrix.
-// Global reads run along a column (contiguous), shared writes are conflict-free in both modes.
+// A half-warp moves a 4 x 4 patch: four rows of a column are one 32-byte sector of the column-major source, and the 16
+// shared-memory words land in 16 different banks in both modes (row stride CH_LD = 4 mod 16).
 template <bool TRANS>
 __device__ __forceinline__ void ch_load_tile(double* dst, const double* __restrict__ src, int n, int row0, int col0) {
-    const int fast = threadIdx.x & 63, slow = threadIdx.x >> 6;
+    const int rsub = threadIdx.x & 3, csub = (threadIdx.x >> 2) & 3, prow = threadIdx.x >> 4;
+    const int r = 4 * prow + rsub, gi = row0 + r;
 #pragma unroll 4
-    for (int p = 0; p < CH_NB; p += 4) {
-        const int gi = row0 + fast, gj = col0 + slow + p;
+    for (int pc = 0; pc < CH_NB / 4; ++pc) {
+        const int c = 4 * pc + csub, gj = col0 + c;
         const double v = (gi < n && gj < n) ? src[(size_t)gj * n + gi] : 0.0;
-        if (TRANS) dst[(slow + p) * CH_LD + fast] = v;
-        else dst[fast * CH_LD + slow + p] = v;
+        if (TRANS) dst[c * CH_LD + r] = v;
+        else dst[r * CH_LD + c] = v;
     }
 }
 
-// Thread (ty, tx) of a 16 x 16 grid owns rows tx + 16 i and columns ty + 16 j of the 64 x 64 tile: the 16 row reads of a
-// half-warp hit 16 different bank pairs (row stride 65 doubles), the column reads are broadcasts, and a half-warp stores
-// 16 consecutive doubles of a column.   acc[i][j] += sum_kk As[tx + 16 i][kk] * Bs[kk][ty + 16 j]
-__device__ __forceinline__ void ch_tile_fma(const double* As, const double* Bs, double (&acc)[4][4]) {
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll 8
-    for (int kk = 0; kk < CH_NB; ++kk) {
-        double a[4], b[4];
+// 64 x 64 x 64 tile product on FP64 tensor-core tiles (mma.sync m8n8k4, DMMA): warp w owns rows 8 w .. 8 w + 7 of the
+// tile and all eight 8-column tiles; lane l = 4 g + t holds, per column tile j, the entries (8 w + g, 8 j + 2 t) and
+// (8 w + g, 8 j + 2 t + 1).   acc[j][e] += sum_kk As[8 w + g][kk] * B(kk, 8 j + 2 t + e)
+// with B(kk, c) = Bs[kk][c] (BT = false) or Bs[c][kk] (BT = true).  DMMA issues at the FP64 FMA rate, but a k-step of
+// four needs 9 shared-memory loads per lane for 8 x 8 x 8 x 4 FMAs per warp where the scalar form needed 8 loads per
+// 16 FMAs per lane: the scalar tile product was bound by the shared-memory pipe at about twice the FP64-pipe time.
+template <bool BT>
+__device__ __forceinline__ void ch_tile_mma(const double* As, const double* Bs, double (&acc)[8][2]) {
+    const int w = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+    const double* ap = As + (8 * w + g) * CH_LD + t;
+    const double* bp = BT ? Bs + g * CH_LD + t : Bs + t * CH_LD + g;
+#pragma unroll 4
+    for (int k0 = 0; k0 < CH_NB; k0 += 4) {
+        const double a = ap[k0];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[(tx + 16 * i) * CH_LD + kk];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[kk * CH_LD + ty + 16 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) {
+            const double b = BT ? bp[8 * j * CH_LD + k0] : bp[k0 * CH_LD + 8 * j];
+            dmma884(acc[j][0], acc[j][1], a, b);
+        }
     }
 }
+
+// the (row, column) inside the 64 x 64 tile of acc[j][e] in ch_tile_mma
+__device__ __forceinline__ int ch_mma_row() { return 8 * (threadIdx.x >> 5) + ((threadIdx.x & 31) >> 2); }
+__device__ __forceinline__ int ch_mma_col(int j, int e) { return 8 * j + 2 * (threadIdx.x & 3) + e; }
 
 // rl ~ 1 / sqrt(x), l ~ sqrt(x) for x > 0 (NaN for x <= 0 or NaN, which is what a failed factorisation should spread).
 __device__ __forceinline__ void ch_rsqrt(double x, double& rl, double& l) {
@@ -196,30 +208,18 @@ __global__ void __launch_bounds__(CH_THREADS) chol_panel_kernel(double* __restri
         return;
     }
     // slab: L_slab = A_slab . inv(L_kk)^T, i.e. out(r, c) = sum_j S[r][j] E[c][j]  (E lower: j <= c)
-    double acc[4][4];
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-    for (int kk = 0; kk < CH_NB; ++kk) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = S[(tx + 16 * i) * CH_LD + kk];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = E[(ty + 16 * j) * CH_LD + kk];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+    ch_tile_mma<true>(S, E, acc);
     const int row0 = k0 + CH_NB * blockIdx.x;
+    const int gi = row0 + ch_mma_row();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int gi = row0 + tx + 16 * i, gj = k0 + ty + 16 * j;
-            if (gi < n && gj < n) A[(size_t)gj * n + gi] = acc[i][j];
+        for (int e = 0; e < 2; ++e) {
+            const int gj = k0 + ch_mma_col(j, e);
+            if (gi < n && gj < n) A[(size_t)gj * n + gi] = acc[j][e];
         }
 }
 
@@ -238,19 +238,17 @@ __global__ void __launch_bounds__(CH_THREADS) chol_update_kernel(double* __restr
     ch_load_tile<false>(As, A, n, i0, k0);                    // As[r][kk] = L(i0 + r, k0 + kk)
     ch_load_tile<true>(Bs, A, n, j0, k0);                     // Bs[kk][c] = L(j0 + c, k0 + kk)
     __syncthreads();
-    double acc[4][4];
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+    ch_tile_mma<false>(As, Bs, acc);
+    const int gi = i0 + ch_mma_row();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    ch_tile_fma(As, Bs, acc);
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
-            if (gi < n && gj < n && gi >= gj) A[(size_t)gj * n + gi] -= acc[i][j];
+        for (int e = 0; e < 2; ++e) {
+            const int gj = j0 + ch_mma_col(j, e);
+            if (gi < n && gj < n && gi >= gj) A[(size_t)gj * n + gi] -= acc[j][e];
         }
 }
 
@@ -282,11 +280,9 @@ __global__ void __launch_bounds__(CH_THREADS) tri_inverse_level_kernel(const dou
     const int base = 2 * h * blockIdx.y;                      // first row / column of this 2h block
     const int i0 = base + h + CH_NB * ti, j0 = base + CH_NB * tj;
     if (i0 >= n) return;                                      // the second half does not exist (uniform per CTA)
-    double acc[4][4];
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
     const int kb_lo = PHASE == 0 ? tj : 0, kb_hi = PHASE == 0 ? hb - 1 : ti;
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
         const int k0 = (PHASE == 0 ? base : base + h) + CH_NB * kb;
@@ -299,16 +295,16 @@ __global__ void __launch_bounds__(CH_THREADS) tri_inverse_level_kernel(const dou
             ch_load_tile<false>(Bs, W, n, k0, j0);            // W21(k, j)
         }
         __syncthreads();
-        ch_tile_fma(As, Bs, acc);
+        ch_tile_mma<false>(As, Bs, acc);
     }
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double* out = PHASE == 0 ? W : X;
+    const int gi = i0 + ch_mma_row();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
-            if (gi < n && gj < n) out[(size_t)gj * n + gi] = PHASE == 0 ? acc[i][j] : -acc[i][j];
+        for (int e = 0; e < 2; ++e) {
+            const int gj = j0 + ch_mma_col(j, e);
+            if (gi < n && gj < n) out[(size_t)gj * n + gi] = PHASE == 0 ? acc[j][e] : -acc[j][e];
         }
 }
 
@@ -323,25 +319,23 @@ __global__ void __launch_bounds__(CH_THREADS) tri_gram_kernel(const double* __re
     const int bj = blockIdx.x - bi * (bi + 1) / 2;
     const int i0 = CH_NB * bi, j0 = CH_NB * bj;
     const int nb = (n + CH_NB - 1) / CH_NB;
-    double acc[4][4];
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
     for (int kb = bi; kb < nb; ++kb) {
         __syncthreads();
         ch_load_tile<true>(As, X, n, CH_NB * kb, i0);         // As[r][kk] = X(k0 + kk, i0 + r)
         ch_load_tile<false>(Bs, X, n, CH_NB * kb, j0);        // Bs[kk][c] = X(k0 + kk, j0 + c)
         __syncthreads();
-        ch_tile_fma(As, Bs, acc);
+        ch_tile_mma<false>(As, Bs, acc);
     }
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int gi = i0 + ch_mma_row();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int gi = i0 + tx + 16 * i, gj = j0 + ty + 16 * j;
-            if (gi < n && gj < n && gi >= gj) out[(size_t)gj * n + gi] = acc[i][j];
+        for (int e = 0; e < 2; ++e) {
+            const int gj = j0 + ch_mma_col(j, e);
+            if (gi < n && gj < n && gi >= gj) out[(size_t)gj * n + gi] = acc[j][e];
         }
 }
 
