@@ -24,9 +24,9 @@ constexpr int FIT_THREADS = 256;
 struct FitParams {
     const double* Xs;       // [n][d] training rows already divided by the length scales
     int n, d;
-    double amplitude;
-    double diag_add;        // noise + alpha, added to the diagonal in that order: (amplitude + noise) + alpha
-    double noise, alpha;
+    const double* hyp;      // device: {amplitude, noise} of this evaluation (read at run time: the launch sequence of an
+                            // evaluation is replayed as a CUDA graph, so nothing that changes with theta is a launch argument)
+    double alpha;           // the estimator's fixed diagonal term: the diagonal is (amplitude + noise) + alpha, in that order
     double* K;              // [n][n] (symmetric; storage order is immaterial)
 };
 
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kbuild_kernel(const FitParams
     }
     __syncthreads();
     const int tj = threadIdx.x & 31, ti0 = threadIdx.x >> 5;
+    const double amplitude = p.hyp[0], noise = p.hyp[1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int ti = ti0 + 8 * q;
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kbuild_kernel(const FitParams
             const double df = xi[ti * ld + k] - xj[tj * ld + k];
             sq = fma(df, df, sq);
         }
-        double v = p.amplitude * base_kernel<KIND>(sq);
-        if (i == j) v = (p.amplitude + p.noise) + p.alpha;
+        double v = amplitude * base_kernel<KIND>(sq);
+        if (i == j) v = (amplitude + noise) + p.alpha;
         p.K[(size_t)i * p.n + j] = v;
         p.K[(size_t)j * p.n + i] = v;
     }
@@ -97,7 +98,7 @@ struct FitGradParams {
     const double* Kinv;     // [n][n]: entry (i, j) with i >= j read at Kinv[j * n + i] (cuSOLVER lower, column major)
     const double* a;        // [n] K^-1 y
     int n, d;
-    double amplitude, noise;
+    const double* hyp;      // device: {amplitude, noise} (see FitParams)
     double* partial;        // [n_blocks][d + 2] per-block sums: amplitude, length scales, noise
 };
 
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_grad_kernel(const FitGradPara
     const int ti = lane;                            // lanes run down a column of the column-major K^-1: coalesced
     double w[4], wg[4];
     double s_amp = 0.0, s_noise = 0.0;
+    const double amplitude = p.hyp[0], noise = p.hyp[1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int tj = warp + 8 * q;
@@ -165,10 +167,10 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_grad_kernel(const FitGradPara
         double kv, gf;
         base_and_gfac<KIND>(sq, kv, gf);
         const double mult = (i == j) ? 1.0 : 2.0;
-        s_amp = fma(mult * inner, p.amplitude * kv, s_amp);
-        if (i == j) s_noise = fma(inner, p.noise, s_noise);
+        s_amp = fma(mult * inner, amplitude * kv, s_amp);
+        if (i == j) s_noise = fma(inner, noise, s_noise);
         w[q] = 1.0;
-        wg[q] = mult * inner * (p.amplitude * gf);
+        wg[q] = mult * inner * (amplitude * gf);
     }
     s_amp = fit_warp_sum(s_amp);
     s_noise = fit_warp_sum(s_noise);

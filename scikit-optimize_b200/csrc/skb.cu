@@ -2318,9 +2318,15 @@ struct FitSlot {
     double* d_Dinv = nullptr;        // [ceil(n / 64)][64][64] inverted diagonal blocks of the factor
     double* d_z = nullptr;           // [n] L^-1 y
     int* d_info = nullptr;
-    double* h_pinned = nullptr;      // [MAX_DIMS] length scales in | [MAX_DIMS + 4] results out | 4 ints info
+    double* h_pinned = nullptr;      // [MAX_DIMS + 4] length scales, amplitude, noise in | [MAX_DIMS + 4] results out | 4 ints info
     bool want_grad = false;
+    // the launch sequence of one evaluation, captured once per (slot, with / without gradient) and replayed: an evaluation
+    // is ~50 small dependent launches, and three searches in lock step made the host's launch rate the limit of a round
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    int graph_nodes[2] = {0, 0};
+    bool graph_failed = false;       // capture or instantiation was refused once: plain launches from then on
 };
+constexpr int FIT_PINNED_DOUBLES = 2 * (MAX_DIMS + 4) + 4;
 constexpr int FIT_MAX_SLOTS = 8;
 struct SolverCtx { cudaStream_t stream; double* h_pinned; };
 static std::vector<SolverCtx> g_ctx_cache[64];
@@ -2340,8 +2346,8 @@ struct skb_fit {
 
 namespace {
 double* slot_h_ls(FitSlot& sl) { return sl.h_pinned; }
-double* slot_h_out(FitSlot& sl) { return sl.h_pinned + MAX_DIMS; }
-int* slot_h_info(FitSlot& sl) { return reinterpret_cast<int*>(sl.h_pinned + 2 * MAX_DIMS + 4); }
+double* slot_h_out(FitSlot& sl) { return sl.h_pinned + MAX_DIMS + 4; }
+int* slot_h_info(FitSlot& sl) { return reinterpret_cast<int*>(sl.h_pinned + 2 * (MAX_DIMS + 4)); }
 
 int fit_alloc(skb_fit* f, double** ptr, size_t count) {
     void* raw = nullptr;
@@ -2368,12 +2374,12 @@ int fit_add_slot(skb_fit* f) {
     }
     if (!sl.stream) {
         CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), (2 * MAX_DIMS + 8) * sizeof(double)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&sl.h_pinned), FIT_PINNED_DOUBLES * sizeof(double)));
     }
     int r;
     if ((r = fit_alloc(f, &sl.d_Xs, n * d)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_a, n)) != SKB_OK) return r;
-    if ((r = fit_alloc(f, &sl.d_ls, d)) != SKB_OK) return r;
+    if ((r = fit_alloc(f, &sl.d_ls, d + 2)) != SKB_OK) return r;       // length scales, then {amplitude, noise}
     if ((r = fit_alloc(f, &sl.d_K, n * n)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_V, n * n)) != SKB_OK) return r;
     if ((r = fit_alloc(f, &sl.d_partial, (size_t)f->n_blocks * (d + 2))) != SKB_OK) return r;
@@ -2393,27 +2399,20 @@ int fit_inverse_from_factor(skb_fit* f, FitSlot& sl, double* out_lower) {
     return tri_gram(sl.d_V, out_lower, f->n, sl.stream);
 }
 
-// queue one evaluation on the slot's stream; nothing here waits for the GPU
-int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
+// The launches of one evaluation on the slot's stream: everything that depends on theta is read from the slot's pinned
+// staging area (length scales, amplitude, noise) by the first copy, so the same sequence serves every theta.
+int fit_enqueue(skb_fit* f, FitSlot& sl, bool want_grad) {
     cudaStream_t s = sl.stream;
     const int n = f->n, d = f->d;
-    const double amplitude = exp(theta[0]), noise = exp(theta[d + 1]);      // exp(-inf) = 0: no noise term
-    double* ls = slot_h_ls(sl);
-    for (int k = 0; k < d; ++k) ls[k] = exp(theta[1 + k]);
-    if (!(amplitude >= 0.0) || !(noise >= 0.0) || std::isinf(amplitude) || std::isinf(noise))
-        return fail(SKB_ERR_INVALID, "non-finite hyper-parameter");
-    sl.want_grad = want_grad;
-    CU(cudaMemcpyAsync(sl.d_ls, ls, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sl.d_ls, slot_h_ls(sl), (size_t)(d + 2) * sizeof(double), cudaMemcpyHostToDevice, s));
     fit_scale_kernel<<<(unsigned)(((size_t)n * d + 255) / 256), 256, 0, s>>>(f->d_X, sl.d_ls, sl.d_Xs, n, d);
     LAUNCHED();
     FitParams kp;
     kp.Xs = sl.d_Xs;
     kp.n = n;
     kp.d = d;
-    kp.amplitude = amplitude;
-    kp.noise = noise;
+    kp.hyp = sl.d_ls + d;
     kp.alpha = f->alpha;
-    kp.diag_add = noise + f->alpha;
     kp.K = sl.d_K;
     const int T = (n + FIT_TILE - 1) / FIT_TILE;
     const size_t smem_k = 2 * (size_t)FIT_TILE * (d + 1) * sizeof(double);
@@ -2443,8 +2442,7 @@ int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
         gp.a = sl.d_a;
         gp.n = n;
         gp.d = d;
-        gp.amplitude = amplitude;
-        gp.noise = noise;
+        gp.hyp = sl.d_ls + d;
         gp.partial = sl.d_partial;
         const size_t smem_g = smem_k + 8 * (size_t)(d + 2) * sizeof(double);
         switch (f->kernel) {
@@ -2460,6 +2458,65 @@ int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
     CU(cudaMemcpyAsync(slot_h_out(sl), sl.d_out, (size_t)(want_grad ? d + 3 : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(slot_h_info(sl), sl.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     return SKB_OK;
+}
+
+// SKB_FIT_GRAPH=0 keeps plain launches (A/B measurements)
+static bool fit_graphs_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SKB_FIT_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// Capture fit_enqueue once for this (slot, gradient flag) into an executable graph.  Returns false (and remembers it) if the
+// runtime refuses; the caller then launches plainly.
+static bool fit_capture(skb_fit* f, FitSlot& sl, bool want_grad) {
+    const int64_t before = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        sl.graph_failed = true;
+        return false;
+    }
+    const int rc = fit_enqueue(f, sl, want_grad);
+    const cudaError_t end = cudaStreamEndCapture(sl.stream, &graph);
+    const int nodes = (int)(g_launches.load() - before);
+    g_launches.fetch_sub(nodes);                              // counted when the graph is launched, not when it is recorded
+    if (rc != SKB_OK || end != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        sl.graph_failed = true;
+        return false;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess || !exec) {
+        cudaGetLastError();
+        sl.graph_failed = true;
+        return false;
+    }
+    sl.exec[want_grad ? 1 : 0] = exec;
+    sl.graph_nodes[want_grad ? 1 : 0] = nodes;
+    return true;
+}
+
+// queue one evaluation on the slot's stream; nothing here waits for the GPU
+int fit_issue(skb_fit* f, FitSlot& sl, const double* theta, bool want_grad) {
+    const int d = f->d;
+    const double amplitude = exp(theta[0]), noise = exp(theta[d + 1]);      // exp(-inf) = 0: no noise term
+    double* ls = slot_h_ls(sl);
+    for (int k = 0; k < d; ++k) ls[k] = exp(theta[1 + k]);
+    if (!(amplitude >= 0.0) || !(noise >= 0.0) || std::isinf(amplitude) || std::isinf(noise))
+        return fail(SKB_ERR_INVALID, "non-finite hyper-parameter");
+    ls[d] = amplitude;
+    ls[d + 1] = noise;
+    sl.want_grad = want_grad;
+    const int g = want_grad ? 1 : 0;
+    if (fit_graphs_enabled() && !sl.graph_failed && (sl.exec[g] || fit_capture(f, sl, want_grad))) {
+        CU(cudaGraphLaunch(sl.exec[g], sl.stream));
+        g_launches.fetch_add(sl.graph_nodes[g]);
+        return SKB_OK;
+    }
+    return fit_enqueue(f, sl, want_grad);
 }
 
 int fit_collect(skb_fit* f, FitSlot& sl, double* lml, double* grad) {
@@ -2483,6 +2540,8 @@ void skb_fit_destroy(skb_fit* f) {
     cudaSetDevice(f->device);
     for (FitSlot& sl : f->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
+        for (int g = 0; g < 2; ++g)
+            if (sl.exec[g]) cudaGraphExecDestroy(sl.exec[g]);
         if (sl.stream && sl.h_pinned) {
             std::lock_guard<std::mutex> lock(g_ctx_mu);
             g_ctx_cache[f->device & 63].push_back(SolverCtx{sl.stream, sl.h_pinned});
