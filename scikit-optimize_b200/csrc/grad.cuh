@@ -38,6 +38,7 @@ struct GradParams {
     double* std_grad;         // [m][d]
     double* acq[3];
     double* acq_grad[3];      // [m][d]
+    int frag0;                // first 8-dimension fragment this launch accumulates gradients for (0; 8 in the second pass of n_dims > 64)
 };
 
 constexpr size_t grad_smem_bytes(int d_pad) {
@@ -81,7 +82,9 @@ __device__ __forceinline__ void kernel_and_gcoef(double sq, double amplitude, do
 //   phase B (DMMA): S[k, c] += sum_j X~_jk P_jc for both weight tiles -- the staged training rows already are the
 //           A operand (dims x rows) in the layout the fragments need, the P tiles are the B operand.
 // The gradient sums follow from  sum_j P_jc (x~_ck - X~_jk) = x~_ck * sum_j P_jc - S[k, c].
-// MF = number of 8-dimension fragments (ceil(d / 8)) the accumulators are sized for.
+// MF = number of 8-dimension fragments (ceil(d / 8), at most 8) the accumulators are sized for.  More than 64 dimensions
+// take a second launch with frag0 = 8: it repeats phase A (distances need every dimension) and accumulates the gradient
+// columns 64 .. d - 1; the per-candidate scalars it writes are the first pass's, bit for bit.
 template <int KIND, int MF>
 __global__ void __launch_bounds__(GRAD_THREADS, 1) grad_contract_kernel(const GradParams p) {
     extern __shared__ __align__(16) unsigned char smem_k3[];
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) grad_contract_kernel(const Gr
                 for (int nf = 0; nf < 2; ++nf) b[a][nf] = P[((size_t)(a * GG + g) * BN + (2 * warp + nf) * 8) * 4 + lane];
 #pragma unroll
             for (int mi = 0; mi < MF; ++mi) {
-                const int dim = mi * 8 + (lane >> 2);
+                const int dim = (p.frag0 + mi) * 8 + (lane >> 2);
                 const double av = dim < d_pad ? xtb[(g * d_pad + dim) * 4 + (lane & 3)] : 0.0;
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
@@ -267,10 +270,10 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) grad_contract_kernel(const Gr
     __syncthreads();
 
     // ---------------- gradients straight from the accumulator fragments ----------------
-    // lane holds dims mi*8 + (lane>>2) and candidates (2*warp+nf)*8 + 2*(lane&3) + {0,1}
+    // lane holds dims (frag0+mi)*8 + (lane>>2) and candidates (2*warp+nf)*8 + 2*(lane&3) + {0,1}
 #pragma unroll
     for (int mi = 0; mi < MF; ++mi) {
-        const int k = mi * 8 + (lane >> 2);
+        const int k = (p.frag0 + mi) * 8 + (lane >> 2);
         if (k >= p.d) continue;
         const double inv_l = 1.0 / p.ls[k];
 #pragma unroll

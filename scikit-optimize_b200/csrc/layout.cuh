@@ -18,7 +18,10 @@ constexpr int TRMM_THREADS = 288;          // 8 DMMA warps + 1 bulk-copy produce
 constexpr int XROWS = 64;                  // training rows per K1 stage
 constexpr int XG = XROWS / 4;              // groups of 4 rows per K1 stage
 constexpr int XS_LD = BN + 1;              // padded leading dimension of the candidate tile in shared memory
-constexpr int MAX_DIMS = 64;
+// Largest n_dims: the candidate tile and two stages of training rows stay resident in shared memory per CTA
+// (K1 208.7 KB, K1 DMMA variant 214.5 KB, K3g 228.7 KB at d_pad = 100, of 227 KB = 232,448 B); beyond 52 dimensions
+// one K1 CTA per SM instead of two.  K3g takes the gradient columns beyond 64 in a second launch (grad.cuh).
+constexpr int MAX_DIMS = 100;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 

@@ -1488,10 +1488,17 @@ int skb_predict_mean_host(skb_state* st, const double* X, int64_t m, double* mea
 }  // extern "C"
 
 template <int KIND>
-static void launch_grad_kind(const GradParams& p, int tiles, size_t smem, cudaStream_t s) {
+static void launch_grad_kind(GradParams p, int tiles, size_t smem, cudaStream_t s) {
+    p.frag0 = 0;
     if (p.d <= 16) grad_contract_kernel<KIND, 2><<<tiles, GRAD_THREADS, smem, s>>>(p);
     else if (p.d <= 32) grad_contract_kernel<KIND, 4><<<tiles, GRAD_THREADS, smem, s>>>(p);
     else grad_contract_kernel<KIND, 8><<<tiles, GRAD_THREADS, smem, s>>>(p);
+    if (p.d > 64) {                       // gradient columns 64 .. d - 1 (MAX_DIMS <= 128: one more pass)
+        p.frag0 = 8;
+        if (p.d <= 96) grad_contract_kernel<KIND, 4><<<tiles, GRAD_THREADS, smem, s>>>(p);
+        else grad_contract_kernel<KIND, 8><<<tiles, GRAD_THREADS, smem, s>>>(p);
+        g_launches.fetch_add(1);
+    }
 }
 
 static int launch_grad(skb_state* st, const GradParams& p, int tiles, cudaStream_t s) {
@@ -2252,6 +2259,16 @@ int chol_set_attributes() {            // per device; called by skb_fit_create w
     CU(cudaFuncSetAttribute((const void*)tri_inverse_level_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU(cudaFuncSetAttribute((const void*)tri_inverse_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU(cudaFuncSetAttribute((const void*)tri_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    // K build / gradient kernels stage two 32-row tiles of the training set: above 48 KB from 95 dimensions on
+    const int fit_k = (int)(2 * (size_t)FIT_TILE * (MAX_DIMS + 1) * sizeof(double)), fit_g = fit_k + (int)(8 * (MAX_DIMS + 2) * sizeof(double));
+    CU(cudaFuncSetAttribute((const void*)fit_kbuild_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_k));
+    CU(cudaFuncSetAttribute((const void*)fit_kbuild_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_k));
+    CU(cudaFuncSetAttribute((const void*)fit_kbuild_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_k));
+    CU(cudaFuncSetAttribute((const void*)fit_kbuild_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_k));
+    CU(cudaFuncSetAttribute((const void*)fit_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_g));
+    CU(cudaFuncSetAttribute((const void*)fit_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_g));
+    CU(cudaFuncSetAttribute((const void*)fit_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_g));
+    CU(cudaFuncSetAttribute((const void*)fit_grad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_g));
     return SKB_OK;
 }
 

@@ -137,8 +137,8 @@ class AbiModel:
         self.calls.append("skb_state_create")
         if desc.n_train <= 0 or desc.n_dims <= 0 or not desc.X_train or not desc.alpha or not desc.L_inv:
             return self._fail(ERR_INVALID, "bad state descriptor")
-        if desc.n_dims > 64:
-            return self._fail(ERR_UNSUPPORTED, "n_dims %d > 64" % desc.n_dims)
+        if desc.n_dims > 100:
+            return self._fail(ERR_UNSUPPORTED, "n_dims %d > 100" % desc.n_dims)
         handle = self._next
         self._next += 1
         self._states[handle] = _State(desc)

@@ -39,7 +39,7 @@ def test_device_lml_not_positive_definite():
     fit.close()
 
 
-@pytest.mark.parametrize("n,d,nu", [(700, 8, 2.5), (1100, 12, 1.5), (33, 1, 2.5)])
+@pytest.mark.parametrize("n,d,nu", [(700, 8, 2.5), (1100, 12, 1.5), (33, 1, 2.5), (260, 100, 2.5), (200, 97, 1.5)])
 def test_estimator_lml_gpu_vs_host(n, d, nu):
     from skopt_b200.learning import GaussianProcessRegressor
     from skopt_b200.learning.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
@@ -132,7 +132,7 @@ def _fixed_kernel_problem(n, d, nu, seed):
 # sizes around the 64-column blocks of the library's own Cholesky / recursive-doubling inverse (csrc/chol.cuh): one block,
 # partial blocks, 2 / 3 / 5 blocks (odd block counts leave a pair without its second half at some level)
 @pytest.mark.parametrize("n,d", [(1, 1), (2, 1), (33, 2), (63, 2), (64, 2), (65, 2), (127, 3), (128, 3), (129, 3), (200, 3),
-                                 (300, 5), (321, 4), (1100, 12)])
+                                 (300, 5), (321, 4), (1100, 12), (150, 100)])
 def test_finalize_matches_host_factorisation(n, d):
     """skb_fit_finalize_host: L_, alpha_ and the lml at theta* against SciPy's Cholesky of the same K."""
     from scipy.linalg import cho_solve, cholesky

@@ -56,6 +56,36 @@ def test_sampling_trajectory_identical(name):
     assert len(res.models) == cfg["n_calls"] - cfg["n_initial_points"] + 1
 
 
+WIDE = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "traj_wide.npz")))
+WIDE_RUNS = json.loads(str(WIDE["runs"]))
+_CATS = list("abcdefghi")
+
+
+def sphere70(x):
+    x = np.asarray(x, dtype=float)
+    return float(np.sum((x - 0.3) ** 2) + np.sin(5.0 * x[0]) * x[3])
+
+
+def mixed66(x):
+    real = sum((v - 0.1 * (i % 7)) ** 2 for i, v in enumerate(x[:40]))
+    ints = sum(0.02 * (v - 3) ** 2 for v in x[40:56])
+    cat = sum((_CATS.index(c) - 4) ** 2 * (0.05 + 0.01 * i) for i, c in enumerate(x[56:]))
+    return float(real + ints + cat)
+
+
+@pytest.mark.parametrize("name", ["real70_sampling_ei", "mixed66_sampling_hedge"])
+def test_wide_space_trajectory_identical(name):
+    """More than 64 model dimensions (oracle/make_golden_wide.py: 70 Real dimensions; 40 Real + 16 Integer + 10
+    Categorical): one K1 CTA per SM, candidates drawn on the device - every suggested point as in the reference."""
+    cfg = WIDE_RUNS[name]
+    kw = {k: v for k, v in cfg.items() if k not in ("func", "dims")}
+    dims = [tuple(d) if not isinstance(d[0], str) else list(d) for d in cfg["dims"]]
+    res = gp_minimize({"sphere70": sphere70, "mixed66": mixed66}[cfg["func"]], dims, **kw)
+    assert res.x_iters == json.loads(str(WIDE[name + "_x_iters"]))
+    assert np.array_equal(np.asarray(res.func_vals), WIDE[name + "_func_vals"])
+    assert res.models[-1].X_train_.shape[1] > 64
+
+
 def test_sampling_trajectory_tiny_noise():
     """noise=1e-10 (benchmarks/bench_*.py): K is nearly singular, where the reference's own variance moves by
     eps*cond(K) with summation order; the run must still reach an equally good minimum and agree on the first

@@ -85,6 +85,9 @@ def test_golden_fixture(name):
     (512, 20, 4096, orc.KIND_RBF, np.inf),
     (1024, 10, 3000, orc.KIND_MATERN, 2.5),
     (37, 50, 200, orc.KIND_MATERN, 2.5),
+    (300, 65, 700, orc.KIND_MATERN, 2.5),      # more than 64 dimensions: one K1 CTA per SM
+    (260, 100, 900, orc.KIND_RBF, np.inf),     # the largest n_dims the shared-memory tiles hold
+    (150, 97, 300, orc.KIND_MATERN, 0.5),
 ])
 def test_synthetic_vs_oracle(n, d, m, kind, nu):
     st = orc.make_synthetic_state(n, d, noise=1e-3, seed=n + d, kind=kind, nu=nu)
@@ -206,6 +209,10 @@ def test_golden_gradients(name):
     (200, 50, 100, orc.KIND_MATERN, 2.5),
     (256, 20, 150, orc.KIND_RBF, np.inf),
     (90, 4, 64, orc.KIND_MATERN, 0.5),
+    (200, 65, 130, orc.KIND_MATERN, 2.5),      # gradient columns 64 .. d - 1 come from a second launch (frag0 = 8)
+    (140, 100, 70, orc.KIND_MATERN, 1.5),
+    (130, 96, 40, orc.KIND_RBF, np.inf),
+    (70, 89, 33, orc.KIND_MATERN, 0.5),
 ])
 def test_synthetic_gradients_vs_oracle_loop(n, d, m, kind, nu):
     """Batched device gradients against a loop of single-point oracle calls (the reference is 1-point only)."""
@@ -295,7 +302,7 @@ def test_empty_candidate_set_and_bad_arguments():
     with pytest.raises(ValueError):
         dev.score(np.zeros((3, 2)), acq_funcs=("UCB",))             # unknown acquisition
     with pytest.raises(skopt_b200._lib.SkbError):
-        engine.DeviceState(engine.HostState(np.zeros((4, 65)), np.zeros(4), np.eye(4), np.ones(65), 3, 1, 0, 0, 0, 1))
+        engine.DeviceState(engine.HostState(np.zeros((4, 101)), np.zeros(4), np.eye(4), np.ones(101), 3, 1, 0, 0, 0, 1))
     dev.close()
 
 

@@ -40,6 +40,8 @@ def test_split_golden_fixture(name, precision):
     (1024, 10, 3000, orc.KIND_MATERN, 2.5),
     (37, 50, 200, orc.KIND_MATERN, 2.5),
     (1, 1, 1, orc.KIND_MATERN, 2.5),
+    (600, 100, 9000, orc.KIND_MATERN, 2.5),   # widest state: the DMMA digit kernel with one CTA per SM
+    (520, 77, 2000, orc.KIND_MATERN, 0.5),
 ])
 @pytest.mark.parametrize("precision", SPLIT_MODES)
 def test_split_synthetic_vs_oracle_and_fp64(n, d, m, kind, nu, precision):

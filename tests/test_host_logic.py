@@ -288,8 +288,8 @@ def test_argument_validation_needs_no_device():
     desc.length_scale, desc.X_train, desc.alpha, desc.L_inv = ls.ctypes.data, x.ctypes.data, a.ctypes.data, li.ctypes.data
     desc.kernel = 9
     assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -2 and "outside the hot-path grammar" in last()
-    desc.kernel, desc.n_dims = 3, 65
-    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -2 and "n_dims 65 > 64" in last()
+    desc.kernel, desc.n_dims = 3, 101
+    assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -2 and "n_dims 101 > 100" in last()
     desc.n_dims = 3
     ls[1] = 0.0
     assert L.skb_state_create(C.byref(desc), 0, C.byref(handle)) == -1 and "length_scale[1] must be > 0" in last()
