@@ -198,21 +198,33 @@ int pool_alloc(int device, void** out, size_t bytes) {
 void pool_free(int device, void* ptr) {
     if (!ptr) return;
     DevicePool& pool = g_pools[device & 63];
-    size_t bytes = 0;
+    std::vector<Block> evict;
+    bool parked = false;
     {
         std::lock_guard<std::mutex> lock(pool.mu);
         auto it = pool.live.find(ptr);
         if (it != pool.live.end()) {
-            bytes = it->second;
+            const size_t bytes = it->second;
             pool.live.erase(it);
-            if (pool.cached_bytes + bytes <= POOL_MAX_CACHED) {
+            if (bytes <= POOL_MAX_CACHED) {
+                // the block just freed is the one most likely to be asked for again (the next state is about this size):
+                // park it and, if the cache is over its limit, give the OLDEST parked blocks back to the driver - in a loop
+                // whose training set grows, those are the sizes nobody will request any more
                 pool.free_blocks.push_back({ptr, bytes});
                 pool.cached_bytes += bytes;
-                return;
+                parked = true;
+                size_t first_kept = 0;
+                while (pool.cached_bytes > POOL_MAX_CACHED && first_kept + 1 < pool.free_blocks.size()) {
+                    pool.cached_bytes -= pool.free_blocks[first_kept].bytes;
+                    evict.push_back(pool.free_blocks[first_kept]);
+                    ++first_kept;
+                }
+                if (first_kept) pool.free_blocks.erase(pool.free_blocks.begin(), pool.free_blocks.begin() + first_kept);
             }
         }
     }
-    cudaFree(ptr);
+    for (auto& b : evict) cudaFree(b.ptr);
+    if (!parked) cudaFree(ptr);
 }
 
 template <typename T>
