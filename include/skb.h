@@ -223,6 +223,22 @@ int skb_topk_dev(skb_state* st, const double* values, int64_t m, int64_t index_o
 int skb_topk_merge_records_dev(int device, const void* gathered, int32_t n_records, int32_t n_acq, int32_t top_k,
                                void* merged, void* stream);
 
+/* The same exchange + merge as ONE kernel over NVLink peer memory instead of an all-gather followed by
+ * skb_topk_merge_records_dev: every rank stores its record into every peer's buffer, raises a flag there, waits for the
+ * world's flags in its own buffer and merges (csrc/topk.cuh, topk_exchange_peer_kernel).  The caller provides the peer
+ * mapping: each rank allocates skb_peer_buffer_bytes() of SYMMETRIC memory, zeroed before the first exchange, and passes
+ * every rank's buffer as it is mapped on this device (torch.distributed._symmetric_memory: rendezvous(...).buffer_ptrs).
+ * seq = 1, 2, 3, ... counts the exchanges of the group and must be the same on all ranks.  `merged` (device) receives
+ * n_acq * (2 top_k + 1) + 1 words: the merged record, then a status word (0, or 1 if a peer did not arrive within
+ * timeout_ms - the merged record is then meaningless).  Requires world <= 8 and n_acq * (2 top_k + 1) <= 1024. */
+typedef struct skb_peer_group {
+    void* buffers[8];     /* [world] device pointers, buffers[rank] is the own one */
+    int32_t rank, world;
+} skb_peer_group;
+int64_t skb_peer_buffer_bytes(void);
+int skb_topk_exchange_peer_dev(int device, const skb_peer_group* group, uint64_t seq, const void* record, int32_t n_acq,
+                               int32_t top_k, void* merged, int32_t timeout_ms, void* stream);
+
 /* ---- candidate generation on the device (the step that feeds the path: optimizer.py:552-553) ----
  * Replaces: `space.rvs(n_points, random_state=rng)` + `space.transform(...)` (skopt/space/space.py:874-903, 942-974;
  * transformers.py:243-276) for "normalize"-warped Real (uniform prior), Integer and Categorical dimensions.

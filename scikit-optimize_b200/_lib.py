@@ -46,6 +46,10 @@ class FitDesc(C.Structure):
                 ("alpha", C.c_double), ("X_train", C.c_void_p), ("y_train", C.c_void_p)]
 
 
+class PeerGroup(C.Structure):
+    _fields_ = [("buffers", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class GradOut(C.Structure):
     _fields_ = [("mean", C.c_void_p), ("std", C.c_void_p), ("mean_grad", C.c_void_p), ("std_grad", C.c_void_p),
                 ("acq", C.c_void_p * 3), ("acq_grad", C.c_void_p * 3)]
@@ -87,6 +91,9 @@ SYMBOLS = [
                                C.c_void_p]),
     ("skb_topk_merge_records_dev", C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p]),
+    ("skb_peer_buffer_bytes", C.c_int64, []),
+    ("skb_topk_exchange_peer_dev", C.c_int, [C.c_int, C.POINTER(PeerGroup), C.c_uint64, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_int32, C.c_void_p]),
     ("skb_mt19937_uniform_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_void_p, C.c_void_p]),
     ("skb_candidates_generate_dev", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32,
                                               C.POINTER(DimDesc), C.c_void_p, C.c_void_p]),

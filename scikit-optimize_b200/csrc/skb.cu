@@ -2093,6 +2093,48 @@ int skb_topk_merge_records_dev(int device, const void* gathered, int32_t n_recor
     return SKB_OK;
 }
 
+int64_t skb_peer_buffer_bytes(void) { return (int64_t)PEER_BUFFER_WORDS * 8; }
+
+int skb_topk_exchange_peer_dev(int device, const skb_peer_group* group, uint64_t seq, const void* record, int32_t n_acq,
+                               int32_t top_k, void* merged, int32_t timeout_ms, void* stream) {
+    if (!group || !record || !merged) return fail(SKB_ERR_INVALID, "group/record/merged is NULL");
+    if (group->world < 1 || group->world > PEER_MAX_WORLD || group->rank < 0 || group->rank >= group->world)
+        return fail(SKB_ERR_INVALID, "rank %d / world %d out of range (world <= %d)", group->rank, group->world, PEER_MAX_WORLD);
+    if (n_acq <= 0 || n_acq > SKB_NUM_ACQ || top_k < 0 || (int64_t)n_acq * (2 * (int64_t)top_k + 1) > PEER_SLOT_WORDS)
+        return fail(SKB_ERR_INVALID, "record of n_acq %d, top_k %d does not fit a peer slot (%d words)", n_acq, top_k, PEER_SLOT_WORDS);
+    if (seq == 0) return fail(SKB_ERR_INVALID, "seq counts from 1");
+    int rc = check_device(device);
+    if (rc != SKB_OK) return rc;
+    PeerExchangeParams p;
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        p.peer[r] = r < group->world ? static_cast<unsigned long long*>(group->buffers[r]) : nullptr;
+        if (r < group->world && !p.peer[r]) return fail(SKB_ERR_INVALID, "buffers[%d] is NULL", r);
+    }
+    p.rec = static_cast<const int64_t*>(record);
+    p.merged = static_cast<int64_t*>(merged);
+    p.rank = group->rank;
+    p.world = group->world;
+    p.n_acq = n_acq;
+    p.k = top_k;
+    p.seq = seq;
+    // the clock-rate attribute is a slow driver query (milliseconds): once per device
+    static std::atomic<int> khz_cache[64];
+    int khz = khz_cache[device & 63].load();
+    if (khz == 0) {
+        CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        khz_cache[device & 63].store(khz);
+    }
+    p.spin_limit = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * (long long)(khz > 0 ? khz : 1500000);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t words = (int64_t)n_acq * (2 * (int64_t)top_k + 1);
+    CU(cudaMemsetAsync(p.merged + words, 0, sizeof(int64_t), s));
+    const size_t smem = (size_t)group->world * (2 * (size_t)top_k + 1) * sizeof(int64_t);
+    if (smem > 48 * 1024) return fail(SKB_ERR_INVALID, "world %d x top_k %d does not fit the merge's shared-memory staging", group->world, top_k);
+    topk_exchange_peer_kernel<<<n_acq, TOPK_THREADS, smem, s>>>(p);
+    LAUNCHED();
+    return SKB_OK;
+}
+
 static int check_device(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

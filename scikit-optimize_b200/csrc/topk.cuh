@@ -144,6 +144,108 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_records_kernel(const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exchange + merge in ONE kernel over NVLink peer memory (the step after the per-rank top-k: SURVEY.md 8e / K4).
+// Every rank owns a symmetric buffer that all peers have mapped (torch symmetric memory supplies the mapping; the
+// kernel only sees pointers).  Block a (one per acquisition) of rank r
+//   1. stores its slices of the local record - values, indices, first-NaN of acquisition a - into slot r of EVERY rank's
+//      buffer (plain stores through the peer mapping), fences at system scope and raises flag (set, a, r) = seq there;
+//   2. waits until its own buffer shows flag (set, a, p) = seq for every rank p (acquire loads at system scope, bounded:
+//      a rank that never arrives sets *status instead of hanging the GPU);
+//   3. copies the world's slices from its own buffer into shared memory with L2-coherent loads and runs the same
+//      block_topk_rounds merge as topk_merge_records_kernel.
+// Two slot sets alternate with seq: a rank can be at most one exchange ahead of a peer (it needs that peer's flag of the
+// current exchange to finish), so set seq & 1 is never overwritten while somebody still reads it.
+// Buffer layout in 8-byte words: [2 sets][PEER_MAX_WORLD ranks][PEER_SLOT_WORDS] records | [2][3 acq][PEER_MAX_WORLD] flags.
+constexpr int PEER_MAX_WORLD = 8;
+constexpr int PEER_SLOT_WORDS = 1024;                       // room for one record: n_acq (2 k + 1) <= 1024
+constexpr int PEER_FLAG_BASE = 2 * PEER_MAX_WORLD * PEER_SLOT_WORDS;
+constexpr int PEER_BUFFER_WORDS = PEER_FLAG_BASE + 2 * 3 * PEER_MAX_WORLD;
+
+struct PeerExchangeParams {
+    unsigned long long* peer[PEER_MAX_WORLD];   // every rank's buffer as mapped on THIS device ([world] used; [rank] is the own one)
+    const int64_t* rec;                          // local packed record (device)
+    int64_t* merged;                             // one record + 1 word: the merged record, then the status word
+    int rank, world, n_acq, k;
+    unsigned long long seq;                      // 1, 2, 3, ... identical on all ranks
+    long long spin_limit;                        // clock64 ticks a rank waits for its peers
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_exchange_peer_kernel(const PeerExchangeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_px[];
+    int64_t* stage = reinterpret_cast<int64_t*>(smem_px);       // [world][2 k + 1]: values | indices | first NaN
+    const int a = blockIdx.x, tid = threadIdx.x, k = p.k, nk = p.n_acq * p.k;
+    const int set = (int)(p.seq & 1ull);
+    const size_t slot_mine = ((size_t)set * PEER_MAX_WORLD + p.rank) * PEER_SLOT_WORDS;
+    // 1. my slices into slot `rank` of every rank's buffer
+    for (int q = 0; q < p.world; ++q) {
+        unsigned long long* dst = p.peer[q] + slot_mine;
+        for (int i = tid; i < k; i += TOPK_THREADS) {
+            dst[a * k + i] = (unsigned long long)p.rec[a * k + i];
+            dst[nk + a * k + i] = (unsigned long long)p.rec[nk + a * k + i];
+        }
+        if (tid == 0) dst[2 * nk + a] = (unsigned long long)p.rec[2 * nk + a];
+    }
+    __threadfence_system();
+    __syncthreads();
+    const size_t flag_off = (size_t)PEER_FLAG_BASE + ((size_t)set * 3 + a) * PEER_MAX_WORLD;
+    if (tid < p.world) st_release_sys(p.peer[tid] + flag_off + p.rank, p.seq);
+    // 2. the world's flags in my own buffer
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    if (tid < p.world) {
+        const unsigned long long* f = p.peer[p.rank] + flag_off + tid;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != p.seq) {
+            if (clock64() - t0 > p.spin_limit) {
+                s_timeout = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    // 3. stage the slices (L2-coherent loads: the lines were written by peers) and merge
+    const unsigned long long* own = p.peer[p.rank] + (size_t)set * PEER_MAX_WORLD * PEER_SLOT_WORDS;
+    const int row = 2 * k + 1;
+    for (int e = tid; e < p.world * k; e += TOPK_THREADS) {
+        const int r = e / k, i = e - r * k;
+        const unsigned long long* src = own + (size_t)r * PEER_SLOT_WORDS;
+        stage[r * row + i] = (int64_t)ld_relaxed_sys(src + a * k + i);
+        stage[r * row + k + i] = (int64_t)ld_relaxed_sys(src + nk + a * k + i);
+    }
+    if (tid < p.world) stage[tid * row + 2 * k] = (int64_t)ld_relaxed_sys(own + (size_t)tid * PEER_SLOT_WORDS + 2 * nk + a);
+    __syncthreads();
+    double* out_v = reinterpret_cast<double*>(p.merged) + (int64_t)a * k;
+    int64_t* out_i = p.merged + (int64_t)nk + (int64_t)a * k;
+    if (k > 0)
+        block_topk_rounds(reinterpret_cast<const double*>(stage), stage + k, (int64_t)p.world * k, 0, k, out_v, out_i, nullptr, k, row);
+    if (tid == 0) {
+        long long mn = INT64_MAX;
+        for (int r = 0; r < p.world; ++r) {
+            const long long v = stage[r * row + 2 * k];
+            if (v >= 0 && v < mn) mn = v;
+        }
+        p.merged[2 * (int64_t)nk + a] = mn == INT64_MAX ? -1 : mn;
+        if (s_timeout) atomicExch(reinterpret_cast<unsigned long long*>(p.merged + (2 * (int64_t)nk + p.n_acq)), 1ull);
+    }
+}
+
 // Padding of an empty candidate set: NaN values, index -1, no NaN seen (what the host entry points pre-fill).
 __global__ void topk_fill_empty_kernel(double* out_v, int64_t* out_i, int64_t* out_nan, int k) {
     for (int j = threadIdx.x; j < k; j += blockDim.x) {

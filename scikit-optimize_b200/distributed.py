@@ -60,12 +60,103 @@ def merge_records_torch(gathered, n_records, n_acq, k, k_out=None):
     return out
 
 
+class PeerExchange(object):
+    """Exchange + merge of the packed records as ONE kernel over NVLink peer memory (csrc/topk.cuh,
+    topk_exchange_peer_kernel; include/skb.h, skb_topk_exchange_peer_dev): every rank stores its record straight into its
+    peers' buffers, raises a flag, waits for the world's flags and merges - no NCCL call and no second launch on the step.
+    torch's symmetric memory supplies the allocation and the peer mapping; the kernel only sees pointers.  One object per
+    process group, created collectively on first use; `seq` counts the group's exchanges (every rank calls in step)."""
+
+    _by_group = {}
+
+    def __init__(self, group, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib, self._C = _lib, C
+        words = int(_lib.lib().skb_peer_buffer_bytes()) // 8
+        self.buf = symm.empty(words, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.handle.barrier()                       # every rank's flags are zero before anybody's first store arrives
+        self.grp = _lib.PeerGroup()
+        self.grp.rank, self.grp.world = int(self.handle.rank), int(self.handle.world_size)
+        for r, ptr in enumerate(self.handle.buffer_ptrs):
+            self.grp.buffers[r] = int(ptr)
+        self.device = device
+        self.seq = 0
+        self.status = []                            # status words (device) of the exchanges not yet looked at
+
+    def fits(self, n_acq, k):
+        return self.grp.world <= 8 and n_acq * (2 * k + 1) <= 1024 and self.grp.world * (2 * k + 1) * 8 <= 48 * 1024
+
+    def exchange(self, rec, n_acq, k, timeout_ms=5000):
+        """merged record (device tensor, nothing waits).  The kernel's status word (a peer that did not arrive within
+        `timeout_ms`) is kept on the device and looked at by check_exchanges() - unpack_record calls it after its own
+        device -> host copy."""
+        if len(self.status) >= 256:
+            check_exchanges()
+        self.seq += 1
+        words = n_acq * (2 * k + 1)
+        out = torch.empty(words + 1, dtype=torch.int64, device=rec.device)
+        s = torch.cuda.current_stream(rec.device)
+        self._lib.check(self._lib.lib().skb_topk_exchange_peer_dev(
+            rec.device.index, self._C.byref(self.grp), self.seq, rec.contiguous().data_ptr(), int(n_acq), int(k),
+            out.data_ptr(), int(timeout_ms), self._C.c_void_p(s.cuda_stream)))
+        self.status.append(out[words:])
+        return out[:words]
+
+    @classmethod
+    def for_group(cls, group, device):
+        """The group's exchange object, or None where peer memory is not available (then NCCL's all-gather is used).
+        SKB_PEER_EXCHANGE=0 switches it off."""
+        import os
+        key = id(group) if group is not None else None
+        if key not in cls._by_group:
+            px = None
+            if os.environ.get("SKB_PEER_EXCHANGE", "1") != "0" and dist.get_backend(group) == "nccl":
+                try:
+                    px = cls(group, device)
+                except Exception as exc:      # noqa: BLE001 - no P2P mapping on this machine: the collective path stays
+                    import warnings
+                    warnings.warn("peer-memory exchange unavailable (%s: %s); using the NCCL all-gather" % (type(exc).__name__, exc))
+                    px = None
+                # the decision must be the same on every rank
+                ok = torch.tensor([1 if px is not None else 0], device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0:
+                    px = None
+            cls._by_group[key] = px
+        return cls._by_group[key]
+
+
+class PeerTimeout(RuntimeError):
+    pass
+
+
+def check_exchanges():
+    """Raise PeerTimeout if any peer-memory exchange since the last call gave up waiting for a rank (its merged record
+    is then meaningless).  One small device -> host copy per group; a no-op when no peer exchange ran."""
+    for px in PeerExchange._by_group.values():
+        if px is not None and px.status:
+            st = torch.cat(px.status).cpu()
+            px.status = []
+            if bool(st.any()):
+                raise PeerTimeout("a rank did not reach the peer-memory exchange in time; the merged record is invalid")
+
+
 def exchange_records(rec, n_acq, k, group=None, k_out=None):
-    """The one collective of the path: all-gather every rank's packed record and merge.  CUDA records merge in one
-    launch of the library's kernel (no host round trip); CPU records (gloo) through merge_records_torch."""
+    """The one exchange of the path.  CUDA records over NCCL groups: ONE kernel that stores the record into every peer's
+    symmetric buffer over NVLink and merges what arrived (PeerExchange); the returned tensor then carries a status word
+    behind the record (0 = every rank arrived).  Otherwise: all-gather every rank's packed record and merge - CUDA
+    records in one launch of the library's merge kernel, CPU records (gloo) through merge_records_torch."""
     world = _world(group)
     if world == 1 and (k_out is None or k_out == k):
         return rec
+    if world > 1 and rec.is_cuda and (k_out is None or k_out == k):
+        px = PeerExchange.for_group(group, rec.device)
+        if px is not None and px.fits(n_acq, k):
+            return px.exchange(rec, n_acq, k)
     if world > 1:
         gathered = torch.empty(world * rec.numel(), dtype=torch.int64, device=rec.device)
         dist.all_gather_into_tensor(gathered, rec.contiguous(), group=group)

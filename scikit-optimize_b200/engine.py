@@ -495,6 +495,9 @@ def unpack_record(rec, acq_funcs, top_k):
     """{acq name: {'topk_val', 'topk_idx', 'first_nan'}} (NumPy) from a packed record (int64 tensor or array, host or
     device): ONE device -> host copy for everything a sharded scoring call returns."""
     words = rec.cpu().numpy() if hasattr(rec, "cpu") else np.asarray(rec)
+    if hasattr(rec, "is_cuda") and rec.is_cuda:
+        from .distributed import check_exchanges
+        check_exchanges()                 # a peer-memory exchange that gave up waiting for a rank raises here
     A, k = len(acq_funcs), int(top_k)
     out = {}
     for j, name in enumerate(acq_funcs):

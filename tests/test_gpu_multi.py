@@ -41,6 +41,34 @@ pts = torch.tensor(opt.Xi, dtype=torch.float64, device="cuda")
 ref = pts.clone(); dist.broadcast(ref, 0)
 assert torch.equal(pts, ref)
 rank = dist.get_rank()
+# the peer-memory exchange (one kernel: NVLink stores + flags + merge) against the all-gather + merge-kernel path and the
+# torch restatement, over many back-to-back exchanges (the two slot sets alternate) with changing record shapes
+from skopt_b200.distributed import PeerExchange, check_exchanges, exchange_records, merge_records_torch
+px = PeerExchange.for_group(None, torch.device("cuda", local))
+print("rank", rank, "peer exchange", "USED" if px is not None else "UNAVAILABLE")
+if px is not None:
+    g = torch.Generator(device="cpu"); g.manual_seed(100 + rank)
+    world = dist.get_world_size()
+    for step in range(40):
+        A, k = [(1, 16), (3, 8), (2, 1), (3, 64), (1, 170)][step %% 5]
+        vals = torch.randn(A * k, generator=g, dtype=torch.float64)
+        if step %% 7 == 3:
+            vals[: k // 2 + 1] = 0.25                       # ties across ranks: the lowest global index wins
+        idx = torch.randperm(10 ** 6, generator=g)[: A * k].to(torch.int64) * world + rank
+        if step %% 9 == 4:
+            idx[-1] = -1                                    # padding entry
+        nan = torch.full((A,), -1, dtype=torch.int64)
+        if step %% 4 == 1:
+            nan[0] = 1000 * (rank + 1) + step
+        rec = torch.cat([vals.view(torch.int64), idx, nan]).cuda()
+        assert px.fits(A, k)
+        fused = exchange_records(rec, A, k)
+        gathered = torch.empty(world * rec.numel(), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered, rec)
+        ref = merge_records_torch(gathered.cpu(), world, A, k)
+        assert torch.equal(fused.cpu(), ref), (step, A, k)
+    check_exchanges()
+    assert px.seq >= 40
 # without shard_group a tell() is local even inside the process group: only rank 0 runs it here, and it must not hang
 if rank == 0:
     solo = Optimizer([(0.0, 1.0)] * 3, "GP", n_initial_points=4, acq_func="EI", acq_optimizer="sampling",
@@ -64,3 +92,4 @@ def test_sharded_scoring_two_gpus(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+    print(out.stdout[-600:])
