@@ -84,6 +84,7 @@ class PeerExchange(object):
         for r, ptr in enumerate(self.handle.buffer_ptrs):
             self.grp.buffers[r] = int(ptr)
         self.device = device
+        self.group = group                          # keeps the group object alive: for_group() keys its cache by id(group)
         self.seq = 0
         self.status = []                            # status words (device) of the exchanges not yet looked at
 
