@@ -114,8 +114,9 @@ def main():
                     nat = np.sqrt(scale) / np.min(st.length_scale) * max(1.0, np.sqrt(scale) / max(sd_g[i], 1e-300))
                     assert np.max(np.abs(g["std_grad"][i] - gs[i])) <= 1e-9 * nat, "std_grad row %d on the natural scale" % i
                     conditioned += 1
+            planes = dev.split_info()[0]
             dev.close()
-            print(tag, "ok  planes", dev_planes(dev) if False else "", flush=True)
+            print(tag, "ok  (split_int8 contracts %d planes)" % planes, flush=True)
         except AssertionError as exc:
             failures += 1
             print(tag, "FAILED:", repr(exc)[:200], flush=True)
@@ -126,10 +127,6 @@ def main():
     print("cases %d  failures %d  (%d precision runs judged by the conditioned acquisition gate)  worst |d var| in units of the gate %.3g  worst split-vs-fp64 |d var| / prior %.3g  (%.0f s)" % (
         cases, failures, conditioned, worst["var"] / 1e-9, worst["split_vs_fp64"], time.time() - t0))
     return 1 if failures else 0
-
-
-def dev_planes(dev):
-    return dev.split_info()
 
 
 def diagnose(st, Xc, y_opt, vtol):
