@@ -32,17 +32,35 @@ constexpr size_t ch_smem_bytes() { return 3 * (size_t)CH_NB * CH_LD * sizeof(dou
 // dst[r][c] = src(row0 + r, col0 + c) (TRANS = false) or src(row0 + c, col0 + r) (TRANS = true); zero outside the matrix.
 // A half-warp moves a 4 x 4 patch: four rows of a column are one 32-byte sector of the column-major source, and the 16
 // shared-memory words land in 16 different banks in both modes (row stride CH_LD = 4 mod 16).
+// The two halves of a tile load: global -> registers (16 independent loads per thread, all in flight at once) and
+// registers -> shared memory.  Kernels fetch every tile they need before they store the first one (one round trip to
+// L2 / HBM instead of one per tile), and the kernels that loop over k blocks fetch the next pair while the tensor-core
+// tiles of the current pair run.
+__device__ __forceinline__ void ch_fetch_tile(double (&v)[CH_NB / 4], const double* __restrict__ src, int n, int row0, int col0) {
+    const int rsub = threadIdx.x & 3, csub = (threadIdx.x >> 2) & 3, prow = threadIdx.x >> 4;
+    const int gi = row0 + 4 * prow + rsub;
+#pragma unroll
+    for (int pc = 0; pc < CH_NB / 4; ++pc) {
+        const int gj = col0 + 4 * pc + csub;
+        v[pc] = (gi < n && gj < n) ? src[(size_t)gj * n + gi] : 0.0;
+    }
+}
+template <bool TRANS>
+__device__ __forceinline__ void ch_store_tile(double* dst, const double (&v)[CH_NB / 4]) {
+    const int rsub = threadIdx.x & 3, csub = (threadIdx.x >> 2) & 3, prow = threadIdx.x >> 4;
+    const int r = 4 * prow + rsub;
+#pragma unroll
+    for (int pc = 0; pc < CH_NB / 4; ++pc) {
+        const int c = 4 * pc + csub;
+        if (TRANS) dst[c * CH_LD + r] = v[pc];
+        else dst[r * CH_LD + c] = v[pc];
+    }
+}
 template <bool TRANS>
 __device__ __forceinline__ void ch_load_tile(double* dst, const double* __restrict__ src, int n, int row0, int col0) {
-    const int rsub = threadIdx.x & 3, csub = (threadIdx.x >> 2) & 3, prow = threadIdx.x >> 4;
-    const int r = 4 * prow + rsub, gi = row0 + r;
-#pragma unroll 4
-    for (int pc = 0; pc < CH_NB / 4; ++pc) {
-        const int c = 4 * pc + csub, gj = col0 + c;
-        const double v = (gi < n && gj < n) ? src[(size_t)gj * n + gi] : 0.0;
-        if (TRANS) dst[c * CH_LD + r] = v;
-        else dst[r * CH_LD + c] = v;
-    }
+    double v[CH_NB / 4];
+    ch_fetch_tile(v, src, n, row0, col0);
+    ch_store_tile<TRANS>(dst, v);
 }
 
 // 64 x 64 x 64 tile product on FP64 tensor-core tiles (mma.sync m8n8k4, DMMA): warp w owns rows 8 w .. 8 w + 7 of the
@@ -158,8 +176,13 @@ __global__ void __launch_bounds__(CH_THREADS) chol_panel_kernel(double* __restri
     double* E = D + CH_NB * CH_LD;                           // [64][65] identity -> inverse of the factor (lower)
     double* S = E + CH_NB * CH_LD;                           // [64][65] this CTA's slab of the panel
     const int tid = threadIdx.x;
-    ch_load_tile<false>(D, A, n, k0, k0);
-    if (blockIdx.x > 0) ch_load_tile<false>(S, A, n, k0 + CH_NB * blockIdx.x, k0);
+    {
+        double vd[CH_NB / 4], vs[CH_NB / 4];
+        ch_fetch_tile(vd, A, n, k0, k0);
+        if (blockIdx.x > 0) ch_fetch_tile(vs, A, n, k0 + CH_NB * blockIdx.x, k0);
+        ch_store_tile<false>(D, vd);
+        if (blockIdx.x > 0) ch_store_tile<false>(S, vs);
+    }
     __syncthreads();
     // rows past the end of the matrix: identity, so that the factor and its inverse stay defined
     if (tid < CH_NB && k0 + tid >= n) {
@@ -235,8 +258,13 @@ __global__ void __launch_bounds__(CH_THREADS) chol_update_kernel(double* __restr
     while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
     const int bj = blockIdx.x - bi * (bi + 1) / 2;
     const int i0 = k0 + CH_NB * (bi + 1), j0 = k0 + CH_NB * (bj + 1);
-    ch_load_tile<false>(As, A, n, i0, k0);                    // As[r][kk] = L(i0 + r, k0 + kk)
-    ch_load_tile<true>(Bs, A, n, j0, k0);                     // Bs[kk][c] = L(j0 + c, k0 + kk)
+    {
+        double va[CH_NB / 4], vb[CH_NB / 4];
+        ch_fetch_tile(va, A, n, i0, k0);
+        ch_fetch_tile(vb, A, n, j0, k0);
+        ch_store_tile<false>(As, va);                         // As[r][kk] = L(i0 + r, k0 + kk)
+        ch_store_tile<true>(Bs, vb);                          // Bs[kk][c] = L(j0 + c, k0 + kk)
+    }
     __syncthreads();
     double acc[8][2];
 #pragma unroll
@@ -284,17 +312,21 @@ __global__ void __launch_bounds__(CH_THREADS) tri_inverse_level_kernel(const dou
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
     const int kb_lo = PHASE == 0 ? tj : 0, kb_hi = PHASE == 0 ? hb - 1 : ti;
+    const double* srcA = PHASE == 0 ? L : X;                  // L21(i, k) | X22(i, k)
+    const double* srcB = PHASE == 0 ? X : W;                  // X11(k, j) | W21(k, j)
+    const int kbase = PHASE == 0 ? base : base + h;
+    double va[CH_NB / 4], vb[CH_NB / 4];
+    ch_fetch_tile(va, srcA, n, i0, kbase + CH_NB * kb_lo);
+    ch_fetch_tile(vb, srcB, n, kbase + CH_NB * kb_lo, j0);
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
-        const int k0 = (PHASE == 0 ? base : base + h) + CH_NB * kb;
         __syncthreads();
-        if (PHASE == 0) {
-            ch_load_tile<false>(As, L, n, i0, k0);            // L21(i, k)
-            ch_load_tile<false>(Bs, X, n, k0, j0);            // X11(k, j)
-        } else {
-            ch_load_tile<false>(As, X, n, i0, k0);            // X22(i, k)
-            ch_load_tile<false>(Bs, W, n, k0, j0);            // W21(k, j)
+        ch_store_tile<false>(As, va);
+        ch_store_tile<false>(Bs, vb);
+        __syncthreads();
+        if (kb < kb_hi) {                                     // the next pair travels while this one is multiplied
+            ch_fetch_tile(va, srcA, n, i0, kbase + CH_NB * (kb + 1));
+            ch_fetch_tile(vb, srcB, n, kbase + CH_NB * (kb + 1), j0);
         }
-        __syncthreads();
         ch_tile_mma<false>(As, Bs, acc);
     }
     double* out = PHASE == 0 ? W : X;
@@ -322,11 +354,18 @@ __global__ void __launch_bounds__(CH_THREADS) tri_gram_kernel(const double* __re
     double acc[8][2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+    double va[CH_NB / 4], vb[CH_NB / 4];
+    ch_fetch_tile(va, X, n, CH_NB * bi, i0);
+    ch_fetch_tile(vb, X, n, CH_NB * bi, j0);
     for (int kb = bi; kb < nb; ++kb) {
         __syncthreads();
-        ch_load_tile<true>(As, X, n, CH_NB * kb, i0);         // As[r][kk] = X(k0 + kk, i0 + r)
-        ch_load_tile<false>(Bs, X, n, CH_NB * kb, j0);        // Bs[kk][c] = X(k0 + kk, j0 + c)
+        ch_store_tile<true>(As, va);                          // As[r][kk] = X(k0 + kk, i0 + r)
+        ch_store_tile<false>(Bs, vb);                         // Bs[kk][c] = X(k0 + kk, j0 + c)
         __syncthreads();
+        if (kb + 1 < nb) {                                    // the next pair travels while this one is multiplied
+            ch_fetch_tile(va, X, n, CH_NB * (kb + 1), i0);
+            ch_fetch_tile(vb, X, n, CH_NB * (kb + 1), j0);
+        }
         ch_tile_mma<false>(As, Bs, acc);
     }
     const int gi = i0 + ch_mma_row();
