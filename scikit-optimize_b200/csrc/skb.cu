@@ -87,6 +87,12 @@ struct skb_state {
     double* d_probe = nullptr;        // [PROBE_ROWS][d] candidates made from the training rows at state creation
     double* d_probe_out = nullptr;    // [4][PROBE_ROWS] posterior mean, std: FP64 path | mean, std: 6-plane split path
     double* d_tn = nullptr;           // [n_pad] squared norms of the scaled training rows (6-plane K1: |x|^2 + |t|^2 - 2 x.t)
+    // The operands of the split-integer path (d_sV, d_Vd, d_tn, d_probe) are packed from the raw device copies of the
+    // caller's arrays by ensure_split_operands - at creation (measured: packing them only on first use saves 8 us of a
+    // 50 us creation, not worth a second state of the object).
+    double* d_linv_raw = nullptr;     // [n][n] row-major L_inv (until the split operands exist)
+    double* d_x_raw = nullptr;        // [n][d] training rows
+    bool split_ready = false;
     // grow-only scratch
     uint64_t scratch_limit = 2ull << 30;
     double* d_Kt = nullptr;      size_t kt_tiles = 0;
@@ -598,6 +604,8 @@ int check_params(const skb_acq_params* p) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+static void release_streams(skb_state* st);
+
 extern "C" {
 
 int skb_abi_version(void) { return SKB_ABI_VERSION; }
@@ -631,7 +639,8 @@ void skb_state_destroy(skb_state* st) {
         if (ev) cudaEventDestroy(ev);
     void* ptrs[] = {st->d_ls, st->d_hw, st->d_Xp, st->d_alpha_p, st->d_Vp, st->d_Ap, st->d_Vd, st->d_sV, st->d_Ad, st->d_sA, st->d_Wt, st->d_Kt, st->d_kdot, st->d_acq[0], st->d_acq[1],
                     st->d_acq[2], st->d_part_v, st->d_part_i, st->d_part_nan, st->d_topk_v, st->d_topk_i,
-                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out, st->d_tn};
+                    st->d_topk_nan, st->d_X, st->d_out, st->d_clamp, st->d_Kt2, st->d_kdot2, st->d_probe, st->d_probe_out, st->d_tn,
+                    st->d_linv_raw, st->d_x_raw};
     for (void* p : ptrs) pool_free(st->device, p);
     for (auto& sp : st->spans) {
         cudaEventDestroy(sp.a);
@@ -640,11 +649,8 @@ void skb_state_destroy(skb_state* st) {
     for (auto& ev : st->chunk_ready) cudaEventDestroy(ev);
     for (auto& ev : st->ev_k1) cudaEventDestroy(ev);
     for (auto& ev : st->ev_k2) cudaEventDestroy(ev);
-    if (st->ev_enter) cudaEventDestroy(st->ev_enter);
     stage_release(st);
-    if (st->aux_stream) cudaStreamDestroy(st->aux_stream);
-    if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
-    if (st->stream) cudaStreamDestroy(st->stream);
+    release_streams(st);
     delete st;
 }
 
@@ -653,6 +659,88 @@ void skb_state_destroy(skb_state* st) {
 // `kind` = cudaMemcpyHostToDevice for caller-owned host arrays (skb_state_create) or cudaMemcpyDeviceToDevice when
 // X_train / alpha / L_inv / K_inv of `desc` already live on `device` (skb_state_create_from_fit)
 static int attach_kinv_impl(skb_state* st, const double* K_inv, cudaMemcpyKind kind);
+// Streams and the entry event are recycled across states: a BO loop creates one state per tell() and drops the previous
+// one, and creating / destroying three streams and an event costs more than the kernels of a small state.
+struct StreamBundle { cudaStream_t stream, copy_stream, aux_stream; cudaEvent_t ev_enter; };
+static std::vector<StreamBundle> g_stream_cache[64];
+static std::mutex g_stream_cache_mu;
+constexpr size_t STREAM_CACHE_MAX = 16;
+
+static int acquire_streams(skb_state* st) {
+    {
+        std::lock_guard<std::mutex> lock(g_stream_cache_mu);
+        auto& cache = g_stream_cache[st->device & 63];
+        if (!cache.empty()) {
+            const StreamBundle b = cache.back();
+            cache.pop_back();
+            st->stream = b.stream;
+            st->copy_stream = b.copy_stream;
+            st->aux_stream = b.aux_stream;
+            st->ev_enter = b.ev_enter;
+            return SKB_OK;
+        }
+    }
+    CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&st->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&st->ev_enter, cudaEventDisableTiming));
+    return SKB_OK;
+}
+
+// called by skb_state_destroy after the device has been synchronised
+static void release_streams(skb_state* st) {
+    if (st->stream && st->copy_stream && st->aux_stream && st->ev_enter) {
+        std::lock_guard<std::mutex> lock(g_stream_cache_mu);
+        auto& cache = g_stream_cache[st->device & 63];
+        if (cache.size() < STREAM_CACHE_MAX) {
+            cache.push_back({st->stream, st->copy_stream, st->aux_stream, st->ev_enter});
+            st->stream = st->copy_stream = st->aux_stream = nullptr;
+            st->ev_enter = nullptr;
+            return;
+        }
+    }
+    if (st->ev_enter) cudaEventDestroy(st->ev_enter);
+    if (st->aux_stream) cudaStreamDestroy(st->aux_stream);
+    if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    st->stream = st->copy_stream = st->aux_stream = nullptr;
+    st->ev_enter = nullptr;
+}
+
+// Operands of the split-integer path from the raw device copies of L_inv and X_train: squared row norms (6-plane K1), the
+// probe candidates of the self-check, power-of-two row scales and the 7 signed 8-bit digit planes per lower-triangular
+// 128 x 32 chunk.  Queued on the state's stream; `wait` = the caller works on other streams and needs them finished.
+static int ensure_split_operands(skb_state* st, bool wait) {
+    if (st->split_ready) return SKB_OK;
+    if (!st->d_linv_raw || !st->d_x_raw) return fail(SKB_ERR_INVALID, "internal: the raw state copies are gone");
+    CU(cudaSetDevice(st->device));
+    const int nI = st->n_pad / BM;
+    int prc;
+#define SKB_PALLOC(ptr, bytes) if ((prc = pool_alloc(st->device, reinterpret_cast<void**>(&(ptr)), (bytes))) != SKB_OK) return prc
+    if (!st->d_tn) SKB_PALLOC(st->d_tn, (size_t)st->n_pad * sizeof(double));
+    if (!st->d_probe) SKB_PALLOC(st->d_probe, (size_t)PROBE_ROWS * st->d * sizeof(double));
+    if (!st->d_sV) SKB_PALLOC(st->d_sV, (size_t)st->n_pad * sizeof(double));
+    if (!st->d_Vd) SKB_PALLOC(st->d_Vd, (size_t)vp_tiles_before(nI) * OZ_A_CHUNK);
+#undef SKB_PALLOC
+    row_sqnorm_kernel<<<(st->n_pad + 255) / 256, 256, 0, st->stream>>>(st->d_Xp, st->d_tn, st->n_pad, st->d_pad);
+    LAUNCHED();
+    make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(st->d_x_raw, st->d_ls, st->d_probe, st->n, st->d,
+                                                                                      st->kernel == SKB_KERNEL_HAMMING ? 1 : 0);
+    LAUNCHED();
+    oz_row_scale_kernel<false><<<st->n_pad, 256, 0, st->stream>>>(st->d_linv_raw, st->d_sV, st->n, st->n_pad);
+    LAUNCHED();
+    oz_pack_linv_kernel<false><<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(st->d_linv_raw, st->d_sV, st->d_Vd, st->n, st->n_pad);
+    LAUNCHED();
+    st->split_ready = true;
+    if (wait) {
+        CU(cudaStreamSynchronize(st->stream));
+        pool_free(st->device, st->d_linv_raw);
+        pool_free(st->device, st->d_x_raw);
+        st->d_linv_raw = st->d_x_raw = nullptr;
+    }
+    return SKB_OK;
+}
+
 static int state_create_impl(const skb_state_desc* desc, int device, skb_state** out, cudaMemcpyKind kind) {
     if (!desc || !out) return fail(SKB_ERR_INVALID, "desc/out is NULL");
     *out = nullptr;
@@ -700,11 +788,8 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
     double *dX = nullptr, *dV = nullptr;
     int rc = SKB_OK;
     auto body = [&]() -> int {
-        CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&st->aux_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&st->ev_enter, cudaEventDisableTiming));
         int prc;
+        if ((prc = acquire_streams(st)) != SKB_OK) return prc;
 #define SKB_PALLOC(ptr, bytes) if ((prc = pool_alloc(device, reinterpret_cast<void**>(&(ptr)), (bytes))) != SKB_OK) return prc
         SKB_PALLOC(st->d_ls, d * sizeof(double));
         SKB_PALLOC(st->d_Xp, (size_t)st->n_pad * st->d_pad * sizeof(double));
@@ -732,25 +817,20 @@ static int state_create_impl(const skb_state_desc* desc, int device, skb_state**
         pack_xtrain_kernel<<<std::min(1024, (st->n_pad * st->d_pad + 255) / 256), 256, 0, st->stream>>>(
             dX, st->d_ls, st->d_Xp, st->n, st->n_pad, st->d, st->d_pad);
         LAUNCHED();
-        SKB_PALLOC(st->d_tn, (size_t)st->n_pad * sizeof(double));
-        row_sqnorm_kernel<<<(st->n_pad + 255) / 256, 256, 0, st->stream>>>(st->d_Xp, st->d_tn, st->n_pad, st->d_pad);
-        LAUNCHED();
-        SKB_PALLOC(st->d_probe, (size_t)PROBE_ROWS * d * sizeof(double));
-        make_probe_kernel<<<(PROBE_ROWS * st->d + 255) / 256, 256, 0, st->stream>>>(dX, st->d_ls, st->d_probe, st->n, st->d,
-                                                                                          hamming ? 1 : 0);
-        LAUNCHED();
         pack_linv_kernel<<<dim3(nI * (BM / BK), nI), 256, 0, st->stream>>>(dV, st->d_Vp, st->n, st->n_pad);
         LAUNCHED();
-        // split-integer operands: row scales, then 7 signed 8-bit digit planes per lower-triangular 128 x 32 chunk
-        SKB_PALLOC(st->d_sV, (size_t)st->n_pad * sizeof(double));
-        SKB_PALLOC(st->d_Vd, (size_t)vp_tiles_before(nI) * OZ_A_CHUNK);
-        oz_row_scale_kernel<false><<<st->n_pad, 256, 0, st->stream>>>(dV, st->d_sV, st->n, st->n_pad);
-        LAUNCHED();
-        oz_pack_linv_kernel<false><<<dim3(nI * (BM / OZ_KC), nI), 256, 0, st->stream>>>(dV, st->d_sV, st->d_Vd, st->n, st->n_pad);
-        LAUNCHED();
+        st->d_linv_raw = dV;
+        st->d_x_raw = dX;
+        dV = dX = nullptr;                                   // owned by the state from here on
+        if ((prc = ensure_split_operands(st, false)) != SKB_OK) return prc;
         st->k_scale = oz_pow2_scale(std::fabs(desc->amplitude) + std::fabs(desc->bias));
 #undef SKB_PALLOC
         CU(cudaStreamSynchronize(st->stream));
+        if (st->split_ready) {                               // packed eagerly: the raw copies have served
+            pool_free(device, st->d_linv_raw);
+            pool_free(device, st->d_x_raw);
+            st->d_linv_raw = st->d_x_raw = nullptr;
+        }
         return set_kernel_attributes(st);
     };
     rc = body();
@@ -1059,6 +1139,8 @@ static int decide_split_planes(skb_state* st, cudaStream_t s);
 // Digit planes a split-integer call of m candidates contracts.  force_planes: 0 = follow the precision mode
 // (SPLIT_INT8_P7: 7; SPLIT_INT8: the state's self-checked choice), 6 / 7 = use that.
 static int split_planes_for_call(skb_state* st, const skb_acq_params* prm, int64_t m, int force_planes, cudaStream_t s, int* planes) {
+    int erc = ensure_split_operands(st, true);                 // a no-op: the operands are packed at creation
+    if (erc != SKB_OK) return erc;
     *planes = 7;
     if (force_planes) *planes = force_planes;
     else if (prm->precision == SKB_PRECISION_SPLIT_INT8) {
@@ -1324,6 +1406,7 @@ static void split_error_bounds(const skb_state* st, double max_sqrt_i_sV, double
 // to 6 planes is through both checks (SKB_PRECISION_SPLIT_INT8_P7 always contracts 7).
 static int decide_split_planes(skb_state* st, cudaStream_t s) {
     int rc;
+    if ((rc = ensure_split_operands(st, true)) != SKB_OK) return rc;
     if (!st->d_probe_out &&
         (rc = pool_alloc(st->device, reinterpret_cast<void**>(&st->d_probe_out), (4 * PROBE_ROWS + 4) * sizeof(double))) != SKB_OK)
         return rc;
@@ -1977,6 +2060,7 @@ int skb_debug_k2o(skb_state* st, int dbg, int64_t tiles64, int reps, double* ms_
     if (!st || !ms_per_launch || tiles64 <= 0 || reps <= 0) return fail(SKB_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(st->device));
     int rc;
+    if ((rc = ensure_split_operands(st, true)) != SKB_OK) return rc;
     const int64_t tiles = (tiles64 + 1) / 2;
     if ((rc = grow(st->device, &st->d_Kt, &st->kt_tiles, (size_t)tiles * st->n_pad * BN)) != SKB_OK) return rc;
     if ((rc = grow(st->device, &st->d_kdot, &st->kdot_cap, (size_t)tiles * BN)) != SKB_OK) return rc;
