@@ -1065,7 +1065,10 @@ static int upload_chunked(skb_state* st, const double* X, int64_t m, int64_t chu
     }
     stager_join(st);
     st->stage_rc = 0;
-    if (!is_pageable(X)) {
+    // Small pageable inputs (the 10 000 x d candidate set of a default tell()) go straight to cudaMemcpyAsync: the driver
+    // stages them itself in less time than starting the helper thread takes; the pinned ring pays off from megabytes on.
+    constexpr size_t DIRECT_UPLOAD_BYTES = 1u << 20;
+    if ((size_t)m * st->d * sizeof(double) <= DIRECT_UPLOAD_BYTES || !is_pageable(X)) {
         size_t ci = 0;
         for (int64_t t0 = 0; t0 < tiles; t0 += chunk_tiles, ++ci) {
             const int64_t c0 = t0 * BN;
