@@ -49,6 +49,12 @@ class _DeviceRows(object):
     def __getitem__(self, i):
         return self.tensor[int(i)].cpu().numpy()
 
+    def rows(self, idx):
+        """The rows `idx` as one (len(idx), n_dims) NumPy array: one gather on the device, one copy to the host."""
+        import torch
+        sel = torch.as_tensor(np.asarray(idx, dtype=np.int64), device=self.tensor.device)
+        return self.tensor.index_select(0, sel).cpu().numpy()
+
 
 class Optimizer(object):
     def __init__(self, dimensions, base_estimator="gp", n_random_starts=None, n_initial_points=10,
@@ -365,17 +371,25 @@ class Optimizer(object):
                 idx = r["first_nan"] if r["first_nan"] >= 0 else int(r["topk_idx"][0])
                 next_xs.append(X[idx])
         else:
-            starts, owner = [], []
+            start_idx, owner = [], []
             for a_i, acq in enumerate(acqs):
                 for idx in res[acq]["topk_idx"]:
                     if idx >= 0:
-                        starts.append(X[int(idx)])
+                        start_idx.append(int(idx))
                         owner.append(a_i)
+            # all restart points of all acquisitions in one fetch (device candidates: one gather + one copy)
+            rows = X.rows(start_idx) if isinstance(X, _DeviceRows) else np.asarray(X)[start_idx]
+            starts = [rows[i] for i in range(len(start_idx))]
+
+            owner_arr = np.asarray(owner, dtype=np.intp)
 
             def evaluate(tasks, Xq):
                 g = dev.score_grad(Xq, y_opt=y_opt, acq_funcs=acqs, xi=xi, kappa=kappa)
-                f = np.array([g[acqs[owner[t]]]["values"][i] for i, t in enumerate(tasks)])
-                G = np.vstack([g[acqs[owner[t]]]["grad"][i] for i, t in enumerate(tasks)])
+                own, row = owner_arr[np.asarray(tasks, dtype=np.intp)], np.arange(len(tasks))
+                if len(acqs) == 1:
+                    return g[acqs[0]]["values"], g[acqs[0]]["grad"]
+                f = np.stack([g[a]["values"] for a in acqs])[own, row]           # row i belongs to acquisition own[i]
+                G = np.stack([g[a]["grad"] for a in acqs])[own, row]
                 return f, G
 
             with warnings.catch_warnings():
