@@ -1518,10 +1518,14 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         if (((params->acq_mask >> a) & 1) && out->acq[a]) ++n_vec;
     const int k = params->top_k;
     if ((rc = grow(st->device, &st->d_out, &st->out_cap, (size_t)n_vec * m + 1)) != SKB_OK) return rc;
+    // the small results live in ONE block - [3 k] values | [3 k] indices | [3] first-NaN | [1] clamp count - so that they
+    // come back in one copy (a sampling-mode tell() asks for nothing else: ten tiny copies were a third of its call)
     const size_t kk = (size_t)3 * std::max(k, 1);
-    if ((rc = grow(st->device, &st->d_topk_v, &st->topk_v_cap, kk)) != SKB_OK) return rc;
-    if ((rc = grow(st->device, &st->d_topk_i, &st->topk_i_cap, kk)) != SKB_OK) return rc;
-    if ((rc = grow(st->device, &st->d_topk_nan, &st->topk_nan_cap, 3)) != SKB_OK) return rc;
+    if ((rc = grow(st->device, &st->d_topk_v, &st->topk_v_cap, 2 * kk + 4)) != SKB_OK) return rc;
+    double* const rec_v = st->d_topk_v;
+    int64_t* const rec_i = reinterpret_cast<int64_t*>(rec_v + kk);
+    int64_t* const rec_nan = rec_i + kk;
+    int64_t* const rec_clamp = rec_nan + 3;
     skb_score_out dout;
     std::memset(&dout, 0, sizeof(dout));
     double* cur = st->d_out;
@@ -1531,12 +1535,12 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         if (!((params->acq_mask >> a) & 1)) continue;
         if (out->acq[a]) { dout.acq[a] = cur; cur += m; }
         if (k > 0) {
-            dout.topk_val[a] = st->d_topk_v + (size_t)a * k;
-            dout.topk_idx[a] = st->d_topk_i + (size_t)a * k;
-            dout.first_nan[a] = st->d_topk_nan + a;
+            dout.topk_val[a] = rec_v + (size_t)a * k;
+            dout.topk_idx[a] = rec_i + (size_t)a * k;
+            dout.first_nan[a] = rec_nan + a;
         }
     }
-    if (out->n_var_clamped) dout.n_var_clamped = reinterpret_cast<int64_t*>(st->d_clamp);
+    if (out->n_var_clamped) dout.n_var_clamped = rec_clamp;
     // the same chunks score_dev_impl will consume (the 6-or-7-plane decision is settled here if it is due)
     int up_planes = 0;
     const bool up_split = is_split(params->precision) && st->n <= SPLIT_MAX_TRAIN;
@@ -1548,15 +1552,34 @@ int skb_score_host(skb_state* st, const double* X, int64_t m, int64_t index_offs
         return rc;
     }
     if ((rc = stage_begin(st)) != SKB_OK) return rc;
-    if ((rc = d2h(st, out->n_var_clamped, st->d_clamp, sizeof(int64_t), s)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->mean, dout.mean, m * sizeof(double), s)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->std, dout.std, m * sizeof(double), s)) != SKB_OK) return rc;
     for (int a = 0; a < 3; ++a) {
         if (!((params->acq_mask >> a) & 1)) continue;
         if ((rc = d2h(st, out->acq[a], dout.acq[a], m * sizeof(double), s)) != SKB_OK) return rc;
-        if (k > 0) {
-            if (!out->topk_val[a] || !out->topk_idx[a])
-                return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+        if (k > 0 && (!out->topk_val[a] || !out->topk_idx[a]))
+            return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+    }
+    // the record block in one copy through the pinned block, handed out after the synchronisation
+    const size_t rec_bytes = (2 * kk + 4) * sizeof(double);
+    const size_t rec_off = (st->h_stage_used + 15) & ~(size_t)15;
+    if (st->h_stage && rec_bytes <= STAGE_MAX_COPY && rec_off + rec_bytes <= STAGE_BYTES) {
+        CU(cudaMemcpyAsync(st->h_stage + rec_off, rec_v, rec_bytes, cudaMemcpyDeviceToHost, s));
+        st->h_stage_used = rec_off + rec_bytes;
+        auto hand = [&](void* host, const void* dev, size_t bytes) {
+            if (host && dev) st->unpack.push_back({host, rec_off + (size_t)((const char*)dev - (const char*)rec_v), bytes});
+        };
+        hand(out->n_var_clamped, dout.n_var_clamped, sizeof(int64_t));
+        for (int a = 0; a < 3; ++a) {
+            if (!((params->acq_mask >> a) & 1) || k <= 0) continue;
+            hand(out->topk_val[a], dout.topk_val[a], k * sizeof(double));
+            hand(out->topk_idx[a], dout.topk_idx[a], k * sizeof(int64_t));
+            hand(out->first_nan[a], dout.first_nan[a], sizeof(int64_t));
+        }
+    } else {
+        if ((rc = d2h(st, out->n_var_clamped, dout.n_var_clamped, sizeof(int64_t), s)) != SKB_OK) return rc;
+        for (int a = 0; a < 3; ++a) {
+            if (!((params->acq_mask >> a) & 1) || k <= 0) continue;
             if ((rc = d2h(st, out->topk_val[a], dout.topk_val[a], k * sizeof(double), s)) != SKB_OK) return rc;
             if ((rc = d2h(st, out->topk_idx[a], dout.topk_idx[a], k * sizeof(int64_t), s)) != SKB_OK) return rc;
             if ((rc = d2h(st, out->first_nan[a], dout.first_nan[a], sizeof(int64_t), s)) != SKB_OK) return rc;
@@ -1774,6 +1797,26 @@ int skb_score_grad_host(skb_state* st, const double* X, int64_t m, const skb_acq
     if ((rc = stage_begin(st)) != SKB_OK) return rc;
     if ((rc = h2d(st, st->d_X, X, (size_t)m * d * sizeof(double), s)) != SKB_OK) return rc;
     if ((rc = skb_score_grad_dev(st, st->d_X, m, prm, &dout, s)) != SKB_OK) return rc;
+    // The requested outputs sit back to back in d_out: small batches (every round of the L-BFGS refinement) come back in
+    // ONE copy into the pinned block instead of up to ten, and are handed out from there after the synchronisation.
+    const size_t total = (size_t)(cur - st->d_out) * sizeof(double);
+    const size_t off0 = (st->h_stage_used + 15) & ~(size_t)15;
+    if (st->h_stage && total > 0 && total <= STAGE_MAX_COPY && off0 + total <= STAGE_BYTES) {
+        CU(cudaMemcpyAsync(st->h_stage + off0, st->d_out, total, cudaMemcpyDeviceToHost, s));
+        st->h_stage_used = off0 + total;
+        auto hand = [&](void* host, const double* dev, size_t count) {
+            if (host && dev) st->unpack.push_back({host, off0 + (size_t)(dev - st->d_out) * sizeof(double), count * sizeof(double)});
+        };
+        hand(out->mean, dout.mean, m);
+        hand(out->std, dout.std, m);
+        hand(out->mean_grad, dout.mean_grad, m * d);
+        hand(out->std_grad, dout.std_grad, m * d);
+        for (int a = 0; a < 3; ++a) {
+            hand(out->acq[a], dout.acq[a], m);
+            hand(out->acq_grad[a], dout.acq_grad[a], m * d);
+        }
+        return stage_finish(st, s);
+    }
     if ((rc = d2h(st, out->mean, dout.mean, m * sizeof(double), s)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->std, dout.std, m * sizeof(double), s)) != SKB_OK) return rc;
     if ((rc = d2h(st, out->mean_grad, dout.mean_grad, m * d * sizeof(double), s)) != SKB_OK) return rc;
