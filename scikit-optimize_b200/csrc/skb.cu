@@ -1339,19 +1339,29 @@ static int score_dev_impl(skb_state* st, const double* X, int64_t m, int64_t ind
     if (top_k > 0) {
         const int nblk = (int)std::min<int64_t>((int64_t)st->sm_count * TOPK_BLOCKS_PER_SM, (m + 1023) / 1024);
         const int64_t slice = (m + nblk - 1) / nblk;
-        if ((rc = grow(st->device, &st->d_part_v, &st->part_v_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
-        if ((rc = grow(st->device, &st->d_part_i, &st->part_i_cap, (size_t)nblk * top_k)) != SKB_OK) return rc;
-        if ((rc = grow(st->device, &st->d_part_nan, &st->part_nan_cap, (size_t)nblk)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_part_v, &st->part_v_cap, (size_t)3 * nblk * top_k)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_part_i, &st->part_i_cap, (size_t)3 * nblk * top_k)) != SKB_OK) return rc;
+        if ((rc = grow(st->device, &st->d_part_nan, &st->part_nan_cap, (size_t)3 * nblk)) != SKB_OK) return rc;
+        // all requested acquisitions in one partial launch (blockIdx.y) and one merge launch
+        TopkBatch tb;
+        std::memset(&tb, 0, sizeof(tb));
+        int n_vec = 0;
         for (int a = 0; a < 3; ++a) {
             if (!((prm->acq_mask >> a) & 1)) continue;
             if (!out->topk_val[a] || !out->topk_idx[a])
                 return fail(SKB_ERR_INVALID, "top_k > 0 but topk_val/topk_idx[%d] is NULL", a);
+            tb.vals[n_vec] = acq_ptr[a];
+            tb.out_v[n_vec] = out->topk_val[a];
+            tb.out_i[n_vec] = out->topk_idx[a];
+            tb.out_nan[n_vec] = out->first_nan[a];
+            ++n_vec;
+        }
+        if (n_vec > 0) {
             if ((rc = span_begin(st, 2, s)) != SKB_OK) return rc;
-            topk_partial_kernel<<<nblk, TOPK_THREADS, 0, s>>>(acq_ptr[a], m, slice, index_offset, top_k, st->d_part_v,
-                                                              st->d_part_i, st->d_part_nan);
+            topk_partial_batch_kernel<<<dim3(nblk, n_vec), TOPK_THREADS, 0, s>>>(tb, m, slice, index_offset, top_k, st->d_part_v,
+                                                                                  st->d_part_i, st->d_part_nan);
             LAUNCHED();
-            topk_merge_kernel<<<1, TOPK_THREADS, 0, s>>>(st->d_part_v, st->d_part_i, st->d_part_nan, nblk, top_k,
-                                                         out->topk_val[a], out->topk_idx[a], out->first_nan[a]);
+            topk_merge_batch_kernel<<<n_vec, TOPK_THREADS, 0, s>>>(tb, st->d_part_v, st->d_part_i, st->d_part_nan, nblk, top_k);
             LAUNCHED();
             if ((rc = span_end(st, s)) != SKB_OK) return rc;
         }

@@ -120,6 +120,41 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(const double* 
     }
 }
 
+// The same two steps for up to three value vectors (the acquisitions of one scoring call) in ONE launch each:
+// blockIdx.y selects the vector.  part_* hold [n_vec][nparts][k] / [n_vec][nparts] partial results.
+struct TopkBatch {
+    const double* vals[3];
+    double* out_v[3];
+    int64_t* out_i[3];
+    int64_t* out_nan[3];
+};
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_partial_batch_kernel(const TopkBatch b, int64_t count, int64_t slice,
+                                                                          int64_t index_offset, int k, double* part_v,
+                                                                          int64_t* part_i, int64_t* part_nan) {
+    const int a = blockIdx.y;
+    const int64_t lo = (int64_t)blockIdx.x * slice;
+    int64_t n = count - lo;
+    if (n > slice) n = slice;
+    if (n < 0) n = 0;
+    const size_t slot = (size_t)a * gridDim.x + blockIdx.x;
+    block_topk_rounds(b.vals[a] + lo, nullptr, n, index_offset + lo, k, part_v + slot * k, part_i + slot * k, part_nan + slot);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_merge_batch_kernel(const TopkBatch b, const double* __restrict__ part_v,
+                                                                        const int64_t* __restrict__ part_i,
+                                                                        const int64_t* __restrict__ part_nan, int nparts, int k) {
+    const int a = blockIdx.x;
+    const size_t base = (size_t)a * nparts;
+    block_topk_rounds(part_v + base * k, part_i + base * k, (int64_t)nparts * k, 0, k, b.out_v[a], b.out_i[a], nullptr);
+    if (threadIdx.x == 0 && b.out_nan[a]) {
+        long long mn = INT64_MAX;
+        for (int q = 0; q < nparts; ++q)
+            if (part_nan[base + q] >= 0 && part_nan[base + q] < mn) mn = part_nan[base + q];
+        *b.out_nan[a] = mn == INT64_MAX ? -1 : mn;
+    }
+}
+
 // Cross-rank merge of packed top-k records (one block per acquisition).  A record is `n_acq * (2 k + 1)` 8-byte words:
 //   [n_acq][k] values (f64) | [n_acq][k] global indices (i64, -1 = padding) | [n_acq] lowest NaN index (i64, -1 = none)
 // `gathered` holds `n_records` of them back to back (what one all-gather of the per-rank records delivers); `merged`
