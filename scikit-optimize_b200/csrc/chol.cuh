@@ -102,9 +102,12 @@ __device__ __forceinline__ void ch_rsqrt(double x, double& rl, double& l) {
     h = fma(h, r, h);
     const double dd = fma(-g, g, x);                         // residual correction of the root
     g = fma(dd, h, g);
+    // x <= 0 or NaN (a failed factorisation, reported through `info`): what sqrt(x) and 1 / sqrt(x) would give, by
+    // selects - calling the FP64 sqrt and division here put ~80 instructions on the critical path of EVERY column
     const bool ok = x > 0.0;
-    l = ok ? g : sqrt(x);
-    rl = ok ? 2.0 * h : 1.0 / sqrt(x);
+    const double bad = x == 0.0 ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
+    l = ok ? g : bad;
+    rl = ok ? 2.0 * h : (x == 0.0 ? __longlong_as_double(0x7ff0000000000000ll) : bad);
 }
 
 // Columns 16 Q .. 16 Q + 15 of the sweep in chol_panel_kernel (see there).
@@ -140,20 +143,32 @@ __device__ __forceinline__ void ch_sweep16(double (&d)[4][4], double (&e)[4][4],
             }
         }
         __syncthreads();
+        // Rank-1 updates without per-element predicates (comparisons and selects per element were most of a column's
+        // instructions): the masks go into the operands - L(r, c) = 0 for r <= c, L(cc, c) = 0 for cc <= c, inverse(c, cc)
+        // = 0 for cc > c - and fma(-0, x, y) = y leaves the finished entries as they are.  Entries above the diagonal of
+        // a diagonal block take garbage; nothing reads them.
+        double lr[4], lc[4], er[4];
 #pragma unroll
         for (int i = Q; i < 4; ++i) {                        // row groups above Q are finished
             const int r = tx + 16 * i;
-            const double lr = r > c ? colv[r] : 0.0;
+            lr[i] = r > c ? colv[r] : 0.0;
+        }
 #pragma unroll
-            for (int j = Q; j < 4; ++j) {                    // block columns that can still be right of c
-                const int cc = ty + 16 * j;
-                if (cc > c && r >= cc) d[i][j] = fma(-lr, colv[cc], d[i][j]);
-            }
+        for (int j = Q; j < 4; ++j) {                        // block columns that can still be right of c
+            const int cc = ty + 16 * j;
+            lc[j] = cc > c ? colv[cc] : 0.0;
+        }
 #pragma unroll
-            for (int j = 0; j <= Q; ++j) {                   // columns of the inverse that can be <= c
-                const int cc = ty + 16 * j;
-                if (cc <= c && r > c) e[i][j] = fma(-lr, rowE[cc], e[i][j]);
-            }
+        for (int j = 0; j <= Q; ++j) {                       // columns of the inverse that can be <= c
+            const int cc = ty + 16 * j;
+            er[j] = cc <= c ? rowE[cc] : 0.0;
+        }
+#pragma unroll
+        for (int i = Q; i < 4; ++i) {
+#pragma unroll
+            for (int j = Q; j <= i; ++j) d[i][j] = fma(-lr[i], lc[j], d[i][j]);
+#pragma unroll
+            for (int j = 0; j <= Q; ++j) e[i][j] = fma(-lr[i], er[j], e[i][j]);
         }
         // publish the next pivot
         if (o < 15) {
