@@ -69,6 +69,17 @@ if px is not None:
         assert torch.equal(fused.cpu(), ref), (step, A, k)
     check_exchanges()
     assert px.seq >= 40
+    # a record that does not fit a peer slot (n_acq (2 k + 1) > 1024 words) takes the all-gather + merge-kernel path
+    A, k = 1, 700
+    assert not px.fits(A, k)
+    vals = torch.randn(A * k, generator=g, dtype=torch.float64)
+    idx = torch.randperm(10 ** 6, generator=g)[: A * k].to(torch.int64) * world + rank
+    rec = torch.cat([vals.view(torch.int64), idx, torch.full((A,), -1, dtype=torch.int64)]).cuda()
+    seq_before = px.seq
+    big = exchange_records(rec, A, k)
+    gathered = torch.empty(world * rec.numel(), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(gathered, rec)
+    assert torch.equal(big.cpu(), merge_records_torch(gathered.cpu(), world, A, k)) and px.seq == seq_before
 # without shard_group a tell() is local even inside the process group: only rank 0 runs it here, and it must not hang
 if rank == 0:
     solo = Optimizer([(0.0, 1.0)] * 3, "GP", n_initial_points=4, acq_func="EI", acq_optimizer="sampling",
