@@ -22,8 +22,10 @@ _EPS = 1e-8
 
 
 def _unit_inclusive(rng, n):
-    """scipy.stats.uniform(loc=0, scale=nextafter(1,2)).rvs(n, random_state=rng): U * scale + loc (space.py:205-209)."""
-    return rng.uniform(0.0, 1.0, size=n) * _INCLUSIVE_ONE + 0.0
+    """scipy.stats.uniform(loc=0, scale=nextafter(1,2)).rvs(n, random_state=rng): U * scale + loc (space.py:205-209).
+    U = rng.uniform(0, 1) is 0.0 + 1.0 * random_sample(), i.e. random_sample() bit for bit (same stream consumption), and
+    adding loc = 0.0 to a non-negative product changes nothing: two array passes less per column."""
+    return rng.random_sample(n) * _INCLUSIVE_ONE
 
 
 def _affine_inclusive(rng, n, loc, width):
@@ -129,6 +131,17 @@ class Real(Dimension):
             Xt = Xt * (self._whigh - self._wlow) + self._wlow
         out = np.clip(self._unwarp(Xt), self.low, self.high)
         return out if self.dtype in (float, "float") else out.astype(self.dtype)
+
+    def _sample_transformed_column(self, rng, n):
+        """transform(_sample_column(rng, n)) for the case the scoring block draws ten thousand times per tell - uniform
+        prior, "normalize", default dtype - with the same draws and the same arithmetic, minus the four range checks
+        (`_from_unit` and `transform` validate caller-supplied values; a fresh draw lies in [0, nextafter(1, 2)] and its
+        clipped image in [low, high], so they cannot fire): 4 array passes instead of 12.  None = not this case."""
+        if self.prior != "uniform" or self.transform_ != "normalize" or self.dtype not in (float, "float"):
+            return None
+        width = self._whigh - self._wlow
+        x = np.clip(_unit_inclusive(rng, n) * width + self._wlow, self.low, self.high)
+        return (x - self._wlow) / width
 
     def inverse_transform(self, Xt):
         """Warped -> original; Python floats (a list, or one float for a scalar) for the default dtype, an array of
@@ -673,8 +686,11 @@ class Space(object):
         rng = check_random_state(random_state)
         cols = []
         for dim in self.dimensions:
-            original = dim._sample_column(rng, n_samples)
-            cols.append(_as_column(dim.transform(original), n_samples))
+            fast = getattr(dim, "_sample_transformed_column", None)
+            col = fast(rng, n_samples) if fast is not None else None
+            if col is None:
+                col = dim.transform(dim._sample_column(rng, n_samples))
+            cols.append(_as_column(col, n_samples))
         return np.ascontiguousarray(np.hstack(cols))
 
 
